@@ -1,0 +1,398 @@
+"""Host-side mirror of the reference crate's public API (reference src/lib.rs:29-36) over the C ABI.
+
+Names, argument meaning and error behaviour follow image-rs/fdeflate 0.4.0-dev:
+
+    decompress_to_vec / decompress_to_vec_bounded      src/decompress.rs:1079, :1111
+    Decompressor {new, read, is_done, ignore_adler32}  src/decompress.rs:96-342
+    DecompressionError / BoundedDecompressionError     src/decompress.rs:13-48, :1090-1102
+    compress_to_vec_ultra_fast, UltraFastCompressor    src/compress/mod.rs:313, src/compress/ultrafast.rs:9-181
+    Compressor::new(w, 0, zlib)  ("stored")            src/compress/mod.rs:69-101, :241-268
+
+plus the batch entry points this project adds (Context.inflate_batch, ...).  All compute happens in
+the CUDA library; this file only packs buffers and maps status codes to exceptions.  The Rust shim
+a maintainer would write against the same C ABI is shown in INTEGRATION.md (no Rust toolchain exists
+in this image, so the host side is mirrored in Python and C++ instead).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _native
+from ._native import FLAG_GENERAL_ONLY, FLAG_IGNORE_ADLER32, NativeLib
+
+STATUS_NAMES = [
+    "Ok", "BadZlibHeader", "InsufficientInput", "InvalidBlockType", "InvalidUncompressedBlockLength",
+    "InvalidHlit", "InvalidHdist", "InvalidCodeLengthRepeat", "BadCodeLengthHuffmanTree",
+    "BadLiteralLengthHuffmanTree", "BadDistanceHuffmanTree", "InvalidLiteralLengthCode", "InvalidDistanceCode",
+    "InputStartsWithRun", "DistanceTooFarBack", "WrongChecksum", "ExtraInput", "OutputTooLarge",
+    "OutputBufferTooSmall",
+]
+ST_OK, ST_INSUFFICIENT_INPUT, ST_OUTPUT_TOO_LARGE = 0, 2, 17
+
+
+class DecompressionError(Exception):
+    """reference src/decompress.rs:13-48; `.kind` is the variant name, `.code` its 1-based index."""
+
+    def __init__(self, code: int):
+        self.code = int(code)
+        self.kind = STATUS_NAMES[self.code] if 0 <= self.code < len(STATUS_NAMES) else f"Unknown({code})"
+        super().__init__(self.kind)
+
+    def __eq__(self, other):
+        return isinstance(other, DecompressionError) and other.code == self.code
+
+    def __hash__(self):
+        return hash(self.code)
+
+
+class BoundedDecompressionError(Exception):
+    """reference src/decompress.rs:1090-1102: DecompressionError{inner} | OutputTooLarge{partial_output}."""
+
+    def __init__(self, inner: DecompressionError | None = None, partial_output: bytes | None = None):
+        self.inner = inner
+        self.partial_output = partial_output
+        self.kind = "OutputTooLarge" if inner is None else "DecompressionError"
+        super().__init__(self.kind if inner is None else f"DecompressionError({inner.kind})")
+
+
+class FdbError(RuntimeError):
+    """batch-level failure (CUDA error / bad argument) reported by the C ABI"""
+
+
+def _align16(x: int) -> int:
+    return (x + 15) & ~15
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data if a.size else 0)
+
+
+class Context:
+    """One fdb_ctx: bound to one GPU, not re-entrant (include/fdeflate_b200.h)."""
+
+    def __init__(self, device: int = 0, lib: NativeLib | None = None):
+        self.lib = lib if lib is not None else _native.default_lib()
+        h = C.c_void_p()
+        rc = self.lib.L.fdb_create(device, C.byref(h))
+        if rc != 0 or not h:
+            raise FdbError(f"fdb_create(device={device}) failed with code {rc}: no usable CUDA device "
+                           f"(fdeflate_b200 has no CPU fallback)")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.L.fdb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise FdbError(f"{what} failed ({rc}): {self.lib.L.fdb_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.L.fdb_launch_count(self._h))
+
+    def last_general_count(self, stream: int = 0) -> int:
+        """streams of the last inflate batch that the fast path handed to the general kernel"""
+        return int(self.lib.L.fdb_last_general_count(self._h, stream))
+
+    # ---- raw packed host-buffer calls ---------------------------------------------------------
+    def inflate_packed(self, in_base: np.ndarray, in_off, in_len, out_base: np.ndarray, out_off, out_cap,
+                       flags: int = 0):
+        n = len(in_off)
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        in_len = np.ascontiguousarray(in_len, dtype=np.uint64)
+        out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
+        out_cap = np.ascontiguousarray(out_cap, dtype=np.uint64)
+        out_len = np.zeros(n, dtype=np.uint64)
+        consumed = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        rc = self.lib.L.fdb_inflate_batch(self._h, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base),
+                                          _ptr(out_off), _ptr(out_cap), _ptr(out_len), _ptr(consumed), _ptr(status),
+                                          n, flags)
+        self._check(rc, "fdb_inflate_batch")
+        return out_len, consumed, status
+
+    def _deflate_packed(self, fn, in_base, in_off, in_len, out_base, out_off, out_cap):
+        n = len(in_off)
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        in_len = np.ascontiguousarray(in_len, dtype=np.uint64)
+        out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
+        out_cap = np.ascontiguousarray(out_cap, dtype=np.uint64)
+        out_len = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        rc = fn(self._h, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off), _ptr(out_cap),
+                _ptr(out_len), _ptr(status), n)
+        self._check(rc, "fdb_deflate_*_batch")
+        return out_len, status
+
+    def deflate_ultrafast_packed(self, in_base, in_off, in_len, out_base, out_off, out_cap):
+        return self._deflate_packed(self.lib.L.fdb_deflate_ultrafast_batch, in_base, in_off, in_len, out_base, out_off,
+                                    out_cap)
+
+    def deflate_stored_packed(self, in_base, in_off, in_len, out_base, out_off, out_cap):
+        return self._deflate_packed(self.lib.L.fdb_deflate_stored_batch, in_base, in_off, in_len, out_base, out_off,
+                                    out_cap)
+
+    # ---- convenience batch calls on lists of bytes ----------------------------------------------
+    @staticmethod
+    def _pack(items: Sequence[bytes], align: int = 16):
+        lens = np.array([len(b) for b in items], dtype=np.uint64)
+        offs = np.zeros(len(items), dtype=np.uint64)
+        pos = 0
+        for i, l in enumerate(lens):
+            offs[i] = pos
+            pos = (pos + int(l) + align - 1) // align * align if align > 1 else pos + int(l)
+        base = np.zeros(max(pos, 1), dtype=np.uint8)
+        for b, o in zip(items, offs):
+            if len(b):
+                base[int(o): int(o) + len(b)] = np.frombuffer(b, dtype=np.uint8)
+        return base, offs, lens
+
+    def inflate_batch(self, streams: Sequence[bytes], out_caps: Sequence[int], flags: int = 0, align: int = 16):
+        """-> (status int32[n], outputs list[bytes], consumed uint64[n]).  outputs[i] holds out_len[i] bytes."""
+        if len(streams) == 0:
+            return np.zeros(0, np.int32), [], np.zeros(0, np.uint64)
+        in_base, in_off, in_len = self._pack(streams, align)
+        caps = np.asarray(out_caps, dtype=np.uint64)
+        out_off = np.zeros(len(caps), dtype=np.uint64)
+        pos = 0
+        for i, c in enumerate(caps):
+            out_off[i] = pos
+            pos = (pos + int(c) + align - 1) // align * align if align > 1 else pos + int(c)
+        out_base = np.zeros(max(pos, 1), dtype=np.uint8)
+        out_len, consumed, status = self.inflate_packed(in_base, in_off, in_len, out_base, out_off, caps, flags)
+        outs = [out_base[int(o): int(o) + int(l)].tobytes() for o, l in zip(out_off, out_len)]
+        return status, outs, consumed
+
+    def _deflate_batch(self, packed_fn, bound_fn, inputs: Sequence[bytes], align: int):
+        if len(inputs) == 0:
+            return []
+        in_base, in_off, in_len = self._pack(inputs, align)
+        caps = np.array([bound_fn(len(b)) for b in inputs], dtype=np.uint64)
+        out_off = np.zeros(len(caps), dtype=np.uint64)
+        pos = 0
+        for i, c in enumerate(caps):
+            out_off[i] = pos
+            pos = (pos + int(c) + align - 1) // align * align if align > 1 else pos + int(c)
+        out_base = np.zeros(max(pos, 1), dtype=np.uint8)
+        out_len, status = packed_fn(in_base, in_off, in_len, out_base, out_off, caps)
+        if (status != 0).any():
+            raise FdbError(f"deflate status {status[status != 0][:4]}")
+        return [out_base[int(o): int(o) + int(l)].tobytes() for o, l in zip(out_off, out_len)]
+
+    def deflate_ultrafast_batch(self, inputs: Sequence[bytes], align: int = 16) -> list[bytes]:
+        return self._deflate_batch(self.deflate_ultrafast_packed, self.lib.L.fdb_deflate_ultrafast_bound, inputs, align)
+
+    def deflate_stored_batch(self, inputs: Sequence[bytes], align: int = 16) -> list[bytes]:
+        return self._deflate_batch(self.deflate_stored_packed, self.lib.L.fdb_deflate_stored_bound, inputs, align)
+
+    # ---- device-pointer calls (ints / torch data_ptr()); enqueue only -----------------------------
+    def inflate_device(self, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_consumed, d_status,
+                       n: int, flags: int = 0, stream: int = 0):
+        rc = self.lib.L.fdb_inflate_batch_device(self._h, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap,
+                                                 d_out_len, d_consumed, d_status, n, flags, stream)
+        self._check(rc, "fdb_inflate_batch_device")
+
+    def deflate_ultrafast_device(self, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_status,
+                                 n: int, stream: int = 0):
+        rc = self.lib.L.fdb_deflate_ultrafast_batch_device(self._h, d_in, d_in_off, d_in_len, d_out, d_out_off,
+                                                           d_out_cap, d_out_len, d_status, n, stream)
+        self._check(rc, "fdb_deflate_ultrafast_batch_device")
+
+    def deflate_stored_device(self, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_status,
+                              n: int, stream: int = 0):
+        rc = self.lib.L.fdb_deflate_stored_batch_device(self._h, d_in, d_in_off, d_in_len, d_out, d_out_off,
+                                                        d_out_cap, d_out_len, d_status, n, stream)
+        self._check(rc, "fdb_deflate_stored_batch_device")
+
+    def synth_tiles_device(self, d_out: int, first_tile: int, n_tiles: int, width: int, height: int, seed: int,
+                           stream: int = 0):
+        rc = self.lib.L.fdb_synth_tiles_device(self._h, d_out, first_tile, n_tiles, width, height, seed, stream)
+        self._check(rc, "fdb_synth_tiles_device")
+
+    def ultrafast_bound(self, n: int) -> int:
+        return int(self.lib.L.fdb_deflate_ultrafast_bound(n))
+
+    def stored_bound(self, n: int) -> int:
+        return int(self.lib.L.fdb_deflate_stored_bound(n))
+
+
+def synth_tiles_host(first_tile: int, n_tiles: int, width: int, height: int, seed: int,
+                     lib: NativeLib | None = None) -> np.ndarray:
+    """Synthetic PNG-filtered RGBA tiles, host version of the device generator."""
+    lib = lib if lib is not None else _native.default_lib()
+    tb = int(lib.L.fdb_synth_tile_bytes(width, height))
+    out = np.zeros(n_tiles * tb, dtype=np.uint8)
+    rc = lib.L.fdb_synth_tiles_host(_ptr(out), first_tile, n_tiles, width, height, seed)
+    if rc != 0:
+        raise FdbError("fdb_synth_tiles_host failed")
+    return out.reshape(n_tiles, tb)
+
+
+# ---- module-level mirror of the reference API -----------------------------------------------------
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def decompress_to_vec_bounded(data: bytes, maxlen: int, ctx: Context | None = None, flags: int = 0) -> bytes:
+    """reference src/decompress.rs:1111-1144.  Raises BoundedDecompressionError."""
+    ctx = ctx or default_context()
+    cap = min(maxlen, max(1024, 4 * len(data)))
+    while True:
+        status, outs, _ = ctx.inflate_batch([bytes(data)], [cap], flags)
+        st = int(status[0])
+        if st == ST_OK:
+            return outs[0]
+        if st == ST_OUTPUT_TOO_LARGE:
+            if cap >= maxlen:
+                raise BoundedDecompressionError(partial_output=outs[0])
+            cap = min(maxlen, cap * 4)  # the reference grows its Vec and carries on (:1132-1134)
+            continue
+        raise BoundedDecompressionError(inner=DecompressionError(st))
+
+
+def decompress_to_vec(data: bytes, ctx: Context | None = None) -> bytes:
+    """reference src/decompress.rs:1079-1087.  Raises DecompressionError."""
+    try:
+        return decompress_to_vec_bounded(data, 1 << 62, ctx)
+    except BoundedDecompressionError as e:
+        if e.inner is not None:
+            raise e.inner from None
+        raise
+
+
+def compress_to_vec_ultra_fast(data: bytes, ctx: Context | None = None) -> bytes:
+    """reference src/compress/mod.rs:313-317."""
+    ctx = ctx or default_context()
+    return ctx.deflate_ultrafast_batch([bytes(data)])[0]
+
+
+def compress_to_vec_stored(data: bytes, ctx: Context | None = None) -> bytes:
+    """compress_to_vec_with_level(data, 0), reference src/compress/mod.rs:299-303 with level 0."""
+    ctx = ctx or default_context()
+    return ctx.deflate_stored_batch([bytes(data)])[0]
+
+
+class Decompressor:
+    """Streaming facade with the reference's read() contract (src/decompress.rs:158-184) on top of the
+    whole-stream batch engine: input is buffered, and every call re-inflates the buffered prefix to
+    find the bytes that became available.  Chunking-invariant by construction; quadratic for
+    byte-wise feeding (the streaming row of SURVEY 8f is future work)."""
+
+    def __init__(self, ctx: Context | None = None):
+        self._ctx = ctx or default_context()
+        self._buf = bytearray()
+        self._emitted = 0
+        self._done = False
+        self._flags = 0
+
+    def ignore_adler32(self):
+        self._flags |= FLAG_IGNORE_ADLER32
+
+    def is_done(self) -> bool:
+        return self._done
+
+    def read(self, data: bytes, output: np.ndarray, output_position: int):
+        if self._done:
+            return 0, 0
+        if output_position > output.size:
+            raise IndexError("output_position out of bounds")  # the reference panics (:189)
+        self._buf += bytes(data)
+        room = output.size - output_position
+        cap = self._emitted + room
+        status, outs, _ = self._ctx.inflate_batch([bytes(self._buf)], [cap], self._flags)
+        st = int(status[0])
+        if st not in (ST_OK, ST_INSUFFICIENT_INPUT, ST_OUTPUT_TOO_LARGE):
+            raise DecompressionError(st)
+        new = outs[0][self._emitted:]
+        output[output_position: output_position + len(new)] = np.frombuffer(new, dtype=np.uint8)
+        self._emitted += len(new)
+        if st == ST_OK:
+            self._done = True
+        return len(data), len(new)
+
+
+class UltraFastCompressor:
+    """reference src/compress/ultrafast.rs:9-181.  `writer` needs a .write(bytes) method.
+
+    The reference's output depends on write_data call boundaries (the zero-run state and the 8-byte
+    chunking are local to each call).  Every call is therefore compressed as its own
+    stream in ONE device batch at finish(), and the token bits are spliced on the host, which
+    reproduces the reference byte for byte for any call pattern."""
+
+    def __init__(self, writer, ctx: Context | None = None):
+        self._w = writer
+        self._ctx = ctx or default_context()
+        self._calls: list[bytes] = []
+
+    def write_data(self, data: bytes):
+        self._calls.append(bytes(data))
+
+    def finish(self):
+        calls = self._calls if self._calls else [b""]
+        streams = self._ctx.deflate_ultrafast_batch(calls)
+        if len(streams) == 1:
+            self._w.write(streams[0])
+            return self._w
+        self._w.write(_splice_ultrafast(streams, calls))
+        return self._w
+
+
+_HEADER_BITS = 53 * 8 + 5
+
+
+def _splice_ultrafast(streams: Sequence[bytes], calls: Sequence[bytes]) -> bytes:
+    import zlib
+
+    acc = int.from_bytes(streams[0][:54], "little") & ((1 << _HEADER_BITS) - 1)
+    nbits = _HEADER_BITS
+    for s in streams:
+        body = int.from_bytes(s[:-4], "little")
+        end = body.bit_length() - 12  # the EOB code (12 bits) ends at the highest set bit
+        tok = (body >> _HEADER_BITS) & ((1 << (end - _HEADER_BITS)) - 1)
+        acc |= tok << nbits
+        nbits += end - _HEADER_BITS
+    acc |= 2303 << nbits
+    nbits += 12
+    out = acc.to_bytes((nbits + 7) // 8, "little")
+    adler = 1
+    for c in calls:
+        adler = zlib.adler32(c, adler)
+    return out + adler.to_bytes(4, "big")
+
+
+class Compressor:
+    """reference src/compress/mod.rs:47-215 restricted to level 0 ("stored").  Levels 1-9 are the
+    reference's sequential LZ77 encoders and are out of scope of the accelerated path."""
+
+    def __init__(self, writer, level: int, zlib: bool, ctx: Context | None = None):
+        if level != 0:
+            raise NotImplementedError("only level 0 (stored) is on the accelerated path")
+        self._w = writer
+        self._zlib = zlib
+        self._ctx = ctx or default_context()
+        self._data = bytearray()
+
+    def write_data(self, data: bytes):
+        self._data += bytes(data)  # stored blocks split at 65535-byte boundaries of the concatenation
+
+    def finish(self):
+        s = self._ctx.deflate_stored_batch([bytes(self._data)])[0]
+        self._w.write(s if self._zlib else s[2:-4])
+        return self._w

@@ -1,0 +1,364 @@
+// capi.cu -- the C ABI of include/fdeflate_b200.h: context, kernel launches, host staging.
+//
+// Compiled by nvcc for sm_100a into libfdeflate_b200.so (the product).  The same file is also
+// compiled by g++ -DFDB_EMUL against tests/emul/ for CPU-side logic tests of the kernels; that
+// build is test infrastructure and is never loaded by the package.
+#include "../../include/fdeflate_b200.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "simt.h"
+#include "fdb_common.h"
+#include "fdb_tables.h"
+#include "adler.cuh"
+#include "inflate_general.cuh"
+#include "inflate_uf.cuh"
+#include "deflate_uf.cuh"
+#include "deflate_stored.cuh"
+#include "synth.cuh"
+
+using namespace fdb;
+
+struct fdb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;  // used by the host-buffer entry points
+    uint32_t* d_counters = nullptr; // [0] K4 next  [1] fallback count  [2] K3 next  [3] deflate next
+    uint32_t* d_worklist = nullptr;
+    size_t worklist_cap = 0;
+    UfEncTables* d_enc = nullptr;
+    UfDecTables* d_dec = nullptr;
+    // host-API staging (grow-only)
+    uint8_t* d_in = nullptr;
+    size_t d_in_cap = 0;
+    uint8_t* d_out = nullptr;
+    size_t d_out_cap = 0;
+    uint64_t* d_meta = nullptr;  // in_off | in_len | out_off | out_cap | out_len | consumed | status(int32)
+    size_t d_meta_cap = 0;
+    uint64_t launches = 0;
+    char err[512] = {0};
+};
+
+static int fail(fdb_ctx* c, const char* what, cudaError_t e) {
+    if (c) snprintf(c->err, sizeof c->err, "%s: %s", what, e == cudaSuccess ? "invalid argument" : cudaGetErrorString(e));
+    return e == cudaSuccess ? -1 : (int)e;
+}
+#define FDB_TRY(call)                                 \
+    do {                                              \
+        cudaError_t e_ = (call);                      \
+        if (e_ != cudaSuccess) return fail(ctx, #call, e_); \
+    } while (0)
+
+extern "C" const char* fdb_version(void) {
+#ifdef FDB_EMUL
+    return "fdeflate_b200 0.1 (SIMT emulator build, tests only)";
+#else
+    return "fdeflate_b200 0.1 (CUDA sm_100a)";
+#endif
+}
+
+extern "C" const char* fdb_last_error(const fdb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" uint64_t fdb_launch_count(const fdb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int64_t fdb_last_general_count(fdb_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return -1;
+    uint32_t v = 0;
+    if (cudaStreamSynchronize((cudaStream_t)cuda_stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, ctx->d_counters + 1, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)v;
+}
+
+extern "C" int fdb_create(int device, fdb_ctx** out) {
+    if (!out) return -1;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return e != cudaSuccess ? (int)e : -2;
+    fdb_ctx* ctx = new (std::nothrow) fdb_ctx();
+    if (!ctx) return -3;
+    ctx->device = device;
+    UfHostTables* ht = new (std::nothrow) UfHostTables();
+    if (!ht || !build_uf_host_tables(*ht)) {
+        delete ht;
+        delete ctx;
+        return -4;
+    }
+    UfEncTables enc;
+    UfDecTables dec;
+    memcpy(enc.lit_tok, ht->lit_tok, sizeof enc.lit_tok);
+    memcpy(enc.tail_tok, ht->tail_tok, sizeof enc.tail_tok);
+    memcpy(enc.header, ht->header, sizeof enc.header);
+    memcpy(dec.table, ht->dec, sizeof dec.table);
+    memcpy(dec.header, ht->header, sizeof dec.header);
+    delete ht;
+    auto bail = [&](cudaError_t err) {
+        int r = fail(ctx, "fdb_create", err);
+        fdb_destroy(ctx);
+        return r;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e);
+    if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail(e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(uint32_t))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc((void**)&ctx->d_enc, sizeof(UfEncTables))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc((void**)&ctx->d_dec, sizeof(UfDecTables))) != cudaSuccess) return bail(e);
+    if ((e = cudaMemcpy(ctx->d_enc, &enc, sizeof enc, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
+    if ((e = cudaMemcpy(ctx->d_dec, &dec, sizeof dec, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
+    if ((e = cudaFuncSetAttribute(inflate_uf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem))) != cudaSuccess)
+        return bail(e);
+    if ((e = cudaFuncSetAttribute(inflate_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem))) != cudaSuccess)
+        return bail(e);
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void fdb_destroy(fdb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_worklist);
+    cudaFree(ctx->d_enc);
+    cudaFree(ctx->d_dec);
+    cudaFree(ctx->d_in);
+    cudaFree(ctx->d_out);
+    cudaFree(ctx->d_meta);
+    delete ctx;
+}
+
+static int grow(fdb_ctx* ctx, void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    size_t ncap = std::max(need + need / 8, (size_t)1 << 20);
+    ncap = (ncap + 255) & ~(size_t)255;
+    if (*p) {
+        FDB_TRY(cudaStreamSynchronize(ctx->stream));
+        FDB_TRY(cudaFree(*p));
+        *p = nullptr;
+        *cap = 0;
+    }
+    FDB_TRY(cudaMalloc(p, ncap));
+    *cap = ncap;
+    return 0;
+}
+
+// ---- inflate ----------------------------------------------------------------------------------
+extern "C" int fdb_inflate_batch_device(fdb_ctx* ctx, const void* d_in_base, const uint64_t* d_in_off,
+                                        const uint64_t* d_in_len, void* d_out_base, const uint64_t* d_out_off,
+                                        const uint64_t* d_out_cap, uint64_t* d_out_len, uint64_t* d_consumed,
+                                        int32_t* d_status, size_t n, uint32_t flags, void* cuda_stream) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (n > 0xffffffffull || !d_in_off || !d_in_len || !d_out_off || !d_out_cap || !d_out_len || !d_status)
+        return fail(ctx, "fdb_inflate_batch_device", cudaSuccess);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    FDB_TRY(cudaSetDevice(ctx->device));
+    if (n > ctx->worklist_cap) {
+        void* p = ctx->d_worklist;
+        size_t cap_bytes = ctx->worklist_cap * sizeof(uint32_t);
+        int r = grow(ctx, &p, &cap_bytes, n * sizeof(uint32_t));
+        ctx->d_worklist = (uint32_t*)p;
+        ctx->worklist_cap = cap_bytes / sizeof(uint32_t);
+        if (r) return r;
+    }
+    InflateBatch b;
+    b.in_base = (const uint8_t*)d_in_base;
+    b.in_off = d_in_off;
+    b.in_len = d_in_len;
+    b.out_base = (uint8_t*)d_out_base;
+    b.out_off = d_out_off;
+    b.out_cap = d_out_cap;
+    b.out_len = d_out_len;
+    b.consumed = d_consumed;
+    b.status = d_status;
+    b.n = (uint32_t)n;
+    b.flags = flags;
+    FDB_TRY(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(uint32_t), st));
+    const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
+    if (!(flags & FDB_FLAG_GENERAL_ONLY)) {
+        uint32_t grid = (uint32_t)std::min<size_t>((n + K4_WARPS - 1) / K4_WARPS, (size_t)sms * 2);
+        FDB_LAUNCH(inflate_uf_kernel, dim3(grid), dim3(K4_WARPS * 32), sizeof(K4Smem), st, b, ctx->d_dec,
+                   ctx->d_counters + 0, ctx->d_worklist, ctx->d_counters + 1);
+        ctx->launches++;
+        FDB_TRY(cudaGetLastError());
+        uint32_t grid3 = (uint32_t)std::min<size_t>(n, (size_t)sms * 10);
+        FDB_LAUNCH(inflate_general_kernel, dim3(grid3), dim3(32), sizeof(K3Smem), st, b,
+                   (const uint32_t*)ctx->d_worklist, (const uint32_t*)(ctx->d_counters + 1), ctx->d_counters + 2);
+        ctx->launches++;
+        FDB_TRY(cudaGetLastError());
+    } else {
+        uint32_t grid3 = (uint32_t)std::min<size_t>(n, (size_t)sms * 10);
+        FDB_LAUNCH(inflate_general_kernel, dim3(grid3), dim3(32), sizeof(K3Smem), st, b, (const uint32_t*)nullptr,
+                   (const uint32_t*)nullptr, ctx->d_counters + 2);
+        ctx->launches++;
+        FDB_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ---- deflate ----------------------------------------------------------------------------------
+static int deflate_device(fdb_ctx* ctx, int kind, const void* d_in_base, const uint64_t* d_in_off,
+                          const uint64_t* d_in_len, void* d_out_base, const uint64_t* d_out_off,
+                          const uint64_t* d_out_cap, uint64_t* d_out_len, int32_t* d_status, size_t n,
+                          void* cuda_stream) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (n > 0xffffffffull || !d_in_off || !d_in_len || !d_out_off || !d_out_cap || !d_out_len || !d_status)
+        return fail(ctx, "fdb_deflate_batch_device", cudaSuccess);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    FDB_TRY(cudaSetDevice(ctx->device));
+    DeflateBatch b;
+    b.in_base = (const uint8_t*)d_in_base;
+    b.in_off = d_in_off;
+    b.in_len = d_in_len;
+    b.out_base = (uint8_t*)d_out_base;
+    b.out_off = d_out_off;
+    b.out_cap = d_out_cap;
+    b.out_len = d_out_len;
+    b.status = d_status;
+    b.n = (uint32_t)n;
+    FDB_TRY(cudaMemsetAsync(ctx->d_counters + 3, 0, sizeof(uint32_t), st));
+    const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
+    if (kind == 0) {
+        uint32_t grid = (uint32_t)std::min<size_t>((n + DEFLATE_WARPS - 1) / DEFLATE_WARPS, (size_t)sms * 8);
+        FDB_LAUNCH(deflate_uf_kernel, dim3(grid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc,
+                   ctx->d_counters + 3);
+    } else {
+        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * 8);
+        FDB_LAUNCH(deflate_stored_kernel, dim3(grid), dim3(STORED_THREADS), 0, st, b, ctx->d_counters + 3);
+    }
+    ctx->launches++;
+    FDB_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fdb_deflate_ultrafast_batch_device(fdb_ctx* ctx, const void* d_in_base, const uint64_t* d_in_off,
+                                                  const uint64_t* d_in_len, void* d_out_base,
+                                                  const uint64_t* d_out_off, const uint64_t* d_out_cap,
+                                                  uint64_t* d_out_len, int32_t* d_status, size_t n,
+                                                  void* cuda_stream) {
+    return deflate_device(ctx, 0, d_in_base, d_in_off, d_in_len, d_out_base, d_out_off, d_out_cap, d_out_len, d_status,
+                          n, cuda_stream);
+}
+extern "C" int fdb_deflate_stored_batch_device(fdb_ctx* ctx, const void* d_in_base, const uint64_t* d_in_off,
+                                               const uint64_t* d_in_len, void* d_out_base, const uint64_t* d_out_off,
+                                               const uint64_t* d_out_cap, uint64_t* d_out_len, int32_t* d_status,
+                                               size_t n, void* cuda_stream) {
+    return deflate_device(ctx, 1, d_in_base, d_in_off, d_in_len, d_out_base, d_out_off, d_out_cap, d_out_len, d_status,
+                          n, cuda_stream);
+}
+
+extern "C" size_t fdb_deflate_ultrafast_bound(size_t n) {
+    // header 53 bytes + 5 bits, <= 12 bits per input byte (run tokens are never longer than the
+    // literals they replace), 12-bit EOB, pad, adler32; rounded up to 16 so slots stay aligned
+    size_t bits = 53 * 8 + 5 + 12 * n + 12;
+    return ((bits + 7) / 8 + 4 + 15) & ~(size_t)15;
+}
+extern "C" size_t fdb_deflate_stored_bound(size_t n) {
+    return (2 + 5 * (n / 65535 + 1) + n + 4 + 15) & ~(size_t)15;
+}
+
+// ---- host-buffer entry points -----------------------------------------------------------------
+struct Span {
+    uint64_t in_span = 0, out_span = 0;
+};
+static Span spans(const uint64_t* in_off, const uint64_t* in_len, const uint64_t* out_off, const uint64_t* out_cap,
+                  size_t n) {
+    Span s;
+    for (size_t i = 0; i < n; i++) {
+        s.in_span = std::max(s.in_span, in_off[i] + in_len[i]);
+        s.out_span = std::max(s.out_span, out_off[i] + out_cap[i]);
+    }
+    return s;
+}
+
+static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                      uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                      uint64_t* consumed, int32_t* status, size_t n, uint32_t flags) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (!in_off || !in_len || !out_off || !out_cap || !out_len || !status)
+        return fail(ctx, "fdb_*_batch", cudaSuccess);
+    FDB_TRY(cudaSetDevice(ctx->device));
+    Span sp = spans(in_off, in_len, out_off, out_cap, n);
+    int r;
+    if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, sp.in_span + 64))) return r;
+    if ((r = grow(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, sp.out_span + 64))) return r;
+    const size_t meta_words = 7 * n;
+    if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, meta_words * sizeof(uint64_t)))) return r;
+    uint64_t* m = ctx->d_meta;
+    uint64_t *d_in_off = m, *d_in_len = m + n, *d_out_off = m + 2 * n, *d_out_cap = m + 3 * n, *d_out_len = m + 4 * n,
+             *d_consumed = m + 5 * n;
+    int32_t* d_status = (int32_t*)(m + 6 * n);
+    cudaStream_t st = ctx->stream;
+    if (sp.in_span) FDB_TRY(cudaMemcpyAsync(ctx->d_in, in_base, sp.in_span, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_in_off, in_off, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_in_len, in_len, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_out_off, out_off, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_out_cap, out_cap, n * 8, cudaMemcpyHostToDevice, st));
+    if (kind == 0)
+        r = fdb_inflate_batch_device(ctx, ctx->d_in, d_in_off, d_in_len, ctx->d_out, d_out_off, d_out_cap, d_out_len,
+                                     d_consumed, d_status, n, flags, st);
+    else
+        r = deflate_device(ctx, kind - 1, ctx->d_in, d_in_off, d_in_len, ctx->d_out, d_out_off, d_out_cap, d_out_len,
+                           d_status, n, st);
+    if (r) return r;
+    FDB_TRY(cudaMemcpyAsync(out_len, d_out_len, n * 8, cudaMemcpyDeviceToHost, st));
+    if (consumed && kind == 0) FDB_TRY(cudaMemcpyAsync(consumed, d_consumed, n * 8, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st));
+    if (sp.out_span) FDB_TRY(cudaMemcpyAsync(out_base, ctx->d_out, sp.out_span, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int fdb_inflate_batch(fdb_ctx* ctx, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                                 uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap,
+                                 uint64_t* out_len, uint64_t* consumed, int32_t* status, size_t n, uint32_t flags) {
+    return host_batch(ctx, 0, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, consumed, status, n, flags);
+}
+extern "C" int fdb_deflate_ultrafast_batch(fdb_ctx* ctx, const uint8_t* in_base, const uint64_t* in_off,
+                                           const uint64_t* in_len, uint8_t* out_base, const uint64_t* out_off,
+                                           const uint64_t* out_cap, uint64_t* out_len, int32_t* status, size_t n) {
+    return host_batch(ctx, 1, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, nullptr, status, n, 0);
+}
+extern "C" int fdb_deflate_stored_batch(fdb_ctx* ctx, const uint8_t* in_base, const uint64_t* in_off,
+                                        const uint64_t* in_len, uint8_t* out_base, const uint64_t* out_off,
+                                        const uint64_t* out_cap, uint64_t* out_len, int32_t* status, size_t n) {
+    return host_batch(ctx, 2, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, nullptr, status, n, 0);
+}
+
+// ---- synthetic tiles --------------------------------------------------------------------------
+extern "C" size_t fdb_synth_tile_bytes(uint32_t width, uint32_t height) {
+    return (size_t)height * (1u + 4u * (size_t)width);
+}
+extern "C" int fdb_synth_tiles_host(uint8_t* out, uint64_t first_tile, uint64_t n_tiles, uint32_t width,
+                                    uint32_t height, uint64_t seed) {
+    if (!out || !width || !height) return -1;
+    const size_t tb = fdb_synth_tile_bytes(width, height);
+    for (uint64_t t = 0; t < n_tiles; t++) {
+        TileParams p = tile_params(seed, first_tile + t, width, height);
+        for (uint32_t y = 0; y < height; y++)
+            for (uint32_t x = 0; x < width; x++) synth_pixel(out + t * tb, p, x, y, width);
+    }
+    return 0;
+}
+extern "C" int fdb_synth_tiles_device(fdb_ctx* ctx, void* d_out, uint64_t first_tile, uint64_t n_tiles, uint32_t width,
+                                      uint32_t height, uint64_t seed, void* cuda_stream) {
+    if (!ctx || !d_out || !width || !height) return -1;
+    if (n_tiles == 0) return 0;
+    FDB_TRY(cudaSetDevice(ctx->device));
+    uint64_t total = n_tiles * (uint64_t)width * height;
+    uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, (uint64_t)std::max(ctx->sm_count, 1) * 16);
+    FDB_LAUNCH(synth_tiles_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)cuda_stream, (uint8_t*)d_out, first_tile,
+               n_tiles, width, height, seed);
+    ctx->launches++;
+    FDB_TRY(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,117 @@
+// fdb_common.h -- definitions shared by host code and kernels.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+namespace fdb {
+
+// Per-stream status = the reference's DecompressionError in declaration order
+// (reference src/decompress.rs:13-48); 17 = BoundedDecompressionError::OutputTooLarge (:1098).
+enum Status : int32_t {
+    ST_OK = 0,
+    ST_BAD_ZLIB_HEADER = 1,
+    ST_INSUFFICIENT_INPUT = 2,
+    ST_INVALID_BLOCK_TYPE = 3,
+    ST_INVALID_UNCOMPRESSED_BLOCK_LENGTH = 4,
+    ST_INVALID_HLIT = 5,
+    ST_INVALID_HDIST = 6,
+    ST_INVALID_CODE_LENGTH_REPEAT = 7,
+    ST_BAD_CODE_LENGTH_HUFFMAN_TREE = 8,
+    ST_BAD_LITERAL_LENGTH_HUFFMAN_TREE = 9,
+    ST_BAD_DISTANCE_HUFFMAN_TREE = 10,
+    ST_INVALID_LITERAL_LENGTH_CODE = 11,
+    ST_INVALID_DISTANCE_CODE = 12,
+    ST_INPUT_STARTS_WITH_RUN = 13,
+    ST_DISTANCE_TOO_FAR_BACK = 14,
+    ST_WRONG_CHECKSUM = 15,
+    ST_EXTRA_INPUT = 16,
+    ST_OUTPUT_TOO_LARGE = 17,
+    // compress side only: caller's slot is smaller than the encoded stream (the reference writes
+    // into a growing Vec and cannot hit this)
+    ST_OUTPUT_BUFFER_TOO_SMALL = 18,
+    // internal: ultra-fast-format fast path declined the stream; the general kernel redoes it
+    ST_PENDING_GENERAL = -1,
+};
+
+enum : uint32_t { FLAG_IGNORE_ADLER32 = 1u };
+
+// One batch of independent zlib streams, all pointers are DEVICE pointers.
+struct InflateBatch {
+    const uint8_t* in_base;
+    const uint64_t* in_off;   // [n] byte offset of stream i in in_base
+    const uint64_t* in_len;   // [n]
+    uint8_t* out_base;
+    const uint64_t* out_off;  // [n] byte offset of slot i in out_base
+    const uint64_t* out_cap;  // [n] slot capacity (= maxlen of decompress_to_vec_bounded)
+    uint64_t* out_len;        // [n] bytes produced
+    uint64_t* consumed;       // [n] input bytes consumed (may be null)
+    int32_t* status;          // [n]
+    uint32_t n;
+    uint32_t flags;
+};
+
+struct DeflateBatch {
+    const uint8_t* in_base;
+    const uint64_t* in_off;
+    const uint64_t* in_len;
+    uint8_t* out_base;
+    const uint64_t* out_off;
+    const uint64_t* out_cap;
+    uint64_t* out_len;
+    int32_t* status;
+    uint32_t n;
+};
+
+// ---- decode-table entry formats (ours; only the decoded bytes have to match the reference) ----
+// litlen entry:
+//   [3:0] nbits  code bits consumed by the entry (both literals for a pair; the length CODE only)
+//   [4] LIT  [5] LIT2 (two literals)  [6] LEN  [7] EOB      none of them: code longer than the table
+//   literal : [15:8] sym1  [23:16] sym2  [27:24] code bits of the first literal
+//   length  : [10:8] extra-bit count  [24:16] base length
+//   [28] QUIRK: fixed-code symbols 286/287, which the reference treats as end-of-block
+//        (reference tables.rs:99-122 + decompress.rs:743-748)
+enum : uint32_t {
+    LL_LIT = 1u << 4,
+    LL_LIT2 = 1u << 5,
+    LL_LEN = 1u << 6,
+    LL_EOB = 1u << 7,
+    LL_QUIRK = 1u << 28,
+};
+// dist entry: [3:0] code bits  [7:4] extra-bit count  [8] VALID  [9] LONG (code > 9 bits)  [31:16] base
+enum : uint32_t { DS_VALID = 1u << 8, DS_LONG = 1u << 9 };
+
+// RFC 1951 length / distance symbol parameters (reference tables.rs:68-88 holds them as arrays)
+#if defined(__CUDACC__) && !defined(FDB_EMUL)
+#define FDB_HD __host__ __device__ __forceinline__
+#else
+#define FDB_HD static inline
+#endif
+FDB_HD uint32_t len_sym_extra(uint32_t sym) {  // sym in 257..285
+    return (sym < 265 || sym == 285) ? 0u : ((sym - 261u) >> 2);
+}
+FDB_HD uint32_t len_sym_base(uint32_t sym) {
+    if (sym < 265) return sym - 254u;
+    if (sym == 285) return 258u;
+    uint32_t e = (sym - 261u) >> 2;
+    return ((4u + ((sym - 261u) & 3u)) << e) + 3u;
+}
+FDB_HD uint32_t dist_sym_extra(uint32_t d) { return d < 4 ? 0u : (d >> 1) - 1u; }  // d in 0..29
+FDB_HD uint32_t dist_sym_base(uint32_t d) {
+    if (d < 4) return d + 1u;
+    uint32_t e = (d >> 1) - 1u;
+    return ((2u + (d & 1u)) << e) + 1u;
+}
+FDB_HD uint32_t make_litlen_entry(uint32_t sym, uint32_t nbits) {
+    if (sym < 256) return nbits | LL_LIT | (sym << 8) | (nbits << 24);
+    if (sym == 256) return nbits | LL_EOB;
+    if (sym < 286) return nbits | LL_LEN | (len_sym_extra(sym) << 8) | (len_sym_base(sym) << 16);
+    return nbits | LL_EOB | LL_QUIRK;
+}
+FDB_HD uint32_t make_dist_entry(uint32_t sym, uint32_t nbits) {
+    if (sym < 30) return nbits | DS_VALID | (dist_sym_extra(sym) << 4) | (dist_sym_base(sym) << 16);
+    return nbits;  // symbols 30/31: invalid distance code
+}
+
+static const uint32_t ADLER_MOD = 65521u;
+
+}  // namespace fdb

@@ -1,0 +1,615 @@
+// inflate_general.cuh -- K3: general zlib inflate, ONE WARP PER STREAM.
+//
+// Replaces (whole-buffer semantics of) the reference's Decompressor::read state machine
+//   src/decompress.rs:179-337  (states), :344-438 (block header), :440-555 (code lengths),
+//   :561-606 (build_tables), :611-1018 (read_compressed) and src/huffman.rs:18-184 (build_table)
+// as driven by decompress_to_vec_bounded (src/decompress.rs:1111-1144).
+//
+// Design (B200): the warp executes the sequential decode loop converged (all lanes carry the same
+// scalar state, table lookups are shared-memory broadcasts) and uses its 32 lanes where the data
+// allows it:
+//   * input  : 128-byte coalesced chunk loads, one 32-bit word per lane, double-buffered in
+//              registers; the 64-bit bit reservoir is refilled with a warp shuffle
+//   * tables : 4096-entry litlen table with two-literal entries + 512-entry distance table, rebuilt
+//              in shared memory per dynamic block by an index-major warp-cooperative canonical
+//              decode (every lane fills 128 entries; no serial codeword walk)
+//   * matches: out[p+i] = out[p-dist + i mod dist] for all i in parallel (overlap-safe because
+//              the source never leaves the already-final region)
+//   * adler32: position-weighted sums over the produced bytes (adler.cuh)
+//
+// Error semantics follow the reference bit for bit in terms of `avail` = bits left in the stream
+// (the reference's nbits gates only bind when its reservoir holds every remaining bit):
+// see DESIGN.md "Inflate semantics".
+#pragma once
+#include "simt.h"
+#include "fdb_common.h"
+#include "adler.cuh"
+
+namespace fdb {
+
+struct K3Smem {
+    uint32_t litlen[4096];
+    uint32_t dist[512];
+    uint32_t first[3][16];  // canonical first code per length  [0]=litlen [1]=dist [2]=code-length code
+    uint32_t lim[3][16];    // (first+cnt) left-aligned to the table width
+    uint16_t off[3][16];    // offset of each length in sorted[]
+    uint16_t cnt[3][16];
+    uint32_t hist[16];
+    uint16_t sorted_lit[288];
+    uint16_t sorted_dist[32];
+    uint16_t sorted_cl[32];
+    uint8_t lens[320];  // litlen lengths at 0..287, distance lengths at 288..319 (reference layout)
+    uint8_t cl_lens[32];
+    uint8_t cl_table[128];  // (sym << 3) | len
+    uint32_t info[4];       // [0] max_len [1] complete flag
+};
+
+// ---- bit reader: warp-shuffle reservoir over coalesced chunk loads ---------------------------
+struct BitReader {
+    const uint8_t* abase;  // 4-byte aligned base address
+    uint64_t first_byte;   // first valid byte, relative to abase
+    uint64_t end_byte;     // one past the last valid byte, relative to abase
+    uint64_t bb;           // reservoir (LSB first); bits past the end of input read as 0
+    uint32_t nb;           // bits in reservoir (counting the zero padding)
+    uint64_t widx;         // next word to pull into the reservoir
+    uint32_t cur, nxt;     // this lane's word of the current / next 32-word chunk
+    uint64_t pos;          // bits consumed since the start of the stream
+    uint64_t tot;          // 8 * in_len
+};
+
+FDB_DEVICE uint32_t br_load_word(const BitReader& r, uint64_t w) {
+    uint64_t o = w << 2;
+    if (o + 4 <= r.first_byte || o >= r.end_byte) return 0;
+    uint32_t v = simt::ldg32((const uint32_t*)(r.abase + o));
+    if (o < r.first_byte) v &= 0xffffffffu << (8u * (uint32_t)(r.first_byte - o));
+    if (o + 4 > r.end_byte) v &= 0xffffffffu >> (8u * (uint32_t)(o + 4 - r.end_byte));
+    return v;
+}
+
+FDB_DEVICE void br_pull(BitReader& r) {  // append one 32-bit word to the reservoir
+    uint32_t w = simt::shfl(r.cur, (unsigned)(r.widx & 31));
+    r.bb |= (uint64_t)w << r.nb;
+    r.nb += 32;
+    r.widx++;
+    if ((r.widx & 31) == 0) {
+        r.cur = r.nxt;
+        r.nxt = br_load_word(r, ((r.widx >> 5) + 1) * 32 + simt::lane_id());
+    }
+}
+
+FDB_DEVICE void br_seek(BitReader& r, uint64_t bitpos) {
+    uint64_t abit = r.first_byte * 8 + bitpos;
+    r.widx = abit >> 5;
+    uint64_t c = r.widx >> 5;
+    r.cur = br_load_word(r, c * 32 + simt::lane_id());
+    r.nxt = br_load_word(r, (c + 1) * 32 + simt::lane_id());
+    r.bb = 0;
+    r.nb = 0;
+    br_pull(r);
+    uint32_t sh = (uint32_t)(abit & 31);
+    r.bb >>= sh;
+    r.nb -= sh;
+    r.pos = bitpos;
+    if (r.nb <= 32) br_pull(r);
+}
+
+FDB_DEVICE void br_init(BitReader& r, const uint8_t* in, uint64_t n) {
+    uintptr_t a = (uintptr_t)in;
+    r.abase = (const uint8_t*)(a & ~(uintptr_t)3);
+    r.first_byte = (uint64_t)(a & 3);
+    r.end_byte = r.first_byte + n;
+    r.tot = n * 8;
+    br_seek(r, 0);
+}
+
+FDB_DEVICE void br_refill(BitReader& r) {  // afterwards nb >= 33
+    while (r.nb <= 32) br_pull(r);
+}
+FDB_DEVICE uint32_t br_peek(const BitReader& r, uint32_t k) {  // k <= 32
+    return (uint32_t)(r.bb & ((1ull << k) - 1ull));
+}
+FDB_DEVICE void br_consume(BitReader& r, uint32_t k) {
+    r.bb >>= k;
+    r.nb -= k;
+    r.pos += k;
+}
+FDB_DEVICE uint64_t br_avail(const BitReader& r) { return r.tot - r.pos; }
+
+// ---- warp-cooperative canonical Huffman set-up (replaces huffman.rs:28-84) --------------------
+// lens[0..nsym) in shared memory.  Fills first/lim/off/cnt[which] and sorted[]; returns through
+// info[0] = max_len (>=1), info[1] = 1 if the code is complete (Kraft sum == 2^max_len).
+FDB_DEVICE void canon_setup(K3Smem& s, int which, const uint8_t* lens, uint32_t nsym, uint16_t* sorted,
+                            uint32_t table_bits) {
+    const unsigned lane = simt::lane_id();
+    if (lane < 16) s.hist[lane] = 0;
+    simt::syncwarp();
+    for (uint32_t i = lane; i < nsym; i += 32) simt::atomic_add(&s.hist[lens[i]], 1u);
+    simt::syncwarp();
+    if (lane == 0) {
+        uint32_t max_len = 15;
+        while (max_len > 1 && s.hist[max_len] == 0) max_len--;
+        uint32_t used = 0, code = 0, o = 0;
+        for (uint32_t L = 1; L <= 15; L++) {
+            uint32_t c = s.hist[L];
+            if (L <= max_len) used = (used << 1) + c;
+            code <<= 1;
+            s.first[which][L] = code;
+            s.cnt[which][L] = (uint16_t)c;
+            s.off[which][L] = (uint16_t)o;
+            code += c;
+            o += c;
+            // exclusive upper bound of length-L codes, left-aligned to table_bits (only L<=table_bits used)
+            s.lim[which][L] = (L <= table_bits) ? (code << (table_bits - L)) : 0u;
+        }
+        s.info[0] = max_len;
+        s.info[1] = (used == (1u << max_len)) ? 1u : 0u;
+    }
+    simt::syncwarp();
+    // sorted[]: symbols ordered by (length, symbol) -- ballot compaction per length
+    uint32_t max_len = s.info[0];
+    for (uint32_t L = 1; L <= max_len; L++) {
+        if (s.cnt[which][L] == 0) continue;
+        uint32_t base = s.off[which][L];
+        for (uint32_t i0 = 0; i0 < nsym; i0 += 32) {
+            uint32_t i = i0 + lane;
+            bool p = (i < nsym) && (lens[i] == L);
+            uint32_t m = simt::ballot(p);
+            if (p) sorted[base + simt::popc(m & simt::lanemask_lt())] = (uint16_t)i;
+            base += simt::popc(m);
+        }
+    }
+    simt::syncwarp();
+}
+
+// canonical decode of a `maxbits`-bit window for codes longer than the primary table
+// (replaces the secondary tables of huffman.rs:139-181).  v = next bits of the stream, LSB first.
+FDB_DEVICE bool canon_long_decode(const K3Smem& s, int which, const uint16_t* sorted, uint32_t v,
+                                  uint32_t from_len, uint32_t* sym, uint32_t* nbits) {
+    uint32_t msb = simt::brev(v) >> 17;  // first 15 stream bits, MSB first
+    for (uint32_t L = from_len; L <= 15; L++) {
+        uint32_t c = msb >> (15 - L);
+        uint32_t d = c - s.first[which][L];
+        if (d < s.cnt[which][L]) {
+            *sym = sorted[s.off[which][L] + d];
+            *nbits = L;
+            return true;
+        }
+    }
+    return false;
+}
+
+// primary litlen table, index-major: every lane decodes 128 of the 4096 indices canonically, then a
+// second pass upgrades single literals to two-literal entries (replaces huffman.rs:92-136).
+FDB_DEVICE void build_litlen_table(K3Smem& s) {
+    const unsigned lane = simt::lane_id();
+    for (uint32_t idx = lane; idx < 4096; idx += 32) {
+        uint32_t v = simt::brev(idx) >> 20;
+        uint32_t e = 0;  // none of LIT/LEN/EOB => long code
+        for (uint32_t L = 1; L <= 12; L++) {
+            if (v < s.lim[0][L]) {
+                uint32_t c = v >> (12 - L);
+                e = make_litlen_entry(s.sorted_lit[s.off[0][L] + c - s.first[0][L]], L);
+                break;
+            }
+        }
+        s.litlen[idx] = e;
+    }
+    simt::syncwarp();
+    for (uint32_t idx = lane; idx < 4096; idx += 32) {
+        uint32_t e = s.litlen[idx];
+        if (!(e & LL_LIT) || (e & LL_LIT2)) continue;
+        uint32_t l1 = e & 15u;
+        if (l1 >= 12) continue;
+        uint32_t e2 = s.litlen[idx >> l1];  // may already be a pair: sym1 / first-literal bits are stable
+        if (!(e2 & LL_LIT)) continue;
+        uint32_t l2 = (e2 >> 24) & 15u;
+        if (l1 + l2 > 12) continue;
+        s.litlen[idx] = (l1 + l2) | LL_LIT | LL_LIT2 | (e & 0xff00u) | (((e2 >> 8) & 0xffu) << 16) | (l1 << 24);
+    }
+    simt::syncwarp();
+}
+
+FDB_DEVICE void build_dist_table(K3Smem& s) {
+    const unsigned lane = simt::lane_id();
+    for (uint32_t idx = lane; idx < 512; idx += 32) {
+        uint32_t v = simt::brev(idx) >> 23;
+        uint32_t e = DS_LONG;
+        for (uint32_t L = 1; L <= 9; L++) {
+            if (v < s.lim[1][L]) {
+                uint32_t c = v >> (9 - L);
+                e = make_dist_entry(s.sorted_dist[s.off[1][L] + c - s.first[1][L]], L);
+                break;
+            }
+        }
+        s.dist[idx] = e;
+    }
+    simt::syncwarp();
+}
+
+// litlen + distance tables from s.lens (reference decompress.rs:561-606). Returns a Status.
+FDB_DEVICE int32_t build_block_tables(K3Smem& s, uint32_t hlit, uint32_t* eof_code, uint32_t* eof_bits) {
+    const unsigned lane = simt::lane_id();
+    if (s.lens[256] == 0) return ST_BAD_LITERAL_LENGTH_HUFFMAN_TREE;  // :563-566
+    canon_setup(s, 0, s.lens, hlit, s.sorted_lit, 12);
+    if (!s.info[1]) return ST_BAD_CODE_LENGTH_HUFFMAN_TREE;  // :570-580 (sic: the reference's variant)
+    build_litlen_table(s);
+    {  // eof code = bit-reversed canonical code of symbol 256 (:582-584)
+        uint32_t L = s.lens[256];
+        uint32_t o = s.off[0][L], c = s.cnt[0][L];
+        uint32_t found = 0;
+        for (uint32_t i0 = 0; i0 < c; i0 += 32) {
+            uint32_t i = i0 + lane;
+            uint32_t m = simt::ballot(i < c && s.sorted_lit[o + i] == 256);
+            if (m) found = i0 + simt::ffs(m) - 1;
+        }
+        uint32_t code = s.first[0][L] + found;
+        *eof_code = simt::brev(code) >> (32 - L);
+        *eof_bits = L;
+    }
+    // distance code (:587-603, huffman.rs:40-59)
+    uint32_t nz = 0;
+    {
+        uint32_t m = simt::ballot(s.lens[288 + lane] != 0);
+        nz = m;
+    }
+    if (nz == 0) {
+        for (uint32_t idx = lane; idx < 512; idx += 32) s.dist[idx] = 0;  // any match => InvalidDistanceCode
+        simt::syncwarp();
+        return ST_OK;
+    }
+    canon_setup(s, 1, s.lens + 288, 32, s.sorted_dist, 9);
+    if (s.info[0] == 1 && s.cnt[1][1] == 1) {  // exactly one 1-bit code
+        uint32_t sym = s.sorted_dist[s.off[1][1]];
+        uint32_t e = make_dist_entry(sym, 1);
+        for (uint32_t idx = lane; idx < 512; idx += 32) s.dist[idx] = (idx & 1) ? 0u : e;
+        simt::syncwarp();
+        return ST_OK;
+    }
+    if (!s.info[1]) return ST_BAD_DISTANCE_HUFFMAN_TREE;
+    build_dist_table(s);
+    return ST_OK;
+}
+
+FDB_DEVICE void load_fixed_lengths(K3Smem& s) {  // RFC 1951 3.2.6 (reference tables.rs:207-232)
+    const unsigned lane = simt::lane_id();
+    for (uint32_t i = lane; i < 320; i += 32) {
+        uint8_t L = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
+        s.lens[i] = L;
+    }
+    simt::syncwarp();
+}
+
+// ---- one compressed block (reference decompress.rs:611-1018, careful-loop semantics) ----------
+struct OutCursor {
+    uint8_t* out;
+    uint64_t pos;
+    uint64_t cap;
+};
+
+FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t eof_code, uint32_t eof_bits,
+                                bool* too_large) {
+    const unsigned lane = simt::lane_id();
+    const uint32_t eof_mask = (1u << eof_bits) - 1u;
+    for (;;) {
+        br_refill(r);
+        uint64_t avail = br_avail(r);
+        if (o.pos == o.cap) {
+            // output exactly full: only an end-of-block code may follow (EOB peek, :1009-1015)
+            if (avail >= 15 && (br_peek(r, 15) & eof_mask) == eof_code) {
+                br_consume(r, eof_bits);
+                return ST_OK;
+            }
+            *too_large = true;
+            return ST_OK;
+        }
+        uint32_t e = s.litlen[br_peek(r, 12)];
+        uint32_t nbits = e & 15u;
+        if (e & LL_LIT) {  // :846-877
+            if (avail < nbits) return ST_INSUFFICIENT_INPUT;
+            bool two = (e & LL_LIT2) != 0;
+            if (lane == 0) o.out[o.pos] = (uint8_t)(e >> 8);
+            if (two && o.pos + 1 == o.cap) {  // second literal does not fit (queued in the reference)
+                o.pos += 1;
+                br_consume(r, nbits);
+                *too_large = true;
+                return ST_OK;
+            }
+            if (two && lane == 1) o.out[o.pos + 1] = (uint8_t)(e >> 16);
+            o.pos += two ? 2 : 1;
+            br_consume(r, nbits);
+            continue;
+        }
+        uint32_t len_base, len_extra;
+        if (e & LL_EOB) {  // :910-918 (includes the 286/287 quirk)
+            if (avail < nbits) return ST_INSUFFICIENT_INPUT;
+            br_consume(r, nbits);
+            return ST_OK;
+        } else if (e & LL_LEN) {
+            len_base = (e >> 16) & 0x1ffu;
+            len_extra = (e >> 8) & 7u;
+        } else {  // code longer than 12 bits (:886-909)
+            uint32_t sym = 0;
+            if (!canon_long_decode(s, 0, s.sorted_lit, br_peek(r, 15), 13, &sym, &nbits))
+                return ST_INVALID_LITERAL_LENGTH_CODE;
+            if (avail < nbits) return ST_INSUFFICIENT_INPUT;
+            if (sym < 256) {
+                if (lane == 0) o.out[o.pos] = (uint8_t)sym;
+                o.pos += 1;
+                br_consume(r, nbits);
+                continue;
+            } else if (sym == 256) {
+                br_consume(r, nbits);
+                return ST_OK;
+            }
+            len_base = len_sym_base(sym);
+            len_extra = len_sym_extra(sym);
+        }
+        // length + distance (:919-967); the reference tests the total against nbits before consuming
+        uint32_t le_bits = nbits + len_extra;  // <= 20
+        uint32_t length = len_base + ((br_peek(r, le_bits) >> nbits) & ((1u << len_extra) - 1u));
+        br_consume(r, le_bits);
+        br_refill(r);
+        uint32_t de = s.dist[br_peek(r, 9)];
+        uint32_t dbits, dextra, dbase;
+        if (de & DS_VALID) {
+            dbits = de & 15u;
+            dextra = (de >> 4) & 15u;
+            dbase = de >> 16;
+        } else if (avail > (uint64_t)le_bits + 9) {  // :932-951
+            if (!(de & DS_LONG)) return ST_INVALID_DISTANCE_CODE;
+            uint32_t dsym = 0;
+            if (!canon_long_decode(s, 1, s.sorted_dist, br_peek(r, 15), 10, &dsym, &dbits))
+                return ST_INVALID_DISTANCE_CODE;
+            if (dsym >= 30) return ST_INVALID_DISTANCE_CODE;
+            dextra = dist_sym_extra(dsym);
+            dbase = dist_sym_base(dsym);
+        } else {
+            return ST_INSUFFICIENT_INPUT;  // `break` with the input exhausted
+        }
+        uint32_t dd_bits = dbits + dextra;  // <= 28
+        uint64_t dist = dbase + ((br_peek(r, dd_bits) >> dbits) & ((1u << dextra) - 1u));
+        if (avail < (uint64_t)le_bits + dd_bits) return ST_INSUFFICIENT_INPUT;  // :961
+        if (dist > o.pos) return ST_DISTANCE_TOO_FAR_BACK;                        // :963
+        br_consume(r, dd_bits);
+
+        uint64_t room = o.cap - o.pos;
+        uint32_t n = length < room ? length : (uint32_t)room;
+        simt::syncwarp();  // earlier stores by other lanes must be visible to the loads below
+        {
+            uint8_t* dst = o.out + o.pos;
+            const uint8_t* src = dst - dist;
+            if (dist >= n) {
+                for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+            } else {
+                uint32_t d32 = (uint32_t)dist;
+                for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i % d32];
+            }
+        }
+        o.pos += n;
+        if (n < length) {  // remainder would be queued (:797-801, :823-827) => output too large
+            *too_large = true;
+            return ST_OK;
+        }
+    }
+}
+
+// ---- whole stream --------------------------------------------------------------------------
+FDB_DEVICE int32_t inflate_stream_general(K3Smem& s, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap,
+                                          uint32_t flags, uint64_t* out_len, uint64_t* consumed) {
+    const unsigned lane = simt::lane_id();
+    BitReader r;
+    br_init(r, in, n);
+    OutCursor o = {out, 0, cap};
+    *out_len = 0;
+    *consumed = 0;
+
+    // zlib header (:226-244)
+    if (br_avail(r) < 16) return ST_INSUFFICIENT_INPUT;
+    {
+        uint32_t cmf = br_peek(r, 8), flg = br_peek(r, 16) >> 8;
+        if ((cmf & 0x0f) != 0x08 || (cmf & 0xf0) > 0x70 || (flg & 0x20) != 0 || ((cmf << 8) | flg) % 31 != 0)
+            return ST_BAD_ZLIB_HEADER;
+        br_consume(r, 16);
+    }
+
+    bool fixed_ready = false;
+    uint32_t fixed_eof_code = 0, fixed_eof_bits = 7;
+    bool too_large = false;
+    for (;;) {
+        br_refill(r);
+        if (br_avail(r) < 10) {  // :346
+            *out_len = o.pos;
+            return ST_INSUFFICIENT_INPUT;
+        }
+        uint32_t hdr = br_peek(r, 3);
+        bool last = (hdr & 1) != 0;
+        uint32_t btype = hdr >> 1;
+        int32_t st = ST_OK;
+        if (btype == 0) {  // stored (:353-370, :271-305)
+            uint32_t align = (8u - (uint32_t)((r.pos + 3) & 7)) & 7u;
+            if (br_avail(r) < 3 + 32 + align) {
+                *out_len = o.pos;
+                return ST_INSUFFICIENT_INPUT;
+            }
+            br_consume(r, 3 + align);
+            br_refill(r);
+            uint32_t v = br_peek(r, 32);
+            uint32_t len = v & 0xffffu, nlen = v >> 16;
+            if (nlen != (len ^ 0xffffu)) return ST_INVALID_UNCOMPRESSED_BLOCK_LENGTH;
+            br_consume(r, 32);
+            uint64_t src_byte = r.pos >> 3;
+            uint64_t in_left = n - src_byte;
+            uint64_t room = o.cap - o.pos;
+            uint64_t ncopy = len;
+            if (ncopy > in_left) ncopy = in_left;
+            if (ncopy > room) ncopy = room;
+            for (uint64_t i = lane; i < ncopy; i += 32) o.out[o.pos + i] = simt::ldg8(in + src_byte + i);
+            o.pos += ncopy;
+            if (ncopy < len) {
+                *out_len = o.pos;
+                // decompress.rs:1128-1136: a full output is reported before an exhausted input
+                return (o.pos == o.cap) ? ST_OUTPUT_TOO_LARGE : ST_INSUFFICIENT_INPUT;
+            }
+            br_seek(r, (src_byte + len) * 8);
+        } else if (btype == 1) {  // fixed (:371-414)
+            br_consume(r, 3);
+            if (!fixed_ready) {
+                load_fixed_lengths(s);
+                st = build_block_tables(s, 288, &fixed_eof_code, &fixed_eof_bits);
+                fixed_ready = true;
+            }
+            if (st == ST_OK) st = decode_block(s, r, o, fixed_eof_code, fixed_eof_bits, &too_large);
+        } else if (btype == 2) {  // dynamic (:415-434, :440-555)
+            if (br_avail(r) < 17) {
+                *out_len = o.pos;
+                return ST_INSUFFICIENT_INPUT;
+            }
+            uint32_t hlit = (br_peek(r, 8) >> 3) + 257;
+            uint32_t hdist = (br_peek(r, 13) >> 8) + 1;
+            uint32_t hclen = (br_peek(r, 17) >> 13) + 4;
+            if (hlit > 286) return ST_INVALID_HLIT;
+            if (hdist > 30) return ST_INVALID_HDIST;
+            br_consume(r, 17);
+            fixed_ready = false;
+            if (br_avail(r) < 3ull * hclen) {
+                *out_len = o.pos;
+                return ST_INSUFFICIENT_INPUT;
+            }
+            if (lane < 32) s.cl_lens[lane] = 0;
+            simt::syncwarp();
+            for (uint32_t i = 0; i < hclen; i++) {
+                br_refill(r);
+                // reference tables.rs:63-65 CLCL_ORDER, packed 5 bits per entry
+                const uint64_t order_lo = 0x22caa324e804a30ull;  // entries 0..11
+                const uint64_t order_hi = 0x3c2e1346cull;  // entries 12..18
+                uint32_t sym = (i < 12) ? (uint32_t)((order_lo >> (5 * i)) & 31u)
+                                        : (uint32_t)((order_hi >> (5 * (i - 12))) & 31u);
+                if (lane == 0) s.cl_lens[sym] = (uint8_t)br_peek(r, 3);
+                br_consume(r, 3);
+            }
+            simt::syncwarp();
+            canon_setup(s, 2, s.cl_lens, 19, s.sorted_cl, 7);
+            if (!s.info[1]) return ST_BAD_CODE_LENGTH_HUFFMAN_TREE;  // :462-472
+            for (uint32_t idx = lane; idx < 128; idx += 32) {
+                uint32_t v = simt::brev(idx) >> 25;
+                uint32_t e = 0;
+                for (uint32_t L = 1; L <= 7; L++) {
+                    if (v < s.lim[2][L]) {
+                        uint32_t c = v >> (7 - L);
+                        e = ((uint32_t)s.sorted_cl[s.off[2][L] + c - s.first[2][L]] << 3) | L;
+                        break;
+                    }
+                }
+                s.cl_table[idx] = (uint8_t)e;
+            }
+            simt::syncwarp();
+            // code lengths (:479-539)
+            uint32_t total = hlit + hdist, nread = 0;
+            while (nread < total) {
+                br_refill(r);
+                uint64_t avail = br_avail(r);
+                if (avail < 7) {
+                    *out_len = o.pos;
+                    return ST_INSUFFICIENT_INPUT;
+                }
+                uint32_t ce = s.cl_table[br_peek(r, 7)];
+                uint32_t clen = ce & 7u, sym = ce >> 3;
+                if (sym <= 15) {
+                    if (lane == 0) s.lens[nread] = (uint8_t)sym;
+                    nread += 1;
+                    br_consume(r, clen);
+                } else {
+                    uint32_t base_repeat = sym == 18 ? 11u : 3u;
+                    uint32_t extra = sym == 16 ? 2u : sym == 17 ? 3u : 7u;
+                    if (avail < clen + extra) {
+                        *out_len = o.pos;
+                        return ST_INSUFFICIENT_INPUT;
+                    }
+                    uint32_t value = 0;
+                    if (sym == 16) {
+                        if (nread == 0) return ST_INVALID_CODE_LENGTH_REPEAT;
+                        simt::syncwarp();
+                        value = s.lens[nread - 1];
+                    }
+                    uint32_t repeat = (br_peek(r, clen + extra) >> clen) + base_repeat;
+                    if (nread + repeat > total) return ST_INVALID_CODE_LENGTH_REPEAT;
+                    simt::syncwarp();
+                    if (lane < repeat) s.lens[nread + lane] = (uint8_t)value;
+                    for (uint32_t i = 32 + lane; i < repeat; i += 32) s.lens[nread + i] = (uint8_t)value;
+                    nread += repeat;
+                    br_consume(r, clen + extra);
+                }
+            }
+            simt::syncwarp();
+            // split into litlen[0..288) and dist[288..320) (:541-549); hdist <= 30 so no overlap issues
+            uint8_t dl = (lane < hdist) ? s.lens[hlit + lane] : (uint8_t)0;
+            simt::syncwarp();
+            for (uint32_t i = hlit + lane; i < 288; i += 32) s.lens[i] = 0;
+            s.lens[288 + lane] = dl;
+            simt::syncwarp();
+            uint32_t eof_code = 0, eof_bits = 0;
+            st = build_block_tables(s, hlit, &eof_code, &eof_bits);
+            if (st == ST_OK) st = decode_block(s, r, o, eof_code, eof_bits, &too_large);
+        } else {
+            return ST_INVALID_BLOCK_TYPE;  // :435
+        }
+        if (st != ST_OK) {
+            *out_len = o.pos;
+            return st;
+        }
+        if (too_large) {
+            *out_len = o.pos;
+            return ST_OUTPUT_TOO_LARGE;
+        }
+        if (last) break;
+    }
+
+    // checksum (:306-326)
+    *out_len = o.pos;
+    uint32_t align = (8u - (uint32_t)(r.pos & 7)) & 7u;
+    if (br_avail(r) < 32 + align) return ST_INSUFFICIENT_INPUT;
+    br_consume(r, align);
+    br_refill(r);
+    uint32_t stored = br_peek(r, 32);
+    stored = simt::byte_perm(stored, 0, 0x0123);  // big-endian on the wire
+    br_consume(r, 32);
+    *consumed = r.pos >> 3;
+    if (!(flags & FLAG_IGNORE_ADLER32)) {
+        simt::syncwarp();
+        uint32_t got = warp_adler32(out, o.pos);
+        if (got != stored) return ST_WRONG_CHECKSUM;
+    }
+    return ST_OK;
+}
+
+// Persistent kernel: one warp per CTA, warps pull stream indices from a device counter.
+// worklist == nullptr: all streams 0..n-1; else the first *work_count entries of worklist.
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(32, 1)
+    inflate_general_kernel(InflateBatch b, const uint32_t* worklist, const uint32_t* work_count, uint32_t* next) {
+    FDB_DYN_SMEM(smem_raw);
+    K3Smem& s = *reinterpret_cast<K3Smem*>(smem_raw);
+    const unsigned lane = simt::lane_id();
+    const uint32_t count = worklist ? *work_count : b.n;
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = simt::atomic_add(next, 1u);
+        idx = simt::shfl(idx, 0);
+        if (idx >= count) break;
+        uint32_t i = worklist ? worklist[idx] : idx;
+        uint64_t out_len = 0, consumed = 0;
+        const uint64_t cap = b.out_cap[i];
+        int32_t st = inflate_stream_general(s, b.in_base + b.in_off[i], b.in_len[i], b.out_base + b.out_off[i], cap,
+                                            b.flags, &out_len, &consumed);
+        // decompress_to_vec_bounded tests "output_index == maxlen" before "input exhausted"
+        // (reference decompress.rs:1128 vs :1135)
+        if (st == ST_INSUFFICIENT_INPUT && out_len == cap) st = ST_OUTPUT_TOO_LARGE;
+        if (lane == 0) {
+            b.status[i] = st;
+            b.out_len[i] = out_len;
+            if (b.consumed) b.consumed[i] = consumed;
+        }
+        simt::syncwarp();
+    }
+}
+
+}  // namespace fdb

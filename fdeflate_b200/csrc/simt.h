@@ -1,0 +1,106 @@
+// simt.h -- thin SIMT vocabulary used by every kernel in this directory.
+//
+// Product build (nvcc, sm_100a): every wrapper is a one-line forward to the CUDA intrinsic.
+//
+// Test-only build (g++ -DFDB_EMUL): the same kernel source is compiled as plain C++ and run by
+// the cooperative-fiber SIMT emulator in simt_emul.h, so that warp-level logic (shuffles, ballots,
+// scans, shared-memory staging) can be exercised against the oracle on a machine without a GPU.
+// The emulator build produces tests/emul/libfdb_emul.so; the package never loads it, and it is
+// not a fallback: fdeflate_b200 raises if libfdeflate_b200.so (the CUDA build) is missing.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef FDB_EMUL
+#include "simt_emul.h"
+#else
+#include <cuda_runtime.h>
+
+#define FDB_DEVICE __device__ __forceinline__
+#define FDB_MEMBER __device__ __forceinline__
+#define FDB_DEVICE_NOINLINE __device__ __noinline__
+#define FDB_GLOBAL __global__
+#define FDB_SHARED __shared__
+#define FDB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define FDB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define FDB_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+#define FDB_FULL 0xffffffffu
+
+namespace simt {
+FDB_DEVICE unsigned lane_id() { return threadIdx.x & 31u; }
+FDB_DEVICE unsigned warp_in_block() { return threadIdx.x >> 5; }
+FDB_DEVICE void syncwarp() { __syncwarp(); }
+FDB_DEVICE void syncthreads() { __syncthreads(); }
+FDB_DEVICE uint32_t shfl(uint32_t v, unsigned src) { return __shfl_sync(FDB_FULL, v, src); }
+FDB_DEVICE int32_t shfl(int32_t v, unsigned src) { return __shfl_sync(FDB_FULL, v, src); }
+FDB_DEVICE uint64_t shfl(uint64_t v, unsigned src) {
+    return (uint64_t)__shfl_sync(FDB_FULL, (unsigned long long)v, src);
+}
+FDB_DEVICE uint32_t shfl_up(uint32_t v, unsigned d) { return __shfl_up_sync(FDB_FULL, v, d); }
+FDB_DEVICE uint64_t shfl_up(uint64_t v, unsigned d) {
+    return (uint64_t)__shfl_up_sync(FDB_FULL, (unsigned long long)v, d);
+}
+FDB_DEVICE uint32_t shfl_down(uint32_t v, unsigned d) { return __shfl_down_sync(FDB_FULL, v, d); }
+FDB_DEVICE uint64_t shfl_down(uint64_t v, unsigned d) {
+    return (uint64_t)__shfl_down_sync(FDB_FULL, (unsigned long long)v, d);
+}
+FDB_DEVICE uint32_t shfl_xor(uint32_t v, unsigned m) { return __shfl_xor_sync(FDB_FULL, v, m); }
+FDB_DEVICE uint64_t shfl_xor(uint64_t v, unsigned m) {
+    return (uint64_t)__shfl_xor_sync(FDB_FULL, (unsigned long long)v, m);
+}
+FDB_DEVICE uint32_t ballot(bool p) { return __ballot_sync(FDB_FULL, p); }
+FDB_DEVICE bool any(bool p) { return __any_sync(FDB_FULL, p) != 0; }
+FDB_DEVICE bool all(bool p) { return __all_sync(FDB_FULL, p) != 0; }
+FDB_DEVICE uint32_t popc(uint32_t v) { return (uint32_t)__popc(v); }
+FDB_DEVICE uint32_t clz(uint32_t v) { return (uint32_t)__clz((int)v); }
+FDB_DEVICE uint32_t ffs(uint32_t v) { return (uint32_t)__ffs((int)v); }  // 1-based, 0 if none
+FDB_DEVICE uint32_t brev(uint32_t v) { return __brev(v); }
+FDB_DEVICE uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+FDB_DEVICE uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+FDB_DEVICE uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
+FDB_DEVICE uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+FDB_DEVICE uint64_t atomic_add(uint64_t* p, uint64_t v) {
+    return (uint64_t)atomicAdd((unsigned long long*)p, (unsigned long long)v);
+}
+FDB_DEVICE uint32_t atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+FDB_DEVICE void threadfence() { __threadfence(); }
+FDB_DEVICE uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
+FDB_DEVICE uint4 ldg128(const uint4* p) { return __ldg(p); }
+FDB_DEVICE uint8_t ldg8(const uint8_t* p) { return __ldg(p); }
+// streaming (evict-first) 16-byte store: output bytes are written once and never re-read by us
+FDB_DEVICE void stcs128(uint4* p, uint4 v) { __stcs(p, v); }
+}  // namespace simt
+#endif
+
+namespace simt {
+// lanes strictly below me
+FDB_DEVICE uint32_t lanemask_lt() { return (1u << lane_id()) - 1u; }
+
+// inclusive warp prefix sums
+FDB_DEVICE uint32_t scan_incl_add(uint32_t v) {
+#pragma unroll
+    for (unsigned d = 1; d < 32; d <<= 1) {
+        uint32_t t = shfl_up(v, d);
+        if (lane_id() >= d) v += t;
+    }
+    return v;
+}
+FDB_DEVICE uint64_t scan_incl_add(uint64_t v) {
+#pragma unroll
+    for (unsigned d = 1; d < 32; d <<= 1) {
+        uint64_t t = shfl_up(v, d);
+        if (lane_id() >= d) v += t;
+    }
+    return v;
+}
+FDB_DEVICE uint64_t reduce_add(uint64_t v) {
+#pragma unroll
+    for (unsigned d = 16; d > 0; d >>= 1) v += shfl_xor(v, d);
+    return v;
+}
+FDB_DEVICE uint32_t reduce_add(uint32_t v) {
+#pragma unroll
+    for (unsigned d = 16; d > 0; d >>= 1) v += shfl_xor(v, d);
+    return v;
+}
+}  // namespace simt

@@ -1,0 +1,135 @@
+/*
+ * fdeflate_b200.h -- C ABI of the B200-native batch zlib codec (libfdeflate_b200.so).
+ *
+ * Drop-in boundary for the hot path of image-rs/fdeflate (reference citations are file:line in the
+ * reference crate, version 0.4.0-dev).  The reference has no FFI of its own (it is a pure-Rust crate,
+ * `#![forbid(unsafe_code)]`, src/lib.rs:21); its boundary is the public Rust API re-exported at
+ * src/lib.rs:29-36.  Each entry point below names the Rust item it replaces; INTEGRATION.md shows the
+ * `extern "C"` block and the thin wrappers a maintainer adds on the Rust side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no allocation crosses the ABI; the caller owns every buffer.
+ *   - a batch is n independent zlib streams: stream i reads in_base[in_off[i] .. +in_len[i]) and writes
+ *     out_base[out_off[i] .. +out_cap[i]).  Slots must not overlap.  Offsets may have any alignment;
+ *     16-byte aligned offsets take the vectorised paths.
+ *   - function return value: 0 = the batch ran; non-zero = batch-level failure (CUDA error or bad
+ *     argument; text via fdb_last_error).  Per-stream results are in status[]; one bad stream never
+ *     aborts the batch.
+ *   - *_device entry points take DEVICE pointers (including the offset/length/result arrays) and
+ *     enqueue on `cuda_stream` without synchronising; the others take HOST pointers, stage through
+ *     device memory owned by the context, and return when the results are in the caller's buffers.
+ *   - device input buffers must be readable up to the next 16-byte boundary past the last stream
+ *     (true for any cudaMalloc'ed buffer).
+ *   - a context is bound to one GPU and is not re-entrant; use one context per host thread.
+ *   - there is no CPU fallback: without a CUDA device fdb_create fails.
+ */
+#ifndef FDEFLATE_B200_H
+#define FDEFLATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Per-stream status.  1..16 = DecompressionError variants in declaration order
+ * (src/decompress.rs:13-48); 17 = BoundedDecompressionError::OutputTooLarge (src/decompress.rs:1098);
+ * 18 = compress side only, the caller's slot is smaller than the encoded stream. */
+enum fdb_status {
+    FDB_OK = 0,
+    FDB_BAD_ZLIB_HEADER = 1,
+    FDB_INSUFFICIENT_INPUT = 2,
+    FDB_INVALID_BLOCK_TYPE = 3,
+    FDB_INVALID_UNCOMPRESSED_BLOCK_LENGTH = 4,
+    FDB_INVALID_HLIT = 5,
+    FDB_INVALID_HDIST = 6,
+    FDB_INVALID_CODE_LENGTH_REPEAT = 7,
+    FDB_BAD_CODE_LENGTH_HUFFMAN_TREE = 8,
+    FDB_BAD_LITERAL_LENGTH_HUFFMAN_TREE = 9,
+    FDB_BAD_DISTANCE_HUFFMAN_TREE = 10,
+    FDB_INVALID_LITERAL_LENGTH_CODE = 11,
+    FDB_INVALID_DISTANCE_CODE = 12,
+    FDB_INPUT_STARTS_WITH_RUN = 13,
+    FDB_DISTANCE_TOO_FAR_BACK = 14,
+    FDB_WRONG_CHECKSUM = 15,
+    FDB_EXTRA_INPUT = 16,
+    FDB_OUTPUT_TOO_LARGE = 17,
+    FDB_OUTPUT_BUFFER_TOO_SMALL = 18
+};
+
+/* flags for the inflate entry points */
+#define FDB_FLAG_IGNORE_ADLER32 1u /* Decompressor::ignore_adler32, src/decompress.rs:154-156 */
+#define FDB_FLAG_GENERAL_ONLY 2u   /* skip the ultra-fast-format fast path (testing / profiling) */
+
+typedef struct fdb_ctx fdb_ctx;
+
+/* Context life cycle.  device = CUDA device ordinal. */
+int fdb_create(int device, fdb_ctx** ctx);
+void fdb_destroy(fdb_ctx* ctx);
+const char* fdb_last_error(const fdb_ctx* ctx);
+const char* fdb_version(void);
+
+/* ---- inflate ---------------------------------------------------------------------------------
+ * Replaces, per stream, decompress_to_vec_bounded(input, maxlen = out_cap[i])
+ * (src/decompress.rs:1111-1144), i.e. the Decompressor::read state machine (src/decompress.rs:179-337)
+ * run to completion.  decompress_to_vec (src/decompress.rs:1079) is the same call with a slot known
+ * to be large enough.  On FDB_OK out_len[i] bytes are valid and equal the reference's Vec; on
+ * FDB_OUTPUT_TOO_LARGE out_len[i] == out_cap[i] and the slot holds the reference's partial_output;
+ * on any other status the slot content is unspecified.  consumed (may be NULL) receives the number
+ * of input bytes read up to and including the adler32 trailer (trailing bytes are ignored, as in the
+ * reference).  adler32 is verified on the device unless FDB_FLAG_IGNORE_ADLER32. */
+int fdb_inflate_batch_device(fdb_ctx* ctx, const void* d_in_base, const uint64_t* d_in_off,
+                             const uint64_t* d_in_len, void* d_out_base, const uint64_t* d_out_off,
+                             const uint64_t* d_out_cap, uint64_t* d_out_len, uint64_t* d_consumed,
+                             int32_t* d_status, size_t n, uint32_t flags, void* cuda_stream);
+int fdb_inflate_batch(fdb_ctx* ctx, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                      uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                      uint64_t* consumed, int32_t* status, size_t n, uint32_t flags);
+
+/* ---- ultra-fast deflate ------------------------------------------------------------------------
+ * Replaces, per stream, compress_to_vec_ultra_fast(input) (src/compress/mod.rs:313-317) =
+ * UltraFastCompressor::new + one write_data(whole input) + finish (src/compress/ultrafast.rs:70-181).
+ * Output bytes are identical to the reference's.  A slot of fdb_deflate_ultrafast_bound(in_len)
+ * bytes always suffices. */
+size_t fdb_deflate_ultrafast_bound(size_t in_len);
+int fdb_deflate_ultrafast_batch_device(fdb_ctx* ctx, const void* d_in_base, const uint64_t* d_in_off,
+                                       const uint64_t* d_in_len, void* d_out_base, const uint64_t* d_out_off,
+                                       const uint64_t* d_out_cap, uint64_t* d_out_len, int32_t* d_status, size_t n,
+                                       void* cuda_stream);
+int fdb_deflate_ultrafast_batch(fdb_ctx* ctx, const uint8_t* in_base, const uint64_t* in_off,
+                                const uint64_t* in_len, uint8_t* out_base, const uint64_t* out_off,
+                                const uint64_t* out_cap, uint64_t* out_len, int32_t* status, size_t n);
+
+/* ---- stored ("level 0") deflate ------------------------------------------------------------------
+ * Replaces Compressor::new(w, 0, true) + one write_data(whole input) + finish()
+ * (src/compress/mod.rs:69-101, :126-156, :194-214, :241-268) -- the north star's StoredOnlyCompressor. */
+size_t fdb_deflate_stored_bound(size_t in_len);
+int fdb_deflate_stored_batch_device(fdb_ctx* ctx, const void* d_in_base, const uint64_t* d_in_off,
+                                    const uint64_t* d_in_len, void* d_out_base, const uint64_t* d_out_off,
+                                    const uint64_t* d_out_cap, uint64_t* d_out_len, int32_t* d_status, size_t n,
+                                    void* cuda_stream);
+int fdb_deflate_stored_batch(fdb_ctx* ctx, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                             uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                             int32_t* status, size_t n);
+
+/* ---- synthetic PNG-filtered RGBA tiles (benchmark / test input) -----------------
+ * Tile t is width x height RGBA8, row 0 Sub-filtered, other rows Paeth-filtered; each row is
+ * 1 filter-type byte + 4*width residual bytes, so a tile is height*(1+4*width) bytes, laid out
+ * back to back.  Integer-only and counter-based, so the host and device versions agree exactly. */
+size_t fdb_synth_tile_bytes(uint32_t width, uint32_t height);
+int fdb_synth_tiles_host(uint8_t* out, uint64_t first_tile, uint64_t n_tiles, uint32_t width, uint32_t height,
+                         uint64_t seed);
+int fdb_synth_tiles_device(fdb_ctx* ctx, void* d_out, uint64_t first_tile, uint64_t n_tiles, uint32_t width,
+                           uint32_t height, uint64_t seed, void* cuda_stream);
+
+/* number of kernels this library has launched through ctx since creation (bench bookkeeping) */
+uint64_t fdb_launch_count(const fdb_ctx* ctx);
+/* how many streams of the most recent inflate batch on this context were declined by the
+ * ultra-fast-format fast path and decoded by the general kernel.  Synchronises `cuda_stream`. */
+int64_t fdb_last_general_count(fdb_ctx* ctx, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

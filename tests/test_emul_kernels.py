@@ -1,0 +1,83 @@
+"""CPU-side logic tests of the CUDA kernel SOURCES, run on the test-only fiber SIMT emulator
+(tests/emul) and checked bit for bit against the oracle.  These cover the host logic and the warp
+algorithms (scans, carries, table builds, sub-sequence synchronisation) on a machine without a GPU;
+the `-m gpu` tests repeat them on the real library and hardware."""
+import random
+
+import pytest
+
+import cases
+import parity
+from fdeflate_b200 import FLAG_GENERAL_ONLY, FLAG_IGNORE_ADLER32
+
+pytestmark = pytest.mark.emul
+
+
+def test_deflate_ultrafast_byte_identical(emul_ctx, oracle):
+    inputs = cases.compress_inputs(5, 25, [10, 100, 1000, 5000, 20000])
+    parity.check_deflate_ultrafast(emul_ctx, inputs, align=16)
+    parity.check_deflate_ultrafast(emul_ctx, inputs[:30], align=1)  # unaligned in/out slots
+
+
+def test_deflate_stored_byte_identical(emul_ctx, oracle):
+    rng = random.Random(2)
+    inputs = [b"", b"a", bytes(65534), bytes(65535), bytes(65536), cases.sparse_bytes(rng, 131070),
+              cases.sparse_bytes(rng, 131071), cases.sparse_bytes(rng, 70000)]
+    parity.check_deflate_stored(emul_ctx, inputs, align=16)
+    parity.check_deflate_stored(emul_ctx, inputs, align=1)
+
+
+def test_inflate_golden_vectors(emul_ctx, oracle):
+    g = [(d, 4096) for _, d in cases.golden_streams()]
+    parity.check_inflate(emul_ctx, g, FLAG_GENERAL_ONLY)
+    parity.check_inflate(emul_ctx, g, FLAG_GENERAL_ONLY | FLAG_IGNORE_ADLER32)
+    parity.check_inflate(emul_ctx, g, 0)
+    st = parity.check_inflate(emul_ctx, g[-3:], FLAG_IGNORE_ADLER32)
+    assert list(st) == [0, 9, 9]  # example1 Ok (281 bytes), examples 2/3 BadLiteralLengthHuffmanTree
+
+
+def test_inflate_general_mixed_streams(emul_ctx, oracle):
+    c = cases.mixed_zlib_cases(21, 25, [0, 1, 5, 100, 1000, 5000, 20000])
+    parity.check_inflate(emul_ctx, c, FLAG_GENERAL_ONLY)
+    parity.check_inflate(emul_ctx, c[:120], FLAG_GENERAL_ONLY | FLAG_IGNORE_ADLER32, align=1)
+
+
+def test_inflate_fast_path_ultrafast_streams(emul_ctx, emul_lib, oracle):
+    from fdeflate_b200 import synth_tiles_host
+
+    rng = random.Random(4)
+    datas = [b"", b"a", bytes(1), bytes(100000)] + [cases.sparse_bytes(rng, n) for n in (100, 1000, 3000, 50000, 120000)]
+    datas += [t.tobytes() for t in synth_tiles_host(0, 2, 256, 256, 99, emul_lib)]
+    streams = [oracle.compress_ultra_fast(d) for d in datas]
+    exact = [(s, len(d)) for s, d in zip(streams, datas)]
+    parity.check_inflate(emul_ctx, exact, 0, expect_general=0)          # every stream stays on the fast path
+    parity.check_inflate(emul_ctx, exact, 0, align=1, expect_general=0)
+    parity.check_inflate(emul_ctx, [(s, c + 7) for s, c in exact], 0, expect_general=0)
+    parity.check_inflate(emul_ctx, [(s, max(0, c - 1)) for s, c in exact], 0)  # OutputTooLarge via the general kernel
+    dmg = []
+    for s, c in exact:
+        dmg += cases.damaged(rng, s, c)
+    parity.check_inflate(emul_ctx, dmg, 0)
+    parity.check_inflate(emul_ctx, dmg, FLAG_IGNORE_ADLER32)
+
+
+def test_inflate_fast_path_foreign_token_sequences(emul_ctx, oracle):
+    crafted = cases.crafted_uf_cases(3)
+    c = [(s, len(e) if e is not None else 100000) for s, e in crafted]
+    for (s, cap), (_, e) in zip(c, crafted):
+        if e is not None:
+            assert oracle.inflate_into(s, cap)[:2] == (0, e)
+    parity.check_inflate(emul_ctx, c, 0)
+
+
+def test_batch_composition_invariance(emul_ctx, oracle):
+    """a stream's result must not depend on its neighbours or its position in the batch."""
+    rng = random.Random(8)
+    c = cases.mixed_zlib_cases(5, 6, [100, 3000])
+    c += [(oracle.compress_ultra_fast(cases.sparse_bytes(rng, 4000)), 4000) for _ in range(5)]
+    base = emul_ctx.inflate_batch([x[0] for x in c], [x[1] for x in c])
+    perm = list(range(len(c)))
+    rng.shuffle(perm)
+    sh = emul_ctx.inflate_batch([c[i][0] for i in perm], [c[i][1] for i in perm])
+    for k, i in enumerate(perm):
+        assert sh[0][k] == base[0][i] and sh[1][k] == base[1][i]

@@ -1,0 +1,174 @@
+"""-m gpu: the product library on a real B200, through the C ABI, against the oracle."""
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+import cases
+import parity
+from fdeflate_b200 import FLAG_GENERAL_ONLY, FLAG_IGNORE_ADLER32
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_is_the_cuda_build(gpu_ctx):
+    assert "CUDA" in gpu_ctx.lib.version()
+
+
+def test_deflate_ultrafast_byte_identical(gpu_ctx, oracle):
+    inputs = cases.compress_inputs(5, 60, [10, 100, 1000, 5000, 20000, 70000, 300000])
+    parity.check_deflate_ultrafast(gpu_ctx, inputs, align=16)
+    parity.check_deflate_ultrafast(gpu_ctx, inputs, align=1)
+
+
+def test_deflate_stored_byte_identical(gpu_ctx, oracle):
+    rng = random.Random(2)
+    inputs = [b"", b"a", bytes(65534), bytes(65535), bytes(65536), cases.sparse_bytes(rng, 131070),
+              cases.sparse_bytes(rng, 131071), cases.sparse_bytes(rng, 700000)]
+    parity.check_deflate_stored(gpu_ctx, inputs, align=16)
+    parity.check_deflate_stored(gpu_ctx, inputs, align=1)
+
+
+def test_inflate_golden_vectors(gpu_ctx, oracle):
+    g = [(d, 4096) for _, d in cases.golden_streams()]
+    parity.check_inflate(gpu_ctx, g, FLAG_GENERAL_ONLY)
+    parity.check_inflate(gpu_ctx, g, FLAG_GENERAL_ONLY | FLAG_IGNORE_ADLER32)
+    parity.check_inflate(gpu_ctx, g, 0)
+    st = parity.check_inflate(gpu_ctx, g[-3:], FLAG_IGNORE_ADLER32)
+    assert list(st) == [0, 9, 9]
+
+
+def test_inflate_general_mixed_streams(gpu_ctx, oracle):
+    # BASELINE config 4: stored / fixed / dynamic, flushes, small windows, long overlapping matches,
+    # 13-15 bit codes, truncations, bit flips, capacity limits
+    c = cases.mixed_zlib_cases(21, 120, [0, 1, 5, 100, 1000, 5000, 20000, 200000])
+    parity.check_inflate(gpu_ctx, c, FLAG_GENERAL_ONLY)
+    parity.check_inflate(gpu_ctx, c, FLAG_GENERAL_ONLY | FLAG_IGNORE_ADLER32, align=1)
+    parity.check_inflate(gpu_ctx, c, 0)
+
+
+def test_inflate_long_constant_runs(gpu_ctx, oracle):
+    # chains of length-258 distance-1 matches (>= 1 MiB) and a 32 KiB-period pattern
+    big = bytes(3 << 20)
+    per = (bytes(range(256)) * 128 * 40)[: 1 << 20]
+    c = [(zlib.compress(big, 6), len(big)), (zlib.compress(per, 9), len(per)),
+         (oracle.compress_ultra_fast(big), len(big))]
+    parity.check_inflate(gpu_ctx, c, 0)
+    parity.check_inflate(gpu_ctx, c, FLAG_GENERAL_ONLY)
+
+
+def test_inflate_fast_path_ultrafast_streams(gpu_ctx, oracle):
+    from fdeflate_b200 import synth_tiles_host
+
+    rng = random.Random(4)
+    datas = [b"", b"a", bytes(1), bytes(100000)] + [cases.sparse_bytes(rng, n) for n in (100, 1000, 3000, 50000, 120000, 900000)]
+    datas += [t.tobytes() for t in synth_tiles_host(0, 24, 256, 256, 99)]
+    streams = [oracle.compress_ultra_fast(d) for d in datas]
+    exact = [(s, len(d)) for s, d in zip(streams, datas)]
+    parity.check_inflate(gpu_ctx, exact, 0, expect_general=0)
+    parity.check_inflate(gpu_ctx, exact, 0, align=1, expect_general=0)
+    parity.check_inflate(gpu_ctx, exact, FLAG_GENERAL_ONLY)
+    parity.check_inflate(gpu_ctx, [(s, c + 7) for s, c in exact], 0, expect_general=0)
+    parity.check_inflate(gpu_ctx, [(s, max(0, c - 1)) for s, c in exact], 0)
+    dmg = []
+    for s, c in exact:
+        dmg += cases.damaged(rng, s, c)
+    parity.check_inflate(gpu_ctx, dmg, 0)
+    parity.check_inflate(gpu_ctx, dmg, FLAG_IGNORE_ADLER32)
+
+
+def test_inflate_fast_path_foreign_token_sequences(gpu_ctx, oracle):
+    crafted = cases.crafted_uf_cases(3, sizes=(0, 1, 2, 10, 100, 1000, 5000, 60000))
+    c = [(s, len(e) if e is not None else 100000) for s, e in crafted]
+    parity.check_inflate(gpu_ctx, c, 0)
+    parity.check_inflate(gpu_ctx, c, FLAG_GENERAL_ONLY)
+
+
+def test_batch_composition_invariance(gpu_ctx, oracle):
+    rng = random.Random(8)
+    c = cases.mixed_zlib_cases(5, 20, [100, 3000, 50000])
+    c += [(oracle.compress_ultra_fast(cases.sparse_bytes(rng, 40000)), 40000) for _ in range(20)]
+    base = gpu_ctx.inflate_batch([x[0] for x in c], [x[1] for x in c])
+    perm = list(range(len(c)))
+    rng.shuffle(perm)
+    sh = gpu_ctx.inflate_batch([c[i][0] for i in perm], [c[i][1] for i in perm])
+    for k, i in enumerate(perm):
+        assert sh[0][k] == base[0][i] and sh[1][k] == base[1][i]
+
+
+def test_config1_single_image_roundtrip(gpu_ctx, oracle):
+    # BASELINE config 1: one 1024x1024 RGBA filtered image, compress then decompress
+    from fdeflate_b200 import compress_to_vec_ultra_fast, decompress_to_vec, synth_tiles_host
+
+    img = synth_tiles_host(0, 1, 1024, 1024, 7)[0].tobytes()
+    assert len(img) == 4195328
+    z = compress_to_vec_ultra_fast(img, gpu_ctx)
+    assert z == oracle.compress_ultra_fast(img)
+    assert decompress_to_vec(z, gpu_ctx) == img == zlib.decompress(z)
+
+
+def _device_batch(gpu_ctx, n_tiles, seed):
+    """config 2/3 at full size, device resident: synth tiles -> compress -> inflate; returns torch tensors"""
+    import torch
+
+    dev = torch.device("cuda:0")
+    tb = 262400
+    tiles = torch.empty(n_tiles * tb, dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    gpu_ctx.synth_tiles_device(tiles.data_ptr(), 0, n_tiles, 256, 256, seed, s)
+    bound = gpu_ctx.ultrafast_bound(tb)
+    u64 = torch.uint64 if hasattr(torch, "uint64") else torch.int64
+    in_off = (torch.arange(n_tiles, dtype=torch.int64, device=dev) * tb)
+    in_len = torch.full((n_tiles,), tb, dtype=torch.int64, device=dev)
+    c_off = (torch.arange(n_tiles, dtype=torch.int64, device=dev) * bound)
+    c_cap = torch.full((n_tiles,), bound, dtype=torch.int64, device=dev)
+    comp = torch.empty(n_tiles * bound, dtype=torch.uint8, device=dev)
+    c_len = torch.zeros(n_tiles, dtype=torch.int64, device=dev)
+    c_st = torch.full((n_tiles,), -7, dtype=torch.int32, device=dev)
+    gpu_ctx.deflate_ultrafast_device(tiles.data_ptr(), in_off.data_ptr(), in_len.data_ptr(), comp.data_ptr(),
+                                     c_off.data_ptr(), c_cap.data_ptr(), c_len.data_ptr(), c_st.data_ptr(), n_tiles, s)
+    out = torch.empty(n_tiles * tb, dtype=torch.uint8, device=dev)
+    o_len = torch.zeros(n_tiles, dtype=torch.int64, device=dev)
+    o_st = torch.full((n_tiles,), -7, dtype=torch.int32, device=dev)
+    gpu_ctx.inflate_device(comp.data_ptr(), c_off.data_ptr(), c_len.data_ptr(), out.data_ptr(), in_off.data_ptr(),
+                           in_len.data_ptr(), o_len.data_ptr(), 0, o_st.data_ptr(), n_tiles, 0, s)
+    torch.cuda.synchronize()
+    return tiles, comp, c_off, c_len, c_st, out, o_len, o_st
+
+
+def test_config2_config3_full_size_properties(gpu_ctx, oracle):
+    """BASELINE configs 2 and 3 at full size (4096 tiles of 256x256 RGBA, 1.07 GB): the oracle is too
+    slow for all of it, so check size-independent properties on everything (round trip equality,
+    all statuses Ok, fast path taken) and byte parity against the oracle on a sample of tiles."""
+    import torch
+
+    n = 4096
+    tiles, comp, c_off, c_len, c_st, out, o_len, o_st = _device_batch(gpu_ctx, n, 2024)
+    assert int((c_st != 0).sum()) == 0 and int((o_st != 0).sum()) == 0
+    assert gpu_ctx.last_general_count(torch.cuda.current_stream().cuda_stream) == 0
+    assert int((o_len != 262400).sum()) == 0
+    assert torch.equal(out, tiles)                      # encode -> decode round trip over 1.07 GB
+    ratio = float(c_len.sum()) / (n * 262400)
+    assert 0.2 < ratio < 0.6
+    host_tiles = tiles.view(n, 262400)
+    lens = c_len.cpu().numpy()
+    offs = c_off.cpu().numpy()
+    for i in (0, 1, 17, 1000, 2047, 4095):
+        t = host_tiles[i].cpu().numpy().tobytes()
+        ref = oracle.compress_ultra_fast(t)
+        got = comp[int(offs[i]): int(offs[i]) + int(lens[i])].cpu().numpy().tobytes()
+        assert got == ref, f"tile {i}: compressed bytes differ from the oracle"
+        assert oracle.decompress_to_vec(got) == (0, t)
+
+
+def test_synth_host_and_device_agree(gpu_ctx):
+    import torch
+
+    from fdeflate_b200 import synth_tiles_host
+
+    h = synth_tiles_host(5, 3, 256, 256, 77)
+    d = torch.empty(3 * 262400, dtype=torch.uint8, device="cuda:0")
+    gpu_ctx.synth_tiles_device(d.data_ptr(), 5, 3, 256, 256, 77, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy().reshape(3, 262400), h)
