@@ -279,6 +279,18 @@ static Span spans(const uint64_t* in_off, const uint64_t* in_len, const uint64_t
     return s;
 }
 
+// If the n slots form an arithmetic progression (same stride, ascending) a single 2-D copy can move
+// only the used prefix of every slot; otherwise the whole span is copied.
+static bool uniform_stride(const uint64_t* off, size_t n, uint64_t* stride) {
+    if (n < 2) return false;
+    uint64_t s = off[1] - off[0];
+    if (off[1] <= off[0]) return false;
+    for (size_t i = 2; i < n; i++)
+        if (off[i] - off[i - 1] != s || off[i] <= off[i - 1]) return false;
+    *stride = s;
+    return true;
+}
+
 static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
                       uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
                       uint64_t* consumed, int32_t* status, size_t n, uint32_t flags) {
@@ -298,11 +310,21 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
              *d_consumed = m + 5 * n;
     int32_t* d_status = (int32_t*)(m + 6 * n);
     cudaStream_t st = ctx->stream;
-    if (sp.in_span) FDB_TRY(cudaMemcpyAsync(ctx->d_in, in_base, sp.in_span, cudaMemcpyHostToDevice, st));
+    // ---- host -> device ----
+    uint64_t stride = 0, max_in = 0;
+    for (size_t i = 0; i < n; i++) max_in = std::max(max_in, in_len[i]);
+    if (uniform_stride(in_off, n, &stride) && max_in <= stride && max_in * n < sp.in_span - sp.in_span / 8) {
+        if (max_in)
+            FDB_TRY(cudaMemcpy2DAsync(ctx->d_in + in_off[0], stride, in_base + in_off[0], stride, max_in, n,
+                                      cudaMemcpyHostToDevice, st));
+    } else if (sp.in_span) {
+        FDB_TRY(cudaMemcpyAsync(ctx->d_in, in_base, sp.in_span, cudaMemcpyHostToDevice, st));
+    }
     FDB_TRY(cudaMemcpyAsync(d_in_off, in_off, n * 8, cudaMemcpyHostToDevice, st));
     FDB_TRY(cudaMemcpyAsync(d_in_len, in_len, n * 8, cudaMemcpyHostToDevice, st));
     FDB_TRY(cudaMemcpyAsync(d_out_off, out_off, n * 8, cudaMemcpyHostToDevice, st));
     FDB_TRY(cudaMemcpyAsync(d_out_cap, out_cap, n * 8, cudaMemcpyHostToDevice, st));
+    // ---- kernels ----
     if (kind == 0)
         r = fdb_inflate_batch_device(ctx, ctx->d_in, d_in_off, d_in_len, ctx->d_out, d_out_off, d_out_cap, d_out_len,
                                      d_consumed, d_status, n, flags, st);
@@ -310,10 +332,20 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
         r = deflate_device(ctx, kind - 1, ctx->d_in, d_in_off, d_in_len, ctx->d_out, d_out_off, d_out_cap, d_out_len,
                            d_status, n, st);
     if (r) return r;
+    // ---- device -> host: results first (their lengths decide how much payload moves) ----
     FDB_TRY(cudaMemcpyAsync(out_len, d_out_len, n * 8, cudaMemcpyDeviceToHost, st));
     if (consumed && kind == 0) FDB_TRY(cudaMemcpyAsync(consumed, d_consumed, n * 8, cudaMemcpyDeviceToHost, st));
     FDB_TRY(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st));
-    if (sp.out_span) FDB_TRY(cudaMemcpyAsync(out_base, ctx->d_out, sp.out_span, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaStreamSynchronize(st));
+    uint64_t max_out = 0;
+    for (size_t i = 0; i < n; i++) max_out = std::max(max_out, out_len[i]);
+    if (uniform_stride(out_off, n, &stride) && max_out <= stride && max_out * n < sp.out_span - sp.out_span / 8) {
+        if (max_out)
+            FDB_TRY(cudaMemcpy2DAsync(out_base + out_off[0], stride, ctx->d_out + out_off[0], stride, max_out, n,
+                                      cudaMemcpyDeviceToHost, st));
+    } else if (sp.out_span) {
+        FDB_TRY(cudaMemcpyAsync(out_base, ctx->d_out, sp.out_span, cudaMemcpyDeviceToHost, st));
+    }
     FDB_TRY(cudaStreamSynchronize(st));
     return 0;
 }

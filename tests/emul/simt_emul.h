@@ -241,6 +241,11 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cuda
     if (n) memmove(d, s, n);
     return cudaSuccess;
 }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h,
+                                            cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < h; r++) memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) {
     if (n) memmove(d, s, n);
     return cudaSuccess;
