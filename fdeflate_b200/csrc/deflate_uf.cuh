@@ -60,11 +60,9 @@ FDB_DEVICE uint32_t clz64(uint64_t v) {  // v != 0
     return hi ? simt::clz(hi) : 32u + simt::clz((uint32_t)v);
 }
 
-struct BitCounter {
-    uint32_t bits;
-    FDB_MEMBER void emit(uint32_t, uint32_t n) { bits += n; }
-};
-
+// Packs (value, nbits <= 32) groups LSB-first into the warp's staging window.  The first word a lane
+// touches may be shared with earlier lanes, so it is kept back (first_word) until the partial-word
+// carry scan has run; every later word is complete and owned by this lane.
 struct BitPacker {
     uint64_t acc;
     uint32_t accn;
@@ -88,55 +86,109 @@ struct BitPacker {
     }
 };
 
-// Tokens of one whole 8-byte chunk inside the run-logic prefix.  x = pending run length entering
-// the chunk; next_continues = the byte after the chunk is a zero that extends the run.
+// The tokens of one 8-byte chunk, in stream order:  head group | 8 per-byte literal tokens | tail group.
+//   lit[j]  = code | nbits << 16 of byte j, or 0 when byte j is swallowed by a run / is past the end
+//   head    = tokens that close a run entering the chunk:   [sym285+dist]? [run tail]   (<= 28 bits)
+//             or, for an all-zero chunk, every token the chunk owes: [lit0]? [sym285+dist]? [run tail]?
+//   tail    = tokens that open a run on the trailing zeros:  [lit0] [run tail if the run ends here]
+struct ChunkTokens {
+    uint32_t lit[8];
+    uint32_t head_v, head_n;
+    uint32_t tail_v, tail_n;
+};
+
+FDB_DEVICE uint32_t lit_bits_sum(const ChunkTokens& t) {
+    // codes are <= 12 bits, so eight of them cannot carry into the nbits field at bit 16
+    uint32_t s = (t.lit[0] + t.lit[1] + t.lit[2]) + (t.lit[3] + t.lit[4] + t.lit[5]) + (t.lit[6] + t.lit[7]);
+    return (s >> 16) + t.head_n + t.tail_n;
+}
+
+// kind 2: whole chunk inside the run-logic prefix (reference ultrafast.rs:98-153); x = pending run
+// length entering the chunk; cont = the byte after the chunk is a zero that extends the run.
+// kind 1: the final partial chunk, `rem` literal bytes (ultrafast.rs:159-164).  kind 0: nothing.
 // Returns the pending run length leaving the chunk.
-template <class E>
-FDB_DEVICE uint32_t walk_chunk(E& e, uint64_t c, uint32_t x, bool next_continues, const uint32_t* lit_tok,
-                               const uint32_t* tail_tok) {
-    uint64_t nz = nonzero_bytes(c);
-    if (nz == 0) {
-        if (x == 0) e.emit(0u, 2u);  // lit 0 opens the run (ultrafast.rs:46)
-        uint32_t r0 = x % 258u;
-        if (r0 == 0 ? (x > 0) : (258u - r0 <= 7u)) e.emit(UF_CODE285_DIST1, 10u);  // :49-52
-        if (!next_continues) {
-            uint32_t t = tail_tok[(x + 7u) % 258u];
-            e.emit(t & 0xffffffu, t >> 24);
+FDB_DEVICE uint32_t chunk_tokens(ChunkTokens& t, uint64_t c, uint32_t kind, uint32_t rem, uint32_t x, bool cont,
+                                 const uint32_t* lit_tok, const uint32_t* tail_tok) {
+    t.head_v = t.head_n = t.tail_v = t.tail_n = 0;
+    const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
+    t.lit[0] = lit_tok[lo & 0xffu];
+    t.lit[1] = lit_tok[(lo >> 8) & 0xffu];
+    t.lit[2] = lit_tok[(lo >> 16) & 0xffu];
+    t.lit[3] = lit_tok[lo >> 24];
+    t.lit[4] = lit_tok[hi & 0xffu];
+    t.lit[5] = lit_tok[(hi >> 8) & 0xffu];
+    t.lit[6] = lit_tok[(hi >> 16) & 0xffu];
+    t.lit[7] = lit_tok[hi >> 24];
+    if (kind != 2) {
+        const uint32_t keep = kind == 1 ? rem : 0u;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++)
+            if (j >= keep) t.lit[j] = 0;
+        return 0;
+    }
+    const uint64_t nz = nonzero_bytes(c);
+    if (nz == 0x8080808080808080ull && x == 0) return 0;  // no zero byte, no run pending: eight plain literals
+    if (nz == 0) {  // all-zero chunk: extends (or opens) a run
+        uint32_t v = 0, n = 0;
+        if (x == 0) n = 2;  // lit 0 opens the run (ultrafast.rs:46); its code is 00
+        const uint32_t r0 = x % 258u;
+        if (r0 == 0 ? (x > 0) : (258u - r0 <= 7u)) {  // a multiple of 258 falls inside: sym 285 + distance 1 (:49-52)
+            v |= UF_CODE285_DIST1 << n;
+            n += 10;
         }
+        if (!cont) {  // the run ends with this chunk (:54-64)
+            const uint32_t tt = tail_tok[(x + 7u) % 258u];
+            v |= (tt & 0xffffffu) << n;
+            n += tt >> 24;
+        }
+        t.head_v = v;
+        t.head_n = n;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) t.lit[j] = 0;
         return x + 8u;
     }
-    uint32_t lead = ctz64(nz) >> 3, trail = clz64(nz) >> 3;
-    uint32_t j = 0;
-    if (x > 0 && lead > 0) {  // run ends inside this chunk (:105-108)
-        uint32_t r0 = x % 258u;
-        if (r0 == 0 || 258u - r0 <= lead - 1u) e.emit(UF_CODE285_DIST1, 10u);
-        uint32_t t = tail_tok[(x + lead - 1u) % 258u];
-        e.emit(t & 0xffffffu, t >> 24);
-        j = lead;
-    }
-    uint64_t cc = c >> (8u * j);
-    for (; j < 8u - trail; j++) {  // literals (:113-116, :125-128, :134-152)
-        uint32_t t = lit_tok[(uint32_t)cc & 0xffu];
-        e.emit(t & 0xffffu, t >> 16);
-        cc >>= 8;
+    const uint32_t lead = ctz64(nz) >> 3, trail = clz64(nz) >> 3;
+    uint32_t first_lit = 0;
+    if (x > 0 && lead > 0) {  // the run entering the chunk ends on its leading zeros (:105-108)
+        uint32_t v = 0, n = 0;
+        const uint32_t r0 = x % 258u;
+        if (r0 == 0 || 258u - r0 <= lead - 1u) {
+            v = UF_CODE285_DIST1;
+            n = 10;
+        }
+        const uint32_t tt = tail_tok[(x + lead - 1u) % 258u];
+        v |= (tt & 0xffffffu) << n;
+        n += tt >> 24;
+        t.head_v = v;
+        t.head_n = n;
+        first_lit = lead;
     }
     if (trail > 0) {  // trailing zeros open a new run (:111, :130)
-        e.emit(0u, 2u);
-        if (!next_continues) {
-            uint32_t t = tail_tok[trail - 1u];
-            e.emit(t & 0xffffffu, t >> 24);
+        uint32_t n = 2;  // lit 0
+        uint32_t v = 0;
+        if (!cont) {
+            const uint32_t tt = tail_tok[trail - 1u];
+            v = (tt & 0xffffffu) << 2;
+            n += tt >> 24;
         }
+        t.tail_v = v;
+        t.tail_n = n;
     }
+    const uint32_t last_lit = 8u - trail;
+#pragma unroll
+    for (uint32_t j = 0; j < 8; j++)
+        if (j < first_lit || j >= last_lit) t.lit[j] = 0;
     return trail;
 }
 
-template <class E>
-FDB_DEVICE void walk_literals(E& e, uint64_t c, uint32_t count, const uint32_t* lit_tok) {  // :159-164
-    for (uint32_t j = 0; j < count; j++) {
-        uint32_t t = lit_tok[(uint32_t)c & 0xffu];
-        e.emit(t & 0xffffu, t >> 16);
-        c >>= 8;
+FDB_DEVICE void emit_chunk(BitPacker& bp, const ChunkTokens& t) {
+    bp.emit(t.head_v, t.head_n);
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k += 2) {
+        const uint32_t a = t.lit[k], b = t.lit[k + 1];
+        bp.emit((a & 0xffffu) | ((b & 0xffffu) << (a >> 16)), (a >> 16) + (b >> 16));
     }
+    bp.emit(t.tail_v, t.tail_n);
 }
 
 FDB_DEVICE uint4 load16_guarded(const uint8_t* in, uint64_t g, uint64_t n, bool aligned) {
@@ -254,16 +306,14 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint32_t* lit_tok, const uint32_t* t
         const bool cont0 = (k1 == 2) && ((q.z & 0xffu) == 0);
         const bool cont1 = next_lane_first != 0;
 
-        // 2. bit lengths and offsets
-        BitCounter bc = {0};
-        uint32_t x1 = 0;
-        if (k0 == 2) x1 = walk_chunk(bc, c0, x0, cont0, lit_tok, tail_tok);
-        else if (k0 == 1) walk_literals(bc, c0, rem, lit_tok);
-        if (k1 == 2) walk_chunk(bc, c1, x1, cont1, lit_tok, tail_tok);
-        else if (k1 == 1) walk_literals(bc, c1, rem, lit_tok);
-        const uint32_t incl_bits = simt::scan_incl_add(bc.bits);
+        // 2. tokens (looked up once, kept in registers), bit lengths and offsets
+        ChunkTokens t0, t1;
+        const uint32_t x1 = chunk_tokens(t0, c0, k0, rem, x0, cont0, lit_tok, tail_tok);
+        chunk_tokens(t1, c1, k1, rem, x1, cont1, lit_tok, tail_tok);
+        const uint32_t my_bits = lit_bits_sum(t0) + lit_bits_sum(t1);
+        const uint32_t incl_bits = simt::scan_incl_add(my_bits);
         const uint32_t total_bits = simt::shfl(incl_bits, 31);
-        const uint64_t o = vbit + (incl_bits - bc.bits);
+        const uint64_t o = vbit + (incl_bits - my_bits);
         const uint64_t wbase = vbit >> 5;
 
         // 3. pack
@@ -273,10 +323,8 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint32_t* lit_tok, const uint32_t* t
         bp.w = bp.w_first = (uint32_t)((o >> 5) - wbase);
         bp.first_word = 0;
         bp.stg = stg;
-        if (k0 == 2) walk_chunk(bp, c0, x0, cont0, lit_tok, tail_tok);
-        else if (k0 == 1) walk_literals(bp, c0, rem, lit_tok);
-        if (k1 == 2) walk_chunk(bp, c1, x1, cont1, lit_tok, tail_tok);
-        else if (k1 == 1) walk_literals(bp, c1, rem, lit_tok);
+        emit_chunk(bp, t0);
+        emit_chunk(bp, t1);
 
         // partial-word carry: g(x) = m ? x | v : v, with m = "this lane did not complete its first word"
         uint32_t gm = (bp.w == bp.w_first) ? 1u : 0u, gv = (uint32_t)bp.acc;

@@ -50,6 +50,12 @@ struct InflateBatch {
     uint32_t flags;
 };
 
+#if defined(__CUDACC__) && !defined(FDB_EMUL)
+#define FDB_HD __host__ __device__ __forceinline__
+#else
+#define FDB_HD static inline
+#endif
+
 struct DeflateBatch {
     const uint8_t* in_base;
     const uint64_t* in_off;
@@ -65,27 +71,25 @@ struct DeflateBatch {
 // ---- decode-table entry formats (ours; only the decoded bytes have to match the reference) ----
 // litlen entry:
 //   [3:0] nbits  code bits consumed by the entry (both literals for a pair; the length CODE only)
-//   [4] LIT  [5] LIT2 (two literals)  [6] LEN  [7] EOB      none of them: code longer than the table
-//   literal : [15:8] sym1  [23:16] sym2  [27:24] code bits of the first literal
-//   length  : [10:8] extra-bit count  [24:16] base length
-//   [28] QUIRK: fixed-code symbols 286/287, which the reference treats as end-of-block
+//   [5:4] number of literals (1 or 2; 0 = not a literal entry)   [6] LEN  [7] EOB
+//         none of LIT/LEN/EOB: code longer than the table
+//   literal : [15:8] sym1  [23:16] sym2 (0 for a single)  [27:24] code bits of the first literal
+//             [29:28] number of literals again, so that `e >> 28` is the byte count (bits 30,31 = 0)
+//   length  : [10:8] extra-bit count  [24:16] base length      (so `e >> 28` == 0)
+//   [31] QUIRK: fixed-code symbols 286/287, which the reference treats as end-of-block
 //        (reference tables.rs:99-122 + decompress.rs:743-748)
 enum : uint32_t {
-    LL_LIT = 1u << 4,
-    LL_LIT2 = 1u << 5,
+    LL_LIT = 3u << 4,   // mask: non-zero for literal entries
+    LL_LIT1 = 1u << 4,  // one literal
+    LL_LIT2 = 2u << 4,  // two literals
     LL_LEN = 1u << 6,
     LL_EOB = 1u << 7,
-    LL_QUIRK = 1u << 28,
+    LL_QUIRK = 1u << 31,
 };
 // dist entry: [3:0] code bits  [7:4] extra-bit count  [8] VALID  [9] LONG (code > 9 bits)  [31:16] base
 enum : uint32_t { DS_VALID = 1u << 8, DS_LONG = 1u << 9 };
 
 // RFC 1951 length / distance symbol parameters (reference tables.rs:68-88 holds them as arrays)
-#if defined(__CUDACC__) && !defined(FDB_EMUL)
-#define FDB_HD __host__ __device__ __forceinline__
-#else
-#define FDB_HD static inline
-#endif
 FDB_HD uint32_t len_sym_extra(uint32_t sym) {  // sym in 257..285
     return (sym < 265 || sym == 285) ? 0u : ((sym - 261u) >> 2);
 }
@@ -102,10 +106,14 @@ FDB_HD uint32_t dist_sym_base(uint32_t d) {
     return ((2u + (d & 1u)) << e) + 1u;
 }
 FDB_HD uint32_t make_litlen_entry(uint32_t sym, uint32_t nbits) {
-    if (sym < 256) return nbits | LL_LIT | (sym << 8) | (nbits << 24);
+    if (sym < 256) return nbits | LL_LIT1 | (sym << 8) | (nbits << 24) | (1u << 28);
     if (sym == 256) return nbits | LL_EOB;
     if (sym < 286) return nbits | LL_LEN | (len_sym_extra(sym) << 8) | (len_sym_base(sym) << 16);
     return nbits | LL_EOB | LL_QUIRK;
+}
+// single-literal entry e1 (first literal, l1 bits) + a second literal sym2 of l2 bits -> pair entry
+FDB_HD uint32_t make_litlen_pair(uint32_t e1, uint32_t sym2, uint32_t l1, uint32_t l2) {
+    return (l1 + l2) | LL_LIT2 | (e1 & 0xff00u) | (sym2 << 16) | (l1 << 24) | (2u << 28);
 }
 FDB_HD uint32_t make_dist_entry(uint32_t sym, uint32_t nbits) {
     if (sym < 30) return nbits | DS_VALID | (dist_sym_extra(sym) << 4) | (dist_sym_base(sym) << 16);

@@ -117,7 +117,7 @@ static inline bool build_uf_host_tables(UfHostTables& t) {
         if (!(e2 & LL_LIT)) continue;
         uint32_t l2 = (e2 >> 24) & 15u;
         if (l1 + l2 > 12) continue;
-        t.dec[idx] = (l1 + l2) | LL_LIT | LL_LIT2 | (e & 0xff00u) | (((e2 >> 8) & 0xffu) << 16) | (l1 << 24);
+        t.dec[idx] = make_litlen_pair(e, (e2 >> 8) & 0xffu, l1, l2);
     }
     return true;
 }

@@ -204,7 +204,7 @@ FDB_DEVICE void build_litlen_table(K3Smem& s) {
         if (!(e2 & LL_LIT)) continue;
         uint32_t l2 = (e2 >> 24) & 15u;
         if (l1 + l2 > 12) continue;
-        s.litlen[idx] = (l1 + l2) | LL_LIT | LL_LIT2 | (e & 0xff00u) | (((e2 >> 8) & 0xffu) << 16) | (l1 << 24);
+        s.litlen[idx] = make_litlen_pair(e, (e2 >> 8) & 0xffu, l1, l2);
     }
     simt::syncwarp();
 }

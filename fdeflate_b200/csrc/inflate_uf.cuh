@@ -37,17 +37,23 @@
 namespace fdb {
 
 static const int K4_WARPS = 16;        // warps per CTA (share one 16 KiB decode table)
-static const uint32_t K4_SUBW = 16;    // 32-bit words of compressed data per lane per segment
+static const uint32_t K4_SUBW = 8;     // 32-bit words of compressed data per lane per segment
 static const uint32_t K4_WARM = 4;     // warm-up words before a lane's sub-sequence
-static const uint32_t K4_TAILW = 4;    // slack after the segment (token overrun + refill look-ahead)
-static const uint32_t K4_STG_WORDS = K4_WARM + 32 * K4_SUBW + K4_TAILW;     // 520
-static const uint32_t K4_STG_PADDED = K4_STG_WORDS + (K4_STG_WORDS >> 4) + 1;
-static const uint32_t K4_WIN = 2048;   // output window bytes
+static const uint32_t K4_TAILW = 3;    // words after it (token overrun + two-word look-ahead)
+static const uint32_t K4_ROWW = K4_WARM + K4_SUBW + K4_TAILW;  // 15 words seen by one lane
+static const uint32_t K4_ROWS_ALLOC = K4_ROWW + 1;             // +1: the look-ahead may touch one more
+static const uint32_t K4_SEG_WORDS = K4_WARM + 32 * K4_SUBW + 4;  // words staged per segment (vectors of 4)
+static const uint32_t K4_LIM_LO = 32u * K4_WARM;               // a lane's sub-sequence, in bits of its row
+static const uint32_t K4_LIM_HI = 32u * (K4_WARM + K4_SUBW);
+static const uint32_t K4_WIN = 4096;   // output window bytes (a segment normally expands to ~2.5 KiB)
 static const uint32_t K4_INVALID = 0xffffffffu;
 
+// Staging is TRANSPOSED and PRIVATE per lane: row i holds the words lane i can ever touch
+// (WARM words before its sub-sequence, the sub-sequence, TAILW after), word c of row i at
+// stg[c * 32 + i].  Every lane therefore reads bank == lane (never a conflict) and walks its row
+// with a constant +128-byte pointer step.  Overlapping words are simply stored twice.
 struct K4Warp {
-    uint32_t stg[K4_STG_PADDED];
-    uint32_t pad_[(4 - (K4_STG_PADDED & 3)) & 3];
+    uint32_t stg[K4_ROWS_ALLOC * 32];
     uint8_t win[K4_WIN + 16];  // +16: one overhang byte for a literal pair straddling the window end
 };
 
@@ -61,100 +67,134 @@ struct UfDecTables {
     uint32_t header[14];   // the constant 54 header bytes
 };
 
-// lane-private LSB-first bit reader over the padded staging buffer
+// lane-private LSB-first bit reader over the lane's staging row: a 32-bit window is one funnel
+// shift of (w0, w1); w2 is fetched one word ahead so the shared-memory latency stays off the
+// decode dependency chain.
 struct LaneBits {
-    uint64_t bb;
-    uint32_t nb;
-    uint32_t gw;  // next staging word
-    uint32_t rp;  // bit position relative to staging word 0
+    uint32_t w0, w1, w2;
+    uint32_t rp;         // bit position relative to the start of the row
+    const uint32_t* nx;  // next word to fetch
 };
-FDB_DEVICE uint32_t stg_word(const uint32_t* stg, uint32_t g) { return stg[g + (g >> 4)]; }
-FDB_DEVICE void lb_start(LaneBits& b, const uint32_t* stg, uint32_t rp) {
+FDB_DEVICE void lb_start(LaneBits& b, const uint32_t* row, uint32_t rp) {
     b.rp = rp;
-    b.gw = rp >> 5;
-    uint32_t sh = rp & 31;
-    b.bb = (uint64_t)(stg_word(stg, b.gw) >> sh);
-    b.nb = 32 - sh;
-    b.gw++;
+    const uint32_t* p = row + (rp >> 5) * 32;
+    b.w0 = p[0];
+    b.w1 = p[32];
+    b.w2 = p[64];
+    b.nx = p + 96;
 }
-FDB_DEVICE void lb_refill(LaneBits& b, const uint32_t* stg) {  // afterwards nb >= 33
-    if (b.nb <= 32) {
-        b.bb |= (uint64_t)stg_word(stg, b.gw) << b.nb;
-        b.nb += 32;
-        b.gw++;
+FDB_DEVICE uint32_t lb_peek(const LaneBits& b) { return simt::funnel_r(b.w0, b.w1, b.rp); }  // shift is mod 32
+FDB_DEVICE void lb_advance(LaneBits& b, uint32_t n) {  // n < 32
+    uint32_t nrp = b.rp + n;
+    if ((nrp ^ b.rp) & 32u) {
+        b.w0 = b.w1;
+        b.w1 = b.w2;
+        b.w2 = *b.nx;
+        b.nx += 32;
     }
-}
-FDB_DEVICE void lb_consume(LaneBits& b, uint32_t n) {
-    b.bb >>= n;
-    b.nb -= n;
-    b.rp += n;
+    b.rp = nrp;
 }
 
 struct LaneCount {
-    uint32_t end;     // bit position (relative) where the lane stopped: first token boundary >= its limit
+    uint32_t end;     // bit position (row-relative) where the lane stopped: first token boundary >= LIM_HI
     uint32_t cnt;     // bytes produced in [start, end)
     uint32_t flags;   // CF_*
     uint32_t lastlit; // last literal value (valid with CF_HASLIT)
 };
 enum : uint32_t { CF_EOB = 1, CF_BAD = 2, CF_HASLIT = 4, CF_MATCH_FIRST = 8 };
 
-// count the bytes of the tokens in [start, limit); stop at the first token boundary >= limit or at EOB
-FDB_DEVICE LaneCount count_tokens(const uint32_t* tab, const uint32_t* stg, uint32_t start, uint32_t limit) {
-    LaneCount c = {0, 0, 0, 0};
+// Count the bytes of the tokens in [start, LIM_HI); stop at the first token boundary >= LIM_HI or at
+// EOB (then end = position of the EOB code).  No early exits inside the loops, so lanes that still
+// iterate stay converged and the others wait at the loop exit.
+FDB_DEVICE LaneCount count_tokens(const uint32_t* tab, const uint32_t* row, uint32_t start, uint32_t active) {
+    LaneCount c = {K4_INVALID, 0, 0, 0};
     LaneBits b;
-    lb_start(b, stg, start);
-    bool first = true;
-    while (b.rp < limit) {
-        lb_refill(b, stg);
-        uint32_t e = tab[(uint32_t)b.bb & 0xfffu];
+    lb_start(b, row, active ? start : 0u);
+    uint32_t laste = 0, cnt = 0, flags = 0;
+    uint32_t stop = active ? 0u : 1u;
+    // main loop: no entry can reach LIM_HI from here (an entry consumes at most 12 + 5 + 1 bits), so
+    // pairs are taken blindly
+    while (!stop && b.rp < K4_LIM_HI - 18) {
+        uint32_t bits = lb_peek(b);
+        uint32_t e = tab[bits & 0xfffu];
         uint32_t n = e & 15u;
+        cnt += e >> 28;
         if (e & LL_LIT) {
-            uint32_t two = (e >> 5) & 1u, l1 = (e >> 24) & 15u;
-            if (two && b.rp + l1 >= limit) {  // the pair's second literal belongs to the next lane
-                two = 0;
-                n = l1;
-            }
-            c.cnt += 1u + two;
-            c.lastlit = two ? ((e >> 16) & 0xffu) : ((e >> 8) & 0xffu);
-            c.flags |= CF_HASLIT;
+            laste = e;
         } else if (e & LL_LEN) {
             uint32_t xb = (e >> 8) & 7u;
-            uint32_t v = (uint32_t)(b.bb >> n);
-            c.cnt += ((e >> 16) & 0x1ffu) + (v & ((1u << xb) - 1u));
-            if ((v >> xb) & 1u) c.flags |= CF_BAD;  // distance code "1" is not in the ultra-fast code
-            if (first) c.flags |= CF_MATCH_FIRST;
+            uint32_t v = bits >> n;
+            if (cnt == 0) flags |= CF_MATCH_FIRST;
+            cnt += ((e >> 16) & 0x1ffu) + (v & ((1u << xb) - 1u));
+            if ((v >> xb) & 1u) flags |= CF_BAD;  // distance code "1" is not in the ultra-fast code
             n += xb + 1u;
         } else {  // end of block
-            c.flags |= CF_EOB;
-            c.end = b.rp;  // position of the EOB code itself
-            return c;
+            flags |= CF_EOB;
+            n = 0;
+            stop = 1;
         }
-        first = false;
-        lb_consume(b, n);
+        lb_advance(b, n);
     }
-    c.end = b.rp;
-    return c;
-}
-
-// warm-up: single tokens from a guessed start until the first boundary >= limit
-FDB_DEVICE uint32_t warm_up(const uint32_t* tab, const uint32_t* stg, uint32_t start, uint32_t limit) {
-    LaneBits b;
-    lb_start(b, stg, start);
-    while (b.rp < limit) {
-        lb_refill(b, stg);
-        uint32_t e = tab[(uint32_t)b.bb & 0xfffu];
+    // tail: the pair that would cross LIM_HI gives its second literal to the next lane
+    while (!stop && b.rp < K4_LIM_HI) {
+        uint32_t bits = lb_peek(b);
+        uint32_t e = tab[bits & 0xfffu];
         uint32_t n = e & 15u;
         if (e & LL_LIT) {
             uint32_t l1 = (e >> 24) & 15u;
-            if ((e & LL_LIT2) && b.rp + l1 >= limit) n = l1;
+            if ((e & LL_LIT2) && b.rp + l1 >= K4_LIM_HI) {
+                n = l1;
+                e = (e & ~(LL_LIT | (3u << 28))) | LL_LIT1 | (1u << 28);
+            }
+            cnt += e >> 28;
+            laste = e;
+        } else if (e & LL_LEN) {
+            uint32_t xb = (e >> 8) & 7u;
+            uint32_t v = bits >> n;
+            if (cnt == 0) flags |= CF_MATCH_FIRST;
+            cnt += ((e >> 16) & 0x1ffu) + (v & ((1u << xb) - 1u));
+            if ((v >> xb) & 1u) flags |= CF_BAD;
+            n += xb + 1u;
+        } else {
+            flags |= CF_EOB;
+            n = 0;
+            stop = 1;
+        }
+        lb_advance(b, n);
+    }
+    if (active) {
+        c.end = b.rp;
+        c.cnt = cnt;
+        c.flags = flags;
+        if (laste) {
+            c.flags |= CF_HASLIT;
+            c.lastlit = (laste & LL_LIT2) ? ((laste >> 16) & 0xffu) : ((laste >> 8) & 0xffu);
+        }
+    }
+    return c;
+}
+
+// warm-up: single tokens from a guessed start until the first boundary >= LIM_LO
+FDB_DEVICE uint32_t warm_up(const uint32_t* tab, const uint32_t* row, uint32_t active) {
+    LaneBits b;
+    lb_start(b, row, 0u);
+    uint32_t stop = active ? 0u : 1u, dead = 0;
+    while (!stop && b.rp < K4_LIM_LO) {
+        uint32_t e = tab[lb_peek(b) & 0xfffu];
+        uint32_t n = e & 15u;
+        if (e & LL_LIT) {
+            uint32_t l1 = (e >> 24) & 15u;
+            if ((e & LL_LIT2) && b.rp + l1 >= K4_LIM_LO) n = l1;
         } else if (e & LL_LEN) {
             n += ((e >> 8) & 7u) + 1u;
         } else {
-            return K4_INVALID;  // speculative EOB: this lane has no valid guess
+            dead = 1;  // speculative EOB: this lane has no valid guess
+            stop = 1;
+            n = 0;
         }
-        lb_consume(b, n);
+        lb_advance(b, n);
     }
-    return b.rp;
+    return (active && !dead) ? b.rp : K4_INVALID;
 }
 
 struct K4Stream {
@@ -169,6 +209,7 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
                                      uint32_t flags, uint64_t* out_len, uint64_t* consumed) {
     const unsigned lane = simt::lane_id();
     uint32_t* stg = ws.stg;
+    const uint32_t* row = ws.stg + lane;
     uint8_t* win = ws.win;
     *out_len = 0;
     *consumed = 0;
@@ -194,36 +235,38 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
     const uint32_t oalign = (uint32_t)((uintptr_t)s.out & 15u);
     uint8_t* const obase = s.out - oalign;  // virtual output position vo = oalign + stream position
 
-    uint64_t seg_word = ((vstart >> 5) >> 2) << 2;  // first segment's word, 16-byte aligned
+    uint64_t seg_word = ((vstart >> 5) >> 2) << 2;  // first word of lane 0's sub-sequence, 16-byte aligned
     uint64_t p0 = vstart;                           // true bit position where lane 0 starts
     uint64_t o0 = 0;                                // bytes produced so far
     uint32_t prev_byte = 0;
     bool have_prev = false;
-    uint64_t win_vo = 0;  // virtual output position of win[0] (multiple of K4_WIN)
+    uint64_t win_vo = 0;  // virtual output position of win[0] (multiple of 16)
     AdlerAcc ad = {0, 0};
 
     // zero the output window
     for (uint32_t v = lane; v < (K4_WIN + 16) / 16; v += 32) ((uint4*)win)[v] = make_uint4(0, 0, 0, 0);
     simt::syncwarp();
 
-    // flush win[0..nbytes) to virtual position win_vo (nbytes multiple of 16 except at stream end)
-    auto flush_window = [&](uint32_t nbytes, uint64_t stream_end_vo) {
-        for (uint32_t v = lane; v < (nbytes + 15) / 16; v += 32) {
+    // Store the finished vectors win[0 .. 16*nvec) at virtual position win_vo, feed adler32, and zero
+    // them again.  Bytes outside [oalign, stream_end_vo) (first / last vector of the stream) are masked.
+    auto flush_vectors = [&](uint32_t nvec, uint64_t stream_end_vo) {
+        for (uint32_t v = lane; v < nvec; v += 32) {
             uint4 q = ((const uint4*)win)[v];
+            ((uint4*)win)[v] = make_uint4(0, 0, 0, 0);
             uint64_t vo = win_vo + 16ull * v;
-            bool head_cut = vo < oalign;                 // first vector of the stream, bytes before out[0]
-            bool tail_cut = vo + 16 > stream_end_vo;     // last vector, bytes after the stream end
+            bool head_cut = vo < oalign;
+            bool tail_cut = vo + 16 > stream_end_vo;
             if (!head_cut && !tail_cut) {
                 simt::stcs128((uint4*)(obase + vo), q);
                 adler_add16(ad, q, vo - oalign);
             } else {
                 uint32_t w[4] = {q.x, q.y, q.z, q.w};
                 for (uint32_t j = 0; j < 16; j++) {
-                    uint64_t b = vo + j;
-                    if (b >= oalign && b < stream_end_vo) {
+                    uint64_t bpos = vo + j;
+                    if (bpos >= oalign && bpos < stream_end_vo) {
                         uint32_t byte = (w[j >> 2] >> (8u * (j & 3u))) & 0xffu;
-                        obase[b] = (uint8_t)byte;
-                        adler_add1(ad, byte, b - oalign);
+                        obase[bpos] = (uint8_t)byte;
+                        adler_add1(ad, byte, bpos - oalign);
                     }
                 }
             }
@@ -232,11 +275,11 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
 
     for (;;) {
         if ((seg_word << 5) >= vend) return ST_PENDING_GENERAL;  // ran off the input without an EOB
-        const uint64_t s0 = seg_word - K4_WARM;                  // staging word 0 (virtual word index)
+        const uint64_t s0 = seg_word - K4_WARM;                  // first staged word (virtual word index)
 
-        // ---- 1. stage ----
+        // ---- 1. stage: coalesced 16-byte loads, every word scattered to the row(s) that can see it ----
         simt::syncwarp();
-        for (uint32_t v = lane; v < K4_STG_WORDS / 4; v += 32) {
+        for (uint32_t v = lane; v < K4_SEG_WORDS / 4; v += 32) {
             uint64_t byte0 = (s0 << 2) + 16ull * v;  // relative to abase
             uint4 q = make_uint4(0, 0, 0, 0);
             if (byte0 + 16 > first_byte && byte0 < end_byte) {
@@ -244,33 +287,35 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
                 if (byte0 < first_byte || byte0 + 16 > end_byte) {
                     uint32_t w[4] = {q.x, q.y, q.z, q.w};
                     for (uint32_t j = 0; j < 16; j++) {
-                        uint64_t b = byte0 + j;
-                        if (b < first_byte || b >= end_byte) w[j >> 2] &= ~(0xffu << (8u * (j & 3u)));
+                        uint64_t bpos = byte0 + j;
+                        if (bpos < first_byte || bpos >= end_byte) w[j >> 2] &= ~(0xffu << (8u * (j & 3u)));
                     }
                     q = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
-            uint32_t g = 4 * v;
-            uint32_t p = g + (g >> 4);
-            stg[p] = q.x; stg[p + 1] = q.y; stg[p + 2] = q.z; stg[p + 3] = q.w;
+            // staged word t = 4v + j is word (t & 7) of row (t >> 3) and word (t & 7) + 8 of the row before
+            const uint32_t r1 = v >> 1, c1 = (v & 1) * 4;
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) {
+                if (r1 < 32) stg[(c1 + j) * 32 + r1] = w4[j];
+                if (r1 >= 1 && c1 + j + 8 < K4_ROWW) stg[(c1 + j + 8) * 32 + (r1 - 1)] = w4[j];
+            }
         }
         simt::syncwarp();
 
         // ---- 2. count ----
-        const uint32_t my_limit_lo = 32u * (K4_WARM + lane * K4_SUBW);  // my boundary B_i
-        const uint32_t my_limit_hi = my_limit_lo + 32u * K4_SUBW;       // B_{i+1}
-        uint32_t start;
+        uint32_t start = warm_up(tab, row, lane != 0);
         if (lane == 0) start = (uint32_t)(p0 - (s0 << 5));
-        else start = warm_up(tab, stg, my_limit_lo - 32u * K4_WARM, my_limit_lo);
-        LaneCount c = {K4_INVALID, 0, 0, 0};
-        if (start != K4_INVALID) c = count_tokens(tab, stg, start, my_limit_hi);
+        LaneCount c = count_tokens(tab, row, start, start != K4_INVALID);
 
-        // ---- 3. verify the chain ----
+        // ---- 3. verify the chain: my start must be my predecessor's end (rows are 32*SUBW bits apart) ----
         uint32_t eob_lane = 32;
         for (;;) {
             uint32_t prev_end = simt::shfl_up(c.end, 1);
             uint32_t prev_flags = simt::shfl_up(c.flags, 1);
-            bool mismatch = (lane > 0) && (start != prev_end || (prev_flags & CF_EOB));
+            uint32_t want = prev_end - 32u * K4_SUBW;
+            bool mismatch = (lane > 0) && (prev_end == K4_INVALID || start != want || (prev_flags & CF_EOB));
             uint32_t mm = simt::ballot(mismatch);
             uint32_t em = simt::ballot((c.flags & CF_EOB) != 0 && start != K4_INVALID);
             uint32_t first_mis = mm ? simt::ffs(mm) - 1 : 32;
@@ -282,15 +327,9 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
             if (first_mis == 32) break;  // every lane verified, no EOB in this segment
             // re-run the lanes whose start disagrees with their predecessor's end
             bool redo = mismatch && !(prev_flags & CF_EOB) && prev_end != K4_INVALID;
-            if (redo) {
-                start = prev_end;
-                c = count_tokens(tab, stg, start, my_limit_hi);
-            } else if (mismatch) {
-                start = K4_INVALID;  // predecessor is itself unresolved or ended the stream
-                c.end = K4_INVALID;
-                c.flags = 0;
-                c.cnt = 0;
-            }
+            if (mismatch) start = redo ? want : K4_INVALID;
+            LaneCount c2 = count_tokens(tab, row, start, redo);
+            if (mismatch) c = c2;  // (unresolved lanes get end = INVALID, cnt = 0, flags = 0)
         }
         if (lane > eob_lane) {
             c.cnt = 0;
@@ -303,6 +342,7 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
         const uint64_t seg_bytes = simt::shfl(incl, 31);
         if (o0 + seg_bytes > s.cap) return ST_PENDING_GENERAL;  // K3 reports OutputTooLarge
         uint64_t op = oalign + o0 + (incl - c.cnt);             // my virtual output position
+        const uint64_t my_end_vo = op + c.cnt;
         uint32_t lit_mask = simt::ballot((c.flags & CF_HASLIT) != 0);
         uint32_t below = lit_mask & simt::lanemask_lt();
         uint32_t src = below ? 31u - simt::clz(below) : 0u;
@@ -316,67 +356,135 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
         }
 
         // ---- 5. write ----
+        // The window base slides with the output: it is the 16-byte vector holding the first byte of
+        // this segment, so a segment whose output fits in K4_WIN is written by all lanes at once.
         const uint64_t seg_end_vo = oalign + o0 + seg_bytes;
         LaneBits b;
-        lb_start(b, stg, start != K4_INVALID ? start : 0u);
-        bool done = (start == K4_INVALID) || (lane > eob_lane);
+        lb_start(b, row, start != K4_INVALID ? start : 0u);
+        uint32_t fin = (start == K4_INVALID || lane > eob_lane) ? 1u : 0u;  // no more tokens to decode
         uint32_t pend = 0;  // bytes of a non-zero fill still owed to later windows
         for (;;) {
             const uint64_t wend = win_vo + K4_WIN;
-            if (!done && op < wend) {
-                uint32_t wp = (uint32_t)(op - win_vo);
-                while (pend && wp < K4_WIN) {
-                    win[wp++] = (uint8_t)fv;
-                    pend--;
+            const bool mine = !(fin && pend == 0) && op < wend;
+            uint32_t wp = mine ? (uint32_t)(op - win_vo) : 0u;
+            if (mine && pend == 0 && my_end_vo <= wend) {
+                // fast path: everything this lane still has to write fits in the window
+                uint8_t* wptr = win + wp;
+                while (!fin && b.rp < K4_LIM_HI - 18) {
+                    uint32_t bits = lb_peek(b);
+                    uint32_t e = tab[bits & 0xfffu];
+                    uint32_t n = e & 15u;
+                    if (e & LL_LIT) {
+                        // both bytes always: a single's second byte is 0 and the next token of this lane
+                        // overwrites it (or it is a zero the stream would have produced anyway)
+                        wptr[0] = (uint8_t)(e >> 8);
+                        wptr[1] = (uint8_t)(e >> 16);
+                        wptr += e >> 28;
+                        fv = (e >> (8u * (e >> 28))) & 0xffu;
+                    } else if (e & LL_LEN) {
+                        uint32_t xb = (e >> 8) & 7u;
+                        uint32_t len = ((e >> 16) & 0x1ffu) + ((bits >> n) & ((1u << xb) - 1u));
+                        n += xb + 1u;
+                        if (fv != 0)
+                            for (uint32_t k = 0; k < len; k++) wptr[k] = (uint8_t)fv;
+                        wptr += len;  // zero runs: the window is zero-initialised, nothing to write
+                    } else {
+                        fin = 1;
+                        n = 0;
+                    }
+                    lb_advance(b, n);
                 }
-                while (!pend && wp < K4_WIN) {
-                    if (b.rp >= my_limit_hi) { done = true; break; }
-                    lb_refill(b, stg);
-                    uint32_t e = tab[(uint32_t)b.bb & 0xfffu];
+                while (!fin && b.rp < K4_LIM_HI) {
+                    uint32_t bits = lb_peek(b);
+                    uint32_t e = tab[bits & 0xfffu];
                     uint32_t n = e & 15u;
                     if (e & LL_LIT) {
                         uint32_t two = (e >> 5) & 1u, l1 = (e >> 24) & 15u;
-                        if (two && b.rp + l1 >= my_limit_hi) {
+                        if (two && b.rp + l1 >= K4_LIM_HI) {
                             two = 0;
                             n = l1;
                         }
-                        win[wp] = (uint8_t)(e >> 8);
+                        wptr[0] = (uint8_t)(e >> 8);
                         fv = (e >> 8) & 0xffu;
                         if (two) {
-                            win[wp + 1] = (uint8_t)(e >> 16);  // may be the overhang byte win[K4_WIN]
+                            wptr[1] = (uint8_t)(e >> 16);
                             fv = (e >> 16) & 0xffu;
                         }
-                        wp += 1u + two;
+                        wptr += 1u + two;
                     } else if (e & LL_LEN) {
                         uint32_t xb = (e >> 8) & 7u;
-                        uint32_t len = ((e >> 16) & 0x1ffu) + ((uint32_t)(b.bb >> n) & ((1u << xb) - 1u));
+                        uint32_t len = ((e >> 16) & 0x1ffu) + ((bits >> n) & ((1u << xb) - 1u));
                         n += xb + 1u;
-                        if (fv == 0) {
-                            wp += len;  // the window is zero-initialised: nothing to write
-                        } else {
-                            while (len && wp < K4_WIN) {
-                                win[wp++] = (uint8_t)fv;
-                                len--;
-                            }
-                            pend = len;
+                        if (fv != 0)
+                            for (uint32_t k = 0; k < len; k++) wptr[k] = (uint8_t)fv;
+                        wptr += len;
+                    } else {
+                        fin = 1;
+                        n = 0;
+                    }
+                    lb_advance(b, n);
+                }
+                fin = 1;
+                wp = (uint32_t)(wptr - win);
+            } else if (mine) {
+                // careful path: this lane's output crosses the window end (long runs) or it still owes
+                // bytes of a non-zero fill; stop at the window end and resume after the flush
+                while (wp < K4_WIN && !(fin && pend == 0)) {
+                    if (pend) {
+                        while (pend && wp < K4_WIN) {
+                            win[wp++] = (uint8_t)fv;
+                            pend--;
                         }
                     } else {
-                        done = true;
-                        break;
+                        uint32_t bits = lb_peek(b);
+                        uint32_t e = tab[bits & 0xfffu];
+                        uint32_t n = e & 15u;
+                        if (e & LL_LIT) {
+                            uint32_t two = (e >> 5) & 1u, l1 = (e >> 24) & 15u;
+                            if (two && b.rp + l1 >= K4_LIM_HI) {
+                                two = 0;
+                                n = l1;
+                            }
+                            win[wp] = (uint8_t)(e >> 8);
+                            fv = (e >> 8) & 0xffu;
+                            if (two) {
+                                win[wp + 1] = (uint8_t)(e >> 16);  // may be the overhang byte win[K4_WIN]
+                                fv = (e >> 16) & 0xffu;
+                            }
+                            wp += 1u + two;
+                        } else if (e & LL_LEN) {
+                            uint32_t xb = (e >> 8) & 7u;
+                            uint32_t len = ((e >> 16) & 0x1ffu) + ((bits >> n) & ((1u << xb) - 1u));
+                            n += xb + 1u;
+                            if (fv == 0) {
+                                wp += len;
+                            } else {
+                                while (len && wp < K4_WIN) {
+                                    win[wp++] = (uint8_t)fv;
+                                    len--;
+                                }
+                                pend = len;
+                            }
+                        } else {
+                            fin = 1;
+                            n = 0;
+                        }
+                        lb_advance(b, n);
+                        if (b.rp >= K4_LIM_HI) fin = 1;
                     }
-                    lb_consume(b, n);
                 }
-                op = win_vo + wp;
             }
+            if (mine) op = win_vo + wp;
             simt::syncwarp();
-            if (seg_end_vo < wend) break;  // window not complete yet: keep it for the next segment
-            flush_window(K4_WIN, ~0ull);
-            simt::syncwarp();
+            if (seg_end_vo < wend) break;  // the rest of this segment fits: leave it in the window
+            // the window is complete: flush all of it and slide by K4_WIN
             uint32_t over = win[K4_WIN];
             simt::syncwarp();
-            for (uint32_t v = lane; v < (K4_WIN + 16) / 16; v += 32) ((uint4*)win)[v] = make_uint4(0, 0, 0, 0);
-            simt::syncwarp();
-            if (lane == 0) win[0] = (uint8_t)over;
+            flush_vectors(K4_WIN / 16, ~0ull);
+            if (lane == 0) {
+                win[K4_WIN] = 0;
+                win[0] = (uint8_t)over;
+            }
             simt::syncwarp();
             win_vo = wend;
         }
@@ -385,12 +493,11 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
         o0 += seg_bytes;
         if (eob_lane < 32) {
             const uint32_t eob_rel = simt::shfl(c.end, eob_lane);
-            const uint64_t eob_end = (s0 << 5) + eob_rel + 12;  // EOB code is 12 bits (sym 256)
+            const uint64_t eob_end = ((s0 + (uint64_t)K4_SUBW * eob_lane) << 5) + eob_rel + 12;  // EOB = 12 bits
             const uint64_t trailer_byte = (eob_end + 7) >> 3;   // relative to abase
             if (trailer_byte + 4 > end_byte) return ST_PENDING_GENERAL;  // truncated: K3 reports it
-            // last partial window
             uint32_t left = (uint32_t)(oalign + o0 - win_vo);
-            flush_window(left, oalign + o0);
+            flush_vectors((left + 15) / 16, oalign + o0);
             simt::syncwarp();
             const uint8_t* t = abase + trailer_byte;
             uint32_t stored = ((uint32_t)simt::ldg8(t) << 24) | ((uint32_t)simt::ldg8(t + 1) << 16) |
@@ -401,14 +508,29 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
             if (!(flags & FLAG_IGNORE_ADLER32) && got != stored) return ST_WRONG_CHECKSUM;
             return ST_OK;
         }
-        p0 = (s0 << 5) + simt::shfl(c.end, 31);
+        // flush the finished vectors of this segment and slide the window base to the vector that
+        // holds the next output byte (its already-written bytes move to win[0..16))
+        {
+            const uint32_t nvec = (uint32_t)((seg_end_vo - win_vo) >> 4);
+            uint4 tail = ((const uint4*)win)[nvec];
+            simt::syncwarp();
+            flush_vectors(nvec, ~0ull);
+            simt::syncwarp();
+            if (nvec > 0 && lane == 0) {
+                ((uint4*)win)[nvec] = make_uint4(0, 0, 0, 0);
+                ((uint4*)win)[0] = tail;
+            }
+            simt::syncwarp();
+            win_vo += 16ull * nvec;
+        }
+        p0 = ((s0 + (uint64_t)K4_SUBW * 31) << 5) + simt::shfl(c.end, 31);
         seg_word += 32 * K4_SUBW;
     }
 }
 
 // Persistent kernel.  Streams the fast path declines are appended to worklist[] (count in *work_count)
 // with status ST_PENDING_GENERAL; the host launches K3 over that list next, on the same stream.
-FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 2)
     inflate_uf_kernel(InflateBatch b, const UfDecTables* tables, uint32_t* next, uint32_t* worklist,
                       uint32_t* work_count) {
     FDB_DYN_SMEM(smem_raw);
