@@ -28,7 +28,11 @@ FDB_DEVICE void adler_add16(AdlerAcc& a, uint4 q, uint64_t pos) {
     t2 = simt::dp4a_u(q.w, 0x0f0e0d0cu, t2);
     a.s1 += t1;
     a.s2 += pos * (uint64_t)t1 + t2;
-    if (a.s2 >> 62) a.s2 %= ADLER_MOD;
+}
+// s2 grows by < 2^12 * pos per vector; callers that stream more than 2^40 weighted bytes through one
+// accumulator call this now and then (once per segment / warp step is plenty)
+FDB_DEVICE void adler_fold(AdlerAcc& a) {
+    if (a.s2 >> 60) a.s2 %= ADLER_MOD;
 }
 
 FDB_DEVICE void adler_add1(AdlerAcc& a, uint32_t byte, uint64_t pos) {
@@ -59,7 +63,10 @@ FDB_DEVICE uint32_t warp_adler32(const uint8_t* buf, uint64_t n) {
     if (lane < head) adler_add1(a, buf[lane], lane);
     uint64_t nvec = (n - head) >> 4;
     const uint4* v = (const uint4*)(buf + head);
-    for (uint64_t i = lane; i < nvec; i += 32) adler_add16(a, v[i], head + (i << 4));
+    for (uint64_t i = lane; i < nvec; i += 32) {
+        adler_add16(a, v[i], head + (i << 4));
+        adler_fold(a);
+    }
     uint64_t done = head + (nvec << 4);
     if (done + lane < n) adler_add1(a, buf[done + lane], done + lane);
     return adler_finish_warp(a, n);

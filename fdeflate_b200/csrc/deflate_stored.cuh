@@ -66,6 +66,7 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(STORED_THREADS, 1) deflate_stored_kernel(Defla
             uint4 q = simt::ldg128((const uint4*)in + v);
             uint64_t p = v << 4;
             adler_add16(ad, q, p);
+            adler_fold(ad);
             uint32_t w[4] = {q.x, q.y, q.z, q.w};
             uint64_t blk = p / 65535;
             uint64_t next_edge = (blk + 1) * 65535;

@@ -38,6 +38,9 @@ static const uint32_t UF_EOB_CODE = 2303u;      // sym 256, 12 bits
 static const uint32_t UF_HEADER_BITS = 53u * 8u + 5u;
 
 static const int DEFLATE_WARPS = 8;
+#ifndef DEFLATE_MIN_CTAS
+#define DEFLATE_MIN_CTAS 3
+#endif
 static const uint32_t STG_WORDS = 320;  // >= 512 bytes * 18 bits / 32 + slack
 
 struct DeflateSmem {
@@ -107,8 +110,8 @@ FDB_DEVICE uint32_t lit_bits_sum(const ChunkTokens& t) {
 // length entering the chunk; cont = the byte after the chunk is a zero that extends the run.
 // kind 1: the final partial chunk, `rem` literal bytes (ultrafast.rs:159-164).  kind 0: nothing.
 // Returns the pending run length leaving the chunk.
-FDB_DEVICE uint32_t chunk_tokens(ChunkTokens& t, uint64_t c, uint32_t kind, uint32_t rem, uint32_t x, bool cont,
-                                 const uint32_t* lit_tok, const uint32_t* tail_tok) {
+FDB_DEVICE uint32_t chunk_tokens(ChunkTokens& t, uint64_t c, uint64_t nz, uint32_t kind, uint32_t rem, uint32_t x,
+                                 bool cont, const uint32_t* lit_tok, const uint32_t* tail_tok) {
     t.head_v = t.head_n = t.tail_v = t.tail_n = 0;
     const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
     t.lit[0] = lit_tok[lo & 0xffu];
@@ -126,7 +129,6 @@ FDB_DEVICE uint32_t chunk_tokens(ChunkTokens& t, uint64_t c, uint32_t kind, uint
             if (j >= keep) t.lit[j] = 0;
         return 0;
     }
-    const uint64_t nz = nonzero_bytes(c);
     if (nz == 0x8080808080808080ull && x == 0) return 0;  // no zero byte, no run pending: eight plain literals
     if (nz == 0) {  // all-zero chunk: extends (or opens) a run
         uint32_t v = 0, n = 0;
@@ -174,10 +176,13 @@ FDB_DEVICE uint32_t chunk_tokens(ChunkTokens& t, uint64_t c, uint32_t kind, uint
         t.tail_v = v;
         t.tail_n = n;
     }
-    const uint32_t last_lit = 8u - trail;
+    if (first_lit | trail) {
+        // one bit per byte that stays a literal: positions [first_lit, 8 - trail)
+        const uint32_t keep = (0xffu << first_lit) & (0xffu >> trail);
 #pragma unroll
-    for (uint32_t j = 0; j < 8; j++)
-        if (j < first_lit || j >= last_lit) t.lit[j] = 0;
+        for (uint32_t j = 0; j < 8; j++)
+            if (!(keep & (1u << j))) t.lit[j] = 0;
+    }
     return trail;
 }
 
@@ -256,27 +261,30 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint32_t* lit_tok, const uint32_t* t
         // adler partial sums
         if (g + 16 <= n) {
             adler_add16(ad, q, g);
+            if ((it & 63) == 63) adler_fold(ad);
         } else if (g < n) {
             uint32_t w[4] = {q.x, q.y, q.z, q.w};
             for (uint32_t j = 0; g + j < n; j++) adler_add1(ad, (w[j >> 2] >> (8u * (j & 3u))) & 0xffu, g + j);
         }
 
         const uint64_t c0 = ((uint64_t)q.y << 32) | q.x, c1 = ((uint64_t)q.w << 32) | q.z;
+        const uint64_t nz0 = nonzero_bytes(c0), nz1 = nonzero_bytes(c1);
         // chunk kinds: 2 = whole chunk in the run-logic prefix, 1 = the final partial chunk, 0 = past the end
-        const uint32_t k0 = (g + 8 <= n8) ? 2u : (g == n8 && rem) ? 1u : 0u;
-        const uint32_t k1 = (g + 16 <= n8) ? 2u : (g + 8 == n8 && rem) ? 1u : 0u;
+        uint32_t k0 = 2u, k1 = 2u;
+        if (base + 512 > n8) {  // only the last warp step of a stream
+            k0 = (g + 8 <= n8) ? 2u : (g == n8 && rem) ? 1u : 0u;
+            k1 = (g + 16 <= n8) ? 2u : (g + 8 == n8 && rem) ? 1u : 0u;
+        }
 
         // 1. run-carry scan.  f(x) = a ? x + b : b
         uint32_t fa, fb;
         {
             uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0;
             if (k0 == 2) {
-                uint64_t nz = nonzero_bytes(c0);
-                if (nz == 0) { a0 = 1; b0 = 8; } else { b0 = clz64(nz) >> 3; }
+                if (nz0 == 0) { a0 = 1; b0 = 8; } else { b0 = clz64(nz0) >> 3; }
             }
             if (k1 == 2) {
-                uint64_t nz = nonzero_bytes(c1);
-                if (nz == 0) { a1 = 1; b1 = 8; } else { b1 = clz64(nz) >> 3; }
+                if (nz1 == 0) { a1 = 1; b1 = 8; } else { b1 = clz64(nz1) >> 3; }
             }
             fa = a0 & a1;
             fb = a1 ? b0 + b1 : b1;
@@ -308,8 +316,8 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint32_t* lit_tok, const uint32_t* t
 
         // 2. tokens (looked up once, kept in registers), bit lengths and offsets
         ChunkTokens t0, t1;
-        const uint32_t x1 = chunk_tokens(t0, c0, k0, rem, x0, cont0, lit_tok, tail_tok);
-        chunk_tokens(t1, c1, k1, rem, x1, cont1, lit_tok, tail_tok);
+        const uint32_t x1 = chunk_tokens(t0, c0, nz0, k0, rem, x0, cont0, lit_tok, tail_tok);
+        chunk_tokens(t1, c1, nz1, k1, rem, x1, cont1, lit_tok, tail_tok);
         const uint32_t my_bits = lit_bits_sum(t0) + lit_bits_sum(t1);
         const uint32_t incl_bits = simt::scan_incl_add(my_bits);
         const uint32_t total_bits = simt::shfl(incl_bits, 31);
@@ -384,7 +392,7 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint32_t* lit_tok, const uint32_t* t
     return overflow ? 0 : total_len;
 }
 
-FDB_GLOBAL void FDB_LAUNCH_BOUNDS(DEFLATE_WARPS * 32, 1)
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(DEFLATE_WARPS * 32, DEFLATE_MIN_CTAS)
     deflate_uf_kernel(DeflateBatch b, const UfEncTables* tables, uint32_t* next) {
     FDB_SHARED DeflateSmem s;
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s.lit_tok[i] = tables->lit_tok[i];

@@ -370,6 +370,7 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
             if (mine && pend == 0 && my_end_vo <= wend) {
                 // fast path: everything this lane still has to write fits in the window
                 uint8_t* wptr = win + wp;
+                uint32_t laste = 0;
                 while (!fin && b.rp < K4_LIM_HI - 18) {
                     uint32_t bits = lb_peek(b);
                     uint32_t e = tab[bits & 0xfffu];
@@ -380,11 +381,12 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
                         wptr[0] = (uint8_t)(e >> 8);
                         wptr[1] = (uint8_t)(e >> 16);
                         wptr += e >> 28;
-                        fv = (e >> (8u * (e >> 28))) & 0xffu;
+                        laste = e;
                     } else if (e & LL_LEN) {
                         uint32_t xb = (e >> 8) & 7u;
                         uint32_t len = ((e >> 16) & 0x1ffu) + ((bits >> n) & ((1u << xb) - 1u));
                         n += xb + 1u;
+                        if (laste) fv = (laste >> (8u * (laste >> 28))) & 0xffu;  // last literal written
                         if (fv != 0)
                             for (uint32_t k = 0; k < len; k++) wptr[k] = (uint8_t)fv;
                         wptr += len;  // zero runs: the window is zero-initialised, nothing to write
@@ -394,6 +396,7 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
                     }
                     lb_advance(b, n);
                 }
+                if (laste) fv = (laste >> (8u * (laste >> 28))) & 0xffu;
                 while (!fin && b.rp < K4_LIM_HI) {
                     uint32_t bits = lb_peek(b);
                     uint32_t e = tab[bits & 0xfffu];
@@ -490,6 +493,7 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
         }
 
         // ---- next segment or finish ----
+        adler_fold(ad);
         o0 += seg_bytes;
         if (eob_lane < 32) {
             const uint32_t eob_rel = simt::shfl(c.end, eob_lane);

@@ -1,0 +1,227 @@
+// fdeflate_b200.hpp -- C++17 host-side mirror of the reference crate's public API over the C ABI
+// (include/fdeflate_b200.h).  Header-only.
+//
+// The reference is a Rust crate and this image has no Rust toolchain, so the host side that a Rust
+// user would get from the shim in INTEGRATION.md is mirrored here in C++: same names, argument
+// meaning and error behaviour as image-rs/fdeflate 0.4.0-dev (src/lib.rs:29-36):
+//
+//   fdeflate::decompress_to_vec            src/decompress.rs:1079   (throws DecompressionError)
+//   fdeflate::decompress_to_vec_bounded    src/decompress.rs:1111   (throws BoundedDecompressionError)
+//   fdeflate::compress_to_vec_ultra_fast   src/compress/mod.rs:313
+//   fdeflate::UltraFastCompressor<W>       src/compress/ultrafast.rs:9-181   (W: anything with write(ptr, n))
+//   fdeflate::Compressor<W>(w, 0, zlib)    src/compress/mod.rs:69-215, level 0 only ("stored")
+//   fdeflate::Batch                        the batch entry points this project adds
+//
+// All compute happens on the GPU behind the C ABI; there is no CPU fallback (Context construction
+// throws without a CUDA device).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "fdeflate_b200.h"
+
+namespace fdeflate {
+
+// src/decompress.rs:13-48, declaration order; values equal the C ABI status codes
+enum class DecompressionErrorKind : int32_t {
+    BadZlibHeader = 1, InsufficientInput, InvalidBlockType, InvalidUncompressedBlockLength, InvalidHlit,
+    InvalidHdist, InvalidCodeLengthRepeat, BadCodeLengthHuffmanTree, BadLiteralLengthHuffmanTree,
+    BadDistanceHuffmanTree, InvalidLiteralLengthCode, InvalidDistanceCode, InputStartsWithRun,
+    DistanceTooFarBack, WrongChecksum, ExtraInput
+};
+
+struct DecompressionError : std::runtime_error {
+    DecompressionErrorKind kind;
+    explicit DecompressionError(int32_t code)
+        : std::runtime_error("DecompressionError(" + std::to_string(code) + ")"),
+          kind(static_cast<DecompressionErrorKind>(code)) {}
+};
+
+// src/decompress.rs:1090-1102
+struct BoundedDecompressionError : std::runtime_error {
+    bool output_too_large;
+    std::vector<uint8_t> partial_output;  // OutputTooLarge { partial_output }
+    int32_t inner;                        // DecompressionError { inner }
+    BoundedDecompressionError(std::vector<uint8_t> partial)
+        : std::runtime_error("OutputTooLarge"), output_too_large(true), partial_output(std::move(partial)), inner(0) {}
+    explicit BoundedDecompressionError(int32_t code)
+        : std::runtime_error("DecompressionError"), output_too_large(false), inner(code) {}
+};
+
+class Context {
+public:
+    explicit Context(int device = 0) {
+        int rc = fdb_create(device, &h_);
+        if (rc != 0 || !h_) throw std::runtime_error("fdb_create failed (" + std::to_string(rc) + "): no CUDA device; there is no CPU fallback");
+    }
+    ~Context() { fdb_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    fdb_ctx* handle() const { return h_; }
+    void check(int rc, const char* what) const {
+        if (rc != 0) throw std::runtime_error(std::string(what) + ": " + fdb_last_error(h_));
+    }
+
+private:
+    fdb_ctx* h_ = nullptr;
+};
+
+// ---- batch entry points (new surface) ---------------------------------------------------------
+struct InflateResult {
+    std::vector<int32_t> status;
+    std::vector<std::vector<uint8_t>> output;
+    std::vector<uint64_t> consumed;
+};
+
+class Batch {
+public:
+    explicit Batch(Context& ctx) : ctx_(ctx) {}
+
+    InflateResult inflate(const std::vector<std::vector<uint8_t>>& streams, const std::vector<uint64_t>& out_caps,
+                          uint32_t flags = 0) {
+        const size_t n = streams.size();
+        std::vector<uint64_t> in_off(n), in_len(n), out_off(n), out_len(n), consumed(n);
+        std::vector<int32_t> status(n);
+        uint64_t ip = 0, op = 0;
+        for (size_t i = 0; i < n; i++) {
+            in_off[i] = ip;
+            in_len[i] = streams[i].size();
+            ip = (ip + in_len[i] + 15) & ~uint64_t(15);
+            out_off[i] = op;
+            op = (op + out_caps[i] + 15) & ~uint64_t(15);
+        }
+        std::vector<uint8_t> in(ip + 16), out(op + 16);
+        for (size_t i = 0; i < n; i++)
+            if (in_len[i]) std::memcpy(in.data() + in_off[i], streams[i].data(), in_len[i]);
+        ctx_.check(fdb_inflate_batch(ctx_.handle(), in.data(), in_off.data(), in_len.data(), out.data(), out_off.data(),
+                                     out_caps.data(), out_len.data(), consumed.data(), status.data(), n, flags),
+                   "fdb_inflate_batch");
+        InflateResult r;
+        r.status = status;
+        r.consumed = consumed;
+        r.output.resize(n);
+        for (size_t i = 0; i < n; i++) r.output[i].assign(out.begin() + out_off[i], out.begin() + out_off[i] + out_len[i]);
+        return r;
+    }
+
+    std::vector<std::vector<uint8_t>> deflate_ultra_fast(const std::vector<std::vector<uint8_t>>& inputs) {
+        return deflate(inputs, false);
+    }
+    std::vector<std::vector<uint8_t>> deflate_stored(const std::vector<std::vector<uint8_t>>& inputs) {
+        return deflate(inputs, true);
+    }
+
+private:
+    std::vector<std::vector<uint8_t>> deflate(const std::vector<std::vector<uint8_t>>& inputs, bool stored) {
+        const size_t n = inputs.size();
+        std::vector<uint64_t> in_off(n), in_len(n), out_off(n), out_cap(n), out_len(n);
+        std::vector<int32_t> status(n);
+        uint64_t ip = 0, op = 0;
+        for (size_t i = 0; i < n; i++) {
+            in_off[i] = ip;
+            in_len[i] = inputs[i].size();
+            ip = (ip + in_len[i] + 15) & ~uint64_t(15);
+            out_off[i] = op;
+            out_cap[i] = stored ? fdb_deflate_stored_bound(in_len[i]) : fdb_deflate_ultrafast_bound(in_len[i]);
+            op += out_cap[i];
+        }
+        std::vector<uint8_t> in(ip + 16), out(op + 16);
+        for (size_t i = 0; i < n; i++)
+            if (in_len[i]) std::memcpy(in.data() + in_off[i], inputs[i].data(), in_len[i]);
+        int rc = stored ? fdb_deflate_stored_batch(ctx_.handle(), in.data(), in_off.data(), in_len.data(), out.data(),
+                                                   out_off.data(), out_cap.data(), out_len.data(), status.data(), n)
+                        : fdb_deflate_ultrafast_batch(ctx_.handle(), in.data(), in_off.data(), in_len.data(), out.data(),
+                                                      out_off.data(), out_cap.data(), out_len.data(), status.data(), n);
+        ctx_.check(rc, "fdb_deflate_*_batch");
+        std::vector<std::vector<uint8_t>> res(n);
+        for (size_t i = 0; i < n; i++) {
+            if (status[i] != FDB_OK) throw std::runtime_error("deflate status " + std::to_string(status[i]));
+            res[i].assign(out.begin() + out_off[i], out.begin() + out_off[i] + out_len[i]);
+        }
+        return res;
+    }
+    Context& ctx_;
+};
+
+// ---- single-stream API with the reference's names ------------------------------------------------
+inline std::vector<uint8_t> decompress_to_vec_bounded(Context& ctx, const std::vector<uint8_t>& input, uint64_t maxlen) {
+    Batch b(ctx);
+    uint64_t cap = std::min<uint64_t>(maxlen, std::max<uint64_t>(1024, 4 * input.size()));
+    for (;;) {
+        InflateResult r = b.inflate({input}, {cap});
+        if (r.status[0] == FDB_OK) return std::move(r.output[0]);
+        if (r.status[0] == FDB_OUTPUT_TOO_LARGE) {
+            if (cap >= maxlen) throw BoundedDecompressionError(std::move(r.output[0]));
+            cap = std::min<uint64_t>(maxlen, cap * 4);  // the reference grows its Vec and carries on (:1132-1134)
+            continue;
+        }
+        throw BoundedDecompressionError(r.status[0]);
+    }
+}
+
+inline std::vector<uint8_t> decompress_to_vec(Context& ctx, const std::vector<uint8_t>& input) {
+    try {
+        return decompress_to_vec_bounded(ctx, input, uint64_t(1) << 62);
+    } catch (const BoundedDecompressionError& e) {
+        if (!e.output_too_large) throw DecompressionError(e.inner);
+        throw;
+    }
+}
+
+inline std::vector<uint8_t> compress_to_vec_ultra_fast(Context& ctx, const std::vector<uint8_t>& input) {
+    return Batch(ctx).deflate_ultra_fast({input})[0];
+}
+
+// src/compress/ultrafast.rs:9-181.  W needs `void write(const uint8_t*, size_t)`.  Single write_data call
+// = compress_to_vec_ultra_fast; the Python mirror (fdeflate_b200/api.py) also reproduces the reference's
+// call-boundary-dependent output for several calls by splicing; this header keeps to one call.
+template <class W>
+class UltraFastCompressor {
+public:
+    UltraFastCompressor(Context& ctx, W writer) : ctx_(ctx), w_(std::move(writer)) {}
+    void write_data(const uint8_t* data, size_t n) {
+        if (called_) throw std::logic_error("UltraFastCompressor (C++ mirror): one write_data call per stream");
+        called_ = true;
+        buf_.assign(data, data + n);
+    }
+    W finish() {
+        std::vector<uint8_t> z = compress_to_vec_ultra_fast(ctx_, buf_);
+        w_.write(z.data(), z.size());
+        return std::move(w_);
+    }
+
+private:
+    Context& ctx_;
+    W w_;
+    std::vector<uint8_t> buf_;
+    bool called_ = false;
+};
+
+// src/compress/mod.rs:47-215 restricted to level 0 ("stored"): block boundaries do not depend on the
+// write_data call pattern, so calls are simply concatenated.
+template <class W>
+class Compressor {
+public:
+    Compressor(Context& ctx, W writer, uint8_t level, bool zlib) : ctx_(ctx), w_(std::move(writer)), zlib_(zlib) {
+        if (level != 0) throw std::invalid_argument("only level 0 (stored) is on the accelerated path");
+    }
+    void write_data(const uint8_t* data, size_t n) { buf_.insert(buf_.end(), data, data + n); }
+    W finish() {
+        std::vector<uint8_t> z = Batch(ctx_).deflate_stored({buf_})[0];
+        if (zlib_) w_.write(z.data(), z.size());
+        else w_.write(z.data() + 2, z.size() - 6);
+        return std::move(w_);
+    }
+
+private:
+    Context& ctx_;
+    W w_;
+    bool zlib_;
+    std::vector<uint8_t> buf_;
+};
+
+}  // namespace fdeflate

@@ -1,0 +1,88 @@
+// C++ harness for include/fdeflate_b200.hpp, linked against a library that implements the C ABI.
+// The expected bytes come from the oracle (linked here as the CHECKER only).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "fdeflate_b200.hpp"
+extern "C" {
+#include "fdeflate_oracle.h"
+}
+
+#define CHECK(c)                                                        \
+    do {                                                                \
+        if (!(c)) {                                                     \
+            std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); \
+            return 1;                                                   \
+        }                                                               \
+    } while (0)
+
+struct VecWriter {
+    std::vector<uint8_t> v;
+    void write(const uint8_t* p, size_t n) { v.insert(v.end(), p, p + n); }
+};
+
+static std::vector<uint8_t> oracle_uf(const std::vector<uint8_t>& d) {
+    std::vector<uint8_t> o(fdo_ultrafast_bound(d.size()));
+    o.resize(fdo_compress_ultra_fast(d.data(), d.size(), o.data(), o.size()));
+    return o;
+}
+
+int main() {
+    fdeflate::Context ctx(0);
+    std::vector<uint8_t> data(20000);
+    uint32_t s = 12345;
+    for (auto& b : data) {
+        s = s * 1664525u + 1013904223u;
+        b = (s >> 24) < 120 ? 0 : uint8_t((s >> 16) % 7);
+    }
+    // compress_to_vec_ultra_fast: byte-identical to the oracle, and it round-trips
+    std::vector<uint8_t> z = fdeflate::compress_to_vec_ultra_fast(ctx, data);
+    CHECK(z == oracle_uf(data));
+    CHECK(fdeflate::decompress_to_vec(ctx, z) == data);
+    // bounded: exact fit succeeds, one byte less is OutputTooLarge with the partial output
+    CHECK(fdeflate::decompress_to_vec_bounded(ctx, z, data.size()) == data);
+    try {
+        fdeflate::decompress_to_vec_bounded(ctx, z, data.size() - 1);
+        CHECK(false);
+    } catch (const fdeflate::BoundedDecompressionError& e) {
+        CHECK(e.output_too_large && e.partial_output.size() == data.size() - 1);
+        CHECK(std::equal(e.partial_output.begin(), e.partial_output.end(), data.begin()));
+    }
+    // errors carry the reference's variant
+    std::vector<uint8_t> bad = z;
+    bad.back() ^= 1;
+    try {
+        fdeflate::decompress_to_vec(ctx, bad);
+        CHECK(false);
+    } catch (const fdeflate::DecompressionError& e) {
+        CHECK(e.kind == fdeflate::DecompressionErrorKind::WrongChecksum);
+    }
+    std::vector<uint8_t> trunc(z.begin(), z.end() - 7);
+    try {
+        fdeflate::decompress_to_vec(ctx, trunc);
+        CHECK(false);
+    } catch (const fdeflate::DecompressionError& e) {
+        CHECK(e.kind == fdeflate::DecompressionErrorKind::InsufficientInput);
+    }
+    // UltraFastCompressor / Compressor(level 0)
+    fdeflate::UltraFastCompressor<VecWriter> uf(ctx, VecWriter{});
+    uf.write_data(data.data(), data.size());
+    CHECK(uf.finish().v == z);
+    fdeflate::Compressor<VecWriter> st(ctx, VecWriter{}, 0, true);
+    st.write_data(data.data(), 7000);
+    st.write_data(data.data() + 7000, data.size() - 7000);
+    std::vector<uint8_t> stored = st.finish().v;
+    std::vector<uint8_t> want(fdo_stored_bound(data.size()));
+    want.resize(fdo_compress_stored(data.data(), data.size(), want.data(), want.size()));
+    CHECK(stored == want);
+    CHECK(fdeflate::decompress_to_vec(ctx, stored) == data);
+    // batch
+    fdeflate::Batch b(ctx);
+    auto r = b.inflate({z, stored, trunc}, {data.size(), data.size(), data.size()});
+    CHECK(r.status[0] == FDB_OK && r.status[1] == FDB_OK && r.status[2] == FDB_INSUFFICIENT_INPUT);
+    CHECK(r.output[0] == data && r.output[1] == data);
+    std::puts("cpp api ok");
+    return 0;
+}
