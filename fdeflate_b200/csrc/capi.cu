@@ -93,7 +93,8 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
     memcpy(enc.lit_tok, ht->lit_tok, sizeof enc.lit_tok);
     memcpy(enc.tail_tok, ht->tail_tok, sizeof enc.tail_tok);
     memcpy(enc.header, ht->header, sizeof enc.header);
-    memcpy(dec.table, ht->dec, sizeof dec.table);
+    memcpy(dec.wt, ht->wt, sizeof dec.wt);
+    memcpy(dec.ct, ht->ct, sizeof dec.ct);
     memcpy(dec.header, ht->header, sizeof dec.header);
     delete ht;
     auto bail = [&](cudaError_t err) {
@@ -183,7 +184,9 @@ extern "C" int fdb_inflate_batch_device(fdb_ctx* ctx, const void* d_in_base, con
     FDB_TRY(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(uint32_t), st));
     const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
     if (!(flags & FDB_FLAG_GENERAL_ONLY)) {
-        uint32_t grid = (uint32_t)std::min<size_t>((n + K4_WARPS - 1) / K4_WARPS, (size_t)sms * 2);
+        // one CTA per SM; with fewer streams than SMs the warps of n CTAs race for them, so a small
+        // batch still spreads over the chip
+        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms);
         FDB_LAUNCH(inflate_uf_kernel, dim3(grid), dim3(K4_WARPS * 32), sizeof(K4Smem), st, b, ctx->d_dec,
                    ctx->d_counters + 0, ctx->d_worklist, ctx->d_counters + 1);
         ctx->launches++;

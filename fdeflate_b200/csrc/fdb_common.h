@@ -120,6 +120,29 @@ FDB_HD uint32_t make_dist_entry(uint32_t sym, uint32_t nbits) {
     return nbits;  // symbols 30/31: invalid distance code
 }
 
+// ---- constant decode tables of the ultra-fast format (K4 only; index = the next 12 stream bits) ----
+// UW "write table", u32:
+//   regular  [23:0]  up to three literal bytes in stream order (unused bytes are 0)
+//            [27:24] bits consumed (1..12)      [31:28] bytes produced (1..12)
+//            - literal entry: the 1..3 leading literals whose codes fit in the 12 bits together
+//            - short-run entry: ONE length token whose code + extra bits + distance bit ("0") fit in
+//              the 12 bits; bytes = 0, produced = the match length (3..12)
+//   special  [31:24] == 0:  [3:0] code bits  [6:4] extra-bit count  [7] end of block  [16:8] base length
+//            - end of block, a length token longer than 12 bits, or a length token with distance bit 1
+// UC "count table", u16 (0 = special, see the write table):
+//   [3:0] bits consumed by the 1..6 leading literals / the one short run     [15:12] bytes they produce
+//   [4] RUN: the entry is a short-run token   [5] ENDNZ: its last byte is non-zero
+//   [6] FIRSTNZ: its first token is a non-zero literal   [10:7] bits of the first token alone
+// Both tables are stored SWIZZLED: the entry for index x lives at slot uf_slot(x).  The low index bits
+// are the first code of the window and are far from uniform (39 % of the bench bytes are the 2-bit
+// code 00), so an unswizzled table sends most lanes to a few banks (measured 4.1-4.9 wavefronts per
+// lookup); folding the high six bits in spreads them.
+enum : uint32_t { UC_RUN = 1u << 4, UC_ENDNZ = 1u << 5, UC_FIRSTNZ = 1u << 6, UW_EOB = 1u << 7 };
+FDB_HD uint32_t uf_slot(uint32_t bits) {
+    const uint32_t x = bits & 0xfffu;
+    return x ^ (x >> 6);
+}
+
 static const uint32_t ADLER_MOD = 65521u;
 
 }  // namespace fdb

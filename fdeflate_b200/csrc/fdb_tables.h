@@ -29,7 +29,8 @@ struct UfHostTables {
     uint32_t lit_tok[256];
     uint32_t tail_tok[258];
     uint32_t header[14];
-    uint32_t dec[4096];
+    uint32_t wt[4096];  // UW write table (fdb_common.h)
+    uint16_t ct[4096];  // UC count table
 };
 
 static inline uint32_t rev_bits(uint32_t v, uint32_t n) {
@@ -95,29 +96,52 @@ static inline bool build_uf_host_tables(UfHostTables& t) {
     }
     memcpy(t.header, hb, 56);
 
-    // decode table: first symbol by prefix match, then pair up literals that fit in 12 bits together
-    for (uint32_t idx = 0; idx < 4096; idx++) {
-        uint32_t e = 0;
+    // decode tables (formats in fdb_common.h): walk the tokens that lie completely inside the 12 index bits
+    auto first_sym = [&](uint32_t v, uint32_t avail, uint32_t* L) -> int {
         for (uint32_t s = 0; s < 286; s++) {
-            uint32_t L = t.len[s];
-            if ((idx & ((1u << L) - 1u)) == t.code[s]) {
-                e = make_litlen_entry(s, L);
-                break;
+            uint32_t l = t.len[s];
+            if (l <= avail && (v & ((1u << l) - 1u)) == t.code[s]) {
+                *L = l;
+                return (int)s;
             }
         }
-        if (!e) return false;
-        t.dec[idx] = e;
-    }
+        return -1;  // the next code does not fit in the bits that are left
+    };
     for (uint32_t idx = 0; idx < 4096; idx++) {
-        uint32_t e = t.dec[idx];
-        if (!(e & LL_LIT)) continue;
-        uint32_t l1 = (e >> 24) & 15u;
-        if (l1 >= 12) continue;
-        uint32_t e2 = t.dec[idx >> l1];
-        if (!(e2 & LL_LIT)) continue;
-        uint32_t l2 = (e2 >> 24) & 15u;
-        if (l1 + l2 > 12) continue;
-        t.dec[idx] = make_litlen_pair(e, (e2 >> 8) & 0xffu, l1, l2);
+        uint32_t L = 0;
+        const int s = first_sym(idx, 12, &L);
+        if (s < 0) return false;  // every code is <= 12 bits
+        if (s < 256) {
+            uint32_t pos = 0, k = 0, bytes = 0, wbits = 0, wk = 0, last = 0;
+            for (;;) {
+                uint32_t l2 = 0;
+                const int s2 = first_sym(idx >> pos, 12 - pos, &l2);
+                if (s2 < 0 || s2 >= 256 || k == 6) break;
+                if (k < 3) {
+                    bytes |= (uint32_t)s2 << (8 * k);
+                    wbits = pos + l2;
+                    wk = k + 1;
+                }
+                pos += l2;
+                k++;
+                last = (uint32_t)s2;
+            }
+            t.wt[uf_slot(idx)] = bytes | (wbits << 24) | (wk << 28);
+            t.ct[uf_slot(idx)] = (uint16_t)(pos | (last ? UC_ENDNZ : 0u) | (s ? UC_FIRSTNZ : 0u) | (L << 7) | (k << 12));
+        } else if (s == 256) {
+            t.wt[uf_slot(idx)] = L | UW_EOB;
+            t.ct[uf_slot(idx)] = 0;
+        } else {
+            const uint32_t xb = len_sym_extra((uint32_t)s), base = len_sym_base((uint32_t)s), tot = L + xb + 1u;
+            const uint32_t len = base + ((idx >> L) & ((1u << xb) - 1u));  // (only meaningful when tot <= 12)
+            if (tot <= 12 && len <= 12 && ((idx >> (L + xb)) & 1u) == 0) {  // (symbol 285 = 258 bytes stays special)
+                t.wt[uf_slot(idx)] = (tot << 24) | (len << 28);
+                t.ct[uf_slot(idx)] = (uint16_t)(tot | UC_RUN | (tot << 7) | (len << 12));
+            } else {
+                t.wt[uf_slot(idx)] = L | (xb << 4) | (base << 8);
+                t.ct[uf_slot(idx)] = 0;
+            }
+        }
     }
     return true;
 }

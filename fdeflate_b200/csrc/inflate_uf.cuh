@@ -36,7 +36,10 @@
 
 namespace fdb {
 
-static const int K4_WARPS = 16;        // warps per CTA (share one 16 KiB decode table)
+#ifndef K4_WARPS_PER_CTA
+#define K4_WARPS_PER_CTA 32
+#endif
+static const int K4_WARPS = K4_WARPS_PER_CTA;  // warps per CTA (one CTA per SM; they share the 24 KiB of tables)
 static const uint32_t K4_SUBW = 8;     // 32-bit words of compressed data per lane per segment
 static const uint32_t K4_WARM = 4;     // warm-up words before a lane's sub-sequence
 static const uint32_t K4_TAILW = 3;    // words after it (token overrun + two-word look-ahead)
@@ -45,6 +48,7 @@ static const uint32_t K4_ROWS_ALLOC = K4_ROWW + 1;             // +1: the look-a
 static const uint32_t K4_SEG_WORDS = K4_WARM + 32 * K4_SUBW + 4;  // words staged per segment (vectors of 4)
 static const uint32_t K4_LIM_LO = 32u * K4_WARM;               // a lane's sub-sequence, in bits of its row
 static const uint32_t K4_LIM_HI = 32u * (K4_WARM + K4_SUBW);
+static const uint32_t K4_PAIR = 24;    // two table entries consume at most 2 x 12 bits
 static const uint32_t K4_WIN = 4096;   // output window bytes (a segment normally expands to ~2.5 KiB)
 static const uint32_t K4_INVALID = 0xffffffffu;
 
@@ -54,143 +58,198 @@ static const uint32_t K4_INVALID = 0xffffffffu;
 // with a constant +128-byte pointer step.  Overlapping words are simply stored twice.
 struct K4Warp {
     uint32_t stg[K4_ROWS_ALLOC * 32];
-    uint8_t win[K4_WIN + 16];  // +16: one overhang byte for a literal pair straddling the window end
+    uint8_t win[K4_WIN + 16];
 };
 
 struct K4Smem {
-    uint32_t table[4096];
+    uint32_t wt[4096];
+    uint16_t ct[4096];
     K4Warp warp[K4_WARPS];
 };
 
 struct UfDecTables {
-    uint32_t table[4096];  // litlen entries (fdb_common.h format) for HUFFMAN_LENGTHS, two-literal entries included
+    uint32_t wt[4096];     // UW write table (fdb_common.h) for HUFFMAN_LENGTHS
+    uint16_t ct[4096];     // UC count table
     uint32_t header[14];   // the constant 54 header bytes
 };
+
+// shared-window addresses of the two tables
+struct UfTabs {
+    simt::saddr wt, ct;
+};
+FDB_DEVICE uint32_t wt_at(const UfTabs& t, uint32_t bits) { return simt::lds32_ro(t.wt + (uf_slot(bits) << 2)); }
+FDB_DEVICE uint32_t ct_at(const UfTabs& t, uint32_t bits) { return simt::lds16_ro(t.ct + (uf_slot(bits) << 1)); }
 
 // lane-private LSB-first bit reader over the lane's staging row: a 32-bit window is one funnel
 // shift of (w0, w1); w2 is fetched one word ahead so the shared-memory latency stays off the
 // decode dependency chain.
 struct LaneBits {
     uint32_t w0, w1, w2;
-    uint32_t rp;         // bit position relative to the start of the row
-    const uint32_t* nx;  // next word to fetch
+    uint32_t rp;      // bit position relative to the start of the row
+    simt::saddr nx;   // next word to fetch
 };
-FDB_DEVICE void lb_start(LaneBits& b, const uint32_t* row, uint32_t rp) {
+FDB_DEVICE void lb_start(LaneBits& b, simt::saddr row, uint32_t rp) {
     b.rp = rp;
-    const uint32_t* p = row + (rp >> 5) * 32;
-    b.w0 = p[0];
-    b.w1 = p[32];
-    b.w2 = p[64];
-    b.nx = p + 96;
+    const simt::saddr p = row + (rp >> 5) * 128u;
+    b.w0 = simt::lds32(p);
+    b.w1 = simt::lds32(p + 128u);
+    b.w2 = simt::lds32(p + 256u);
+    b.nx = p + 384u;
 }
 FDB_DEVICE uint32_t lb_peek(const LaneBits& b) { return simt::funnel_r(b.w0, b.w1, b.rp); }  // shift is mod 32
 FDB_DEVICE void lb_advance(LaneBits& b, uint32_t n) {  // n < 32
-    uint32_t nrp = b.rp + n;
+    const uint32_t nrp = b.rp + n;
     if ((nrp ^ b.rp) & 32u) {
         b.w0 = b.w1;
         b.w1 = b.w2;
-        b.w2 = *b.nx;
-        b.nx += 32;
+        b.w2 = simt::lds32(b.nx);
+        b.nx += 128u;
     }
     b.rp = nrp;
 }
 
+// A special write-table entry that is not the end of block: a length token read from the 32-bit
+// window `bits`.  Sets the bits it occupies (code + extra + distance bit), its length, and whether
+// its distance bit is 1 (a distance the ultra-fast code does not have).
+FDB_DEVICE void uf_long_run(uint32_t w, uint32_t bits, uint32_t& n, uint32_t& len, uint32_t& bad_dist) {
+    const uint32_t nc = w & 15u, xb = (w >> 4) & 7u, v = bits >> nc;
+    len = ((w >> 8) & 0x1ffu) + (v & ((1u << xb) - 1u));
+    bad_dist = (v >> xb) & 1u;
+    n = nc + xb + 1u;
+}
+
 struct LaneCount {
-    uint32_t end;     // bit position (row-relative) where the lane stopped: first token boundary >= LIM_HI
-    uint32_t cnt;     // bytes produced in [start, end)
-    uint32_t flags;   // CF_*
-    uint32_t lastlit; // last literal value (valid with CF_HASLIT)
+    uint32_t end;    // bit position (row-relative) where the lane stopped: first token boundary >= LIM_HI
+    uint32_t cnt;    // bytes produced in [start, end)
+    uint32_t flags;  // CF_*
 };
-enum : uint32_t { CF_EOB = 1, CF_BAD = 2, CF_HASLIT = 4, CF_MATCH_FIRST = 8 };
+// CF_BAD: a token the fast path does not decode (distance bit 1, or a run that follows a non-zero
+// byte inside this lane).  CF_FIRSTRUN / CF_LASTNZ let the warp check the same across lanes.
+enum : uint32_t { CF_EOB = 1, CF_BAD = 2, CF_FIRSTRUN = 4, CF_LASTNZ = 8 };
 
 // Count the bytes of the tokens in [start, LIM_HI); stop at the first token boundary >= LIM_HI or at
 // EOB (then end = position of the EOB code).  No early exits inside the loops, so lanes that still
 // iterate stay converged and the others wait at the loop exit.
-FDB_DEVICE LaneCount count_tokens(const uint32_t* tab, const uint32_t* row, uint32_t start, uint32_t active) {
-    LaneCount c = {K4_INVALID, 0, 0, 0};
+FDB_DEVICE LaneCount count_tokens(const UfTabs& t, simt::saddr row, uint32_t start, uint32_t active) {
+    LaneCount c = {K4_INVALID, 0, 0};
     LaneBits b;
     lb_start(b, row, active ? start : 0u);
-    uint32_t laste = 0, cnt = 0, flags = 0;
+    uint32_t cnt = 0, flags = 0;
+    uint32_t prev = 0;  // bit 4 = the previous byte is non-zero (UC_ENDNZ of the last entry, moved onto UC_RUN)
+    uint32_t bad = 0;   // bit 4 = some run followed a non-zero byte, or had distance bit 1
     uint32_t stop = active ? 0u : 1u;
-    // main loop: no entry can reach LIM_HI from here (an entry consumes at most 12 + 5 + 1 bits), so
-    // pairs are taken blindly
-    while (!stop && b.rp < K4_LIM_HI - 18) {
-        uint32_t bits = lb_peek(b);
-        uint32_t e = tab[bits & 0xfffu];
-        uint32_t n = e & 15u;
-        cnt += e >> 28;
-        if (e & LL_LIT) {
-            laste = e;
-        } else if (e & LL_LEN) {
-            uint32_t xb = (e >> 8) & 7u;
-            uint32_t v = bits >> n;
-            if (cnt == 0) flags |= CF_MATCH_FIRST;
-            cnt += ((e >> 16) & 0x1ffu) + (v & ((1u << xb) - 1u));
-            if ((v >> xb) & 1u) flags |= CF_BAD;  // distance code "1" is not in the ultra-fast code
-            n += xb + 1u;
-        } else {  // end of block
-            flags |= CF_EOB;
-            n = 0;
-            stop = 1;
+    {  // does the lane open with a run token?
+        const uint32_t bits = lb_peek(b);
+        const uint32_t c1 = ct_at(t, bits);
+        uint32_t fr = c1 & UC_RUN;
+        if (c1 == 0) fr = (wt_at(t, bits) & UW_EOB) ? 0u : 1u;
+        if (fr) flags |= CF_FIRSTRUN;
+    }
+    // main loop: two entries per 32-bit window; together they consume <= 24 bits, so neither can
+    // cross LIM_HI.  A special second entry reads as "0 bits, 0 bytes" and comes back as a first entry.
+    while (!stop && b.rp <= K4_LIM_HI - K4_PAIR) {
+        const uint32_t bits = lb_peek(b);
+        const uint32_t c1 = ct_at(t, bits);
+        uint32_t n;
+        if (c1 == 0) {
+            const uint32_t w = wt_at(t, bits);
+            if (w & UW_EOB) {
+                flags |= CF_EOB;
+                stop = 1;
+                n = 0;
+            } else {
+                uint32_t len, bd;
+                uf_long_run(w, bits, n, len, bd);
+                cnt += len;
+                bad |= (bd << 4) | prev;
+                prev = 0;
+            }
+        } else {
+            n = c1 & 15u;
+            cnt += c1 >> 12;
+            bad |= prev & c1;
+            prev = c1 >> 1;
+            const uint32_t c2 = ct_at(t, bits >> n);
+            n += c2 & 15u;
+            cnt += c2 >> 12;
+            bad |= prev & c2;
+            prev = c2 ? (c2 >> 1) : prev;
         }
         lb_advance(b, n);
     }
-    // tail: the pair that would cross LIM_HI gives its second literal to the next lane
+    // tail: single tokens up to the first token boundary >= LIM_HI
     while (!stop && b.rp < K4_LIM_HI) {
-        uint32_t bits = lb_peek(b);
-        uint32_t e = tab[bits & 0xfffu];
-        uint32_t n = e & 15u;
-        if (e & LL_LIT) {
-            uint32_t l1 = (e >> 24) & 15u;
-            if ((e & LL_LIT2) && b.rp + l1 >= K4_LIM_HI) {
-                n = l1;
-                e = (e & ~(LL_LIT | (3u << 28))) | LL_LIT1 | (1u << 28);
+        const uint32_t bits = lb_peek(b);
+        const uint32_t c1 = ct_at(t, bits);
+        uint32_t n;
+        if (c1 == 0) {
+            const uint32_t w = wt_at(t, bits);
+            if (w & UW_EOB) {
+                flags |= CF_EOB;
+                stop = 1;
+                n = 0;
+            } else {
+                uint32_t len, bd;
+                uf_long_run(w, bits, n, len, bd);
+                cnt += len;
+                bad |= (bd << 4) | prev;
+                prev = 0;
             }
-            cnt += e >> 28;
-            laste = e;
-        } else if (e & LL_LEN) {
-            uint32_t xb = (e >> 8) & 7u;
-            uint32_t v = bits >> n;
-            if (cnt == 0) flags |= CF_MATCH_FIRST;
-            cnt += ((e >> 16) & 0x1ffu) + (v & ((1u << xb) - 1u));
-            if ((v >> xb) & 1u) flags |= CF_BAD;
-            n += xb + 1u;
+        } else if (c1 & UC_RUN) {
+            n = c1 & 15u;
+            cnt += c1 >> 12;
+            bad |= prev & c1;
+            prev = 0;
         } else {
-            flags |= CF_EOB;
-            n = 0;
-            stop = 1;
+            n = (c1 >> 7) & 15u;
+            cnt += 1u;
+            prev = (c1 & UC_FIRSTNZ) >> 2;
         }
         lb_advance(b, n);
     }
     if (active) {
         c.end = b.rp;
         c.cnt = cnt;
-        c.flags = flags;
-        if (laste) {
-            c.flags |= CF_HASLIT;
-            c.lastlit = (laste & LL_LIT2) ? ((laste >> 16) & 0xffu) : ((laste >> 8) & 0xffu);
-        }
+        c.flags = flags | ((bad & UC_RUN) ? CF_BAD : 0u) | ((prev & UC_RUN) ? CF_LASTNZ : 0u);
     }
     return c;
 }
 
-// warm-up: single tokens from a guessed start until the first boundary >= LIM_LO
-FDB_DEVICE uint32_t warm_up(const uint32_t* tab, const uint32_t* row, uint32_t active) {
+// warm-up: tokens from a guessed start until the first boundary >= LIM_LO
+FDB_DEVICE uint32_t warm_up(const UfTabs& t, simt::saddr row, uint32_t active) {
     LaneBits b;
     lb_start(b, row, 0u);
     uint32_t stop = active ? 0u : 1u, dead = 0;
-    while (!stop && b.rp < K4_LIM_LO) {
-        uint32_t e = tab[lb_peek(b) & 0xfffu];
-        uint32_t n = e & 15u;
-        if (e & LL_LIT) {
-            uint32_t l1 = (e >> 24) & 15u;
-            if ((e & LL_LIT2) && b.rp + l1 >= K4_LIM_LO) n = l1;
-        } else if (e & LL_LEN) {
-            n += ((e >> 8) & 7u) + 1u;
+    while (!stop && b.rp <= K4_LIM_LO - K4_PAIR) {
+        const uint32_t bits = lb_peek(b);
+        const uint32_t c1 = ct_at(t, bits);
+        uint32_t n;
+        if (c1 == 0) {
+            const uint32_t w = wt_at(t, bits);
+            n = (w & 15u) + ((w >> 4) & 7u) + 1u;
+            if (w & UW_EOB) {  // speculative EOB: this lane has no valid guess
+                dead = 1;
+                stop = 1;
+                n = 0;
+            }
         } else {
-            dead = 1;  // speculative EOB: this lane has no valid guess
-            stop = 1;
-            n = 0;
+            n = c1 & 15u;
+            n += ct_at(t, bits >> n) & 15u;
+        }
+        lb_advance(b, n);
+    }
+    while (!stop && b.rp < K4_LIM_LO) {
+        const uint32_t bits = lb_peek(b);
+        const uint32_t c1 = ct_at(t, bits);
+        uint32_t n = (c1 >> 7) & 15u;  // the first token alone
+        if (c1 == 0) {
+            const uint32_t w = wt_at(t, bits);
+            n = (w & 15u) + ((w >> 4) & 7u) + 1u;
+            if (w & UW_EOB) {
+                dead = 1;
+                stop = 1;
+                n = 0;
+            }
         }
         lb_advance(b, n);
     }
@@ -205,12 +264,13 @@ struct K4Stream {
 };
 
 // Returns ST_OK / ST_WRONG_CHECKSUM, or ST_PENDING_GENERAL when the stream must go to K3.
-FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K4Warp& ws, const K4Stream& s,
+FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4Warp& ws, const K4Stream& s,
                                      uint32_t flags, uint64_t* out_len, uint64_t* consumed) {
     const unsigned lane = simt::lane_id();
     uint32_t* stg = ws.stg;
-    const uint32_t* row = ws.stg + lane;
+    const simt::saddr row = simt::smem_addr(ws.stg + lane);
     uint8_t* win = ws.win;
+    const simt::saddr win_s = simt::smem_addr(ws.win);
     *out_len = 0;
     *consumed = 0;
 
@@ -238,8 +298,10 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
     uint64_t seg_word = ((vstart >> 5) >> 2) << 2;  // first word of lane 0's sub-sequence, 16-byte aligned
     uint64_t p0 = vstart;                           // true bit position where lane 0 starts
     uint64_t o0 = 0;                                // bytes produced so far
-    uint32_t prev_byte = 0;
-    bool have_prev = false;
+    // Every match of the format replicates the previous byte, and the encoder only ever emits one
+    // after a zero.  prev_nz = "the previous byte is non-zero, or there is none": a run token in
+    // that state is not decoded here (K3 replicates the byte, or reports DistanceTooFarBack).
+    uint32_t prev_nz = 1;
     uint64_t win_vo = 0;  // virtual output position of win[0] (multiple of 16)
     AdlerAcc ad = {0, 0};
 
@@ -279,7 +341,11 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
 
         // ---- 1. stage: coalesced 16-byte loads, every word scattered to the row(s) that can see it ----
         simt::syncwarp();
-        for (uint32_t v = lane; v < K4_SEG_WORDS / 4; v += 32) {
+        // (lane l takes vectors 2l, 2l+1, then 64+l: within one store instruction every lane writes a
+        // different row, i.e. a different bank)
+        for (uint32_t it = 0; it < 3; it++) {
+            const uint32_t v = it < 2 ? 2u * lane + it : 64u + lane;
+            if (v >= K4_SEG_WORDS / 4) continue;
             uint64_t byte0 = (s0 << 2) + 16ull * v;  // relative to abase
             uint4 q = make_uint4(0, 0, 0, 0);
             if (byte0 + 16 > first_byte && byte0 < end_byte) {
@@ -305,9 +371,9 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
         simt::syncwarp();
 
         // ---- 2. count ----
-        uint32_t start = warm_up(tab, row, lane != 0);
+        uint32_t start = warm_up(t, row, lane != 0);
         if (lane == 0) start = (uint32_t)(p0 - (s0 << 5));
-        LaneCount c = count_tokens(tab, row, start, start != K4_INVALID);
+        LaneCount c = count_tokens(t, row, start, start != K4_INVALID);
 
         // ---- 3. verify the chain: my start must be my predecessor's end (rows are 32*SUBW bits apart) ----
         uint32_t eob_lane = 32;
@@ -328,7 +394,7 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
             // re-run the lanes whose start disagrees with their predecessor's end
             bool redo = mismatch && !(prev_flags & CF_EOB) && prev_end != K4_INVALID;
             if (mismatch) start = redo ? want : K4_INVALID;
-            LaneCount c2 = count_tokens(tab, row, start, redo);
+            LaneCount c2 = count_tokens(t, row, start, redo);
             if (mismatch) c = c2;  // (unresolved lanes get end = INVALID, cnt = 0, flags = 0)
         }
         if (lane > eob_lane) {
@@ -343,151 +409,129 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
         if (o0 + seg_bytes > s.cap) return ST_PENDING_GENERAL;  // K3 reports OutputTooLarge
         uint64_t op = oalign + o0 + (incl - c.cnt);             // my virtual output position
         const uint64_t my_end_vo = op + c.cnt;
-        uint32_t lit_mask = simt::ballot((c.flags & CF_HASLIT) != 0);
-        uint32_t below = lit_mask & simt::lanemask_lt();
-        uint32_t src = below ? 31u - simt::clz(below) : 0u;
-        uint32_t from_lane = simt::shfl(c.lastlit, src);
-        uint32_t fv = below ? from_lane : prev_byte;
-        bool fv_known = below ? true : have_prev;
-        if (simt::any((c.flags & CF_MATCH_FIRST) && !fv_known)) return ST_PENDING_GENERAL;  // match at position 0
-        if (lit_mask) {
-            prev_byte = simt::shfl(c.lastlit, 31u - simt::clz(lit_mask));
-            have_prev = true;
+        {
+            // a lane that opens with a run needs a zero byte before it: the last byte of the nearest
+            // lane below that produced anything, else the last byte of the previous segment
+            const uint32_t has_mask = simt::ballot(c.cnt != 0);
+            const uint32_t nz_mask = simt::ballot(c.cnt != 0 && (c.flags & CF_LASTNZ) != 0);
+            const uint32_t below = has_mask & simt::lanemask_lt();
+            const uint32_t pred_nz = below ? ((nz_mask >> (31u - simt::clz(below))) & 1u) : prev_nz;
+            if (simt::any(c.cnt != 0 && (c.flags & CF_FIRSTRUN) != 0 && pred_nz != 0)) return ST_PENDING_GENERAL;
+            if (has_mask) prev_nz = (nz_mask >> (31u - simt::clz(has_mask))) & 1u;
         }
 
         // ---- 5. write ----
         // The window base slides with the output: it is the 16-byte vector holding the first byte of
         // this segment, so a segment whose output fits in K4_WIN is written by all lanes at once.
+        // Only literals are stored; runs are zeros and the window is zero-initialised.
         const uint64_t seg_end_vo = oalign + o0 + seg_bytes;
         LaneBits b;
         lb_start(b, row, start != K4_INVALID ? start : 0u);
         uint32_t fin = (start == K4_INVALID || lane > eob_lane) ? 1u : 0u;  // no more tokens to decode
-        uint32_t pend = 0;  // bytes of a non-zero fill still owed to later windows
         for (;;) {
             const uint64_t wend = win_vo + K4_WIN;
-            const bool mine = !(fin && pend == 0) && op < wend;
+            const bool mine = !fin && op < wend;
             uint32_t wp = mine ? (uint32_t)(op - win_vo) : 0u;
-            if (mine && pend == 0 && my_end_vo <= wend) {
+            if (mine && my_end_vo <= wend) {
                 // fast path: everything this lane still has to write fits in the window
-                uint8_t* wptr = win + wp;
-                uint32_t laste = 0;
-                while (!fin && b.rp < K4_LIM_HI - 18) {
-                    uint32_t bits = lb_peek(b);
-                    uint32_t e = tab[bits & 0xfffu];
-                    uint32_t n = e & 15u;
-                    if (e & LL_LIT) {
-                        // both bytes always: a single's second byte is 0 and the next token of this lane
-                        // overwrites it (or it is a zero the stream would have produced anyway)
-                        wptr[0] = (uint8_t)(e >> 8);
-                        wptr[1] = (uint8_t)(e >> 16);
-                        wptr += e >> 28;
-                        laste = e;
-                    } else if (e & LL_LEN) {
-                        uint32_t xb = (e >> 8) & 7u;
-                        uint32_t len = ((e >> 16) & 0x1ffu) + ((bits >> n) & ((1u << xb) - 1u));
-                        n += xb + 1u;
-                        if (laste) fv = (laste >> (8u * (laste >> 28))) & 0xffu;  // last literal written
-                        if (fv != 0)
-                            for (uint32_t k = 0; k < len; k++) wptr[k] = (uint8_t)fv;
-                        wptr += len;  // zero runs: the window is zero-initialised, nothing to write
+                simt::saddr wptr = win_s + wp;
+                while (!fin && b.rp <= K4_LIM_HI - K4_PAIR) {
+                    const uint32_t bits = lb_peek(b);
+                    const uint32_t e1 = wt_at(t, bits);
+                    const uint32_t k1 = e1 >> 28;
+                    uint32_t n;
+                    if (k1 == 0) {
+                        if (e1 & UW_EOB) {
+                            fin = 1;
+                            n = 0;
+                        } else {
+                            uint32_t len, bd;
+                            uf_long_run(e1, bits, n, len, bd);
+                            wptr += len;
+                        }
                     } else {
-                        fin = 1;
-                        n = 0;
+                        // exact stores: the byte after this lane's last one belongs to the next lane
+                        simt::sts8(wptr, e1);
+                        if (k1 >= 2) simt::sts8(wptr + 1, e1 >> 8);
+                        if (k1 >= 3) simt::sts8(wptr + 2, e1 >> 16);
+                        wptr += k1;
+                        n = (e1 >> 24) & 15u;
+                        const uint32_t e2 = wt_at(t, bits >> n);  // special: 0 bytes, 0 bits -> next trip
+                        const uint32_t k2 = e2 >> 28;
+                        if (k2 >= 1) simt::sts8(wptr, e2);
+                        if (k2 >= 2) simt::sts8(wptr + 1, e2 >> 8);
+                        if (k2 >= 3) simt::sts8(wptr + 2, e2 >> 16);
+                        wptr += k2;
+                        n += (e2 >> 24) & 15u;
                     }
                     lb_advance(b, n);
                 }
-                if (laste) fv = (laste >> (8u * (laste >> 28))) & 0xffu;
-                while (!fin && b.rp < K4_LIM_HI) {
-                    uint32_t bits = lb_peek(b);
-                    uint32_t e = tab[bits & 0xfffu];
-                    uint32_t n = e & 15u;
-                    if (e & LL_LIT) {
-                        uint32_t two = (e >> 5) & 1u, l1 = (e >> 24) & 15u;
-                        if (two && b.rp + l1 >= K4_LIM_HI) {
-                            two = 0;
-                            n = l1;
+                while (!fin && b.rp < K4_LIM_HI) {  // single tokens up to the first boundary >= LIM_HI
+                    const uint32_t bits = lb_peek(b);
+                    const uint32_t e = wt_at(t, bits);
+                    const uint32_t k = e >> 28;
+                    uint32_t n;
+                    if (k == 0) {
+                        if (e & UW_EOB) {
+                            fin = 1;
+                            n = 0;
+                        } else {
+                            uint32_t len, bd;
+                            uf_long_run(e, bits, n, len, bd);
+                            wptr += len;
                         }
-                        wptr[0] = (uint8_t)(e >> 8);
-                        fv = (e >> 8) & 0xffu;
-                        if (two) {
-                            wptr[1] = (uint8_t)(e >> 16);
-                            fv = (e >> 16) & 0xffu;
-                        }
-                        wptr += 1u + two;
-                    } else if (e & LL_LEN) {
-                        uint32_t xb = (e >> 8) & 7u;
-                        uint32_t len = ((e >> 16) & 0x1ffu) + ((bits >> n) & ((1u << xb) - 1u));
-                        n += xb + 1u;
-                        if (fv != 0)
-                            for (uint32_t k = 0; k < len; k++) wptr[k] = (uint8_t)fv;
-                        wptr += len;
                     } else {
-                        fin = 1;
-                        n = 0;
+                        const uint32_t c1 = ct_at(t, bits);
+                        if (c1 & UC_RUN) {
+                            wptr += k;
+                            n = (e >> 24) & 15u;
+                        } else {
+                            simt::sts8(wptr, e);
+                            wptr += 1u;
+                            n = (c1 >> 7) & 15u;
+                        }
                     }
                     lb_advance(b, n);
                 }
                 fin = 1;
-                wp = (uint32_t)(wptr - win);
+                wp = (uint32_t)(wptr - win_s);
             } else if (mine) {
-                // careful path: this lane's output crosses the window end (long runs) or it still owes
-                // bytes of a non-zero fill; stop at the window end and resume after the flush
-                while (wp < K4_WIN && !(fin && pend == 0)) {
-                    if (pend) {
-                        while (pend && wp < K4_WIN) {
-                            win[wp++] = (uint8_t)fv;
-                            pend--;
-                        }
-                    } else {
-                        uint32_t bits = lb_peek(b);
-                        uint32_t e = tab[bits & 0xfffu];
-                        uint32_t n = e & 15u;
-                        if (e & LL_LIT) {
-                            uint32_t two = (e >> 5) & 1u, l1 = (e >> 24) & 15u;
-                            if (two && b.rp + l1 >= K4_LIM_HI) {
-                                two = 0;
-                                n = l1;
-                            }
-                            win[wp] = (uint8_t)(e >> 8);
-                            fv = (e >> 8) & 0xffu;
-                            if (two) {
-                                win[wp + 1] = (uint8_t)(e >> 16);  // may be the overhang byte win[K4_WIN]
-                                fv = (e >> 16) & 0xffu;
-                            }
-                            wp += 1u + two;
-                        } else if (e & LL_LEN) {
-                            uint32_t xb = (e >> 8) & 7u;
-                            uint32_t len = ((e >> 16) & 0x1ffu) + ((bits >> n) & ((1u << xb) - 1u));
-                            n += xb + 1u;
-                            if (fv == 0) {
-                                wp += len;
-                            } else {
-                                while (len && wp < K4_WIN) {
-                                    win[wp++] = (uint8_t)fv;
-                                    len--;
-                                }
-                                pend = len;
-                            }
-                        } else {
+                // careful path: this lane's output crosses the window end (long runs); single tokens,
+                // stop at the window end and resume after the flush
+                while (wp < K4_WIN && !fin) {
+                    const uint32_t bits = lb_peek(b);
+                    const uint32_t e = wt_at(t, bits);
+                    const uint32_t k = e >> 28;
+                    uint32_t n;
+                    if (k == 0) {
+                        if (e & UW_EOB) {
                             fin = 1;
                             n = 0;
+                        } else {
+                            uint32_t len, bd;
+                            uf_long_run(e, bits, n, len, bd);
+                            wp += len;
                         }
-                        lb_advance(b, n);
-                        if (b.rp >= K4_LIM_HI) fin = 1;
+                    } else {
+                        const uint32_t c1 = ct_at(t, bits);
+                        if (c1 & UC_RUN) {
+                            wp += k;
+                            n = (e >> 24) & 15u;
+                        } else {
+                            simt::sts8(win_s + wp, e);
+                            wp += 1u;
+                            n = (c1 >> 7) & 15u;
+                        }
                     }
+                    lb_advance(b, n);
+                    if (b.rp >= K4_LIM_HI) fin = 1;
                 }
             }
             if (mine) op = win_vo + wp;
             simt::syncwarp();
             if (seg_end_vo < wend) break;  // the rest of this segment fits: leave it in the window
             // the window is complete: flush all of it and slide by K4_WIN
-            uint32_t over = win[K4_WIN];
-            simt::syncwarp();
             flush_vectors(K4_WIN / 16, ~0ull);
-            if (lane == 0) {
-                win[K4_WIN] = 0;
-                win[0] = (uint8_t)over;
-            }
             simt::syncwarp();
             win_vo = wend;
         }
@@ -503,9 +547,9 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
             uint32_t left = (uint32_t)(oalign + o0 - win_vo);
             flush_vectors((left + 15) / 16, oalign + o0);
             simt::syncwarp();
-            const uint8_t* t = abase + trailer_byte;
-            uint32_t stored = ((uint32_t)simt::ldg8(t) << 24) | ((uint32_t)simt::ldg8(t + 1) << 16) |
-                              ((uint32_t)simt::ldg8(t + 2) << 8) | (uint32_t)simt::ldg8(t + 3);
+            const uint8_t* tr = abase + trailer_byte;
+            uint32_t stored = ((uint32_t)simt::ldg8(tr) << 24) | ((uint32_t)simt::ldg8(tr + 1) << 16) |
+                              ((uint32_t)simt::ldg8(tr + 2) << 8) | (uint32_t)simt::ldg8(tr + 3);
             uint32_t got = adler_finish_warp(ad, o0);
             *out_len = o0;
             *consumed = trailer_byte + 4 - first_byte;
@@ -532,19 +576,23 @@ FDB_DEVICE int32_t inflate_uf_stream(const uint32_t* tab, const uint32_t* hdr, K
     }
 }
 
-// Persistent kernel.  Streams the fast path declines are appended to worklist[] (count in *work_count)
-// with status ST_PENDING_GENERAL; the host launches K3 over that list next, on the same stream.
-FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 2)
+// Persistent kernel, one CTA per SM.  Streams the fast path declines are appended to worklist[]
+// (count in *work_count) with status ST_PENDING_GENERAL; the host launches K3 over that list next,
+// on the same stream.
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
     inflate_uf_kernel(InflateBatch b, const UfDecTables* tables, uint32_t* next, uint32_t* worklist,
                       uint32_t* work_count) {
     FDB_DYN_SMEM(smem_raw);
     K4Smem& sm = *reinterpret_cast<K4Smem*>(smem_raw);
     FDB_SHARED uint32_t hdr[14];
-    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) sm.table[i] = tables->table[i];
+    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) sm.wt[i] = tables->wt[i];
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x)
+        ((uint32_t*)sm.ct)[i] = ((const uint32_t*)tables->ct)[i];
     if (threadIdx.x < 14) hdr[threadIdx.x] = tables->header[threadIdx.x];
     simt::syncthreads();
     const unsigned lane = simt::lane_id();
     K4Warp& ws = sm.warp[simt::warp_in_block()];
+    const UfTabs t = {simt::smem_addr(sm.wt), simt::smem_addr(sm.ct)};
     for (;;) {
         uint32_t i = 0;
         if (lane == 0) i = simt::atomic_add(next, 1u);
@@ -552,7 +600,7 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 2)
         if (i >= b.n) break;
         K4Stream s = {b.in_base + b.in_off[i], b.in_len[i], b.out_base + b.out_off[i], b.out_cap[i]};
         uint64_t out_len = 0, consumed = 0;
-        int32_t st = inflate_uf_stream(sm.table, hdr, ws, s, b.flags, &out_len, &consumed);
+        int32_t st = inflate_uf_stream(t, hdr, ws, s, b.flags, &out_len, &consumed);
         if (lane == 0) {
             b.status[i] = st;
             b.out_len[i] = out_len;

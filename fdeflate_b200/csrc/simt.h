@@ -69,6 +69,36 @@ FDB_DEVICE uint4 ldg128(const uint4* p) { return __ldg(p); }
 FDB_DEVICE uint8_t ldg8(const uint8_t* p) { return __ldg(p); }
 // streaming (evict-first) 16-byte store: output bytes are written once and never re-read by us
 FDB_DEVICE void stcs128(uint4* p, uint4 v) { __stcs(p, v); }
+
+// ---- explicit shared-window addressing --------------------------------------------------------
+// Hot decode loops keep 32-bit shared-memory addresses in registers and issue ld/st.shared directly;
+// with generic pointers the compiler re-derives the shared window base inside the loop.
+//   *_ro : constant tables (filled before the CTA barrier); the compiler may schedule these freely.
+//   others: staging rows / output windows that change between warp barriers; they are ordered with
+//           the surrounding C++ accesses by the "memory" clobber.
+typedef uint32_t saddr;
+FDB_DEVICE saddr smem_addr(const void* p) {
+    saddr a = (saddr)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));  // opaque: keep the address in a register instead of re-deriving it per use
+    return a;
+}
+FDB_DEVICE uint32_t lds32_ro(saddr a) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+FDB_DEVICE uint32_t lds16_ro(saddr a) {
+    uint32_t v;
+    asm("{\n\t.reg .u16 t;\n\tld.shared.u16 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(a));
+    return v;
+}
+FDB_DEVICE uint32_t lds32(saddr a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+FDB_DEVICE void sts8(saddr a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+FDB_DEVICE void sts32(saddr a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 }  // namespace simt
 #endif
 

@@ -217,6 +217,14 @@ static inline uint32_t ldg32(const uint32_t* p) { return *p; }
 static inline uint4 ldg128(const uint4* p) { return *p; }
 static inline uint8_t ldg8(const uint8_t* p) { return *p; }
 static inline void stcs128(uint4* p, uint4 v) { *p = v; }
+// explicit shared-window addressing: plain host pointers here
+typedef uintptr_t saddr;
+static inline saddr smem_addr(const void* p) { return (saddr)p; }
+static inline uint32_t lds32_ro(saddr a) { return *(const uint32_t*)a; }
+static inline uint32_t lds16_ro(saddr a) { return *(const uint16_t*)a; }
+static inline uint32_t lds32(saddr a) { return *(const uint32_t*)a; }
+static inline void sts8(saddr a, uint32_t v) { *(uint8_t*)a = (uint8_t)v; }
+static inline void sts32(saddr a, uint32_t v) { *(uint32_t*)a = v; }
 }  // namespace simt
 
 // ---- CUDA runtime stubs used by capi.cu --------------------------------------------------------

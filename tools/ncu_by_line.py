@@ -48,7 +48,8 @@ def main():
     hdr = rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
     ie, it, isamp = ix["Instructions Executed"], ix["Thread Instructions Executed"], ix["# Samples"]
-    agg = defaultdict(lambda: [0, 0, 0])
+    iwf, iwfi = ix.get("L1 Wavefronts Shared"), ix.get("L1 Wavefronts Shared Ideal")
+    agg = defaultdict(lambda: [0, 0, 0, 0, 0])
     body = rows[2:]
     if len(body) != len(lines):
         print(f"warning: {len(body)} ncu instructions vs {len(lines)} disassembled")
@@ -60,6 +61,9 @@ def main():
         a[0] += int(r[ie])
         a[1] += int(r[it])
         a[2] += int(r[isamp]) if r[isamp].isdigit() else 0
+        if iwf is not None and r[iwf].isdigit():
+            a[3] += int(r[iwf])
+            a[4] += int(r[iwfi]) if r[iwfi].isdigit() else 0
         tot += int(r[ie])
     tsamp = sum(a[2] for a in agg.values())
     print(f"total warp instructions {tot:,}  samples {tsamp:,}")
@@ -70,6 +74,12 @@ def main():
             srcs[f] = p[0].read_text().splitlines() if p else []
         text = srcs[f][l - 1].strip()[:90] if 0 < l <= len(srcs[f]) else ""
         print(f"{a[0] / tot * 100:5.1f}% inst  {a[2] / max(tsamp, 1) * 100:5.1f}% samp  thr/inst {a[1] / max(a[0], 1):5.1f}  {f}:{l:<4} {text}")
+    twf = sum(a[3] for a in agg.values())
+    if twf:
+        print(f"shared-memory wavefronts {twf:,} (ideal {sum(a[4] for a in agg.values()):,}), by source line:")
+        for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][3])[:16]:
+            text = srcs.get(f, [""] * l)[l - 1].strip()[:80] if f in srcs and 0 < l <= len(srcs[f]) else ""
+            print(f"{a[3] / twf * 100:5.1f}% wavefronts  x{a[3] / max(a[4], 1):4.2f} of ideal  {f}:{l:<4} {text}")
 
 
 if __name__ == "__main__":
