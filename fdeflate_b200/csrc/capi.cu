@@ -90,7 +90,11 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
     }
     UfEncTables enc;
     UfDecTables dec;
-    memcpy(enc.lit_tok, ht->lit_tok, sizeof enc.lit_tok);
+    memset(enc.lit, 0, sizeof enc.lit);
+    for (int i = 0; i < 256; i++) {
+        enc.lit[i].x = ht->code[i];
+        enc.lit[i].y = ht->len[i];
+    }
     memcpy(enc.tail_tok, ht->tail_tok, sizeof enc.tail_tok);
     memcpy(enc.header, ht->header, sizeof enc.header);
     memcpy(dec.wt, ht->wt, sizeof dec.wt);
@@ -230,7 +234,9 @@ static int deflate_device(fdb_ctx* ctx, int kind, const void* d_in_base, const u
     FDB_TRY(cudaMemsetAsync(ctx->d_counters + 3, 0, sizeof(uint32_t), st));
     const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
     if (kind == 0) {
-        uint32_t grid = (uint32_t)std::min<size_t>((n + DEFLATE_WARPS - 1) / DEFLATE_WARPS, (size_t)sms * 8);
+        // persistent: every resident warp pulls streams from one counter, so SMs stay evenly loaded
+        // even when the batch is not a multiple of the chip's warp slots
+        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * DEFLATE_MIN_CTAS);
         FDB_LAUNCH(deflate_uf_kernel, dim3(grid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc,
                    ctx->d_counters + 3);
     } else {

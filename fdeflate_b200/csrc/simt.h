@@ -57,6 +57,12 @@ FDB_DEVICE uint32_t ffs(uint32_t v) { return (uint32_t)__ffs((int)v); }  // 1-ba
 FDB_DEVICE uint32_t brev(uint32_t v) { return __brev(v); }
 FDB_DEVICE uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
 FDB_DEVICE uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+// full prmt.b32: selector nibble bit 3 replicates the sign of the selected byte (__byte_perm masks it off)
+FDB_DEVICE uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+    return r;
+}
 FDB_DEVICE uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
 FDB_DEVICE uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 FDB_DEVICE uint64_t atomic_add(uint64_t* p, uint64_t v) {
@@ -90,6 +96,11 @@ FDB_DEVICE uint32_t lds32_ro(saddr a) {
 FDB_DEVICE uint32_t lds16_ro(saddr a) {
     uint32_t v;
     asm("{\n\t.reg .u16 t;\n\tld.shared.u16 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(a));
+    return v;
+}
+FDB_DEVICE uint2 lds64_ro(saddr a) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
 FDB_DEVICE uint32_t lds32(saddr a) {

@@ -180,7 +180,7 @@ static inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return (uint32_t)(v >> (s & 31u));
 }
-static inline uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) {
+static inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
     uint8_t bytes[8];
     memcpy(bytes, &a, 4);
     memcpy(bytes + 4, &b, 4);
@@ -193,6 +193,7 @@ static inline uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) {
     }
     return r;
 }
+static inline uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) { return prmt(a, b, s & 0x7777u); }
 static inline uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) {
     for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xff) * ((b >> (8 * i)) & 0xff);
     return c;
@@ -222,6 +223,7 @@ typedef uintptr_t saddr;
 static inline saddr smem_addr(const void* p) { return (saddr)p; }
 static inline uint32_t lds32_ro(saddr a) { return *(const uint32_t*)a; }
 static inline uint32_t lds16_ro(saddr a) { return *(const uint16_t*)a; }
+static inline uint2 lds64_ro(saddr a) { return *(const uint2*)a; }
 static inline uint32_t lds32(saddr a) { return *(const uint32_t*)a; }
 static inline void sts8(saddr a, uint32_t v) { *(uint8_t*)a = (uint8_t)v; }
 static inline void sts32(saddr a, uint32_t v) { *(uint32_t*)a = v; }
