@@ -20,6 +20,7 @@ EXPORTS = [
     "fdb_deflate_ultrafast_bound", "fdb_deflate_ultrafast_batch_device", "fdb_deflate_ultrafast_batch",
     "fdb_deflate_stored_bound", "fdb_deflate_stored_batch_device", "fdb_deflate_stored_batch",
     "fdb_synth_tile_bytes", "fdb_synth_tiles_host", "fdb_synth_tiles_device", "fdb_launch_count", "fdb_last_general_count",
+    "fdb_set_pipeline_chunk",
 ]
 
 FLAG_IGNORE_ADLER32 = 1
@@ -72,6 +73,8 @@ class NativeLib:
         L.fdb_synth_tiles_device.argtypes = [vp, vp, u64, u64, u32, u32, u64, vp]
         L.fdb_launch_count.restype = u64
         L.fdb_launch_count.argtypes = [vp]
+        L.fdb_set_pipeline_chunk.restype = C.c_int
+        L.fdb_set_pipeline_chunk.argtypes = [vp, sz]
         L.fdb_last_general_count.restype = C.c_int64
         L.fdb_last_general_count.argtypes = [vp, vp]
 

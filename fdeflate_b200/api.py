@@ -102,6 +102,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.L.fdb_launch_count(self._h))
 
+    def set_pipeline_chunk(self, nbytes: int = 0):
+        """slot span per chunk of the host-buffer pipeline (0 = default 128 MiB); a tuning knob"""
+        self._check(self.lib.L.fdb_set_pipeline_chunk(self._h, nbytes), "fdb_set_pipeline_chunk")
+
     def last_general_count(self, stream: int = 0) -> int:
         """streams of the last inflate batch that the fast path handed to the general kernel"""
         return int(self.lib.L.fdb_last_general_count(self._h, stream))

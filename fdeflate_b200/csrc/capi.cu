@@ -24,10 +24,26 @@
 
 using namespace fdb;
 
+// One pipeline lane of the host-buffer entry points: its own CUDA stream, work counters and fallback
+// work list, so that chunks of one batch can overlap (H2D of chunk k+1 | kernels of chunk k | D2H of k-1).
+struct fdb_lane {
+    cudaStream_t st = nullptr;
+    uint32_t* d_counters = nullptr;  // same layout as fdb_ctx::d_counters
+    uint32_t* d_worklist = nullptr;
+    size_t worklist_cap = 0;
+};
+static const int FDB_LANES = 4;
+
 struct fdb_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;  // used by the host-buffer entry points
+    cudaStream_t stream = nullptr;  // lane 0 of the host-buffer entry points
+    fdb_lane lanes[FDB_LANES];
+    cudaEvent_t meta_ready = nullptr;
+    uint8_t* h_res = nullptr;       // pinned: per-stream results of the host-buffer entry points
+    size_t h_res_cap = 0;
+    int64_t last_general_host = -1; // fallback count of the last host-buffer inflate (-1: ask the device)
+    uint64_t chunk_bytes = 128ull << 20;  // slot span per pipeline chunk
     uint32_t* d_counters = nullptr; // [0] K4 next  [1] fallback count  [2] K3 next  [3] deflate next
     uint32_t* d_worklist = nullptr;
     size_t worklist_cap = 0;
@@ -64,9 +80,15 @@ extern "C" const char* fdb_version(void) {
 
 extern "C" const char* fdb_last_error(const fdb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" uint64_t fdb_launch_count(const fdb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int fdb_set_pipeline_chunk(fdb_ctx* ctx, size_t bytes) {
+    if (!ctx) return -1;
+    ctx->chunk_bytes = bytes ? bytes : (128ull << 20);
+    return 0;
+}
 
 extern "C" int64_t fdb_last_general_count(fdb_ctx* ctx, void* cuda_stream) {
     if (!ctx) return -1;
+    if (ctx->last_general_host >= 0) return ctx->last_general_host;
     uint32_t v = 0;
     if (cudaStreamSynchronize((cudaStream_t)cuda_stream) != cudaSuccess) return -1;
     if (cudaMemcpy(&v, ctx->d_counters + 1, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
@@ -110,6 +132,12 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
     if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail(e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(uint32_t))) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreateWithFlags(&ctx->meta_ready, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+    ctx->lanes[0].st = ctx->stream;
+    for (int l = 0; l < FDB_LANES; l++) {
+        if (l && (e = cudaStreamCreateWithFlags(&ctx->lanes[l].st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc((void**)&ctx->lanes[l].d_counters, 16 * sizeof(uint32_t))) != cudaSuccess) return bail(e);
+    }
     if ((e = cudaMalloc((void**)&ctx->d_enc, sizeof(UfEncTables))) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc((void**)&ctx->d_dec, sizeof(UfDecTables))) != cudaSuccess) return bail(e);
     if ((e = cudaMemcpy(ctx->d_enc, &enc, sizeof enc, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
@@ -125,10 +153,17 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
 extern "C" void fdb_destroy(fdb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaStreamDestroy(ctx->stream);
+    for (int l = 0; l < FDB_LANES; l++) {
+        if (ctx->lanes[l].st) {
+            cudaStreamSynchronize(ctx->lanes[l].st);
+            cudaStreamDestroy(ctx->lanes[l].st);
+        }
+        cudaFree(ctx->lanes[l].d_counters);
+        cudaFree(ctx->lanes[l].d_worklist);
     }
+    if (!ctx->lanes[0].st && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->meta_ready) cudaEventDestroy(ctx->meta_ready);
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_worklist);
     cudaFree(ctx->d_enc);
@@ -144,7 +179,8 @@ static int grow(fdb_ctx* ctx, void** p, size_t* cap, size_t need) {
     size_t ncap = std::max(need + need / 8, (size_t)1 << 20);
     ncap = (ncap + 255) & ~(size_t)255;
     if (*p) {
-        FDB_TRY(cudaStreamSynchronize(ctx->stream));
+        for (int l = 0; l < FDB_LANES; l++)
+            if (ctx->lanes[l].st) FDB_TRY(cudaStreamSynchronize(ctx->lanes[l].st));
         FDB_TRY(cudaFree(*p));
         *p = nullptr;
         *cap = 0;
@@ -155,6 +191,43 @@ static int grow(fdb_ctx* ctx, void** p, size_t* cap, size_t need) {
 }
 
 // ---- inflate ----------------------------------------------------------------------------------
+// K4 over the whole batch, then K3 over the streams K4 declined (or K3 alone with FDB_FLAG_GENERAL_ONLY)
+static int launch_inflate(fdb_ctx* ctx, const InflateBatch& b, uint32_t* counters, uint32_t** worklist,
+                          size_t* worklist_cap, cudaStream_t st) {
+    const size_t n = b.n;
+    if (n > *worklist_cap) {
+        void* p = *worklist;
+        size_t cap_bytes = *worklist_cap * sizeof(uint32_t);
+        int r = grow(ctx, &p, &cap_bytes, n * sizeof(uint32_t));
+        *worklist = (uint32_t*)p;
+        *worklist_cap = cap_bytes / sizeof(uint32_t);
+        if (r) return r;
+    }
+    FDB_TRY(cudaMemsetAsync(counters, 0, 4 * sizeof(uint32_t), st));
+    const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
+    if (!(b.flags & FDB_FLAG_GENERAL_ONLY)) {
+        // one CTA per SM; with fewer streams than SMs the warps of n CTAs race for them, so a small
+        // batch still spreads over the chip
+        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms);
+        FDB_LAUNCH(inflate_uf_kernel, dim3(grid), dim3(K4_WARPS * 32), sizeof(K4Smem), st, b, ctx->d_dec, counters + 0,
+                   *worklist, counters + 1);
+        ctx->launches++;
+        FDB_TRY(cudaGetLastError());
+        uint32_t grid3 = (uint32_t)std::min<size_t>(n, (size_t)sms * 10);
+        FDB_LAUNCH(inflate_general_kernel, dim3(grid3), dim3(32), sizeof(K3Smem), st, b, (const uint32_t*)*worklist,
+                   (const uint32_t*)(counters + 1), counters + 2);
+        ctx->launches++;
+        FDB_TRY(cudaGetLastError());
+    } else {
+        uint32_t grid3 = (uint32_t)std::min<size_t>(n, (size_t)sms * 10);
+        FDB_LAUNCH(inflate_general_kernel, dim3(grid3), dim3(32), sizeof(K3Smem), st, b, (const uint32_t*)nullptr,
+                   (const uint32_t*)nullptr, counters + 2);
+        ctx->launches++;
+        FDB_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
 extern "C" int fdb_inflate_batch_device(fdb_ctx* ctx, const void* d_in_base, const uint64_t* d_in_off,
                                         const uint64_t* d_in_len, void* d_out_base, const uint64_t* d_out_off,
                                         const uint64_t* d_out_cap, uint64_t* d_out_len, uint64_t* d_consumed,
@@ -163,16 +236,7 @@ extern "C" int fdb_inflate_batch_device(fdb_ctx* ctx, const void* d_in_base, con
     if (n == 0) return 0;
     if (n > 0xffffffffull || !d_in_off || !d_in_len || !d_out_off || !d_out_cap || !d_out_len || !d_status)
         return fail(ctx, "fdb_inflate_batch_device", cudaSuccess);
-    cudaStream_t st = (cudaStream_t)cuda_stream;
     FDB_TRY(cudaSetDevice(ctx->device));
-    if (n > ctx->worklist_cap) {
-        void* p = ctx->d_worklist;
-        size_t cap_bytes = ctx->worklist_cap * sizeof(uint32_t);
-        int r = grow(ctx, &p, &cap_bytes, n * sizeof(uint32_t));
-        ctx->d_worklist = (uint32_t*)p;
-        ctx->worklist_cap = cap_bytes / sizeof(uint32_t);
-        if (r) return r;
-    }
     InflateBatch b;
     b.in_base = (const uint8_t*)d_in_base;
     b.in_off = d_in_off;
@@ -185,32 +249,30 @@ extern "C" int fdb_inflate_batch_device(fdb_ctx* ctx, const void* d_in_base, con
     b.status = d_status;
     b.n = (uint32_t)n;
     b.flags = flags;
-    FDB_TRY(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(uint32_t), st));
-    const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
-    if (!(flags & FDB_FLAG_GENERAL_ONLY)) {
-        // one CTA per SM; with fewer streams than SMs the warps of n CTAs race for them, so a small
-        // batch still spreads over the chip
-        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms);
-        FDB_LAUNCH(inflate_uf_kernel, dim3(grid), dim3(K4_WARPS * 32), sizeof(K4Smem), st, b, ctx->d_dec,
-                   ctx->d_counters + 0, ctx->d_worklist, ctx->d_counters + 1);
-        ctx->launches++;
-        FDB_TRY(cudaGetLastError());
-        uint32_t grid3 = (uint32_t)std::min<size_t>(n, (size_t)sms * 10);
-        FDB_LAUNCH(inflate_general_kernel, dim3(grid3), dim3(32), sizeof(K3Smem), st, b,
-                   (const uint32_t*)ctx->d_worklist, (const uint32_t*)(ctx->d_counters + 1), ctx->d_counters + 2);
-        ctx->launches++;
-        FDB_TRY(cudaGetLastError());
-    } else {
-        uint32_t grid3 = (uint32_t)std::min<size_t>(n, (size_t)sms * 10);
-        FDB_LAUNCH(inflate_general_kernel, dim3(grid3), dim3(32), sizeof(K3Smem), st, b, (const uint32_t*)nullptr,
-                   (const uint32_t*)nullptr, ctx->d_counters + 2);
-        ctx->launches++;
-        FDB_TRY(cudaGetLastError());
-    }
-    return 0;
+    ctx->last_general_host = -1;
+    return launch_inflate(ctx, b, ctx->d_counters, &ctx->d_worklist, &ctx->worklist_cap, (cudaStream_t)cuda_stream);
 }
 
 // ---- deflate ----------------------------------------------------------------------------------
+static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_t* counter, cudaStream_t st) {
+    const size_t n = b.n;
+    FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+    const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
+    if (kind == 0) {
+        // persistent: every resident warp pulls streams from one counter, so SMs stay evenly loaded
+        // even when the batch is not a multiple of the chip's warp slots
+        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * DEFLATE_MIN_CTAS);
+        FDB_LAUNCH(deflate_uf_kernel, dim3(grid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc,
+                   counter);
+    } else {
+        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * 8);
+        FDB_LAUNCH(deflate_stored_kernel, dim3(grid), dim3(STORED_THREADS), 0, st, b, counter);
+    }
+    ctx->launches++;
+    FDB_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int deflate_device(fdb_ctx* ctx, int kind, const void* d_in_base, const uint64_t* d_in_off,
                           const uint64_t* d_in_len, void* d_out_base, const uint64_t* d_out_off,
                           const uint64_t* d_out_cap, uint64_t* d_out_len, int32_t* d_status, size_t n,
@@ -219,7 +281,6 @@ static int deflate_device(fdb_ctx* ctx, int kind, const void* d_in_base, const u
     if (n == 0) return 0;
     if (n > 0xffffffffull || !d_in_off || !d_in_len || !d_out_off || !d_out_cap || !d_out_len || !d_status)
         return fail(ctx, "fdb_deflate_batch_device", cudaSuccess);
-    cudaStream_t st = (cudaStream_t)cuda_stream;
     FDB_TRY(cudaSetDevice(ctx->device));
     DeflateBatch b;
     b.in_base = (const uint8_t*)d_in_base;
@@ -231,21 +292,7 @@ static int deflate_device(fdb_ctx* ctx, int kind, const void* d_in_base, const u
     b.out_len = d_out_len;
     b.status = d_status;
     b.n = (uint32_t)n;
-    FDB_TRY(cudaMemsetAsync(ctx->d_counters + 3, 0, sizeof(uint32_t), st));
-    const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
-    if (kind == 0) {
-        // persistent: every resident warp pulls streams from one counter, so SMs stay evenly loaded
-        // even when the batch is not a multiple of the chip's warp slots
-        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * DEFLATE_MIN_CTAS);
-        FDB_LAUNCH(deflate_uf_kernel, dim3(grid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc,
-                   ctx->d_counters + 3);
-    } else {
-        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * 8);
-        FDB_LAUNCH(deflate_stored_kernel, dim3(grid), dim3(STORED_THREADS), 0, st, b, ctx->d_counters + 3);
-    }
-    ctx->launches++;
-    FDB_TRY(cudaGetLastError());
-    return 0;
+    return launch_deflate(ctx, kind, b, ctx->d_counters + 3, (cudaStream_t)cuda_stream);
 }
 
 extern "C" int fdb_deflate_ultrafast_batch_device(fdb_ctx* ctx, const void* d_in_base, const uint64_t* d_in_off,
@@ -300,12 +347,30 @@ static bool uniform_stride(const uint64_t* off, size_t n, uint64_t* stride) {
     return true;
 }
 
+// Copies rows [a, b) of a slot array between host and device: one 2-D copy of the used prefix of every
+// slot when the slots are evenly spaced and mostly empty, else the contiguous span.
+static int copy_rows(fdb_ctx* ctx, uint8_t* dst_base, const uint8_t* src_base, const uint64_t* off, size_t a, size_t b,
+                     uint64_t width, uint64_t last_extent, bool uniform, uint64_t stride, cudaMemcpyKind kind,
+                     cudaStream_t st) {
+    const size_t rows = b - a;
+    const uint64_t span = off[b - 1] + last_extent - off[a];
+    if (uniform && rows > 1 && width <= stride && width * rows < span - span / 8) {
+        if (width) FDB_TRY(cudaMemcpy2DAsync(dst_base + off[a], stride, src_base + off[a], stride, width, rows, kind, st));
+    } else if (span) {
+        FDB_TRY(cudaMemcpyAsync(dst_base + off[a], src_base + off[a], span, kind, st));
+    }
+    return 0;
+}
+
+// Host-buffer batches run as a pipeline of chunks over FDB_LANES CUDA streams: while chunk k is in the
+// kernels, chunk k+1 is on its way to the device and chunk k-1 on its way back (PCIe is full duplex),
+// so a call costs about max(H2D, D2H) instead of H2D + kernels + D2H.
 static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
                       uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
                       uint64_t* consumed, int32_t* status, size_t n, uint32_t flags) {
     if (!ctx) return -1;
     if (n == 0) return 0;
-    if (!in_off || !in_len || !out_off || !out_cap || !out_len || !status)
+    if (n > 0xffffffffull || !in_off || !in_len || !out_off || !out_cap || !out_len || !status)
         return fail(ctx, "fdb_*_batch", cudaSuccess);
     FDB_TRY(cudaSetDevice(ctx->device));
     Span sp = spans(in_off, in_len, out_off, out_cap, n);
@@ -318,44 +383,111 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     uint64_t *d_in_off = m, *d_in_len = m + n, *d_out_off = m + 2 * n, *d_out_cap = m + 3 * n, *d_out_len = m + 4 * n,
              *d_consumed = m + 5 * n;
     int32_t* d_status = (int32_t*)(m + 6 * n);
-    cudaStream_t st = ctx->stream;
-    // ---- host -> device ----
-    uint64_t stride = 0, max_in = 0;
-    for (size_t i = 0; i < n; i++) max_in = std::max(max_in, in_len[i]);
-    if (uniform_stride(in_off, n, &stride) && max_in <= stride && max_in * n < sp.in_span - sp.in_span / 8) {
-        if (max_in)
-            FDB_TRY(cudaMemcpy2DAsync(ctx->d_in + in_off[0], stride, in_base + in_off[0], stride, max_in, n,
-                                      cudaMemcpyHostToDevice, st));
-    } else if (sp.in_span) {
-        FDB_TRY(cudaMemcpyAsync(ctx->d_in, in_base, sp.in_span, cudaMemcpyHostToDevice, st));
+
+    // chunking needs slots laid out in ascending order (what every packer produces); anything else is one chunk
+    bool ascending = true;
+    for (size_t i = 1; i < n && ascending; i++)
+        ascending = in_off[i] >= in_off[i - 1] + in_len[i - 1] && out_off[i] >= out_off[i - 1] + out_cap[i - 1];
+    size_t nchunk = 1;
+    if (ascending)
+        nchunk = (size_t)std::min<uint64_t>(std::min<uint64_t>((sp.in_span + sp.out_span) / ctx->chunk_bytes, 64), n);
+    if (nchunk < 1) nchunk = 1;
+    const size_t per = (n + nchunk - 1) / nchunk;
+    nchunk = (n + per - 1) / per;
+
+    // pinned landing area for the per-stream results
+    const size_t res_bytes = n * (8 + 8 + 4) + nchunk * 4 + 64;
+    if (res_bytes > ctx->h_res_cap) {
+        for (int l = 0; l < FDB_LANES; l++) FDB_TRY(cudaStreamSynchronize(ctx->lanes[l].st));
+        if (ctx->h_res) FDB_TRY(cudaFreeHost(ctx->h_res));
+        ctx->h_res = nullptr;
+        ctx->h_res_cap = 0;
+        FDB_TRY(cudaMallocHost((void**)&ctx->h_res, res_bytes + res_bytes / 4));
+        ctx->h_res_cap = res_bytes + res_bytes / 4;
     }
-    FDB_TRY(cudaMemcpyAsync(d_in_off, in_off, n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_in_len, in_len, n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_out_off, out_off, n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_out_cap, out_cap, n * 8, cudaMemcpyHostToDevice, st));
-    // ---- kernels ----
-    if (kind == 0)
-        r = fdb_inflate_batch_device(ctx, ctx->d_in, d_in_off, d_in_len, ctx->d_out, d_out_off, d_out_cap, d_out_len,
-                                     d_consumed, d_status, n, flags, st);
-    else
-        r = deflate_device(ctx, kind - 1, ctx->d_in, d_in_off, d_in_len, ctx->d_out, d_out_off, d_out_cap, d_out_len,
-                           d_status, n, st);
-    if (r) return r;
-    // ---- device -> host: results first (their lengths decide how much payload moves) ----
-    FDB_TRY(cudaMemcpyAsync(out_len, d_out_len, n * 8, cudaMemcpyDeviceToHost, st));
-    if (consumed && kind == 0) FDB_TRY(cudaMemcpyAsync(consumed, d_consumed, n * 8, cudaMemcpyDeviceToHost, st));
-    FDB_TRY(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st));
-    FDB_TRY(cudaStreamSynchronize(st));
-    uint64_t max_out = 0;
-    for (size_t i = 0; i < n; i++) max_out = std::max(max_out, out_len[i]);
-    if (uniform_stride(out_off, n, &stride) && max_out <= stride && max_out * n < sp.out_span - sp.out_span / 8) {
-        if (max_out)
-            FDB_TRY(cudaMemcpy2DAsync(out_base + out_off[0], stride, ctx->d_out + out_off[0], stride, max_out, n,
-                                      cudaMemcpyDeviceToHost, st));
-    } else if (sp.out_span) {
-        FDB_TRY(cudaMemcpyAsync(out_base, ctx->d_out, sp.out_span, cudaMemcpyDeviceToHost, st));
+    uint64_t* h_out_len = (uint64_t*)ctx->h_res;
+    uint64_t* h_consumed = h_out_len + n;
+    int32_t* h_status = (int32_t*)(h_consumed + n);
+    uint32_t* h_general = (uint32_t*)(h_status + n);
+
+    uint64_t in_stride = 0, out_stride = 0;
+    const bool in_uniform = uniform_stride(in_off, n, &in_stride), out_uniform = uniform_stride(out_off, n, &out_stride);
+
+    // stream descriptors: once, ahead of every lane
+    cudaStream_t st0 = ctx->lanes[0].st;
+    FDB_TRY(cudaMemcpyAsync(d_in_off, in_off, n * 8, cudaMemcpyHostToDevice, st0));
+    FDB_TRY(cudaMemcpyAsync(d_in_len, in_len, n * 8, cudaMemcpyHostToDevice, st0));
+    FDB_TRY(cudaMemcpyAsync(d_out_off, out_off, n * 8, cudaMemcpyHostToDevice, st0));
+    FDB_TRY(cudaMemcpyAsync(d_out_cap, out_cap, n * 8, cudaMemcpyHostToDevice, st0));
+    FDB_TRY(cudaEventRecord(ctx->meta_ready, st0));
+    for (int l = 1; l < FDB_LANES; l++) FDB_TRY(cudaStreamWaitEvent(ctx->lanes[l].st, ctx->meta_ready, 0));
+
+    auto issue = [&](size_t k) -> int {  // H2D, kernels, results D2H of chunk k
+        const size_t a = k * per, b = std::min(n, a + per);
+        fdb_lane& ln = ctx->lanes[k % FDB_LANES];
+        uint64_t max_in = 0;
+        for (size_t i = a; i < b; i++) max_in = std::max(max_in, in_len[i]);
+        int rr = copy_rows(ctx, ctx->d_in, in_base, in_off, a, b, max_in, in_len[b - 1], in_uniform, in_stride,
+                           cudaMemcpyHostToDevice, ln.st);
+        if (rr) return rr;
+        if (kind == 0) {
+            InflateBatch ib;
+            ib.in_base = ctx->d_in;
+            ib.in_off = d_in_off + a;
+            ib.in_len = d_in_len + a;
+            ib.out_base = ctx->d_out;
+            ib.out_off = d_out_off + a;
+            ib.out_cap = d_out_cap + a;
+            ib.out_len = d_out_len + a;
+            ib.consumed = d_consumed + a;
+            ib.status = d_status + a;
+            ib.n = (uint32_t)(b - a);
+            ib.flags = flags;
+            if ((rr = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st))) return rr;
+            FDB_TRY(cudaMemcpyAsync(h_consumed + a, d_consumed + a, (b - a) * 8, cudaMemcpyDeviceToHost, ln.st));
+            FDB_TRY(cudaMemcpyAsync(h_general + k, ln.d_counters + 1, 4, cudaMemcpyDeviceToHost, ln.st));
+        } else {
+            DeflateBatch db;
+            db.in_base = ctx->d_in;
+            db.in_off = d_in_off + a;
+            db.in_len = d_in_len + a;
+            db.out_base = ctx->d_out;
+            db.out_off = d_out_off + a;
+            db.out_cap = d_out_cap + a;
+            db.out_len = d_out_len + a;
+            db.status = d_status + a;
+            db.n = (uint32_t)(b - a);
+            if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st))) return rr;
+        }
+        FDB_TRY(cudaMemcpyAsync(h_out_len + a, d_out_len + a, (b - a) * 8, cudaMemcpyDeviceToHost, ln.st));
+        FDB_TRY(cudaMemcpyAsync(h_status + a, d_status + a, (b - a) * 4, cudaMemcpyDeviceToHost, ln.st));
+        return 0;
+    };
+    auto finish = [&](size_t k) -> int {  // the results decide how much payload comes back
+        const size_t a = k * per, b = std::min(n, a + per);
+        fdb_lane& ln = ctx->lanes[k % FDB_LANES];
+        FDB_TRY(cudaStreamSynchronize(ln.st));
+        uint64_t max_out = 0;
+        for (size_t i = a; i < b; i++) max_out = std::max(max_out, h_out_len[i]);
+        return copy_rows(ctx, out_base, ctx->d_out, out_off, a, b, max_out, h_out_len[b - 1], out_uniform, out_stride,
+                         cudaMemcpyDeviceToHost, ln.st);
+    };
+    const size_t depth = FDB_LANES - 1;  // chunks in flight ahead of the one being finished
+    for (size_t k = 0; k < nchunk; k++) {
+        if ((r = issue(k))) return r;
+        if (k >= depth && (r = finish(k - depth))) return r;
     }
-    FDB_TRY(cudaStreamSynchronize(st));
+    for (size_t k = nchunk > depth ? nchunk - depth : 0; k < nchunk; k++)
+        if ((r = finish(k))) return r;
+    for (int l = 0; l < FDB_LANES; l++) FDB_TRY(cudaStreamSynchronize(ctx->lanes[l].st));
+    memcpy(out_len, h_out_len, n * 8);
+    memcpy(status, h_status, n * 4);
+    if (kind == 0) {
+        if (consumed) memcpy(consumed, h_consumed, n * 8);
+        int64_t g = 0;
+        for (size_t k = 0; k < nchunk; k++) g += h_general[k];
+        ctx->last_general_host = (flags & FDB_FLAG_GENERAL_ONLY) ? 0 : g;
+    }
     return 0;
 }
 

@@ -123,6 +123,12 @@ int fdb_synth_tiles_host(uint8_t* out, uint64_t first_tile, uint64_t n_tiles, ui
 int fdb_synth_tiles_device(fdb_ctx* ctx, void* d_out, uint64_t first_tile, uint64_t n_tiles, uint32_t width,
                            uint32_t height, uint64_t seed, void* cuda_stream);
 
+/* Host-buffer batches (fdb_inflate_batch, fdb_deflate_*_batch) are pipelined: the batch is cut into
+ * chunks of about `bytes` of slot span and chunk k+1 is copied to the device while chunk k is in the
+ * kernels and chunk k-1 is copied back.  0 restores the default (128 MiB).  A tuning knob, not part of
+ * the reference's interface; results do not depend on it. */
+int fdb_set_pipeline_chunk(fdb_ctx* ctx, size_t bytes);
+
 /* number of kernels this library has launched through ctx since creation (bench bookkeeping) */
 uint64_t fdb_launch_count(const fdb_ctx* ctx);
 /* how many streams of the most recent inflate batch on this context were declined by the

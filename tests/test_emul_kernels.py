@@ -81,3 +81,25 @@ def test_batch_composition_invariance(emul_ctx, oracle):
     sh = emul_ctx.inflate_batch([c[i][0] for i in perm], [c[i][1] for i in perm])
     for k, i in enumerate(perm):
         assert sh[0][k] == base[0][i] and sh[1][k] == base[1][i]
+
+
+def test_host_pipeline_chunking_does_not_change_results(emul_ctx, oracle):
+    """The host-buffer entry points cut a batch into chunks that overlap copies and kernels; results
+    must not depend on the chunk size (here: tiny chunks, so every batch becomes many chunks)."""
+    rng = random.Random(12)
+    inputs = cases.compress_inputs(9, 12, [100, 3000, 20000])
+    mixed = cases.mixed_zlib_cases(31, 8, [0, 100, 5000])
+    uf = [(oracle.compress_ultra_fast(d), len(d)) for d in inputs[:40]]
+    try:
+        emul_ctx.set_pipeline_chunk(4096)
+        parity.check_deflate_ultrafast(emul_ctx, inputs, align=16)
+        parity.check_deflate_stored(emul_ctx, inputs[:20], align=16)
+        parity.check_inflate(emul_ctx, uf, 0, expect_general=0)
+        parity.check_inflate(emul_ctx, mixed + uf, 0)
+        parity.check_inflate(emul_ctx, mixed, FLAG_GENERAL_ONLY)
+        dmg = []
+        for s, c in uf[:10]:
+            dmg += cases.damaged(rng, s, c)
+        parity.check_inflate(emul_ctx, dmg, 0)
+    finally:
+        emul_ctx.set_pipeline_chunk(0)

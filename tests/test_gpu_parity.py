@@ -172,3 +172,25 @@ def test_synth_host_and_device_agree(gpu_ctx):
     gpu_ctx.synth_tiles_device(d.data_ptr(), 5, 3, 256, 256, 77, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(d.cpu().numpy().reshape(3, 262400), h)
+
+
+def test_host_pipeline_chunking_does_not_change_results(gpu_ctx, oracle):
+    """Host-buffer batches overlap copies and kernels chunk by chunk over several CUDA streams; results
+    must not depend on the chunk size (tiny chunks here: every batch becomes up to 64 chunks)."""
+    rng = random.Random(12)
+    inputs = cases.compress_inputs(9, 40, [100, 3000, 20000, 70000])
+    mixed = cases.mixed_zlib_cases(31, 30, [0, 100, 5000, 50000])
+    uf = [(oracle.compress_ultra_fast(d), len(d)) for d in inputs]
+    try:
+        gpu_ctx.set_pipeline_chunk(16384)
+        parity.check_deflate_ultrafast(gpu_ctx, inputs, align=16)
+        parity.check_deflate_stored(gpu_ctx, inputs[:30], align=16)
+        parity.check_inflate(gpu_ctx, uf, 0, expect_general=0)
+        parity.check_inflate(gpu_ctx, mixed + uf, 0)
+        parity.check_inflate(gpu_ctx, mixed, FLAG_GENERAL_ONLY)
+        dmg = []
+        for s, c in uf[:20]:
+            dmg += cases.damaged(rng, s, c)
+        parity.check_inflate(gpu_ctx, dmg, 0)
+    finally:
+        gpu_ctx.set_pipeline_chunk(0)
