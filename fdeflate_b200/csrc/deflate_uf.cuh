@@ -23,6 +23,8 @@
 #pragma once
 #include "simt.h"
 #include "fdb_common.h"
+#include <type_traits>
+
 #include "adler.cuh"
 
 namespace fdb {
@@ -73,13 +75,12 @@ struct BitPacker {
     FDB_MEMBER void emit(uint32_t v, uint32_t n) {  // v < 2^n, n <= 32
         const uint64_t sh = (uint64_t)v << accn;
         lo |= (uint32_t)sh;
-        hi |= (uint32_t)(sh >> 32);
+        hi = (uint32_t)(sh >> 32);  // (hi carries nothing between emits: accn < 32)
         accn += n;
         if (accn >= 32) {
             simt::sts32(wa, lo);
             wa += 4;
             lo = hi;
-            hi = 0;
             accn -= 32;
         }
     }
@@ -122,13 +123,13 @@ FDB_DEVICE void chunk_plan(ChunkPlan& t, uint64_t nz /* the chunk, little-endian
     // the run ends inside this chunk (:54-64, :105-108)
     const bool ends = z != 0 && !(allz && cont);
     const uint32_t n0 = (k2 && allz && !pending) ? 2u : 0u;  // lit 0 opens a run inside an all-zero chunk (:46)
-    const uint32_t tt = ends ? tail_tok[wrap ? q - 258u : q] : 0u;
+    const uint32_t tt = tail_tok[ends ? (wrap ? q - 258u : q) : 0u];  // (tail_tok[0] == 0: nothing owed)
     const uint32_t n1 = cross ? n0 + 10u : n0;
     t.head_v = (cross ? (UF_CODE285_DIST1 << n0) : 0u) | ((tt & 0xffffffu) << n1);
     t.head_n = n1 + (tt >> 24);
     // trailing zeros open a new run (:111, :130): lit 0, then the run's tail if it ends right here
     const bool has_tail = k2 && trail != 0;
-    const uint32_t tt2 = (has_tail && !cont) ? tail_tok[trail - 1u] : 0u;
+    const uint32_t tt2 = tail_tok[(has_tail && !cont) ? trail - 1u : 0u];
     t.tail_v = (tt2 & 0xffffffu) << 2;
     t.tail_n = (has_tail ? 2u : 0u) + (tt2 >> 24);
     // one bit per byte that stays a literal: positions [z, 8 - trail); the final partial chunk keeps `rem`
@@ -221,7 +222,10 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok
     // "is the first byte of the next step zero": needed by lane 31 long before that step's data, so it
     // is fetched one step earlier than the data itself
     uint32_t nfb_next = iters > 1 ? simt::ldg8(in + 512) : 1u;  // (the raw byte: compared when it is used)
-    for (uint64_t it = 0; it < iters; it++) {
+    // One 512-byte warp step.  FULL: every chunk of the step is a whole chunk inside the run-logic prefix
+    // (all steps of a stream but the last one or two), which removes every end-of-input test.
+    auto step = [&](uint64_t it, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
         const uint64_t base = it << 9;
         const uint64_t g = base + (uint64_t)lane * 16;
         uint4 q = nxt;
@@ -230,7 +234,7 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok
         if (it + 2 < iters) nfb_next = simt::ldg8(in + base + 1024);
 
         // adler partial sums
-        if (g + 16 <= n) {
+        if (FULL || g + 16 <= n) {
             adler_add16(ad, q, g);
             if ((it & 63) == 63) adler_fold(ad);
         } else if (g < n) {
@@ -242,7 +246,7 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok
         const uint64_t nz0 = c0, nz1 = c1;  // (only "== 0", ctz and clz are taken of these)
         // chunk kinds: 2 = whole chunk in the run-logic prefix, 1 = the final partial chunk, 0 = past the end
         uint32_t k0 = 2u, k1 = 2u;
-        if (base + 512 > n8) {  // only the last warp step of a stream
+        if (!FULL) {  // only the last warp step(s) of a stream
             k0 = (g + 8 <= n8) ? 2u : (g == n8 && rem) ? 1u : 0u;
             k1 = (g + 16 <= n8) ? 2u : (g + 8 == n8 && rem) ? 1u : 0u;
         }
@@ -352,9 +356,19 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok
             const uint32_t fit = cap_words > wbase ? (uint32_t)(cap_words - wbase < nwords ? cap_words - wbase : nwords) : 0u;
             uint32_t* const dst = obase + wbase;
             if (fit < nwords) overflow = true;
-            for (uint32_t k = lane; k < fit; k += 32) dst[k] = simt::lds32(stg_s + 4u * k);
+            // a step normally completes ~55 words: two straight-line rounds, then a loop for the rest
+            if (lane < fit) dst[lane] = simt::lds32(stg_s + 4u * lane);
+            if (lane + 32 < fit) dst[lane + 32] = simt::lds32(stg_s + 4u * lane + 128u);
+#pragma unroll 1
+            for (uint32_t k = lane + 64; k < fit; k += 32) dst[k] = simt::lds32(stg_s + 4u * k);
         }
         simt::syncwarp();
+    };
+    for (uint64_t it = 0; it < iters; it++) {
+        if ((it << 9) + 512 <= n8)
+            step(it, std::true_type{});
+        else
+            step(it, std::false_type{});
     }
 
     // ---- finish (ultrafast.rs:170-181): EOB, pad to a byte, adler32 big-endian ----

@@ -133,14 +133,16 @@ FDB_HD uint32_t make_dist_entry(uint32_t sym, uint32_t nbits) {
 //   [3:0] bits consumed by the 1..6 leading literals / the one short run     [15:12] bytes they produce
 //   [4] RUN: the entry is a short-run token   [5] ENDNZ: its last byte is non-zero
 //   [6] FIRSTNZ: its first token is a non-zero literal   [10:7] bits of the first token alone
-// Both tables are stored SWIZZLED: the entry for index x lives at slot uf_slot(x).  The low index bits
-// are the first code of the window and are far from uniform (39 % of the bench bytes are the 2-bit
-// code 00), so an unswizzled table sends most lanes to a few banks (measured 4.1-4.9 wavefronts per
-// lookup); folding the high six bits in spreads them.
+// Both tables are stored BIT-REVERSED: the entry for index x lives at slot uf_slot(x) = the 12 index
+// bits in reverse order.  The low index bits are the first code of the window and are far from uniform
+// (39 % of the bench bytes are the 2-bit code 00), so a table in natural order sends most lanes to a
+// few banks (measured 4.1-4.9 wavefronts per lookup); reversed, the bank is chosen by index bits 7..11.
+// On the device this is BREV + one shift, cheaper than masking the index.
 enum : uint32_t { UC_RUN = 1u << 4, UC_ENDNZ = 1u << 5, UC_FIRSTNZ = 1u << 6, UW_EOB = 1u << 7 };
 FDB_HD uint32_t uf_slot(uint32_t bits) {
-    const uint32_t x = bits & 0xfffu;
-    return x ^ (x >> 6);
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < 12; i++) r |= ((bits >> i) & 1u) << (11u - i);
+    return r;
 }
 
 static const uint32_t ADLER_MOD = 65521u;

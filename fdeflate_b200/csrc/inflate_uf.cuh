@@ -77,8 +77,8 @@ struct UfDecTables {
 struct UfTabs {
     simt::saddr wt, ct;
 };
-FDB_DEVICE uint32_t wt_at(const UfTabs& t, uint32_t bits) { return simt::lds32_ro(t.wt + (uf_slot(bits) << 2)); }
-FDB_DEVICE uint32_t ct_at(const UfTabs& t, uint32_t bits) { return simt::lds16_ro(t.ct + (uf_slot(bits) << 1)); }
+FDB_DEVICE uint32_t wt_at(const UfTabs& t, uint32_t bits) { return simt::lds32_ro(t.wt + ((simt::brev(bits) >> 18) & 0x3ffcu)); }  // 4 * uf_slot(bits)
+FDB_DEVICE uint32_t ct_at(const UfTabs& t, uint32_t bits) { return simt::lds16_ro(t.ct + ((simt::brev(bits) >> 19) & 0x1ffeu)); }  // 2 * uf_slot(bits)
 
 // lane-private LSB-first bit reader over the lane's staging row: a 32-bit window is one funnel
 // shift of (w0, w1); w2 is fetched one word ahead so the shared-memory latency stays off the
