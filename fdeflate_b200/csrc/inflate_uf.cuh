@@ -312,6 +312,18 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
     // Store the finished vectors win[0 .. 16*nvec) at virtual position win_vo, feed adler32, and zero
     // them again.  Bytes outside [oalign, stream_end_vo) (first / last vector of the stream) are masked.
     auto flush_vectors = [&](uint32_t nvec, uint64_t stream_end_vo) {
+        if (win_vo >= oalign && win_vo + 16ull * nvec <= stream_end_vo) {
+            // every vector lies inside the stream (all segments but the first / last of a stream)
+            uint8_t* const dst = obase + win_vo;
+            const uint64_t pos0 = win_vo - oalign;
+            for (uint32_t v = lane; v < nvec; v += 32) {
+                uint4 q = ((const uint4*)win)[v];
+                ((uint4*)win)[v] = make_uint4(0, 0, 0, 0);
+                simt::stcs128((uint4*)(dst + 16u * v), q);
+                adler_add16(ad, q, pos0 + 16u * v);
+            }
+            return;
+        }
         for (uint32_t v = lane; v < nvec; v += 32) {
             uint4 q = ((const uint4*)win)[v];
             ((uint4*)win)[v] = make_uint4(0, 0, 0, 0);
@@ -343,12 +355,20 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
         simt::syncwarp();
         // (lane l takes vectors 2l, 2l+1, then 64+l: within one store instruction every lane writes a
         // different row, i.e. a different bank)
+        const bool seg_inside = (s0 << 2) >= first_byte && (s0 << 2) + 4ull * K4_SEG_WORDS <= end_byte;
+        if (seg_inside) {
+            // the next segment's lines are needed in a few thousand cycles: start them towards L2 now
+            const uint64_t pf = (s0 << 2) + 4u * 32u * K4_SUBW + 128u * lane;
+            if (lane < 9 && pf < end_byte) simt::prefetch_l2(abase + pf);  // (only lines that hold stream bytes)
+        }
         for (uint32_t it = 0; it < 3; it++) {
             const uint32_t v = it < 2 ? 2u * lane + it : 64u + lane;
             if (v >= K4_SEG_WORDS / 4) continue;
             uint64_t byte0 = (s0 << 2) + 16ull * v;  // relative to abase
             uint4 q = make_uint4(0, 0, 0, 0);
-            if (byte0 + 16 > first_byte && byte0 < end_byte) {
+            if (seg_inside) {
+                q = simt::ldg128((const uint4*)(abase + byte0));
+            } else if (byte0 + 16 > first_byte && byte0 < end_byte) {
                 q = simt::ldg128((const uint4*)(abase + byte0));
                 if (byte0 < first_byte || byte0 + 16 > end_byte) {
                     uint32_t w[4] = {q.x, q.y, q.z, q.w};
