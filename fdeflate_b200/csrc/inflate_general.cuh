@@ -286,10 +286,73 @@ struct OutCursor {
     uint64_t cap;
 };
 
+// Matches are not executed one by one: the warp keeps decoding and parks up to 32 of them, one per
+// lane, then executes the whole batch at once.  A match whose source ends before the first parked
+// destination cannot depend on any match of the batch ("early": every lane copies its own, all loads
+// in flight together -- the global round trip is paid once per batch instead of once per match);
+// the others ("late": overlapping or near sources, e.g. distance-1 runs) follow in stream order with
+// the warp-wide copy.  Literals are stored directly; they never alias a parked destination.
+struct MatchQueue {
+    uint64_t dst;   // this lane's parked match: output position,
+    uint32_t len;   //   bytes to produce (already clipped to the slot),
+    uint32_t dist;  //   distance
+    uint32_t qn;    // matches parked (warp-uniform)
+};
+
+FDB_DEVICE void mq_flush(uint8_t* out, MatchQueue& q) {
+    const unsigned lane = simt::lane_id();
+    if (q.qn == 0) return;
+    simt::syncwarp();  // literal stores by lane 0/1 must be visible to the loads below
+    const bool active = lane < q.qn;
+    const uint64_t first_dst = simt::shfl(q.dst, 0);
+    const bool early = active && (q.dst - q.dist + q.len <= first_dst);
+    if (early) {
+        uint8_t* d = out + q.dst;
+        const uint8_t* s = d - q.dist;
+        uint32_t i = 0;
+        for (; i + 8 <= q.len; i += 8) {  // eight independent loads, then eight stores
+            uint8_t b0 = s[i], b1 = s[i + 1], b2 = s[i + 2], b3 = s[i + 3];
+            uint8_t b4 = s[i + 4], b5 = s[i + 5], b6 = s[i + 6], b7 = s[i + 7];
+            d[i] = b0; d[i + 1] = b1; d[i + 2] = b2; d[i + 3] = b3;
+            d[i + 4] = b4; d[i + 5] = b5; d[i + 6] = b6; d[i + 7] = b7;
+        }
+        uint8_t t[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) t[j] = (i + j < q.len) ? s[i + j] : (uint8_t)0;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++)
+            if (i + j < q.len) d[i + j] = t[j];
+    }
+    uint32_t late = simt::ballot(active && !early);
+    while (late) {
+        const uint32_t k = simt::ffs(late) - 1;
+        late &= late - 1;
+        const uint64_t kd = simt::shfl(q.dst, k);
+        const uint32_t n = simt::shfl(q.len, k), d32 = simt::shfl(q.dist, k);
+        simt::syncwarp();  // everything before this match in stream order is complete
+        uint8_t* d = out + kd;
+        const uint8_t* s = d - d32;
+        if (d32 >= n) {
+            for (uint32_t i = lane; i < n; i += 32) d[i] = s[i];
+        } else {
+            for (uint32_t i = lane; i < n; i += 32) d[i] = s[i % d32];
+        }
+    }
+    simt::syncwarp();
+    q.qn = 0;
+}
+
 FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t eof_code, uint32_t eof_bits,
                                 bool* too_large) {
     const unsigned lane = simt::lane_id();
     const uint32_t eof_mask = (1u << eof_bits) - 1u;
+    MatchQueue mq = {0, 0, 0, 0};
+// every way out of the block first completes the parked matches
+#define K3_RETURN(x)          \
+    do {                      \
+        mq_flush(o.out, mq);  \
+        return (x);           \
+    } while (0)
     for (;;) {
         br_refill(r);
         uint64_t avail = br_avail(r);
@@ -297,22 +360,22 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
             // output exactly full: only an end-of-block code may follow (EOB peek, :1009-1015)
             if (avail >= 15 && (br_peek(r, 15) & eof_mask) == eof_code) {
                 br_consume(r, eof_bits);
-                return ST_OK;
+                K3_RETURN(ST_OK);
             }
             *too_large = true;
-            return ST_OK;
+            K3_RETURN(ST_OK);
         }
         uint32_t e = s.litlen[br_peek(r, 12)];
         uint32_t nbits = e & 15u;
         if (e & LL_LIT) {  // :846-877
-            if (avail < nbits) return ST_INSUFFICIENT_INPUT;
+            if (avail < nbits) K3_RETURN(ST_INSUFFICIENT_INPUT);
             bool two = (e & LL_LIT2) != 0;
             if (lane == 0) o.out[o.pos] = (uint8_t)(e >> 8);
             if (two && o.pos + 1 == o.cap) {  // second literal does not fit (queued in the reference)
                 o.pos += 1;
                 br_consume(r, nbits);
                 *too_large = true;
-                return ST_OK;
+                K3_RETURN(ST_OK);
             }
             if (two && lane == 1) o.out[o.pos + 1] = (uint8_t)(e >> 16);
             o.pos += two ? 2 : 1;
@@ -321,17 +384,17 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
         }
         uint32_t len_base, len_extra;
         if (e & LL_EOB) {  // :910-918 (includes the 286/287 quirk)
-            if (avail < nbits) return ST_INSUFFICIENT_INPUT;
+            if (avail < nbits) K3_RETURN(ST_INSUFFICIENT_INPUT);
             br_consume(r, nbits);
-            return ST_OK;
+            K3_RETURN(ST_OK);
         } else if (e & LL_LEN) {
             len_base = (e >> 16) & 0x1ffu;
             len_extra = (e >> 8) & 7u;
         } else {  // code longer than 12 bits (:886-909)
             uint32_t sym = 0;
             if (!canon_long_decode(s, 0, s.sorted_lit, br_peek(r, 15), 13, &sym, &nbits))
-                return ST_INVALID_LITERAL_LENGTH_CODE;
-            if (avail < nbits) return ST_INSUFFICIENT_INPUT;
+                K3_RETURN(ST_INVALID_LITERAL_LENGTH_CODE);
+            if (avail < nbits) K3_RETURN(ST_INSUFFICIENT_INPUT);
             if (sym < 256) {
                 if (lane == 0) o.out[o.pos] = (uint8_t)sym;
                 o.pos += 1;
@@ -339,7 +402,7 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
                 continue;
             } else if (sym == 256) {
                 br_consume(r, nbits);
-                return ST_OK;
+                K3_RETURN(ST_OK);
             }
             len_base = len_sym_base(sym);
             len_extra = len_sym_extra(sym);
@@ -356,41 +419,38 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
             dextra = (de >> 4) & 15u;
             dbase = de >> 16;
         } else if (avail > (uint64_t)le_bits + 9) {  // :932-951
-            if (!(de & DS_LONG)) return ST_INVALID_DISTANCE_CODE;
+            if (!(de & DS_LONG)) K3_RETURN(ST_INVALID_DISTANCE_CODE);
             uint32_t dsym = 0;
             if (!canon_long_decode(s, 1, s.sorted_dist, br_peek(r, 15), 10, &dsym, &dbits))
-                return ST_INVALID_DISTANCE_CODE;
-            if (dsym >= 30) return ST_INVALID_DISTANCE_CODE;
+                K3_RETURN(ST_INVALID_DISTANCE_CODE);
+            if (dsym >= 30) K3_RETURN(ST_INVALID_DISTANCE_CODE);
             dextra = dist_sym_extra(dsym);
             dbase = dist_sym_base(dsym);
         } else {
-            return ST_INSUFFICIENT_INPUT;  // `break` with the input exhausted
+            K3_RETURN(ST_INSUFFICIENT_INPUT);  // `break` with the input exhausted
         }
         uint32_t dd_bits = dbits + dextra;  // <= 28
         uint64_t dist = dbase + ((br_peek(r, dd_bits) >> dbits) & ((1u << dextra) - 1u));
-        if (avail < (uint64_t)le_bits + dd_bits) return ST_INSUFFICIENT_INPUT;  // :961
-        if (dist > o.pos) return ST_DISTANCE_TOO_FAR_BACK;                        // :963
+        if (avail < (uint64_t)le_bits + dd_bits) K3_RETURN(ST_INSUFFICIENT_INPUT);  // :961
+        if (dist > o.pos) K3_RETURN(ST_DISTANCE_TOO_FAR_BACK);                        // :963
         br_consume(r, dd_bits);
 
         uint64_t room = o.cap - o.pos;
         uint32_t n = length < room ? length : (uint32_t)room;
-        simt::syncwarp();  // earlier stores by other lanes must be visible to the loads below
-        {
-            uint8_t* dst = o.out + o.pos;
-            const uint8_t* src = dst - dist;
-            if (dist >= n) {
-                for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
-            } else {
-                uint32_t d32 = (uint32_t)dist;
-                for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i % d32];
-            }
+        if (lane == mq.qn) {
+            mq.dst = o.pos;
+            mq.len = n;
+            mq.dist = (uint32_t)dist;
         }
+        mq.qn++;
         o.pos += n;
         if (n < length) {  // remainder would be queued (:797-801, :823-827) => output too large
             *too_large = true;
-            return ST_OK;
+            K3_RETURN(ST_OK);
         }
+        if (mq.qn == 32) mq_flush(o.out, mq);
     }
+#undef K3_RETURN
 }
 
 // ---- whole stream --------------------------------------------------------------------------
