@@ -42,6 +42,10 @@ struct K3Smem {
     uint8_t cl_lens[32];
     uint8_t cl_table[128];  // (sym << 3) | len
     uint32_t info[4];       // [0] max_len [1] complete flag
+    // parallel block decode (decode_block_parallel): transposed per-lane staging rows and the
+    // parked matches of one segment in stream order
+    uint32_t pstg[17 * 32];
+    uint2 pmatch[640];      // {x = destination relative to the segment's first byte, y = len | dist << 16}
 };
 
 // ---- bit reader: warp-shuffle reservoir over coalesced chunk loads ---------------------------
@@ -342,6 +346,453 @@ FDB_DEVICE void mq_flush(uint8_t* out, MatchQueue& q) {
     q.qn = 0;
 }
 
+// ---- parallel block decode ---------------------------------------------------------------------
+// The scheme of K4 (inflate_uf.cuh) with the block's OWN tables: per segment of 32 x 8 words every lane
+// decodes a different sub-sequence of the block.  Lanes warm up on the 128 bits before their
+// sub-sequence (Huffman codes self-synchronise), count the bytes and matches of their tokens, the chain
+// "my start == my predecessor's end" is verified from lane 0 (exact) upwards, scans give every token
+// its output position, then lanes decode again: literals go straight to their final place, matches
+// are parked in stream order and executed 32 at a time (mq-style early / late split).
+// It only ever COMMITS regular segments.  On anything else -- a code or distance it cannot decode,
+// a distance too far back, the slot or the input running out, too many matches -- it stops at the last
+// committed token boundary and the sequential reader (exact reference semantics) carries on from there.
+static const uint32_t P_SUBW = 8, P_WARM = 4, P_TAILW = 4;
+static const uint32_t P_ROWW = P_WARM + P_SUBW + P_TAILW;        // 16 words seen by one lane (+1 look-ahead)
+static const uint32_t P_SEG_WORDS = P_WARM + 32 * P_SUBW + 4;    // staged per segment (vectors of 4)
+static const uint32_t P_LIM_LO = 32u * P_WARM, P_LIM_HI = 32u * (P_WARM + P_SUBW);
+static const uint32_t P_MAXM = 640;
+static const uint32_t P_INVALID = 0xffffffffu;
+
+struct GLane {  // lane-private LSB-first reader over a transposed staging row (cf. LaneBits in inflate_uf.cuh)
+    uint32_t w0, w1, w2, rp;
+    const uint32_t* nx;
+};
+FDB_DEVICE void gl_start(GLane& b, const uint32_t* row, uint32_t rp) {
+    b.rp = rp;
+    const uint32_t* p = row + (rp >> 5) * 32;
+    b.w0 = p[0];
+    b.w1 = p[32];
+    b.w2 = p[64];
+    b.nx = p + 96;
+}
+FDB_DEVICE void gl_advance(GLane& b, uint32_t n) {  // n <= 48
+    if (n >= 32) {
+        b.w0 = b.w1;
+        b.w1 = b.w2;
+        b.w2 = *b.nx;
+        b.nx += 32;
+        b.rp += 32;
+        n -= 32;
+    }
+    const uint32_t nrp = b.rp + n;
+    if ((nrp ^ b.rp) & 32u) {
+        b.w0 = b.w1;
+        b.w1 = b.w2;
+        b.w2 = *b.nx;
+        b.nx += 32;
+    }
+    b.rp = nrp;
+}
+
+enum : uint32_t { GT_LIT = 0, GT_MATCH = 1, GT_EOB = 2, GT_BAD = 3 };
+struct GTok {
+    uint32_t kind;
+    uint32_t nbits;  // bits of the token (both literals of a pair)
+    uint32_t bytes;  // bytes it produces
+    uint32_t lit;    // literal(s), first in the low byte
+    uint32_t dist;
+};
+// One token at the reader's position.  A literal pair is split when its second literal would start
+// at or after `limit` (sub-sequences hand over on token boundaries).
+FDB_DEVICE void g_token(const K3Smem& s, const GLane& b, uint32_t limit, GTok& t) {
+    const uint32_t bits = simt::funnel_r(b.w0, b.w1, b.rp);
+    const uint32_t e = s.litlen[bits & 0xfffu];
+    uint32_t nbits = e & 15u;
+    t.dist = 0;
+    if (e & LL_LIT) {
+        const uint32_t l1 = (e >> 24) & 15u;
+        const bool two = (e & LL_LIT2) != 0 && b.rp + l1 < limit;
+        t.kind = GT_LIT;
+        t.nbits = two ? nbits : l1;
+        t.bytes = two ? 2u : 1u;
+        t.lit = (e >> 8) & (two ? 0xffffu : 0xffu);
+        return;
+    }
+    uint32_t len_base, len_extra;
+    if (e & LL_EOB) {  // (includes the fixed-code 286/287 quirk)
+        t.kind = GT_EOB;
+        t.nbits = nbits;
+        t.bytes = 0;
+        t.lit = 0;
+        return;
+    } else if (e & LL_LEN) {
+        len_base = (e >> 16) & 0x1ffu;
+        len_extra = (e >> 8) & 7u;
+    } else {  // code longer than the table
+        uint32_t sym = 0;
+        if (!canon_long_decode(s, 0, s.sorted_lit, bits & 0x7fffu, 13, &sym, &nbits)) {
+            t.kind = GT_BAD;
+            t.nbits = 0;
+            t.bytes = 0;
+            t.lit = 0;
+            return;
+        }
+        if (sym <= 256) {
+            t.kind = sym < 256 ? GT_LIT : GT_EOB;
+            t.nbits = nbits;
+            t.bytes = sym < 256 ? 1u : 0u;
+            t.lit = sym & 0xffu;
+            return;
+        }
+        len_base = len_sym_base(sym);
+        len_extra = len_sym_extra(sym);
+    }
+    const uint32_t n1 = nbits + len_extra;  // <= 20
+    const uint32_t length = len_base + ((bits >> nbits) & ((1u << len_extra) - 1u));
+    const uint32_t hi = simt::funnel_r(b.w1, b.w2, b.rp);
+    const uint32_t dw = simt::funnel_r(bits, hi, n1);  // the 32 bits behind the length
+    const uint32_t de = s.dist[dw & 0x1ffu];
+    uint32_t dbits, dextra, dbase;
+    if (de & DS_VALID) {
+        dbits = de & 15u;
+        dextra = (de >> 4) & 15u;
+        dbase = de >> 16;
+    } else {
+        uint32_t dsym = 0;
+        if (!(de & DS_LONG) || !canon_long_decode(s, 1, s.sorted_dist, dw & 0x7fffu, 10, &dsym, &dbits) ||
+            dsym >= 30) {
+            t.kind = GT_BAD;
+            t.nbits = 0;
+            t.bytes = 0;
+            t.lit = 0;
+            return;
+        }
+        dextra = dist_sym_extra(dsym);
+        dbase = dist_sym_base(dsym);
+    }
+    t.kind = GT_MATCH;
+    t.nbits = n1 + dbits + dextra;  // <= 48
+    t.bytes = length;
+    t.lit = 0;
+    t.dist = dbase + ((dw >> dbits) & ((1u << dextra) - 1u));
+}
+
+struct GCount {
+    uint32_t end;    // first token boundary >= LIM_HI (row-relative), or the position of the EOB code
+    uint32_t cnt;    // bytes produced by the tokens in [start, end)
+    uint32_t nm;     // matches among them
+    uint32_t flags;  // GF_*
+    uint32_t eobn;   // bits of the EOB code (with GF_EOB)
+};
+enum : uint32_t { GF_EOB = 1, GF_BAD = 2 };
+
+FDB_DEVICE GCount g_count(const K3Smem& s, const uint32_t* row, uint32_t start, bool active) {
+    GCount c = {P_INVALID, 0, 0, 0, 0};
+    GLane b;
+    gl_start(b, row, active ? start : 0u);
+    uint32_t cnt = 0, nm = 0, flags = 0, eobn = 0;
+    bool stop = !active;
+    while (!stop && b.rp < P_LIM_HI) {
+        GTok t;
+        g_token(s, b, P_LIM_HI, t);
+        if (t.kind >= GT_EOB) {
+            flags |= t.kind == GT_EOB ? GF_EOB : GF_BAD;
+            eobn = t.nbits;
+            stop = true;
+        } else {
+            cnt += t.bytes;
+            nm += t.kind;  // GT_MATCH == 1
+            gl_advance(b, t.nbits);
+        }
+    }
+    if (active) {
+        c.end = b.rp;
+        c.cnt = cnt;
+        c.nm = nm;
+        c.flags = flags;
+        c.eobn = eobn;
+    }
+    return c;
+}
+
+FDB_DEVICE uint32_t g_warm_up(const K3Smem& s, const uint32_t* row, bool active) {
+    GLane b;
+    gl_start(b, row, 0u);
+    bool stop = !active, dead = false;
+    while (!stop && b.rp < P_LIM_LO) {
+        GTok t;
+        g_token(s, b, P_LIM_LO, t);
+        if (t.kind >= GT_EOB) {  // speculative end of block / undecodable: this lane has no valid guess
+            dead = true;
+            stop = true;
+        } else {
+            gl_advance(b, t.nbits);
+        }
+    }
+    return (active && !dead) ? b.rp : P_INVALID;
+}
+
+// Returns true when the block ended here (EOB consumed, r positioned behind it); false when the
+// sequential decoder has to continue from (r, o), which then sit on the last committed token boundary.
+FDB_DEVICE bool decode_block_parallel(K3Smem& s, BitReader& r, OutCursor& o) {
+    const unsigned lane = simt::lane_id();
+    uint32_t* stg = s.pstg;
+    const uint32_t* row = s.pstg + lane;
+    // virtual bit / byte coordinates relative to a 16-byte aligned base at or below the stream
+    // (the base lies 64 bytes further down so that the warm-up words of the first segment have
+    // non-negative indices; nothing below the stream's first byte is ever loaded)
+    const uint8_t* in = r.abase + r.first_byte;
+    const uint8_t* abase = (const uint8_t*)((uintptr_t)in & ~(uintptr_t)15) - 64;
+    const uint64_t first_byte = (uint64_t)((uintptr_t)in & 15u) + 64;
+    const uint64_t end_byte = first_byte + (r.tot >> 3);
+    uint64_t p0 = first_byte * 8 + r.pos;  // true bit position of the next token
+    bool ended = false;
+
+    for (;;) {
+        // enough input for a whole segment plus look-ahead, and room for the typical output?
+        const uint64_t seg_word = ((p0 >> 5) >> 2) << 2;
+        const uint64_t s0 = seg_word - P_WARM;
+        if (((s0 + P_SEG_WORDS) << 2) + 8 > end_byte) break;  // near the end of the input: sequential
+        if (o.cap - o.pos < 4096) break;
+
+        // ---- stage (as in K4: lane l takes vectors 2l, 2l+1, then 64+l; every store hits its own bank) ----
+        simt::syncwarp();
+        for (uint32_t it = 0; it < 3; it++) {
+            const uint32_t v = it < 2 ? 2u * lane + it : 64u + lane;
+            if (v >= P_SEG_WORDS / 4) continue;
+            const uint64_t byte0 = (s0 << 2) + 16ull * v;
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (byte0 + 16 > first_byte) {
+                q = simt::ldg128((const uint4*)(abase + byte0));
+                if (byte0 < first_byte) {  // bytes in front of the stream read as 0
+                    uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                    for (uint32_t j = 0; j < 16; j++)
+                        if (byte0 + j < first_byte) w[j >> 2] &= ~(0xffu << (8u * (j & 3u)));
+                    q = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            const uint32_t r1 = v >> 1, c1 = (v & 1) * 4;
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) {
+                if (r1 < 32) stg[(c1 + j) * 32 + r1] = w4[j];
+                if (r1 >= 1 && r1 <= 32) stg[(c1 + j + 8) * 32 + (r1 - 1)] = w4[j];
+            }
+        }
+        simt::syncwarp();
+
+        // ---- warm up, count ----
+        uint32_t start = g_warm_up(s, row, lane != 0);
+        if (lane == 0) start = (uint32_t)(p0 - (s0 << 5));
+        GCount c = g_count(s, row, start, start != P_INVALID);
+
+        // ---- verify the chain (rows are 32 * SUBW bits apart) ----
+        uint32_t eob_lane = 32;
+        for (;;) {
+            const uint32_t prev_end = simt::shfl_up(c.end, 1);
+            const uint32_t prev_flags = simt::shfl_up(c.flags, 1);
+            const uint32_t want = prev_end - 32u * P_SUBW;
+            const bool mismatch = (lane > 0) && (prev_end == P_INVALID || start != want || (prev_flags & (GF_EOB | GF_BAD)));
+            const uint32_t mm = simt::ballot(mismatch);
+            const uint32_t em = simt::ballot((c.flags & (GF_EOB | GF_BAD)) != 0 && start != P_INVALID);
+            const uint32_t first_mis = mm ? simt::ffs(mm) - 1 : 32;
+            const uint32_t first_eob = em ? simt::ffs(em) - 1 : 32;
+            if (first_eob < first_mis) {  // the block ends (or turns undecodable) inside a verified lane
+                eob_lane = first_eob;
+                break;
+            }
+            if (first_mis == 32) break;
+            const bool redo = mismatch && !(prev_flags & (GF_EOB | GF_BAD)) && prev_end != P_INVALID;
+            if (mismatch) start = redo ? want : P_INVALID;
+            GCount c2 = g_count(s, row, start, redo);
+            if (mismatch) c = c2;
+        }
+        if (lane > eob_lane) {
+            c.cnt = 0;
+            c.nm = 0;
+            c.flags = 0;
+        }
+        // an undecodable token in a verified lane: commit nothing of this segment
+        if (simt::any((c.flags & GF_BAD) != 0)) break;
+
+        // ---- scan ----
+        const uint32_t incl = simt::scan_incl_add(c.cnt);
+        const uint32_t seg_bytes = simt::shfl(incl, 31);
+        const uint32_t mincl = simt::scan_incl_add(c.nm);
+        const uint32_t seg_matches = simt::shfl(mincl, 31);
+        if ((uint64_t)seg_bytes + 2 > o.cap - o.pos || seg_matches > P_MAXM) break;
+        const uint64_t o0 = o.pos;
+
+        // ---- write: literals in place, matches parked in stream order ----
+        {
+            GLane b;
+            gl_start(b, row, start != P_INVALID ? start : 0u);
+            uint32_t rel = incl - c.cnt;     // my first byte, relative to o0
+            uint32_t mi = mincl - c.nm;      // my first match
+            bool fin = start == P_INVALID || lane > eob_lane;
+            bool bad = false;
+            while (!fin && b.rp < P_LIM_HI) {
+                GTok t;
+                g_token(s, b, P_LIM_HI, t);
+                if (t.kind == GT_LIT) {
+                    o.out[o0 + rel] = (uint8_t)t.lit;
+                    if (t.bytes == 2) o.out[o0 + rel + 1] = (uint8_t)(t.lit >> 8);
+                } else if (t.kind == GT_MATCH) {
+                    if ((uint64_t)t.dist > o0 + rel) bad = true;  // DistanceTooFarBack: the sequential decoder reports it
+                    s.pmatch[mi] = make_uint2(rel, t.bytes | (t.dist << 16));
+                    mi++;
+                } else {
+                    fin = true;
+                }
+                rel += t.bytes;
+                if (!fin) gl_advance(b, t.nbits);
+            }
+            if (simt::any(bad)) break;
+        }
+        simt::syncwarp();
+
+        // ---- execute the parked matches, 32 at a time ----
+        for (uint32_t m0 = 0; m0 < seg_matches; m0 += 32) {
+            const uint32_t k = m0 + lane;
+            const bool active = k < seg_matches;
+            const uint2 rec = active ? s.pmatch[k] : make_uint2(0, 0);
+            const uint32_t mlen = rec.y & 0xffffu, mdist = rec.y >> 16;  // (a distance of 32768 wraps to 0x8000: fits)
+            const uint64_t dst = o0 + rec.x;
+            const uint64_t first_dst = o0 + simt::shfl(rec.x, 0);
+            simt::syncwarp();  // literals and earlier batches are complete
+            const bool early = active && (dst - mdist + mlen <= first_dst);
+            if (early) {
+                uint8_t* d = o.out + dst;
+                const uint8_t* sp = d - mdist;
+                uint32_t i = 0;
+                for (; i + 8 <= mlen; i += 8) {
+                    uint8_t b0 = sp[i], b1 = sp[i + 1], b2 = sp[i + 2], b3 = sp[i + 3];
+                    uint8_t b4 = sp[i + 4], b5 = sp[i + 5], b6 = sp[i + 6], b7 = sp[i + 7];
+                    d[i] = b0; d[i + 1] = b1; d[i + 2] = b2; d[i + 3] = b3;
+                    d[i + 4] = b4; d[i + 5] = b5; d[i + 6] = b6; d[i + 7] = b7;
+                }
+                uint8_t tb[8];
+#pragma unroll
+                for (uint32_t j = 0; j < 8; j++) tb[j] = (i + j < mlen) ? sp[i + j] : (uint8_t)0;
+#pragma unroll
+                for (uint32_t j = 0; j < 8; j++)
+                    if (i + j < mlen) d[i + j] = tb[j];
+            }
+            uint32_t late = simt::ballot(active && !early);
+            while (late) {
+                const uint32_t kk = simt::ffs(late) - 1;
+                late &= late - 1;
+                const uint64_t kd = simt::shfl(dst, kk);
+                const uint32_t n = simt::shfl(mlen, kk), d32 = simt::shfl(mdist, kk);
+                simt::syncwarp();
+                uint8_t* d = o.out + kd;
+                const uint8_t* sp = d - d32;
+                if (d32 >= n) {
+                    for (uint32_t i = lane; i < n; i += 32) d[i] = sp[i];
+                } else {
+                    for (uint32_t i = lane; i < n; i += 32) d[i] = sp[i % d32];
+                }
+            }
+        }
+        simt::syncwarp();
+
+        // ---- commit ----
+        o.pos = o0 + seg_bytes;
+        if (eob_lane < 32) {
+            const uint32_t eob_rel = simt::shfl(c.end, eob_lane), eob_n = simt::shfl(c.eobn, eob_lane);
+            p0 = ((s0 + (uint64_t)P_SUBW * eob_lane) << 5) + eob_rel + eob_n;  // behind the EOB code
+            ended = true;
+            break;
+        }
+        p0 = ((s0 + (uint64_t)P_SUBW * 31) << 5) + simt::shfl(c.end, 31);
+    }
+    br_seek(r, p0 - first_byte * 8);
+    return ended;
+}
+
+// Fast path of decode_block: the same tokens through a lean, warp-uniform reader (three words in
+// registers, the next one fetched a word ahead with a shuffle), taken only while the input has at
+// least 64 more bits and the slot room for a longest match plus a literal pair.  It never reports
+// anything: at the end of the block's reach, an end-of-block code, a code longer than the tables, an
+// invalid code or a distance too far back it stops AT the token boundary and the careful loop below
+// (the reference's careful loop, decompress.rs:836-1007) takes over from there.
+FDB_DEVICE void decode_block_fast(K3Smem& s, BitReader& r, OutCursor& o, MatchQueue& mq) {
+    const unsigned lane = simt::lane_id();
+    const uint64_t avail = br_avail(r);
+    if (avail < 128 || o.cap - o.pos < 264) return;
+    const uint64_t budget = avail - 64;
+    const uint32_t max_used = budget > 0x7fffff00ull ? 0x7fffff00u : (uint32_t)budget;
+    const uint64_t out_limit = o.cap - 262;  // a token may add up to 258 bytes
+
+    // ---- reader over the 128-byte input chunks (one word per lane) ----
+    const uint64_t abit = r.first_byte * 8 + r.pos;
+    uint64_t fetch = abit >> 5;  // next word to pull
+    uint64_t c = fetch >> 5;     // chunk held in `cur`
+    uint32_t cur = br_load_word(r, c * 32 + lane), nxt = br_load_word(r, (c + 1) * 32 + lane);
+    auto pull = [&]() -> uint32_t {
+        const uint32_t w = simt::shfl(cur, (unsigned)(fetch & 31));
+        fetch++;
+        if ((fetch & 31) == 0) {
+            cur = nxt;
+            c++;
+            nxt = br_load_word(r, (c + 1) * 32 + lane);
+        }
+        return w;
+    };
+    uint32_t w0 = pull(), w1 = pull(), w2 = pull();
+    uint32_t rp = (uint32_t)(abit & 31);  // bit offset of the next token inside w0 (kept < 32 by advance)
+    auto advance = [&](uint32_t n) {     // n < 32
+        const uint32_t nrp = rp + n;
+        if (nrp & 32u) {
+            w0 = w1;
+            w1 = w2;
+            w2 = pull();
+        }
+        rp = nrp & 31u;
+    };
+
+    uint32_t used = 0;
+    uint64_t pos = o.pos;
+    while (used <= max_used && pos <= out_limit) {
+        const uint32_t bits = simt::funnel_r(w0, w1, rp);
+        const uint32_t e = s.litlen[bits & 0xfffu];
+        const uint32_t n = e & 15u;
+        if (e & LL_LIT) {
+            const uint32_t k = e >> 28;  // 1 or 2 literals
+            if (lane < k) o.out[pos + lane] = (uint8_t)(e >> (8u + 8u * lane));
+            pos += k;
+            used += n;
+            advance(n);
+            continue;
+        }
+        if (!(e & LL_LEN)) break;  // end of block, 286/287, or a code longer than the table
+        const uint32_t xb = (e >> 8) & 7u;
+        const uint32_t length = ((e >> 16) & 0x1ffu) + ((bits >> n) & ((1u << xb) - 1u));
+        const uint32_t n1 = n + xb;  // <= 17
+        // the 32 bits behind the length: a second window over (w1, w2), shifted into place
+        const uint32_t hi = simt::funnel_r(w1, w2, rp);
+        const uint32_t dbitsw = simt::funnel_r(bits, hi, n1);
+        const uint32_t de = s.dist[dbitsw & 0x1ffu];
+        if (!(de & DS_VALID)) break;  // long or invalid distance code
+        const uint32_t dbits = de & 15u, dextra = (de >> 4) & 15u;
+        const uint32_t dist = (de >> 16) + ((dbitsw >> dbits) & ((1u << dextra) - 1u));
+        if (dist > pos) break;  // DistanceTooFarBack, reported by the careful loop
+        if (lane == mq.qn) {
+            mq.dst = pos;
+            mq.len = length;
+            mq.dist = dist;
+        }
+        mq.qn++;
+        pos += length;
+        used += n1 + dbits + dextra;
+        advance(n1);
+        advance(dbits + dextra);  // <= 22
+        if (mq.qn == 32) mq_flush(o.out, mq);
+    }
+    o.pos = pos;
+    br_seek(r, r.pos + used);
+}
+
 FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t eof_code, uint32_t eof_bits,
                                 bool* too_large) {
     const unsigned lane = simt::lane_id();
@@ -353,7 +804,10 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
         mq_flush(o.out, mq);  \
         return (x);           \
     } while (0)
+    if (decode_block_parallel(s, r, o)) return ST_OK;
     for (;;) {
+        // as far as the fast path gets, then ONE token (or the end of the block) the careful way
+        decode_block_fast(s, r, o, mq);
         br_refill(r);
         uint64_t avail = br_avail(r);
         if (o.pos == o.cap) {
