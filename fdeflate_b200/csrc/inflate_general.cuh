@@ -199,18 +199,31 @@ FDB_DEVICE void build_litlen_table(K3Smem& s) {
         s.litlen[idx] = e;
     }
     simt::syncwarp();
-    for (uint32_t idx = lane; idx < 4096; idx += 32) {
-        uint32_t e = s.litlen[idx];
-        if (!(e & LL_LIT) || (e & LL_LIT2)) continue;
-        uint32_t l1 = e & 15u;
-        if (l1 >= 12) continue;
-        uint32_t e2 = s.litlen[idx >> l1];  // may already be a pair: sym1 / first-literal bits are stable
-        if (!(e2 & LL_LIT)) continue;
-        uint32_t l2 = (e2 >> 24) & 15u;
-        if (l1 + l2 > 12) continue;
-        s.litlen[idx] = make_litlen_pair(e, (e2 >> 8) & 0xffu, l1, l2);
+    // second pass, 128 indices at a time: read (the entry and the one its second literal would come
+    // from), barrier, write -- so no lane reads an entry another lane is upgrading at that moment.
+    // An entry read here may already be a pair from an earlier round: its first literal and that
+    // literal's bit count are the same in both forms.
+    for (uint32_t base = 0; base < 4096; base += 128) {
+        uint32_t ne[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t idx = base + 32 * k + lane;
+            const uint32_t e = s.litlen[idx];
+            ne[k] = e;
+            if (!(e & LL_LIT) || (e & LL_LIT2)) continue;
+            const uint32_t l1 = e & 15u;
+            if (l1 >= 12) continue;
+            const uint32_t e2 = s.litlen[idx >> l1];
+            if (!(e2 & LL_LIT)) continue;
+            const uint32_t l2 = (e2 >> 24) & 15u;
+            if (l1 + l2 > 12) continue;
+            ne[k] = make_litlen_pair(e, (e2 >> 8) & 0xffu, l1, l2);
+        }
+        simt::syncwarp();
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) s.litlen[base + 32 * k + lane] = ne[k];
+        simt::syncwarp();
     }
-    simt::syncwarp();
 }
 
 FDB_DEVICE void build_dist_table(K3Smem& s) {
@@ -365,22 +378,22 @@ static const uint32_t P_INVALID = 0xffffffffu;
 
 struct GLane {  // lane-private LSB-first reader over a transposed staging row (cf. LaneBits in inflate_uf.cuh)
     uint32_t w0, w1, w2, rp;
-    const uint32_t* nx;
+    simt::saddr nx;
 };
-FDB_DEVICE void gl_start(GLane& b, const uint32_t* row, uint32_t rp) {
+FDB_DEVICE void gl_start(GLane& b, simt::saddr row, uint32_t rp) {
     b.rp = rp;
-    const uint32_t* p = row + (rp >> 5) * 32;
-    b.w0 = p[0];
-    b.w1 = p[32];
-    b.w2 = p[64];
-    b.nx = p + 96;
+    const simt::saddr p = row + (rp >> 5) * 128u;
+    b.w0 = simt::lds32(p);
+    b.w1 = simt::lds32(p + 128u);
+    b.w2 = simt::lds32(p + 256u);
+    b.nx = p + 384u;
 }
 FDB_DEVICE void gl_advance(GLane& b, uint32_t n) {  // n <= 48
     if (n >= 32) {
         b.w0 = b.w1;
         b.w1 = b.w2;
-        b.w2 = *b.nx;
-        b.nx += 32;
+        b.w2 = simt::lds32(b.nx);
+        b.nx += 128u;
         b.rp += 32;
         n -= 32;
     }
@@ -388,11 +401,16 @@ FDB_DEVICE void gl_advance(GLane& b, uint32_t n) {  // n <= 48
     if ((nrp ^ b.rp) & 32u) {
         b.w0 = b.w1;
         b.w1 = b.w2;
-        b.w2 = *b.nx;
-        b.nx += 32;
+        b.w2 = simt::lds32(b.nx);
+        b.nx += 128u;
     }
     b.rp = nrp;
 }
+
+// shared-window addresses of the block's tables
+struct GTabs {
+    simt::saddr litlen, dist;
+};
 
 enum : uint32_t { GT_LIT = 0, GT_MATCH = 1, GT_EOB = 2, GT_BAD = 3 };
 struct GTok {
@@ -404,9 +422,9 @@ struct GTok {
 };
 // One token at the reader's position.  A literal pair is split when its second literal would start
 // at or after `limit` (sub-sequences hand over on token boundaries).
-FDB_DEVICE void g_token(const K3Smem& s, const GLane& b, uint32_t limit, GTok& t) {
+FDB_DEVICE void g_token(const K3Smem& s, const GTabs& tb, const GLane& b, uint32_t limit, GTok& t) {
     const uint32_t bits = simt::funnel_r(b.w0, b.w1, b.rp);
-    const uint32_t e = s.litlen[bits & 0xfffu];
+    const uint32_t e = simt::lds32_ro(tb.litlen + ((bits & 0xfffu) << 2));
     uint32_t nbits = e & 15u;
     t.dist = 0;
     if (e & LL_LIT) {
@@ -451,7 +469,7 @@ FDB_DEVICE void g_token(const K3Smem& s, const GLane& b, uint32_t limit, GTok& t
     const uint32_t length = len_base + ((bits >> nbits) & ((1u << len_extra) - 1u));
     const uint32_t hi = simt::funnel_r(b.w1, b.w2, b.rp);
     const uint32_t dw = simt::funnel_r(bits, hi, n1);  // the 32 bits behind the length
-    const uint32_t de = s.dist[dw & 0x1ffu];
+    const uint32_t de = simt::lds32_ro(tb.dist + ((dw & 0x1ffu) << 2));
     uint32_t dbits, dextra, dbase;
     if (de & DS_VALID) {
         dbits = de & 15u;
@@ -486,7 +504,7 @@ struct GCount {
 };
 enum : uint32_t { GF_EOB = 1, GF_BAD = 2 };
 
-FDB_DEVICE GCount g_count(const K3Smem& s, const uint32_t* row, uint32_t start, bool active) {
+FDB_DEVICE GCount g_count(const K3Smem& s, const GTabs& tb, simt::saddr row, uint32_t start, bool active) {
     GCount c = {P_INVALID, 0, 0, 0, 0};
     GLane b;
     gl_start(b, row, active ? start : 0u);
@@ -494,7 +512,7 @@ FDB_DEVICE GCount g_count(const K3Smem& s, const uint32_t* row, uint32_t start, 
     bool stop = !active;
     while (!stop && b.rp < P_LIM_HI) {
         GTok t;
-        g_token(s, b, P_LIM_HI, t);
+        g_token(s, tb, b, P_LIM_HI, t);
         if (t.kind >= GT_EOB) {
             flags |= t.kind == GT_EOB ? GF_EOB : GF_BAD;
             eobn = t.nbits;
@@ -515,13 +533,13 @@ FDB_DEVICE GCount g_count(const K3Smem& s, const uint32_t* row, uint32_t start, 
     return c;
 }
 
-FDB_DEVICE uint32_t g_warm_up(const K3Smem& s, const uint32_t* row, bool active) {
+FDB_DEVICE uint32_t g_warm_up(const K3Smem& s, const GTabs& tb, simt::saddr row, bool active) {
     GLane b;
     gl_start(b, row, 0u);
     bool stop = !active, dead = false;
     while (!stop && b.rp < P_LIM_LO) {
         GTok t;
-        g_token(s, b, P_LIM_LO, t);
+        g_token(s, tb, b, P_LIM_LO, t);
         if (t.kind >= GT_EOB) {  // speculative end of block / undecodable: this lane has no valid guess
             dead = true;
             stop = true;
@@ -537,7 +555,8 @@ FDB_DEVICE uint32_t g_warm_up(const K3Smem& s, const uint32_t* row, bool active)
 FDB_DEVICE bool decode_block_parallel(K3Smem& s, BitReader& r, OutCursor& o) {
     const unsigned lane = simt::lane_id();
     uint32_t* stg = s.pstg;
-    const uint32_t* row = s.pstg + lane;
+    const simt::saddr row = simt::smem_addr(s.pstg + lane);
+    const GTabs tb = {simt::smem_addr(s.litlen), simt::smem_addr(s.dist)};
     // virtual bit / byte coordinates relative to a 16-byte aligned base at or below the stream
     // (the base lies 64 bytes further down so that the warm-up words of the first segment have
     // non-negative indices; nothing below the stream's first byte is ever loaded)
@@ -582,9 +601,9 @@ FDB_DEVICE bool decode_block_parallel(K3Smem& s, BitReader& r, OutCursor& o) {
         simt::syncwarp();
 
         // ---- warm up, count ----
-        uint32_t start = g_warm_up(s, row, lane != 0);
+        uint32_t start = g_warm_up(s, tb, row, lane != 0);
         if (lane == 0) start = (uint32_t)(p0 - (s0 << 5));
-        GCount c = g_count(s, row, start, start != P_INVALID);
+        GCount c = g_count(s, tb, row, start, start != P_INVALID);
 
         // ---- verify the chain (rows are 32 * SUBW bits apart) ----
         uint32_t eob_lane = 32;
@@ -604,7 +623,7 @@ FDB_DEVICE bool decode_block_parallel(K3Smem& s, BitReader& r, OutCursor& o) {
             if (first_mis == 32) break;
             const bool redo = mismatch && !(prev_flags & (GF_EOB | GF_BAD)) && prev_end != P_INVALID;
             if (mismatch) start = redo ? want : P_INVALID;
-            GCount c2 = g_count(s, row, start, redo);
+            GCount c2 = g_count(s, tb, row, start, redo);
             if (mismatch) c = c2;
         }
         if (lane > eob_lane) {
@@ -633,7 +652,7 @@ FDB_DEVICE bool decode_block_parallel(K3Smem& s, BitReader& r, OutCursor& o) {
             bool bad = false;
             while (!fin && b.rp < P_LIM_HI) {
                 GTok t;
-                g_token(s, b, P_LIM_HI, t);
+                g_token(s, tb, b, P_LIM_HI, t);
                 if (t.kind == GT_LIT) {
                     o.out[o0 + rel] = (uint8_t)t.lit;
                     if (t.bytes == 2) o.out[o0 + rel + 1] = (uint8_t)(t.lit >> 8);
@@ -651,33 +670,42 @@ FDB_DEVICE bool decode_block_parallel(K3Smem& s, BitReader& r, OutCursor& o) {
         }
         simt::syncwarp();
 
-        // ---- execute the parked matches, 32 at a time ----
+        // ---- execute the parked matches ----
+        // One lane copies one match: `len` independent byte loads, then the stores.
+        auto copy_own = [&](uint64_t dst, uint32_t mlen, uint32_t mdist) {
+            uint8_t* d = o.out + dst;
+            const uint8_t* sp = d - mdist;
+            uint32_t i = 0;
+            for (; i + 8 <= mlen; i += 8) {
+                uint8_t b0 = sp[i], b1 = sp[i + 1], b2 = sp[i + 2], b3 = sp[i + 3];
+                uint8_t b4 = sp[i + 4], b5 = sp[i + 5], b6 = sp[i + 6], b7 = sp[i + 7];
+                d[i] = b0; d[i + 1] = b1; d[i + 2] = b2; d[i + 3] = b3;
+                d[i + 4] = b4; d[i + 5] = b5; d[i + 6] = b6; d[i + 7] = b7;
+            }
+            uint8_t tb8[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++) tb8[j] = (i + j < mlen) ? sp[i + j] : (uint8_t)0;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++)
+                if (i + j < mlen) d[i + j] = tb8[j];
+        };
+        // (A segment-wide pass for matches whose source ends before the segment's first destination was
+        // tried and measured slower: 47 vs 54 GB/s on level-6 tiles.)
+        // In stream order, 32 at a time: "early" = source ends before the first destination of the batch,
+        // executed lane-parallel; "late" = overlapping / near sources, one after another with the
+        // warp-wide copy.
         for (uint32_t m0 = 0; m0 < seg_matches; m0 += 32) {
             const uint32_t k = m0 + lane;
-            const bool active = k < seg_matches;
-            const uint2 rec = active ? s.pmatch[k] : make_uint2(0, 0);
-            const uint32_t mlen = rec.y & 0xffffu, mdist = rec.y >> 16;  // (a distance of 32768 wraps to 0x8000: fits)
+            const uint2 rec = k < seg_matches ? s.pmatch[k] : make_uint2(0, 0);
+            const uint32_t mlen = rec.y & 0xffffu, mdist = rec.y >> 16;
+            const bool active = mlen != 0;
+            const uint32_t am = simt::ballot(active);
+            if (am == 0) continue;
             const uint64_t dst = o0 + rec.x;
-            const uint64_t first_dst = o0 + simt::shfl(rec.x, 0);
+            const uint64_t first_dst = o0 + simt::shfl(rec.x, simt::ffs(am) - 1);
             simt::syncwarp();  // literals and earlier batches are complete
             const bool early = active && (dst - mdist + mlen <= first_dst);
-            if (early) {
-                uint8_t* d = o.out + dst;
-                const uint8_t* sp = d - mdist;
-                uint32_t i = 0;
-                for (; i + 8 <= mlen; i += 8) {
-                    uint8_t b0 = sp[i], b1 = sp[i + 1], b2 = sp[i + 2], b3 = sp[i + 3];
-                    uint8_t b4 = sp[i + 4], b5 = sp[i + 5], b6 = sp[i + 6], b7 = sp[i + 7];
-                    d[i] = b0; d[i + 1] = b1; d[i + 2] = b2; d[i + 3] = b3;
-                    d[i + 4] = b4; d[i + 5] = b5; d[i + 6] = b6; d[i + 7] = b7;
-                }
-                uint8_t tb[8];
-#pragma unroll
-                for (uint32_t j = 0; j < 8; j++) tb[j] = (i + j < mlen) ? sp[i + j] : (uint8_t)0;
-#pragma unroll
-                for (uint32_t j = 0; j < 8; j++)
-                    if (i + j < mlen) d[i + j] = tb[j];
-            }
+            if (early) copy_own(dst, mlen, mdist);
             uint32_t late = simt::ballot(active && !early);
             while (late) {
                 const uint32_t kk = simt::ffs(late) - 1;

@@ -3,6 +3,7 @@
 algorithms (scans, carries, table builds, sub-sequence synchronisation) on a machine without a GPU;
 the `-m gpu` tests repeat them on the real library and hardware."""
 import random
+import zlib
 
 import pytest
 
@@ -103,3 +104,45 @@ def test_host_pipeline_chunking_does_not_change_results(emul_ctx, oracle):
         parity.check_inflate(emul_ctx, dmg, 0)
     finally:
         emul_ctx.set_pipeline_chunk(0)
+
+
+def test_inflate_parallel_block_decode(emul_ctx, oracle):
+    """Streams long enough for the general kernel's sub-sequence-parallel block decode (dynamic and
+    fixed blocks, flush points, literal-only and match-heavy data, codes longer than the tables, runs
+    of distance-1 matches), with exact-fit / one-short slots and truncated inputs: status and bytes
+    must equal the oracle's (the parallel path only commits regular segments and hands everything
+    else to the sequential reader at a token boundary)."""
+    from fdeflate_b200 import synth_tiles_host
+
+    rng = random.Random(77)
+    tile = synth_tiles_host(3, 1, 256, 256, 5, emul_ctx.lib)[0].tobytes()
+    text = bytes(rng.choice(b"abcdefghij klmnop\n") for _ in range(60000))
+    skew = bytes(min(255, int(rng.expovariate(0.08))) for _ in range(50000))  # 13-15 bit codes
+    rnd = bytes(rng.getrandbits(8) for _ in range(30000))
+    mix = tile[:40000] + bytes(20000) + text[:30000] + bytes([7]) * 9000
+    c = []
+    for data in (tile[:70000], text, skew, rnd, mix):
+        for lvl in (1, 6, 9):
+            c.append((zlib.compress(data, lvl), data))
+        co = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
+        c.append((co.compress(data) + co.flush(), data))
+        co = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_HUFFMAN_ONLY)
+        c.append((co.compress(data) + co.flush(), data))
+        co, parts = zlib.compressobj(6), []
+        for i in range(0, len(data), 17000):
+            parts += [co.compress(data[i:i + 17000]), co.flush(zlib.Z_SYNC_FLUSH if i % 2 else zlib.Z_FULL_FLUSH)]
+        c.append((b"".join(parts) + co.flush(), data))
+    exact = [(s, len(d)) for s, d in c]
+    st = parity.check_inflate(emul_ctx, exact, FLAG_GENERAL_ONLY)
+    assert (st == 0).all()
+    parity.check_inflate(emul_ctx, exact, 0, align=1)
+    parity.check_inflate(emul_ctx, [(s, n - 1) for s, n in exact], FLAG_GENERAL_ONLY)       # OutputTooLarge
+    parity.check_inflate(emul_ctx, [(s, n // 2 + 5) for s, n in exact], FLAG_GENERAL_ONLY)  # ... mid-stream
+    cut = []
+    for s, n in exact:
+        cut += [(s[: len(s) - 5], n), (s[: len(s) // 2], n), (s[: max(0, len(s) - 1500)], n)]
+        b = bytearray(s)
+        b[len(b) // 2] ^= 0x10  # a flipped bit mid-stream: whatever the oracle says
+        cut.append((bytes(b), n))
+    parity.check_inflate(emul_ctx, cut, FLAG_GENERAL_ONLY)
+    parity.check_inflate(emul_ctx, cut, FLAG_GENERAL_ONLY | FLAG_IGNORE_ADLER32)

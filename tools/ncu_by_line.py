@@ -36,7 +36,7 @@ def main():
         if m:
             cur = (Path(m.group(1)).name, int(m.group(2)))
             continue
-        if func and re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+        if func and re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
             order[func].append(cur)
     fn = [f for f in order if kernel in f]
     if not fn:
