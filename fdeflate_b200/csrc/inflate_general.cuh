@@ -420,20 +420,21 @@ struct GTok {
     uint32_t lit;    // literal(s), first in the low byte
     uint32_t dist;
 };
-// One token at the reader's position.  A literal pair is split when its second literal would start
-// at or after `limit` (sub-sequences hand over on token boundaries).
-FDB_DEVICE void g_token(const K3Smem& s, const GTabs& tb, const GLane& b, uint32_t limit, GTok& t) {
+// One table entry at the reader's position -- a token, or a pair of literals.  Pairs are NOT split at
+// sub-sequence boundaries: lanes hand over on ENTRY boundaries, so the verified chain is exactly the
+// sequence of entries the sequential decoder would take from the same start.  (Which literal opens a
+// pair matters at a truncated end of input: the reference wants the bits of both literals of an entry,
+// decompress.rs:852, so status and output there depend on the pairing.)
+FDB_DEVICE void g_token(const K3Smem& s, const GTabs& tb, const GLane& b, GTok& t) {
     const uint32_t bits = simt::funnel_r(b.w0, b.w1, b.rp);
     const uint32_t e = simt::lds32_ro(tb.litlen + ((bits & 0xfffu) << 2));
     uint32_t nbits = e & 15u;
     t.dist = 0;
     if (e & LL_LIT) {
-        const uint32_t l1 = (e >> 24) & 15u;
-        const bool two = (e & LL_LIT2) != 0 && b.rp + l1 < limit;
         t.kind = GT_LIT;
-        t.nbits = two ? nbits : l1;
-        t.bytes = two ? 2u : 1u;
-        t.lit = (e >> 8) & (two ? 0xffffu : 0xffu);
+        t.nbits = nbits;
+        t.bytes = e >> 28;  // 1 or 2
+        t.lit = (e >> 8) & 0xffffu;  // (the second byte of a single is 0)
         return;
     }
     uint32_t len_base, len_extra;
@@ -512,7 +513,7 @@ FDB_DEVICE GCount g_count(const K3Smem& s, const GTabs& tb, simt::saddr row, uin
     bool stop = !active;
     while (!stop && b.rp < P_LIM_HI) {
         GTok t;
-        g_token(s, tb, b, P_LIM_HI, t);
+        g_token(s, tb, b, t);
         if (t.kind >= GT_EOB) {
             flags |= t.kind == GT_EOB ? GF_EOB : GF_BAD;
             eobn = t.nbits;
@@ -539,7 +540,7 @@ FDB_DEVICE uint32_t g_warm_up(const K3Smem& s, const GTabs& tb, simt::saddr row,
     bool stop = !active, dead = false;
     while (!stop && b.rp < P_LIM_LO) {
         GTok t;
-        g_token(s, tb, b, P_LIM_LO, t);
+        g_token(s, tb, b, t);
         if (t.kind >= GT_EOB) {  // speculative end of block / undecodable: this lane has no valid guess
             dead = true;
             stop = true;
@@ -652,7 +653,7 @@ FDB_DEVICE bool decode_block_parallel(K3Smem& s, BitReader& r, OutCursor& o) {
             bool bad = false;
             while (!fin && b.rp < P_LIM_HI) {
                 GTok t;
-                g_token(s, tb, b, P_LIM_HI, t);
+                g_token(s, tb, b, t);
                 if (t.kind == GT_LIT) {
                     o.out[o0 + rel] = (uint8_t)t.lit;
                     if (t.bytes == 2) o.out[o0 + rel + 1] = (uint8_t)(t.lit >> 8);
@@ -832,10 +833,14 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
         mq_flush(o.out, mq);  \
         return (x);           \
     } while (0)
+#ifndef K3_NO_PARALLEL
     if (decode_block_parallel(s, r, o)) return ST_OK;
+#endif
     for (;;) {
         // as far as the fast path gets, then ONE token (or the end of the block) the careful way
+#ifndef K3_NO_FAST
         decode_block_fast(s, r, o, mq);
+#endif
         br_refill(r);
         uint64_t avail = br_avail(r);
         if (o.pos == o.cap) {
