@@ -308,20 +308,59 @@ def ours(args, rank: int, local_rank: int, world: int):
     h_c_off, h_c_cap = hn(c_off.cpu()).astype(np.uint64), hn(c_cap.cpu()).astype(np.uint64)
     np_tiles, np_comp, np_out = hn(h_tiles), hn(h_comp), hn(h_out)
 
-    def step_host():
+    def step_host_serial():
         clen, st = ctx.deflate_ultrafast_packed(np_tiles, h_t_off, h_t_len, np_comp, h_c_off, h_c_cap)
         olen, _, st2 = ctx.inflate_packed(np_comp, h_c_off, clen, np_out, h_t_off, h_t_len, 0)
         return clen, st, olen, st2
 
-    clen, st, olen, st2 = step_host()  # warm-up (allocates the context's staging buffers)
+    clen, st, olen, st2 = step_host_serial()  # warm-up (allocates the context's staging buffers)
     assert (st == 0).all() and (st2 == 0).all() and (olen == TILE_BYTES).all()
     assert bool((h_out == h_tiles).all())
+
+    # The two directions of a step are independent batches (as in the device-resident step above), and
+    # their PCIe traffic is complementary: deflate moves 1.07 GB up and 0.44 GB down, inflate the other
+    # way round.  Two contexts driven from two host threads (contexts are concurrent, include/fdeflate_b200.h)
+    # keep both directions of the full-duplex link busy.  --e2e-serial runs one call after the other.
+    ctx2 = F.Context(local_rank)
+    h_comp2 = torch.zeros(n * bound, dtype=torch.uint8, pin_memory=True)
+    np_comp2 = hn(h_comp2)
+    from concurrent.futures import ThreadPoolExecutor
+
+    pool = ThreadPoolExecutor(2)
+
+    # the inflate leg reads its streams packed back to back (16-byte aligned), the way compressed tiles are
+    # kept at rest; the deflate leg writes into slots of the worst-case size, the only layout a caller can
+    # prepare before the sizes are known
+    p_off = np.zeros(n, dtype=np.uint64)
+    p_off[1:] = np.cumsum((clen[:-1] + np.uint64(15)) & ~np.uint64(15))
+    h_packed = torch.zeros(int(p_off[-1] + clen[-1]) + 16, dtype=torch.uint8, pin_memory=True)
+    np_packed = hn(h_packed)
+    for i in range(n):
+        np_packed[int(p_off[i]):int(p_off[i]) + int(clen[i])] = np_comp[int(h_c_off[i]):int(h_c_off[i]) + int(clen[i])]
+
+    def step_host_overlapped():
+        fa = pool.submit(ctx2.deflate_ultrafast_packed, np_tiles, h_t_off, h_t_len, np_comp2, h_c_off, h_c_cap)
+        fb = pool.submit(ctx.inflate_packed, np_packed, p_off, clen, np_out, h_t_off, h_t_len, 0)
+        clen2, st_a = fa.result()
+        olen_b, _, st_b = fb.result()
+        return clen2, st_a, olen_b, st_b
+
+    step_host = step_host_serial if args.e2e_serial else step_host_overlapped
+    h_out.zero_()
+    clen2, st_a, olen_b, st_b = step_host()  # warm-up of the second context, and the check of this mode
+    assert (st_a == 0).all() and (st_b == 0).all() and (olen_b == TILE_BYTES).all() and (clen2 == clen).all()
+    assert bool((h_out == h_tiles).all())
+    if not args.e2e_serial:
+        for i in range(0, n, max(1, n // 64)):  # (bytes past a stream's length are unspecified)
+            a0 = int(h_c_off[i])
+            assert bool((h_comp2[a0:a0 + int(clen[i])] == h_comp[a0:a0 + int(clen[i])]).all()), "overlapped deflate output differs"
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_host()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    pool.shutdown()
     h2d = int(n * TILE_BYTES + int(clen.sum()) + 2 * 4 * 8 * n)
     d2h = int(n * TILE_BYTES + int(clen.sum()) + 2 * (8 + 8 + 4) * n)
 
@@ -367,7 +406,8 @@ def ours(args, rank: int, local_rank: int, world: int):
                 },
             },
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "fdb_deflate_ultrafast_batch + fdb_inflate_batch, pinned host buffers"},
+                    "steps": e2e_steps, "api": "fdb_deflate_ultrafast_batch + fdb_inflate_batch, pinned host buffers, " +
+                           ("one call after the other" if args.e2e_serial else "the two calls issued concurrently on two contexts")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "verified": "inflate(deflate(x)) == x on all streams; re-encode byte-identical; fast path on 100% of streams",
@@ -392,6 +432,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=4096, help="streams per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-serial", action="store_true", help="end-to-end leg: deflate call, then inflate call (no overlap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

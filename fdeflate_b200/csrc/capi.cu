@@ -10,7 +10,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "simt.h"
 #include "fdb_common.h"
@@ -32,14 +34,20 @@ struct fdb_lane {
     uint32_t* d_worklist = nullptr;
     size_t worklist_cap = 0;
 };
-static const int FDB_LANES = 4;
+static const int FDB_LANES = 8;        // compute lanes created per context
+static const int FDB_MAX_CHUNKS = 64;  // chunks per host-buffer call (one event pair each)
 
 struct fdb_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;  // lane 0 of the host-buffer entry points
     fdb_lane lanes[FDB_LANES];
-    cudaEvent_t meta_ready = nullptr;
+    int n_lanes = 4;                // lanes in use (FDB_PIPELINE_LANES overrides; a tuning knob)
+    int depth = 4;                  // chunks in flight ahead of the payload copies (FDB_PIPELINE_DEPTH)
+    cudaStream_t h2d_st = nullptr;  // every chunk's input travels on this stream, in order   (shared per device,
+    cudaStream_t d2h_st = nullptr;  // every chunk's payload travels back on this one          see fdb_xfer)
+    cudaEvent_t ev_in[FDB_MAX_CHUNKS] = {nullptr};   // chunk k's input is on the device
+    cudaEvent_t ev_res[FDB_MAX_CHUNKS] = {nullptr};  // chunk k's kernels are done (its per-stream results are on the host)
     uint8_t* h_res = nullptr;       // pinned: per-stream results of the host-buffer entry points
     size_t h_res_cap = 0;
     int64_t last_general_host = -1; // fallback count of the last host-buffer inflate (-1: ask the device)
@@ -59,6 +67,58 @@ struct fdb_ctx {
     uint64_t launches = 0;
     char err[512] = {0};
 };
+
+// ---- optional timeline of the host pipeline (FDB_TRACE=<file>): one line per chunk with the device times
+// (ms since the first traced call of the process) at which its H2D began / ended, its kernels ended and
+// its payload D2H began / ended.  Diagnostic only; off unless the variable is set.
+struct fdb_trace_chunk {
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+static cudaEvent_t g_trace_base = nullptr;
+static const char* trace_path() {
+    static const char* p = getenv("FDB_TRACE");
+    return (p && *p) ? p : nullptr;
+}
+
+// The copy streams are shared by every context on a device: copies of one direction then execute in the
+// order the host threads queued them.  (Per-context copy streams are separate hardware channels, and a
+// channel that always has a copy queued was seen to keep the copy engine until its whole batch was through,
+// starving the other context for 20 ms.)
+struct fdb_xfer {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    int refs = 0;
+};
+static std::mutex g_xfer_mu;
+static fdb_xfer g_xfer[64];
+
+static cudaError_t xfer_acquire(int device, cudaStream_t* h2d, cudaStream_t* d2h) {
+    std::lock_guard<std::mutex> g(g_xfer_mu);
+    fdb_xfer& x = g_xfer[device & 63];
+    if (x.refs == 0) {
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&x.h2d, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&x.d2h, cudaStreamNonBlocking)) != cudaSuccess) {
+            cudaStreamDestroy(x.h2d);
+            x.h2d = nullptr;
+            return e;
+        }
+    }
+    x.refs++;
+    *h2d = x.h2d;
+    *d2h = x.d2h;
+    return cudaSuccess;
+}
+static void xfer_release(int device) {
+    std::lock_guard<std::mutex> g(g_xfer_mu);
+    fdb_xfer& x = g_xfer[device & 63];
+    if (x.refs > 0 && --x.refs == 0) {
+        cudaStreamSynchronize(x.h2d);
+        cudaStreamSynchronize(x.d2h);
+        cudaStreamDestroy(x.h2d);
+        cudaStreamDestroy(x.d2h);
+        x.h2d = x.d2h = nullptr;
+    }
+}
 
 static int fail(fdb_ctx* c, const char* what, cudaError_t e) {
     if (c) snprintf(c->err, sizeof c->err, "%s: %s", what, e == cudaSuccess ? "invalid argument" : cudaGetErrorString(e));
@@ -132,9 +192,21 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
     if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail(e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(uint32_t))) != cudaSuccess) return bail(e);
-    if ((e = cudaEventCreateWithFlags(&ctx->meta_ready, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+    if ((e = xfer_acquire(device, &ctx->h2d_st, &ctx->d2h_st)) != cudaSuccess) return bail(e);
+    for (int k = 0; k < FDB_MAX_CHUNKS; k++) {
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_res[k], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+    }
+    if (const char* nl = getenv("FDB_PIPELINE_LANES")) {
+        int v = atoi(nl);
+        if (v >= 1 && v <= FDB_LANES) ctx->n_lanes = v;
+    }
+    if (const char* nd = getenv("FDB_PIPELINE_DEPTH")) {
+        int v = atoi(nd);
+        if (v >= 1 && v <= FDB_MAX_CHUNKS) ctx->depth = v;
+    }
     ctx->lanes[0].st = ctx->stream;
-    for (int l = 0; l < FDB_LANES; l++) {
+    for (int l = 0; l < ctx->n_lanes; l++) {
         if (l && (e = cudaStreamCreateWithFlags(&ctx->lanes[l].st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
         if ((e = cudaMalloc((void**)&ctx->lanes[l].d_counters, 16 * sizeof(uint32_t))) != cudaSuccess) return bail(e);
     }
@@ -162,7 +234,11 @@ extern "C" void fdb_destroy(fdb_ctx* ctx) {
         cudaFree(ctx->lanes[l].d_worklist);
     }
     if (!ctx->lanes[0].st && ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->meta_ready) cudaEventDestroy(ctx->meta_ready);
+    for (int k = 0; k < FDB_MAX_CHUNKS; k++) {
+        if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
+        if (ctx->ev_res[k]) cudaEventDestroy(ctx->ev_res[k]);
+    }
+    if (ctx->h2d_st) xfer_release(ctx->device);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_worklist);
@@ -181,6 +257,8 @@ static int grow(fdb_ctx* ctx, void** p, size_t* cap, size_t need) {
     if (*p) {
         for (int l = 0; l < FDB_LANES; l++)
             if (ctx->lanes[l].st) FDB_TRY(cudaStreamSynchronize(ctx->lanes[l].st));
+        if (ctx->h2d_st) FDB_TRY(cudaStreamSynchronize(ctx->h2d_st));
+        if (ctx->d2h_st) FDB_TRY(cudaStreamSynchronize(ctx->d2h_st));
         FDB_TRY(cudaFree(*p));
         *p = nullptr;
         *cap = 0;
@@ -192,8 +270,11 @@ static int grow(fdb_ctx* ctx, void** p, size_t* cap, size_t need) {
 
 // ---- inflate ----------------------------------------------------------------------------------
 // K4 over the whole batch, then K3 over the streams K4 declined (or K3 alone with FDB_FLAG_GENERAL_ONLY)
+// dense = the batch is one chunk of a pipeline: pack its streams onto as few SMs as they fill, so that the
+// kernels of the chunks in flight (and of other contexts) run side by side instead of each one holding
+// every SM with a warp or two.
 static int launch_inflate(fdb_ctx* ctx, const InflateBatch& b, uint32_t* counters, uint32_t** worklist,
-                          size_t* worklist_cap, cudaStream_t st) {
+                          size_t* worklist_cap, cudaStream_t st, bool dense = false) {
     const size_t n = b.n;
     if (n > *worklist_cap) {
         void* p = *worklist;
@@ -208,7 +289,7 @@ static int launch_inflate(fdb_ctx* ctx, const InflateBatch& b, uint32_t* counter
     if (!(b.flags & FDB_FLAG_GENERAL_ONLY)) {
         // one CTA per SM; with fewer streams than SMs the warps of n CTAs race for them, so a small
         // batch still spreads over the chip
-        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms);
+        uint32_t grid = (uint32_t)std::min<size_t>(dense ? (n + K4_WARPS - 1) / K4_WARPS : n, (size_t)sms);
         FDB_LAUNCH(inflate_uf_kernel, dim3(grid), dim3(K4_WARPS * 32), sizeof(K4Smem), st, b, ctx->d_dec, counters + 0,
                    *worklist, counters + 1);
         ctx->launches++;
@@ -254,14 +335,16 @@ extern "C" int fdb_inflate_batch_device(fdb_ctx* ctx, const void* d_in_base, con
 }
 
 // ---- deflate ----------------------------------------------------------------------------------
-static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_t* counter, cudaStream_t st) {
+static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_t* counter, cudaStream_t st,
+                          bool dense = false) {
     const size_t n = b.n;
     FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
     const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
     if (kind == 0) {
         // persistent: every resident warp pulls streams from one counter, so SMs stay evenly loaded
         // even when the batch is not a multiple of the chip's warp slots
-        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * DEFLATE_MIN_CTAS);
+        uint32_t grid = (uint32_t)std::min<size_t>(dense ? (n + DEFLATE_WARPS - 1) / DEFLATE_WARPS : n,
+                                                   (size_t)sms * DEFLATE_MIN_CTAS);
         FDB_LAUNCH(deflate_uf_kernel, dim3(grid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc,
                    counter);
     } else {
@@ -362,9 +445,12 @@ static int copy_rows(fdb_ctx* ctx, uint8_t* dst_base, const uint8_t* src_base, c
     return 0;
 }
 
-// Host-buffer batches run as a pipeline of chunks over FDB_LANES CUDA streams: while chunk k is in the
-// kernels, chunk k+1 is on its way to the device and chunk k-1 on its way back (PCIe is full duplex),
-// so a call costs about max(H2D, D2H) instead of H2D + kernels + D2H.
+// Host-buffer batches run as a pipeline of chunks.  Every chunk's input is queued at once, in order, on
+// one host-to-device stream (the staging buffers hold the whole batch, so nothing waits for a slot); each
+// chunk's kernels run on one of n_lanes compute streams as soon as its input has landed, followed by a
+// small copy of its per-stream results; the host picks the results up in order and they decide how much
+// payload goes back on the device-to-host stream.  Both directions of the (full duplex) link therefore
+// stay busy from the first chunk to the last, and a call costs about max(H2D, D2H) + one chunk.
 static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
                       uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
                       uint64_t* consumed, int32_t* status, size_t n, uint32_t flags) {
@@ -377,12 +463,10 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     int r;
     if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, sp.in_span + 64))) return r;
     if ((r = grow(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, sp.out_span + 64))) return r;
-    const size_t meta_words = 7 * n;
+    const size_t meta_words = 4 * n;
     if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, meta_words * sizeof(uint64_t)))) return r;
     uint64_t* m = ctx->d_meta;
-    uint64_t *d_in_off = m, *d_in_len = m + n, *d_out_off = m + 2 * n, *d_out_cap = m + 3 * n, *d_out_len = m + 4 * n,
-             *d_consumed = m + 5 * n;
-    int32_t* d_status = (int32_t*)(m + 6 * n);
+    uint64_t *d_in_off = m, *d_in_len = m + n, *d_out_off = m + 2 * n, *d_out_cap = m + 3 * n;
 
     // chunking needs slots laid out in ascending order (what every packer produces); anything else is one chunk
     bool ascending = true;
@@ -390,15 +474,31 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
         ascending = in_off[i] >= in_off[i - 1] + in_len[i - 1] && out_off[i] >= out_off[i - 1] + out_cap[i - 1];
     size_t nchunk = 1;
     if (ascending)
-        nchunk = (size_t)std::min<uint64_t>(std::min<uint64_t>((sp.in_span + sp.out_span) / ctx->chunk_bytes, 64), n);
+        nchunk = (size_t)std::min<uint64_t>(std::min<uint64_t>((sp.in_span + sp.out_span) / ctx->chunk_bytes, FDB_MAX_CHUNKS), n);
     if (nchunk < 1) nchunk = 1;
     const size_t per = (n + nchunk - 1) / nchunk;
     nchunk = (n + per - 1) / per;
 
-    // pinned landing area for the per-stream results
+    std::vector<fdb_trace_chunk> trace;
+    if (trace_path()) {
+        if (!g_trace_base) {
+            FDB_TRY(cudaEventCreate(&g_trace_base));
+            FDB_TRY(cudaEventRecord(g_trace_base, ctx->h2d_st));
+            FDB_TRY(cudaEventSynchronize(g_trace_base));
+        }
+        trace.resize(nchunk);
+        for (auto& tc : trace)
+            for (auto& e : tc.ev) FDB_TRY(cudaEventCreate(&e));
+    }
+    auto mark = [&](size_t k, int which, cudaStream_t st) {
+        if (!trace.empty()) cudaEventRecord(trace[k].ev[which], st);
+    };
+
+    // The per-stream results live in pinned host memory and the kernels write them there directly (mapped
+    // memory: a few bytes per stream over PCIe), so no copy stands between "kernels done" and the host
+    // knowing how much payload to fetch.
     const size_t res_bytes = n * (8 + 8 + 4) + nchunk * 4 + 64;
     if (res_bytes > ctx->h_res_cap) {
-        for (int l = 0; l < FDB_LANES; l++) FDB_TRY(cudaStreamSynchronize(ctx->lanes[l].st));
         if (ctx->h_res) FDB_TRY(cudaFreeHost(ctx->h_res));
         ctx->h_res = nullptr;
         ctx->h_res_cap = 0;
@@ -413,23 +513,27 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     uint64_t in_stride = 0, out_stride = 0;
     const bool in_uniform = uniform_stride(in_off, n, &in_stride), out_uniform = uniform_stride(out_off, n, &out_stride);
 
-    // stream descriptors: once, ahead of every lane
-    cudaStream_t st0 = ctx->lanes[0].st;
-    FDB_TRY(cudaMemcpyAsync(d_in_off, in_off, n * 8, cudaMemcpyHostToDevice, st0));
-    FDB_TRY(cudaMemcpyAsync(d_in_len, in_len, n * 8, cudaMemcpyHostToDevice, st0));
-    FDB_TRY(cudaMemcpyAsync(d_out_off, out_off, n * 8, cudaMemcpyHostToDevice, st0));
-    FDB_TRY(cudaMemcpyAsync(d_out_cap, out_cap, n * 8, cudaMemcpyHostToDevice, st0));
-    FDB_TRY(cudaEventRecord(ctx->meta_ready, st0));
-    for (int l = 1; l < FDB_LANES; l++) FDB_TRY(cudaStreamWaitEvent(ctx->lanes[l].st, ctx->meta_ready, 0));
+    // stream descriptors: once, ahead of every chunk's input on the same stream
+    const int L = ctx->n_lanes;
+    cudaStream_t hs = ctx->h2d_st, ds = ctx->d2h_st;
+    FDB_TRY(cudaMemcpyAsync(d_in_off, in_off, n * 8, cudaMemcpyHostToDevice, hs));
+    FDB_TRY(cudaMemcpyAsync(d_in_len, in_len, n * 8, cudaMemcpyHostToDevice, hs));
+    FDB_TRY(cudaMemcpyAsync(d_out_off, out_off, n * 8, cudaMemcpyHostToDevice, hs));
+    FDB_TRY(cudaMemcpyAsync(d_out_cap, out_cap, n * 8, cudaMemcpyHostToDevice, hs));
+    const bool dense = nchunk > 1;
 
-    auto issue = [&](size_t k) -> int {  // H2D, kernels, results D2H of chunk k
+    auto issue = [&](size_t k) -> int {  // input, kernels and results of chunk k
         const size_t a = k * per, b = std::min(n, a + per);
-        fdb_lane& ln = ctx->lanes[k % FDB_LANES];
+        fdb_lane& ln = ctx->lanes[k % L];
         uint64_t max_in = 0;
         for (size_t i = a; i < b; i++) max_in = std::max(max_in, in_len[i]);
+        mark(k, 0, hs);
         int rr = copy_rows(ctx, ctx->d_in, in_base, in_off, a, b, max_in, in_len[b - 1], in_uniform, in_stride,
-                           cudaMemcpyHostToDevice, ln.st);
+                           cudaMemcpyHostToDevice, hs);
         if (rr) return rr;
+        mark(k, 1, hs);
+        FDB_TRY(cudaEventRecord(ctx->ev_in[k], hs));
+        FDB_TRY(cudaStreamWaitEvent(ln.st, ctx->ev_in[k], 0));
         if (kind == 0) {
             InflateBatch ib;
             ib.in_base = ctx->d_in;
@@ -438,14 +542,13 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             ib.out_base = ctx->d_out;
             ib.out_off = d_out_off + a;
             ib.out_cap = d_out_cap + a;
-            ib.out_len = d_out_len + a;
-            ib.consumed = d_consumed + a;
-            ib.status = d_status + a;
+            ib.out_len = h_out_len + a;
+            ib.consumed = h_consumed + a;
+            ib.status = h_status + a;
             ib.n = (uint32_t)(b - a);
             ib.flags = flags;
-            if ((rr = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st))) return rr;
-            FDB_TRY(cudaMemcpyAsync(h_consumed + a, d_consumed + a, (b - a) * 8, cudaMemcpyDeviceToHost, ln.st));
-            FDB_TRY(cudaMemcpyAsync(h_general + k, ln.d_counters + 1, 4, cudaMemcpyDeviceToHost, ln.st));
+            ib.general_out = h_general + k;
+            if ((rr = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, dense))) return rr;
         } else {
             DeflateBatch db;
             db.in_base = ctx->d_in;
@@ -454,32 +557,59 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             db.out_base = ctx->d_out;
             db.out_off = d_out_off + a;
             db.out_cap = d_out_cap + a;
-            db.out_len = d_out_len + a;
-            db.status = d_status + a;
+            db.out_len = h_out_len + a;
+            db.status = h_status + a;
             db.n = (uint32_t)(b - a);
-            if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st))) return rr;
+            if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st, dense))) return rr;
         }
-        FDB_TRY(cudaMemcpyAsync(h_out_len + a, d_out_len + a, (b - a) * 8, cudaMemcpyDeviceToHost, ln.st));
-        FDB_TRY(cudaMemcpyAsync(h_status + a, d_status + a, (b - a) * 4, cudaMemcpyDeviceToHost, ln.st));
+        mark(k, 2, ln.st);
+        FDB_TRY(cudaEventRecord(ctx->ev_res[k], ln.st));
         return 0;
     };
-    auto finish = [&](size_t k) -> int {  // the results decide how much payload comes back
+    auto finish = [&](size_t k) -> int {  // the results (already on the host) decide how much payload comes back
         const size_t a = k * per, b = std::min(n, a + per);
-        fdb_lane& ln = ctx->lanes[k % FDB_LANES];
-        FDB_TRY(cudaStreamSynchronize(ln.st));
         uint64_t max_out = 0;
         for (size_t i = a; i < b; i++) max_out = std::max(max_out, h_out_len[i]);
-        return copy_rows(ctx, out_base, ctx->d_out, out_off, a, b, max_out, h_out_len[b - 1], out_uniform, out_stride,
-                         cudaMemcpyDeviceToHost, ln.st);
+        mark(k, 3, ds);
+        int rr = copy_rows(ctx, out_base, ctx->d_out, out_off, a, b, max_out, h_out_len[b - 1], out_uniform, out_stride,
+                           cudaMemcpyDeviceToHost, ds);
+        mark(k, 4, ds);
+        return rr;
     };
-    const size_t depth = FDB_LANES - 1;  // chunks in flight ahead of the one being finished
-    for (size_t k = 0; k < nchunk; k++) {
-        if ((r = issue(k))) return r;
-        if (k >= depth && (r = finish(k - depth))) return r;
+    // The host keeps at most `depth` chunks between "input queued" and "payload queued": enough to cover the
+    // kernels' latency, few enough that another context's copies are never stuck behind a long queue of ours
+    // (copies of one direction execute in the order they were queued, whatever their stream).
+    const size_t depth = (size_t)ctx->depth;
+    size_t issued = 0, fin = 0;  // chunks [0, fin) have their payload on the way back
+    while (fin < nchunk) {
+        while (fin < issued && cudaEventQuery(ctx->ev_res[fin]) == cudaSuccess)
+            if ((r = finish(fin++))) return r;
+        if (issued < nchunk && issued < fin + depth) {
+            if ((r = issue(issued++))) return r;
+            continue;
+        }
+        if (fin < issued) {
+            FDB_TRY(cudaEventSynchronize(ctx->ev_res[fin]));
+            if ((r = finish(fin++))) return r;
+        }
     }
-    for (size_t k = nchunk > depth ? nchunk - depth : 0; k < nchunk; k++)
-        if ((r = finish(k))) return r;
-    for (int l = 0; l < FDB_LANES; l++) FDB_TRY(cudaStreamSynchronize(ctx->lanes[l].st));
+    FDB_TRY(cudaStreamSynchronize(ds));
+    FDB_TRY(cudaStreamSynchronize(hs));
+    for (int l = 0; l < L; l++) FDB_TRY(cudaStreamSynchronize(ctx->lanes[l].st));
+    if (!trace.empty()) {
+        if (FILE* f = fopen(trace_path(), "a")) {
+            for (size_t k = 0; k < nchunk; k++) {
+                float t[5] = {0, 0, 0, 0, 0};
+                for (int j = 0; j < 5; j++) cudaEventElapsedTime(&t[j], g_trace_base, trace[k].ev[j]);
+                fprintf(f, "ctx %p kind %d chunk %zu/%zu lane %zu streams %zu h2d %.3f %.3f kern_end %.3f d2h %.3f %.3f\n",
+                        (void*)ctx, kind, k, nchunk, k % (size_t)L, std::min(n, (k + 1) * per) - k * per, t[0], t[1], t[2],
+                        t[3], t[4]);
+            }
+            fclose(f);
+        }
+        for (auto& tc : trace)
+            for (auto& e : tc.ev) cudaEventDestroy(e);
+    }
     memcpy(out_len, h_out_len, n * 8);
     memcpy(status, h_status, n * 4);
     if (kind == 0) {

@@ -48,6 +48,7 @@ struct InflateBatch {
     int32_t* status;          // [n]
     uint32_t n;
     uint32_t flags;
+    uint32_t* general_out = nullptr;  // if set: receives how many streams the fast path handed to the general kernel
 };
 
 #if defined(__CUDACC__) && !defined(FDB_EMUL)

@@ -1137,6 +1137,7 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(32, 1)
     K3Smem& s = *reinterpret_cast<K3Smem*>(smem_raw);
     const unsigned lane = simt::lane_id();
     const uint32_t count = worklist ? *work_count : b.n;
+    if (b.general_out && blockIdx.x == 0 && lane == 0) *b.general_out = worklist ? count : 0u;
     for (;;) {
         uint32_t idx = 0;
         if (lane == 0) idx = simt::atomic_add(next, 1u);
