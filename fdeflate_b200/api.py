@@ -111,6 +111,10 @@ class Context:
         return int(self.lib.L.fdb_last_general_count(self._h, stream))
 
     # ---- raw packed host-buffer calls ---------------------------------------------------------
+    def last_split_spans(self, stream: int = 0) -> int:
+        """spans the long streams of the most recent inflate batch were cut into (0 = one warp per stream)"""
+        return int(self.lib.L.fdb_last_split_spans(self._h, stream))
+
     def inflate_packed(self, in_base: np.ndarray, in_off, in_len, out_base: np.ndarray, out_off, out_cap,
                        flags: int = 0):
         n = len(in_off)

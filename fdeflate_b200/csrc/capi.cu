@@ -28,11 +28,21 @@ using namespace fdb;
 
 // One pipeline lane of the host-buffer entry points: its own CUDA stream, work counters and fallback
 // work list, so that chunks of one batch can overlap (H2D of chunk k+1 | kernels of chunk k | D2H of k-1).
+// scratch of the span-by-span inflate path (FDB_FLAG_SPLIT_LARGE), grown on first use
+struct fdb_split_scratch {
+    K4Item* items = nullptr;
+    size_t items_bytes = 0;
+    uint32_t* per_stream = nullptr;  // item0 | nspans | need | done | failed, n words each
+    size_t per_stream_bytes = 0;
+};
+static const uint32_t FDB_SPLIT_ITEMS = 1u << 18;  // spans per batch (16 GiB of compressed input)
+
 struct fdb_lane {
     cudaStream_t st = nullptr;
     uint32_t* d_counters = nullptr;  // same layout as fdb_ctx::d_counters
     uint32_t* d_worklist = nullptr;
     size_t worklist_cap = 0;
+    fdb_split_scratch split;
 };
 static const int FDB_LANES = 8;        // compute lanes created per context
 static const int FDB_MAX_CHUNKS = 64;  // chunks per host-buffer call (one event pair each)
@@ -51,10 +61,13 @@ struct fdb_ctx {
     uint8_t* h_res = nullptr;       // pinned: per-stream results of the host-buffer entry points
     size_t h_res_cap = 0;
     int64_t last_general_host = -1; // fallback count of the last host-buffer inflate (-1: ask the device)
+    int64_t last_split_host = -1;   // spans of the last host-buffer inflate (-1: ask the device)
     uint64_t chunk_bytes = 128ull << 20;  // slot span per pipeline chunk
     uint32_t* d_counters = nullptr; // [0] K4 next  [1] fallback count  [2] K3 next  [3] deflate next
+                                    // [4] spans reserved  [5..7] next span of the count / scan / write pass
     uint32_t* d_worklist = nullptr;
     size_t worklist_cap = 0;
+    fdb_split_scratch split;
     UfEncTables* d_enc = nullptr;
     UfDecTables* d_dec = nullptr;
     // host-API staging (grow-only)
@@ -155,6 +168,15 @@ extern "C" int64_t fdb_last_general_count(fdb_ctx* ctx, void* cuda_stream) {
     return (int64_t)v;
 }
 
+extern "C" int64_t fdb_last_split_spans(fdb_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return -1;
+    if (ctx->last_split_host >= 0) return ctx->last_split_host;
+    uint32_t v = 0;
+    if (cudaStreamSynchronize((cudaStream_t)cuda_stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, ctx->d_counters + 4, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)std::min<uint32_t>(v, FDB_SPLIT_ITEMS);
+}
+
 extern "C" int fdb_create(int device, fdb_ctx** out) {
     if (!out) return -1;
     *out = nullptr;
@@ -218,6 +240,10 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
         return bail(e);
     if ((e = cudaFuncSetAttribute(inflate_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem))) != cudaSuccess)
         return bail(e);
+    if ((e = cudaFuncSetAttribute(inflate_uf_split_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem))) != cudaSuccess)
+        return bail(e);
+    if ((e = cudaFuncSetAttribute(inflate_uf_split_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem))) != cudaSuccess)
+        return bail(e);
     *out = ctx;
     return 0;
 }
@@ -232,6 +258,8 @@ extern "C" void fdb_destroy(fdb_ctx* ctx) {
         }
         cudaFree(ctx->lanes[l].d_counters);
         cudaFree(ctx->lanes[l].d_worklist);
+        cudaFree(ctx->lanes[l].split.items);
+        cudaFree(ctx->lanes[l].split.per_stream);
     }
     if (!ctx->lanes[0].st && ctx->stream) cudaStreamDestroy(ctx->stream);
     for (int k = 0; k < FDB_MAX_CHUNKS; k++) {
@@ -242,6 +270,8 @@ extern "C" void fdb_destroy(fdb_ctx* ctx) {
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_worklist);
+    cudaFree(ctx->split.items);
+    cudaFree(ctx->split.per_stream);
     cudaFree(ctx->d_enc);
     cudaFree(ctx->d_dec);
     cudaFree(ctx->d_in);
@@ -274,8 +304,19 @@ static int grow(fdb_ctx* ctx, void** p, size_t* cap, size_t need) {
 // kernels of the chunks in flight (and of other contexts) run side by side instead of each one holding
 // every SM with a warp or two.
 static int launch_inflate(fdb_ctx* ctx, const InflateBatch& b, uint32_t* counters, uint32_t** worklist,
-                          size_t* worklist_cap, cudaStream_t st, bool dense = false) {
+                          size_t* worklist_cap, cudaStream_t st, bool dense = false, fdb_split_scratch* ss = nullptr) {
     const size_t n = b.n;
+    const bool split = ss && (b.flags & FDB_FLAG_SPLIT_LARGE) && !(b.flags & FDB_FLAG_GENERAL_ONLY);
+    if (split) {
+        int r;
+        void* p = ss->items;
+        if ((r = grow(ctx, &p, &ss->items_bytes, (size_t)FDB_SPLIT_ITEMS * sizeof(K4Item)))) return r;
+        ss->items = (K4Item*)p;
+        p = ss->per_stream;
+        r = grow(ctx, &p, &ss->per_stream_bytes, 5 * n * sizeof(uint32_t));
+        ss->per_stream = (uint32_t*)p;
+        if (r) return r;
+    }
     if (n > *worklist_cap) {
         void* p = *worklist;
         size_t cap_bytes = *worklist_cap * sizeof(uint32_t);
@@ -284,14 +325,40 @@ static int launch_inflate(fdb_ctx* ctx, const InflateBatch& b, uint32_t* counter
         *worklist_cap = cap_bytes / sizeof(uint32_t);
         if (r) return r;
     }
-    FDB_TRY(cudaMemsetAsync(counters, 0, 4 * sizeof(uint32_t), st));
+    FDB_TRY(cudaMemsetAsync(counters, 0, 8 * sizeof(uint32_t), st));
     const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
+    const uint32_t* split_item0 = nullptr;
+    if (split) {
+        // long ultra-fast-format streams, span by span: plan, count, scan, write (inflate_uf.cuh)
+        K4Split sp;
+        sp.items = ss->items;
+        sp.item_cap = FDB_SPLIT_ITEMS;
+        sp.n_items = counters + 4;
+        sp.item0 = ss->per_stream;
+        sp.nspans = ss->per_stream + n;
+        sp.need = ss->per_stream + 2 * n;
+        sp.done = ss->per_stream + 3 * n;
+        sp.failed = ss->per_stream + 4 * n;
+        sp.next_count = counters + 5;
+        sp.next_scan = counters + 6;
+        sp.next_write = counters + 7;
+        split_item0 = sp.item0;
+        FDB_LAUNCH(inflate_uf_plan_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0, st, b, (const UfDecTables*)ctx->d_dec, sp);
+        FDB_LAUNCH(inflate_uf_split_count_kernel, dim3(sms), dim3(K4_WARPS * 32), sizeof(K4Smem), st, b,
+                   (const UfDecTables*)ctx->d_dec, sp);
+        FDB_LAUNCH(inflate_uf_split_scan_kernel, dim3((uint32_t)std::min<size_t>((n + 7) / 8, (size_t)sms * 4)), dim3(256), 0, st, b, sp,
+                   *worklist, counters + 1);
+        FDB_LAUNCH(inflate_uf_split_write_kernel, dim3(sms), dim3(K4_WARPS * 32), sizeof(K4Smem), st, b,
+                   (const UfDecTables*)ctx->d_dec, sp, *worklist, counters + 1);
+        ctx->launches += 4;
+        FDB_TRY(cudaGetLastError());
+    }
     if (!(b.flags & FDB_FLAG_GENERAL_ONLY)) {
         // one CTA per SM; with fewer streams than SMs the warps of n CTAs race for them, so a small
         // batch still spreads over the chip
         uint32_t grid = (uint32_t)std::min<size_t>(dense ? (n + K4_WARPS - 1) / K4_WARPS : n, (size_t)sms);
         FDB_LAUNCH(inflate_uf_kernel, dim3(grid), dim3(K4_WARPS * 32), sizeof(K4Smem), st, b, ctx->d_dec, counters + 0,
-                   *worklist, counters + 1);
+                   *worklist, counters + 1, split_item0);
         ctx->launches++;
         FDB_TRY(cudaGetLastError());
         uint32_t grid3 = (uint32_t)std::min<size_t>(n, (size_t)sms * 10);
@@ -331,7 +398,9 @@ extern "C" int fdb_inflate_batch_device(fdb_ctx* ctx, const void* d_in_base, con
     b.n = (uint32_t)n;
     b.flags = flags;
     ctx->last_general_host = -1;
-    return launch_inflate(ctx, b, ctx->d_counters, &ctx->d_worklist, &ctx->worklist_cap, (cudaStream_t)cuda_stream);
+    ctx->last_split_host = -1;
+    return launch_inflate(ctx, b, ctx->d_counters, &ctx->d_worklist, &ctx->worklist_cap, (cudaStream_t)cuda_stream, false,
+                          &ctx->split);
 }
 
 // ---- deflate ----------------------------------------------------------------------------------
@@ -497,7 +566,7 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     // The per-stream results live in pinned host memory and the kernels write them there directly (mapped
     // memory: a few bytes per stream over PCIe), so no copy stands between "kernels done" and the host
     // knowing how much payload to fetch.
-    const size_t res_bytes = n * (8 + 8 + 4) + nchunk * 4 + 64;
+    const size_t res_bytes = n * (8 + 8 + 4) + nchunk * 8 + 64;
     if (res_bytes > ctx->h_res_cap) {
         if (ctx->h_res) FDB_TRY(cudaFreeHost(ctx->h_res));
         ctx->h_res = nullptr;
@@ -509,6 +578,8 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     uint64_t* h_consumed = h_out_len + n;
     int32_t* h_status = (int32_t*)(h_consumed + n);
     uint32_t* h_general = (uint32_t*)(h_status + n);
+    uint32_t* h_split = h_general + nchunk;
+    memset(h_split, 0, nchunk * sizeof(uint32_t));
 
     uint64_t in_stride = 0, out_stride = 0;
     const bool in_uniform = uniform_stride(in_off, n, &in_stride), out_uniform = uniform_stride(out_off, n, &out_stride);
@@ -547,8 +618,11 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             ib.status = h_status + a;
             ib.n = (uint32_t)(b - a);
             ib.flags = flags;
+            if (max_in >= K4_SPLIT_MIN_BYTES) ib.flags |= FDB_FLAG_SPLIT_LARGE;  // long streams: many warps each
             ib.general_out = h_general + k;
-            if ((rr = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, dense))) return rr;
+            ib.split_out = h_split + k;
+            if ((rr = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, dense, &ln.split)))
+                return rr;
         } else {
             DeflateBatch db;
             db.in_base = ctx->d_in;
@@ -617,6 +691,9 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
         int64_t g = 0;
         for (size_t k = 0; k < nchunk; k++) g += h_general[k];
         ctx->last_general_host = (flags & FDB_FLAG_GENERAL_ONLY) ? 0 : g;
+        int64_t sp_total = 0;
+        for (size_t k = 0; k < nchunk; k++) sp_total += h_split[k];
+        ctx->last_split_host = sp_total;
     }
     return 0;
 }

@@ -49,6 +49,7 @@ struct InflateBatch {
     uint32_t n;
     uint32_t flags;
     uint32_t* general_out = nullptr;  // if set: receives how many streams the fast path handed to the general kernel
+    uint32_t* split_out = nullptr;    // if set (and FDB_FLAG_SPLIT_LARGE): receives how many spans long streams were cut into
 };
 
 #if defined(__CUDACC__) && !defined(FDB_EMUL)

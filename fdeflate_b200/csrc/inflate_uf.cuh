@@ -263,20 +263,82 @@ struct K4Stream {
     uint64_t cap;
 };
 
-// Returns ST_OK / ST_WRONG_CHECKSUM, or ST_PENDING_GENERAL when the stream must go to K3.
-FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4Warp& ws, const K4Stream& s,
-                                     uint32_t flags, uint64_t* out_len, uint64_t* consumed) {
+// ---- spans: a long stream decoded by several warps --------------------------------------------
+// A stream whose compressed size is many segments long is cut into SPANS of K4_SPAN_SEGS segments on
+// the stream's own segment grid.  Where a span starts is not known in advance, so it is found the way a
+// lane finds its sub-sequence: a COUNT pass starts one whole segment early at a guessed bit, drops
+// that segment (by its end the walk sits on true token boundaries, Huffman self-synchronisation over
+// 8192 bits), then counts the bytes of its own segments; the position where it started counting must
+// equal the position where the span before it stopped, and span 0 starts at the exact first data bit, so
+// equality along the chain proves every span (split_scan_kernel; anything else sends the stream to K3).
+// A prefix sum of the byte counts gives every span its output offset, and a WRITE pass decodes the spans
+// again, each into its own part of the slot.  K4_WHOLE is the ordinary one-warp-per-stream decode.
+enum : int { K4_WHOLE = 0, K4_COUNT = 1, K4_WRITE = 2 };
+static const uint32_t K4_SPAN_SEGS = 64;                            // segments per span (64 KiB of compressed data)
+static const uint64_t K4_SPAN_WORDS = (uint64_t)K4_SPAN_SEGS * 32 * K4_SUBW;
+enum : uint32_t { SP_EOB = 1, SP_FIRSTRUN = 2, SP_LASTNZ = 4, SP_DEAD = 8, SP_SKIP = 16, SP_SYNCFAIL = 32 };
+static const uint32_t K4_NO_ITEM = 0xffffffffu;
+static const uint64_t K4_SPLIT_MIN_BYTES = 4ull * K4_SPAN_WORDS * 4;  // streams of >= 4 spans (256 KiB) are split
+
+// One span of one split stream (device scratch, filled by the three passes in turn).
+struct K4Item {
+    uint32_t stream, j;
+    uint32_t flags;    // SP_* (count pass; SP_SKIP by the scan)
+    uint32_t prev_nz;  // scan: state of the byte before the span
+    uint64_t p_start, p_end, bytes, trailer_byte;  // count pass
+    uint64_t o0;       // scan: output bytes before the span
+    uint64_t s1, s2;   // write pass: adler partial sums (s2 reduced mod 65521)
+};
+// Per-batch bookkeeping of the split path (device scratch).
+struct K4Split {
+    K4Item* items;
+    uint32_t item_cap;
+    uint32_t* n_items;     // counter
+    uint32_t* item0;       // [n] first item of stream i, or K4_NO_ITEM
+    uint32_t* nspans;      // [n] spans reserved for stream i
+    uint32_t* need;        // [n] spans up to and including the one with the end-of-block code (scan)
+    uint32_t* done;        // [n] spans written so far
+    uint32_t* failed;      // [n] some span's write pass gave up
+    uint32_t* next_count;  // work counters of the three persistent passes
+    uint32_t* next_scan;
+    uint32_t* next_write;
+};
+
+struct K4Span {
+    uint64_t seg_word;   // first word of lane 0's sub-sequence in the span's first segment
+    uint64_t stop_word;  // no segment starts at or beyond this word
+    uint64_t p0;         // bit where decoding starts: exact, or a guess when `discard`
+    uint64_t o0;         // K4_WRITE: output bytes before the span
+    uint32_t prev_nz;    // K4_WRITE: "the byte before the span is non-zero, or there is none"
+    uint32_t discard;    // K4_COUNT: the first segment only synchronises
+};
+struct K4SpanOut {
+    uint64_t p_start;       // K4_COUNT: exact bit the counting started from
+    uint64_t p_end;         // first token of the next span, or the position of the end-of-block code
+    uint64_t bytes;         // K4_COUNT: bytes produced by [p_start, p_end)
+    uint64_t trailer_byte;  // SP_EOB: where the adler32 trailer starts (relative to the 16-byte aligned base)
+    uint32_t flags;         // SP_*
+    AdlerAcc ad;            // K4_WRITE: this lane's partial sums over the span's bytes
+};
+
+// K4_WHOLE: returns ST_OK / ST_WRONG_CHECKSUM, or ST_PENDING_GENERAL when the stream must go to K3.
+// K4_COUNT / K4_WRITE: ST_OK with *so filled, or ST_PENDING_GENERAL.
+template <int MODE>
+FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& ws, const K4Stream& s, uint32_t flags,
+                                  uint64_t* out_len, uint64_t* consumed, const K4Span* sp, K4SpanOut* so) {
     const unsigned lane = simt::lane_id();
     uint32_t* stg = ws.stg;
     const simt::saddr row = simt::smem_addr(ws.stg + lane);
     uint8_t* win = ws.win;
     const simt::saddr win_s = simt::smem_addr(ws.win);
-    *out_len = 0;
-    *consumed = 0;
+    if (MODE == K4_WHOLE) {
+        *out_len = 0;
+        *consumed = 0;
+    }
 
     // ---- header must be the ultra-fast constant (ultrafast.rs:82-91) ----
     if (s.n < 54 + 2 + 4) return ST_PENDING_GENERAL;
-    {
+    if (MODE == K4_WHOLE) {
         bool ok = true;
         for (uint32_t j = lane; j < 54; j += 32) {
             uint32_t want = (hdr[j >> 2] >> (8u * (j & 3u))) & 0xffu;
@@ -304,6 +366,28 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
     uint32_t prev_nz = 1;
     uint64_t win_vo = 0;  // virtual output position of win[0] (multiple of 16)
     AdlerAcc ad = {0, 0};
+    uint64_t lo_vo = oalign;  // virtual output position of the first byte this call may store
+    uint32_t sync_seg = 0;    // K4_COUNT: the current segment only synchronises
+    uint32_t first_seen = 0;  // K4_COUNT: some segment of the span has produced output
+    if (MODE != K4_WHOLE) {
+        seg_word = sp->seg_word;
+        p0 = sp->p0;
+        so->p_start = sp->p0;
+        so->p_end = 0;
+        so->bytes = 0;
+        so->trailer_byte = 0;
+        so->flags = 0;
+    }
+    if (MODE == K4_COUNT) {
+        prev_nz = 0;  // what the first token needs of the byte before it is recorded (SP_FIRSTRUN), not tested
+        sync_seg = sp->discard;
+    }
+    if (MODE == K4_WRITE) {
+        o0 = sp->o0;
+        prev_nz = sp->prev_nz;
+        lo_vo = oalign + o0;
+        win_vo = lo_vo & ~(uint64_t)15;
+    }
 
     // zero the output window
     for (uint32_t v = lane; v < (K4_WIN + 16) / 16; v += 32) ((uint4*)win)[v] = make_uint4(0, 0, 0, 0);
@@ -312,7 +396,7 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
     // Store the finished vectors win[0 .. 16*nvec) at virtual position win_vo, feed adler32, and zero
     // them again.  Bytes outside [oalign, stream_end_vo) (first / last vector of the stream) are masked.
     auto flush_vectors = [&](uint32_t nvec, uint64_t stream_end_vo) {
-        if (win_vo >= oalign && win_vo + 16ull * nvec <= stream_end_vo) {
+        if (win_vo >= lo_vo && win_vo + 16ull * nvec <= stream_end_vo) {
             // every vector lies inside the stream (all segments but the first / last of a stream)
             uint8_t* const dst = obase + win_vo;
             const uint64_t pos0 = win_vo - oalign;
@@ -328,7 +412,7 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
             uint4 q = ((const uint4*)win)[v];
             ((uint4*)win)[v] = make_uint4(0, 0, 0, 0);
             uint64_t vo = win_vo + 16ull * v;
-            bool head_cut = vo < oalign;
+            bool head_cut = vo < lo_vo;
             bool tail_cut = vo + 16 > stream_end_vo;
             if (!head_cut && !tail_cut) {
                 simt::stcs128((uint4*)(obase + vo), q);
@@ -337,7 +421,7 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
                 uint32_t w[4] = {q.x, q.y, q.z, q.w};
                 for (uint32_t j = 0; j < 16; j++) {
                     uint64_t bpos = vo + j;
-                    if (bpos >= oalign && bpos < stream_end_vo) {
+                    if (bpos >= lo_vo && bpos < stream_end_vo) {
                         uint32_t byte = (w[j >> 2] >> (8u * (j & 3u))) & 0xffu;
                         obase[bpos] = (uint8_t)byte;
                         adler_add1(ad, byte, bpos - oalign);
@@ -348,6 +432,21 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
     };
 
     for (;;) {
+        if (MODE != K4_WHOLE && seg_word >= sp->stop_word) {
+            // the span ends here, on the first token boundary at or after its last segment
+            so->p_end = p0;
+            if (MODE == K4_COUNT) {
+                so->bytes = o0;
+                so->flags |= prev_nz ? SP_LASTNZ : 0u;
+            }
+            if (MODE == K4_WRITE) {
+                const uint32_t left = (uint32_t)(oalign + o0 - win_vo);
+                flush_vectors((left + 15) / 16, oalign + o0);
+                simt::syncwarp();
+                so->ad = ad;
+            }
+            return ST_OK;
+        }
         if ((seg_word << 5) >= vend) return ST_PENDING_GENERAL;  // ran off the input without an EOB
         const uint64_t s0 = seg_word - K4_WARM;                  // first staged word (virtual word index)
 
@@ -421,6 +520,18 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
             c.cnt = 0;
             c.flags = 0;
         }
+        if (MODE == K4_COUNT && sync_seg) {
+            // only where this segment ends matters; a walk that began on a guess may have read anything
+            if (eob_lane < 32) {  // the guessed walk read an end-of-block code before it synchronised: guess again
+                so->flags |= SP_SYNCFAIL;
+                return ST_PENDING_GENERAL;
+            }
+            sync_seg = 0;
+            p0 = ((s0 + (uint64_t)K4_SUBW * 31) << 5) + simt::shfl(c.end, 31);
+            so->p_start = p0;
+            seg_word += 32 * K4_SUBW;
+            continue;
+        }
         if (simt::any((c.flags & CF_BAD) != 0)) return ST_PENDING_GENERAL;
 
         // ---- 4. scan ----
@@ -437,6 +548,13 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
             const uint32_t below = has_mask & simt::lanemask_lt();
             const uint32_t pred_nz = below ? ((nz_mask >> (31u - simt::clz(below))) & 1u) : prev_nz;
             if (simt::any(c.cnt != 0 && (c.flags & CF_FIRSTRUN) != 0 && pred_nz != 0)) return ST_PENDING_GENERAL;
+            if (MODE == K4_COUNT && !first_seen && has_mask) {
+                // does the span open with a run?  (its first token is the first token of the first lane that
+                // produced anything; whether the byte before it is a zero is known to the span before)
+                first_seen = 1;
+                const uint32_t fr_mask = simt::ballot(c.cnt != 0 && (c.flags & CF_FIRSTRUN) != 0);
+                if ((fr_mask >> (simt::ffs(has_mask) - 1u)) & 1u) so->flags |= SP_FIRSTRUN;
+            }
             if (has_mask) prev_nz = (nz_mask >> (31u - simt::clz(has_mask))) & 1u;
         }
 
@@ -448,7 +566,7 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
         LaneBits b;
         lb_start(b, row, start != K4_INVALID ? start : 0u);
         uint32_t fin = (start == K4_INVALID || lane > eob_lane) ? 1u : 0u;  // no more tokens to decode
-        for (;;) {
+        for (; MODE != K4_COUNT;) {
             const uint64_t wend = win_vo + K4_WIN;
             const bool mine = !fin && op < wend;
             uint32_t wp = mine ? (uint32_t)(op - win_vo) : 0u;
@@ -564,9 +682,23 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
             const uint64_t eob_end = ((s0 + (uint64_t)K4_SUBW * eob_lane) << 5) + eob_rel + 12;  // EOB = 12 bits
             const uint64_t trailer_byte = (eob_end + 7) >> 3;   // relative to abase
             if (trailer_byte + 4 > end_byte) return ST_PENDING_GENERAL;  // truncated: K3 reports it
+            if (MODE != K4_WHOLE) {
+                so->p_end = eob_end - 12;
+                so->trailer_byte = trailer_byte;
+                so->flags |= SP_EOB;
+            }
+            if (MODE == K4_COUNT) {
+                so->bytes = o0;
+                so->flags |= prev_nz ? SP_LASTNZ : 0u;
+                return ST_OK;
+            }
             uint32_t left = (uint32_t)(oalign + o0 - win_vo);
             flush_vectors((left + 15) / 16, oalign + o0);
             simt::syncwarp();
+            if (MODE == K4_WRITE) {
+                so->ad = ad;
+                return ST_OK;
+            }
             const uint8_t* tr = abase + trailer_byte;
             uint32_t stored = ((uint32_t)simt::ldg8(tr) << 24) | ((uint32_t)simt::ldg8(tr + 1) << 16) |
                               ((uint32_t)simt::ldg8(tr + 2) << 8) | (uint32_t)simt::ldg8(tr + 3);
@@ -578,7 +710,7 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
         }
         // flush the finished vectors of this segment and slide the window base to the vector that
         // holds the next output byte (its already-written bytes move to win[0..16))
-        {
+        if (MODE != K4_COUNT) {
             const uint32_t nvec = (uint32_t)((seg_end_vo - win_vo) >> 4);
             uint4 tail = ((const uint4*)win)[nvec];
             simt::syncwarp();
@@ -596,12 +728,17 @@ FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4War
     }
 }
 
+FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4Warp& ws, const K4Stream& s,
+                                     uint32_t flags, uint64_t* out_len, uint64_t* consumed) {
+    return inflate_uf_run<K4_WHOLE>(t, hdr, ws, s, flags, out_len, consumed, nullptr, nullptr);
+}
+
 // Persistent kernel, one CTA per SM.  Streams the fast path declines are appended to worklist[]
 // (count in *work_count) with status ST_PENDING_GENERAL; the host launches K3 over that list next,
 // on the same stream.
 FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
     inflate_uf_kernel(InflateBatch b, const UfDecTables* tables, uint32_t* next, uint32_t* worklist,
-                      uint32_t* work_count) {
+                      uint32_t* work_count, const uint32_t* split_item0) {
     FDB_DYN_SMEM(smem_raw);
     K4Smem& sm = *reinterpret_cast<K4Smem*>(smem_raw);
     FDB_SHARED uint32_t hdr[14];
@@ -618,6 +755,7 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
         if (lane == 0) i = simt::atomic_add(next, 1u);
         i = simt::shfl(i, 0);
         if (i >= b.n) break;
+        if (split_item0 && split_item0[i] != K4_NO_ITEM) continue;  // decoded span by span (below)
         K4Stream s = {b.in_base + b.in_off[i], b.in_len[i], b.out_base + b.out_off[i], b.out_cap[i]};
         uint64_t out_len = 0, consumed = 0;
         int32_t st = inflate_uf_stream(t, hdr, ws, s, b.flags, &out_len, &consumed);
@@ -626,6 +764,274 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
             b.out_len[i] = out_len;
             if (b.consumed) b.consumed[i] = consumed;
             if (st == ST_PENDING_GENERAL) worklist[simt::atomic_add(work_count, 1u)] = i;
+        }
+        simt::syncwarp();
+    }
+}
+
+// ---- split path, pass 0: which streams are decoded span by span --------------------------------
+FDB_DEVICE void k4_geometry(const uint8_t* in, uint64_t n, uint64_t* first_byte, uint64_t* seg0, uint64_t* end_word) {
+    *first_byte = (uint64_t)((uintptr_t)in & 15u);
+    const uint64_t vstart = *first_byte * 8 + 53 * 8 + 5;
+    *seg0 = ((vstart >> 5) >> 2) << 2;
+    *end_word = ((*first_byte + n) * 8 + 31) >> 5;
+}
+
+FDB_GLOBAL void inflate_uf_plan_kernel(InflateBatch b, const UfDecTables* tables, K4Split sp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    sp.item0[i] = K4_NO_ITEM;
+    sp.nspans[i] = 0;
+    sp.need[i] = 0;
+    sp.done[i] = 0;
+    sp.failed[i] = 0;
+    const uint64_t n = b.in_len[i];
+    if (n < K4_SPLIT_MIN_BYTES) return;
+    const uint8_t* in = b.in_base + b.in_off[i];
+    for (uint32_t j = 0; j < 54; j++) {  // the constant header (ultrafast.rs:82-91)
+        uint32_t want = (tables->header[j >> 2] >> (8u * (j & 3u))) & 0xffu;
+        uint32_t got = simt::ldg8(in + j);
+        if (j == 53) got &= 0x1fu;
+        if (got != want) return;
+    }
+    uint64_t first_byte, seg0, end_word;
+    k4_geometry(in, n, &first_byte, &seg0, &end_word);
+    const uint64_t S = (end_word - seg0 + K4_SPAN_WORDS - 1) / K4_SPAN_WORDS;
+    if (S < 2 || S > 0x7fffffffull) return;
+    const uint32_t base = simt::atomic_add(sp.n_items, (uint32_t)S);
+    if ((uint64_t)base + S > sp.item_cap) return;  // scratch exhausted: this stream stays with one warp
+    sp.item0[i] = base;
+    sp.nspans[i] = (uint32_t)S;
+    for (uint32_t j = 0; j < (uint32_t)S; j++) {
+        K4Item& it = sp.items[base + j];
+        it.stream = i;
+        it.j = j;
+        it.flags = SP_DEAD;
+    }
+}
+
+FDB_DEVICE uint32_t k4_item_count(const K4Split& sp) {
+    const uint32_t c = *sp.n_items;
+    return c < sp.item_cap ? c : sp.item_cap;
+}
+// items past the capacity were never reserved as a whole stream: an item is live iff its stream points at it
+FDB_DEVICE bool k4_item_live(const K4Split& sp, uint32_t idx, const K4Item& it, uint32_t n) {
+    return it.stream < n && sp.item0[it.stream] != K4_NO_ITEM && sp.item0[it.stream] + it.j == idx;
+}
+
+struct K4Tables {
+    UfTabs t;
+    K4Warp* ws;
+};
+FDB_DEVICE K4Tables k4_load_tables(unsigned char* smem_raw, const UfDecTables* tables) {
+    K4Smem& sm = *reinterpret_cast<K4Smem*>(smem_raw);
+    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) sm.wt[i] = tables->wt[i];
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x)
+        ((uint32_t*)sm.ct)[i] = ((const uint32_t*)tables->ct)[i];
+    simt::syncthreads();
+    K4Tables r = {{simt::smem_addr(sm.wt), simt::smem_addr(sm.ct)}, &sm.warp[simt::warp_in_block()]};
+    return r;
+}
+
+// ---- pass 1: synchronise and count every span ------------------------------------------------
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
+    inflate_uf_split_count_kernel(InflateBatch b, const UfDecTables* tables, K4Split sp) {
+    FDB_DYN_SMEM(smem_raw);
+    const uint32_t count = k4_item_count(sp);
+    if (b.split_out && blockIdx.x == 0 && threadIdx.x == 0) *b.split_out = count;
+    if (count == 0) return;
+    const K4Tables kt = k4_load_tables(smem_raw, tables);
+    const unsigned lane = simt::lane_id();
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = simt::atomic_add(sp.next_count, 1u);
+        idx = simt::shfl(idx, 0);
+        if (idx >= count) break;
+        K4Item& it = sp.items[idx];
+        if (!k4_item_live(sp, idx, it, b.n)) continue;
+        const uint32_t i = it.stream, j = it.j;
+        K4Stream s = {b.in_base + b.in_off[i], b.in_len[i], b.out_base + b.out_off[i], b.out_cap[i]};
+        uint64_t first_byte, seg0, end_word;
+        k4_geometry(s.in, s.n, &first_byte, &seg0, &end_word);
+        K4Span span;
+        span.stop_word = seg0 + (uint64_t)(j + 1) * K4_SPAN_WORDS;
+        span.o0 = 0;
+        span.prev_nz = 0;
+        if (j == 0) {
+            span.seg_word = seg0;
+            span.p0 = first_byte * 8 + 53 * 8 + 5;
+            span.discard = 0;
+        } else {
+            span.seg_word = seg0 + (uint64_t)j * K4_SPAN_WORDS - 32 * K4_SUBW;  // one segment early
+            span.p0 = span.seg_word << 5;
+            span.discard = 1;
+        }
+        K4SpanOut so;
+        int32_t st = inflate_uf_run<K4_COUNT>(kt.t, nullptr, *kt.ws, s, b.flags, nullptr, nullptr, &span, &so);
+        // A walk that starts on a guessed bit can run into an end-of-block pattern before it reaches a true
+        // token boundary (likely only on data made of 12-bit codes); another starting bit reads other tokens.
+        for (uint32_t retry = 1; retry < 10 && st != ST_OK && (so.flags & SP_SYNCFAIL); retry++) {
+            span.p0 = (span.seg_word << 5) + 3u * retry;
+            st = inflate_uf_run<K4_COUNT>(kt.t, nullptr, *kt.ws, s, b.flags, nullptr, nullptr, &span, &so);
+        }
+        if (lane == 0) {
+            it.p_start = so.p_start;
+            it.p_end = so.p_end;
+            it.bytes = so.bytes;
+            it.trailer_byte = so.trailer_byte;
+            it.flags = st == ST_OK ? so.flags : SP_DEAD;
+        }
+        simt::syncwarp();
+    }
+}
+
+// ---- pass 2: chain check and output offsets, one warp per split stream -------------------------
+// Span 0 starts at the exact first data bit; span j is proven by p_start[j] == p_end[j-1].  The stream is
+// handed to the general kernel if the chain breaks anywhere before the span that holds the end-of-block
+// code, if a span opens with a run behind a non-zero byte, or if the output does not fit the slot.
+FDB_GLOBAL void inflate_uf_split_scan_kernel(InflateBatch b, K4Split sp, uint32_t* worklist, uint32_t* work_count) {
+    const unsigned lane = simt::lane_id();
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = simt::atomic_add(sp.next_scan, 1u);
+        i = simt::shfl(i, 0);
+        if (i >= b.n) break;
+        const uint32_t base = sp.item0[i];
+        if (base == K4_NO_ITEM) continue;
+        const uint32_t S = sp.nspans[i];
+        bool ok = true;
+        uint32_t need = 0;           // spans up to and including the end-of-block span
+        uint64_t carry_end = 0;      // p_end of the span before this group of 32
+        uint32_t carry_nz = 1;       // "the byte before this group is non-zero, or there is none"
+        uint64_t carry_bytes = 0;
+        for (uint32_t g = 0; g < S && ok && need == 0; g += 32) {
+            const uint32_t j = g + lane;
+            const bool have = j < S;
+            K4Item it;
+            it.flags = SP_DEAD;
+            it.p_start = it.p_end = it.bytes = 0;
+            if (have) it = sp.items[base + j];
+            const uint32_t eob_mask = simt::ballot(have && !(it.flags & SP_DEAD) && (it.flags & SP_EOB));
+            const uint32_t upto = eob_mask ? simt::ffs(eob_mask) - 1u : 31u;  // last lane that matters in this group
+            uint64_t prev_end = simt::shfl_up(it.p_end, 1);
+            uint32_t prev_flags = simt::shfl_up(it.flags, 1);
+            if (lane == 0) {
+                prev_end = carry_end;
+                prev_flags = carry_nz ? SP_LASTNZ : 0u;
+            }
+            const bool relevant = have && lane <= upto;
+            bool bad = relevant && (it.flags & SP_DEAD);
+            bad = bad || (relevant && j > 0 && it.p_start != prev_end);
+            bad = bad || (relevant && (it.flags & SP_FIRSTRUN) && (prev_flags & SP_LASTNZ));
+            if (simt::any(bad)) ok = false;
+            const uint64_t incl = simt::scan_incl_add((uint64_t)(relevant ? it.bytes : 0ull));
+            const uint64_t o0 = carry_bytes + incl - (relevant ? it.bytes : 0ull);
+            if (simt::any(relevant && o0 + it.bytes > b.out_cap[i])) ok = false;
+            if (ok && relevant) {
+                sp.items[base + j].o0 = o0;
+                sp.items[base + j].prev_nz = (prev_flags & SP_LASTNZ) ? 1u : 0u;
+            }
+            if (eob_mask) need = g + upto + 1u;
+            // (only full groups carry over)
+            carry_end = simt::shfl(it.p_end, 31);
+            carry_nz = (simt::shfl(it.flags, 31) & SP_LASTNZ) ? 1u : 0u;
+            carry_bytes += simt::shfl(incl, 31);
+        }
+        if (need == 0) ok = false;  // no end of block anywhere: truncated, the general kernel reports it
+        if (ok) {
+            for (uint32_t j = need + lane; j < S; j += 32) sp.items[base + j].flags |= SP_SKIP;  // behind the end of block
+            if (lane == 0) sp.need[i] = need;
+        } else {
+            for (uint32_t j = lane; j < S; j += 32) sp.items[base + j].flags |= SP_SKIP;
+            if (lane == 0) {
+                b.status[i] = ST_PENDING_GENERAL;
+                b.out_len[i] = 0;
+                if (b.consumed) b.consumed[i] = 0;
+                worklist[simt::atomic_add(work_count, 1u)] = i;
+            }
+        }
+        simt::syncwarp();
+    }
+}
+
+// ---- pass 3: decode every span into its part of the slot; the last one to finish closes the stream ----
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
+    inflate_uf_split_write_kernel(InflateBatch b, const UfDecTables* tables, K4Split sp, uint32_t* worklist,
+                                  uint32_t* work_count) {
+    FDB_DYN_SMEM(smem_raw);
+    const uint32_t count = k4_item_count(sp);
+    if (count == 0) return;
+    const K4Tables kt = k4_load_tables(smem_raw, tables);
+    const unsigned lane = simt::lane_id();
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = simt::atomic_add(sp.next_write, 1u);
+        idx = simt::shfl(idx, 0);
+        if (idx >= count) break;
+        K4Item& it = sp.items[idx];
+        if (!k4_item_live(sp, idx, it, b.n) || (it.flags & SP_SKIP)) continue;
+        const uint32_t i = it.stream, j = it.j;
+        K4Stream s = {b.in_base + b.in_off[i], b.in_len[i], b.out_base + b.out_off[i], b.out_cap[i]};
+        uint64_t first_byte, seg0, end_word;
+        k4_geometry(s.in, s.n, &first_byte, &seg0, &end_word);
+        K4Span span;
+        span.seg_word = seg0 + (uint64_t)j * K4_SPAN_WORDS;
+        span.stop_word = span.seg_word + K4_SPAN_WORDS;
+        span.p0 = it.p_start;
+        span.o0 = it.o0;
+        span.prev_nz = it.prev_nz;
+        span.discard = 0;
+        K4SpanOut so;
+        const int32_t st = inflate_uf_run<K4_WRITE>(kt.t, nullptr, *kt.ws, s, b.flags, nullptr, nullptr, &span, &so);
+        uint64_t s1 = 0, s2 = 0;
+        if (st == ST_OK) {
+            s1 = simt::reduce_add(so.ad.s1);
+            s2 = simt::reduce_add(so.ad.s2 % ADLER_MOD) % ADLER_MOD;
+        }
+        uint32_t prior = 0;
+        if (lane == 0) {
+            it.s1 = s1;
+            it.s2 = s2;
+            // the walk must end where the count pass said it would
+            if (st != ST_OK || so.p_end != it.p_end) sp.failed[i] = 1;
+            simt::threadfence();
+            prior = simt::atomic_add(&sp.done[i], 1u);
+        }
+        prior = simt::shfl(prior, 0);
+        const uint32_t need = sp.need[i];
+        if (prior + 1 != need) continue;
+        // every span of the stream is written: checksum, lengths, status
+        simt::threadfence();
+        const K4Item* its = sp.items + sp.item0[i];
+        uint64_t t1 = 0, t2 = 0;
+        for (uint32_t k = lane; k < need; k += 32) {
+            t1 += ((volatile const K4Item*)its)[k].s1;
+            t2 += ((volatile const K4Item*)its)[k].s2;
+        }
+        t1 = simt::reduce_add(t1);
+        t2 = simt::reduce_add(t2) % ADLER_MOD;
+        const K4Item& last = its[need - 1];
+        const uint64_t total = ((volatile const K4Item&)last).o0 + ((volatile const K4Item&)last).bytes;
+        const uint64_t trailer_byte = ((volatile const K4Item&)last).trailer_byte;
+        if (lane == 0) {
+            const uint8_t* abase = (const uint8_t*)((uintptr_t)s.in & ~(uintptr_t)15);
+            const uint8_t* tr = abase + trailer_byte;
+            const uint32_t stored = ((uint32_t)simt::ldg8(tr) << 24) | ((uint32_t)simt::ldg8(tr + 1) << 16) |
+                                    ((uint32_t)simt::ldg8(tr + 2) << 8) | (uint32_t)simt::ldg8(tr + 3);
+            const uint32_t s1m = (uint32_t)(t1 % ADLER_MOD), s2m = (uint32_t)t2, nm = (uint32_t)(total % ADLER_MOD);
+            const uint32_t A = (1u + s1m) % ADLER_MOD;
+            const uint32_t B = (uint32_t)(((uint64_t)nm + (uint64_t)nm * s1m % ADLER_MOD + ADLER_MOD - s2m) % ADLER_MOD);
+            const uint32_t got = (B << 16) | A;
+            if (((volatile uint32_t*)sp.failed)[i]) {
+                b.status[i] = ST_PENDING_GENERAL;
+                b.out_len[i] = 0;
+                if (b.consumed) b.consumed[i] = 0;
+                worklist[simt::atomic_add(work_count, 1u)] = i;
+            } else {
+                b.out_len[i] = total;
+                if (b.consumed) b.consumed[i] = trailer_byte + 4 - first_byte;
+                b.status[i] = (!(b.flags & FLAG_IGNORE_ADLER32) && got != stored) ? ST_WRONG_CHECKSUM : ST_OK;
+            }
         }
         simt::syncwarp();
     }

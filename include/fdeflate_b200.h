@@ -61,6 +61,9 @@ enum fdb_status {
 /* flags for the inflate entry points */
 #define FDB_FLAG_IGNORE_ADLER32 1u /* Decompressor::ignore_adler32, src/decompress.rs:154-156 */
 #define FDB_FLAG_GENERAL_ONLY 2u   /* skip the ultra-fast-format fast path (testing / profiling) */
+#define FDB_FLAG_SPLIT_LARGE 4u    /* device-pointer calls: decode ultra-fast-format streams of >= 256 KiB with many
+                                      warps each (three extra small launches per batch).  The host-buffer calls
+                                      turn it on by themselves when a batch holds such a stream. */
 
 typedef struct fdb_ctx fdb_ctx;
 
@@ -134,6 +137,9 @@ uint64_t fdb_launch_count(const fdb_ctx* ctx);
 /* how many streams of the most recent inflate batch on this context were declined by the
  * ultra-fast-format fast path and decoded by the general kernel.  Synchronises `cuda_stream`. */
 int64_t fdb_last_general_count(fdb_ctx* ctx, void* cuda_stream);
+/* how many spans the long streams of the most recent inflate batch on this context were cut into
+ * (0 = every stream was decoded by one warp).  Synchronises `cuda_stream`. */
+int64_t fdb_last_split_spans(fdb_ctx* ctx, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -146,3 +146,58 @@ def test_inflate_parallel_block_decode(emul_ctx, oracle):
         cut.append((bytes(b), n))
     parity.check_inflate(emul_ctx, cut, FLAG_GENERAL_ONLY)
     parity.check_inflate(emul_ctx, cut, FLAG_GENERAL_ONLY | FLAG_IGNORE_ADLER32)
+
+
+def _long_uf_cases(oracle, lib, seed):
+    """ultra-fast-format streams long enough (>= 256 KiB compressed) for the span-by-span inflate path"""
+    from fdeflate_b200 import synth_tiles_host
+
+    rng = random.Random(seed)
+    noise = bytes(rng.getrandbits(8) for _ in range(290000))                      # ~12 bits per byte
+    tile = synth_tiles_host(7, 1, 1024, 160, 5, lib)[0].tobytes()                 # PNG-filtered rows
+    # literals with zero runs of every length placed across span boundaries (a run token belongs to the span
+    # its code starts in), and a run longer than a whole span's worth of output
+    runs, lits = bytearray(), 0
+    while lits < 230000:
+        k = rng.choice((1, 3, 50, 4000))
+        runs += bytes(rng.getrandbits(8) | 1 for _ in range(k))
+        runs += bytes(rng.choice((1, 7, 8, 9, 64, 258, 259, 517, 3000, 70000)))
+        lits += k
+    datas = [noise, tile, bytes(runs), noise[:200000] + bytes(300000) + noise[200000:]]
+    return [(oracle.compress_ultra_fast(d), d) for d in datas]
+
+
+def test_inflate_long_streams_span_by_span(emul_ctx, emul_lib, oracle):
+    """Long ultra-fast-format streams are cut into spans decoded by different warps (count pass from a
+    guessed bit, chain check, write pass).  Bytes, lengths, consumed and status must equal the oracle's,
+    whatever the slot alignment; damaged / truncated / short-slot cases must come out as the oracle says
+    (the span path declines them and the general kernel reports)."""
+    c = _long_uf_cases(oracle, emul_lib, 41)
+    assert all(len(s) >= 262144 for s, _ in c)
+    exact = [(s, len(d)) for s, d in c]
+    parity.check_inflate(emul_ctx, exact, 0, expect_general=0)
+    assert emul_ctx.last_split_spans() >= 4 * len(c) - 4   # the streams really took the span path
+    parity.check_inflate(emul_ctx, exact, 0, align=1, expect_general=0)
+    assert emul_ctx.last_split_spans() > 0
+    # mixed with short streams and general zlib streams in one batch
+    small = [(oracle.compress_ultra_fast(d), len(d)) for d in cases.compress_inputs(2, 6, [100, 5000])]
+    mixed = cases.mixed_zlib_cases(4, 6, [100, 3000])
+    parity.check_inflate(emul_ctx, small[:5] + exact[:2] + mixed[:10] + exact[2:] + small[5:10], 0)
+    # slots: generous, one short, half
+    parity.check_inflate(emul_ctx, [(s, n + 100) for s, n in exact], 0, expect_general=0)
+    parity.check_inflate(emul_ctx, [(s, n - 1) for s, n in exact], 0)
+    parity.check_inflate(emul_ctx, [(s, n // 2) for s, n in exact[:2]], 0)
+    # damage: truncation, a flipped bit early / late, a wrong checksum, trailing bytes
+    rng = random.Random(5)
+    dmg = []
+    for s, n in exact[:3]:
+        dmg += [(s[: len(s) - 3], n), (s[: len(s) // 2], n), (s + b"xyz", n)]
+        for pos in (60, len(s) // 3, len(s) - 10):
+            b = bytearray(s)
+            b[pos] ^= 1 << rng.randrange(8)
+            dmg.append((bytes(b), n))
+        b = bytearray(s)
+        b[-1] ^= 0xff
+        dmg.append((bytes(b), n))
+    parity.check_inflate(emul_ctx, dmg, 0)
+    parity.check_inflate(emul_ctx, dmg[::2], FLAG_IGNORE_ADLER32)

@@ -236,3 +236,60 @@ def test_inflate_parallel_block_decode(gpu_ctx, oracle):
         cut.append((bytes(b), n))
     parity.check_inflate(gpu_ctx, cut, FLAG_GENERAL_ONLY)
     parity.check_inflate(gpu_ctx, cut, FLAG_GENERAL_ONLY | FLAG_IGNORE_ADLER32)
+
+
+def test_inflate_long_streams_span_by_span(gpu_ctx, oracle):
+    """GPU twin of the emulator test: long ultra-fast-format streams decoded span by span by many warps
+    (count pass from a guessed bit, chain check, write pass) must equal the oracle bit for bit; damaged,
+    truncated and short-slot cases must come out exactly as the oracle says."""
+    from test_emul_kernels import _long_uf_cases
+
+    c = _long_uf_cases(oracle, gpu_ctx.lib, 41) + _long_uf_cases(oracle, gpu_ctx.lib, 42)
+    exact = [(s, len(d)) for s, d in c]
+    for align in (16, 1):
+        parity.check_inflate(gpu_ctx, exact, 0, align=align, expect_general=0)
+        assert gpu_ctx.last_split_spans() >= 4 * len(c) - 8
+    small = [(oracle.compress_ultra_fast(d), len(d)) for d in cases.compress_inputs(2, 20, [100, 5000, 70000])]
+    mixed = cases.mixed_zlib_cases(4, 10, [100, 3000, 50000])
+    parity.check_inflate(gpu_ctx, small[:30] + exact[:3] + mixed[:40] + exact[3:] + small[30:60], 0)
+    parity.check_inflate(gpu_ctx, [(s, n + 100) for s, n in exact], 0, expect_general=0)
+    parity.check_inflate(gpu_ctx, [(s, n - 1) for s, n in exact], 0)
+    parity.check_inflate(gpu_ctx, [(s, n // 2) for s, n in exact], 0)
+    rng = random.Random(5)
+    dmg = []
+    for s, n in exact:
+        dmg += [(s[: len(s) - 3], n), (s[: len(s) // 2], n), (s + b"xyz", n)]
+        for pos in (60, len(s) // 3, len(s) - 10):
+            b = bytearray(s)
+            b[pos] ^= 1 << rng.randrange(8)
+            dmg.append((bytes(b), n))
+        b = bytearray(s)
+        b[-1] ^= 0xff
+        dmg.append((bytes(b), n))
+    parity.check_inflate(gpu_ctx, dmg, 0)
+    parity.check_inflate(gpu_ctx, dmg, FLAG_IGNORE_ADLER32)
+
+
+def test_config5_ragged_large_streams_roundtrip(gpu_ctx, oracle):
+    """BASELINE configs[4] at a reduced count: streams of 64 KiB .. 16 MiB (log-uniform) through the
+    host-buffer calls: deflate -> inflate must give the input back, the biggest and a few others are
+    compared with the oracle byte for byte, and the long ones must have taken the span path."""
+    from fdeflate_b200 import synth_tiles_host
+
+    rng = np.random.default_rng(5)
+    sizes = np.exp(rng.uniform(np.log(64 << 10), np.log(16 << 20), 24))
+    row = 1 + 4 * 1024
+    datas = [synth_tiles_host(100 + i, 1, 1024, max(1, int(sz) // row), 5, gpu_ctx.lib)[0].tobytes() for i, sz in enumerate(sizes)]
+    datas.append(bytes(3 << 20))                                     # one run of 3 MiB
+    datas.append(np.random.default_rng(6).integers(0, 256, 2 << 20, dtype=np.uint8).tobytes())  # incompressible
+    comp = gpu_ctx.deflate_ultrafast_batch(datas)
+    order = np.argsort([len(d) for d in datas])
+    for i in list(order[-2:]) + list(order[:3]):
+        assert comp[i] == oracle.compress_ultra_fast(datas[i])
+    st, outs, cons = gpu_ctx.inflate_batch(comp, [len(d) for d in datas])
+    assert (st == 0).all() and gpu_ctx.last_general_count() == 0
+    assert gpu_ctx.last_split_spans() > 0
+    for d, o, s, k in zip(datas, outs, comp, cons):
+        assert o == d and k == len(s)
+    for d, s in zip(datas, comp):
+        assert zlib.adler32(d) == int.from_bytes(s[-4:], "big")
