@@ -111,6 +111,10 @@ class Context:
         return int(self.lib.L.fdb_last_general_count(self._h, stream))
 
     # ---- raw packed host-buffer calls ---------------------------------------------------------
+    def set_split_large(self, on: bool = True):
+        """device-pointer calls: decode / encode long streams with many warps each (see fdeflate_b200.h)"""
+        self._check(self.lib.L.fdb_set_split_large(self._h, 1 if on else 0), "fdb_set_split_large")
+
     def last_split_spans(self, stream: int = 0) -> int:
         """spans the long streams of the most recent inflate batch were cut into (0 = one warp per stream)"""
         return int(self.lib.L.fdb_last_split_spans(self._h, stream))

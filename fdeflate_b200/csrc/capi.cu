@@ -36,6 +36,13 @@ struct fdb_split_scratch {
     size_t per_stream_bytes = 0;
 };
 static const uint32_t FDB_SPLIT_ITEMS = 1u << 18;  // spans per batch (16 GiB of compressed input)
+// ... and of the segment-by-segment deflate path
+struct fdb_dsplit_scratch {
+    DfItem* items = nullptr;
+    size_t items_bytes = 0;
+    uint32_t* per_stream = nullptr;  // item0 | nseg | adler, n words each
+    size_t per_stream_bytes = 0;
+};
 
 struct fdb_lane {
     cudaStream_t st = nullptr;
@@ -43,6 +50,7 @@ struct fdb_lane {
     uint32_t* d_worklist = nullptr;
     size_t worklist_cap = 0;
     fdb_split_scratch split;
+    fdb_dsplit_scratch dsplit;
 };
 static const int FDB_LANES = 8;        // compute lanes created per context
 static const int FDB_MAX_CHUNKS = 64;  // chunks per host-buffer call (one event pair each)
@@ -68,6 +76,8 @@ struct fdb_ctx {
     uint32_t* d_worklist = nullptr;
     size_t worklist_cap = 0;
     fdb_split_scratch split;
+    fdb_dsplit_scratch dsplit;
+    int split_large = 0;            // device-pointer calls: long streams by many warps (fdb_set_split_large)
     UfEncTables* d_enc = nullptr;
     UfDecTables* d_dec = nullptr;
     // host-API staging (grow-only)
@@ -168,6 +178,12 @@ extern "C" int64_t fdb_last_general_count(fdb_ctx* ctx, void* cuda_stream) {
     return (int64_t)v;
 }
 
+extern "C" int fdb_set_split_large(fdb_ctx* ctx, int on) {
+    if (!ctx) return -1;
+    ctx->split_large = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" int64_t fdb_last_split_spans(fdb_ctx* ctx, void* cuda_stream) {
     if (!ctx) return -1;
     if (ctx->last_split_host >= 0) return ctx->last_split_host;
@@ -260,6 +276,8 @@ extern "C" void fdb_destroy(fdb_ctx* ctx) {
         cudaFree(ctx->lanes[l].d_worklist);
         cudaFree(ctx->lanes[l].split.items);
         cudaFree(ctx->lanes[l].split.per_stream);
+        cudaFree(ctx->lanes[l].dsplit.items);
+        cudaFree(ctx->lanes[l].dsplit.per_stream);
     }
     if (!ctx->lanes[0].st && ctx->stream) cudaStreamDestroy(ctx->stream);
     for (int k = 0; k < FDB_MAX_CHUNKS; k++) {
@@ -272,6 +290,8 @@ extern "C" void fdb_destroy(fdb_ctx* ctx) {
     cudaFree(ctx->d_worklist);
     cudaFree(ctx->split.items);
     cudaFree(ctx->split.per_stream);
+    cudaFree(ctx->dsplit.items);
+    cudaFree(ctx->dsplit.per_stream);
     cudaFree(ctx->d_enc);
     cudaFree(ctx->d_dec);
     cudaFree(ctx->d_in);
@@ -396,7 +416,7 @@ extern "C" int fdb_inflate_batch_device(fdb_ctx* ctx, const void* d_in_base, con
     b.consumed = d_consumed;
     b.status = d_status;
     b.n = (uint32_t)n;
-    b.flags = flags;
+    b.flags = flags | (ctx->split_large ? FDB_FLAG_SPLIT_LARGE : 0u);
     ctx->last_general_host = -1;
     ctx->last_split_host = -1;
     return launch_inflate(ctx, b, ctx->d_counters, &ctx->d_worklist, &ctx->worklist_cap, (cudaStream_t)cuda_stream, false,
@@ -405,17 +425,50 @@ extern "C" int fdb_inflate_batch_device(fdb_ctx* ctx, const void* d_in_base, con
 
 // ---- deflate ----------------------------------------------------------------------------------
 static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_t* counter, cudaStream_t st,
-                          bool dense = false) {
+                          bool dense = false, fdb_dsplit_scratch* ss = nullptr) {
     const size_t n = b.n;
+    // counter = counters + 3; the segment path uses counters[8..11] of the same block
     FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
     const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
+    const uint32_t* split_item0 = nullptr;
+    if (kind == 0 && ss) {
+        // long inputs, segment by segment: plan, count, scan, write (deflate_uf.cuh)
+        int r;
+        void* p = ss->items;
+        if ((r = grow(ctx, &p, &ss->items_bytes, (size_t)FDB_SPLIT_ITEMS * sizeof(DfItem)))) return r;
+        ss->items = (DfItem*)p;
+        p = ss->per_stream;
+        r = grow(ctx, &p, &ss->per_stream_bytes, 3 * n * sizeof(uint32_t));
+        ss->per_stream = (uint32_t*)p;
+        if (r) return r;
+        uint32_t* c8 = counter + 5;
+        FDB_TRY(cudaMemsetAsync(c8, 0, 4 * sizeof(uint32_t), st));
+        DfSplit sp;
+        sp.items = ss->items;
+        sp.item_cap = FDB_SPLIT_ITEMS;
+        sp.n_items = c8;
+        sp.item0 = ss->per_stream;
+        sp.nseg = ss->per_stream + n;
+        sp.adler = ss->per_stream + 2 * n;
+        sp.next_count = c8 + 1;
+        sp.next_scan = c8 + 2;
+        sp.next_write = c8 + 3;
+        split_item0 = sp.item0;
+        const uint32_t pgrid = sms * DEFLATE_MIN_CTAS;
+        FDB_LAUNCH(deflate_uf_plan_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0, st, b, sp);
+        FDB_LAUNCH(deflate_uf_split_count_kernel, dim3(pgrid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc, sp);
+        FDB_LAUNCH(deflate_uf_split_scan_kernel, dim3((uint32_t)std::min<size_t>((n + 7) / 8, (size_t)sms * 4)), dim3(256), 0, st, b, sp);
+        FDB_LAUNCH(deflate_uf_split_write_kernel, dim3(pgrid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc, sp);
+        ctx->launches += 4;
+        FDB_TRY(cudaGetLastError());
+    }
     if (kind == 0) {
         // persistent: every resident warp pulls streams from one counter, so SMs stay evenly loaded
         // even when the batch is not a multiple of the chip's warp slots
         uint32_t grid = (uint32_t)std::min<size_t>(dense ? (n + DEFLATE_WARPS - 1) / DEFLATE_WARPS : n,
                                                    (size_t)sms * DEFLATE_MIN_CTAS);
         FDB_LAUNCH(deflate_uf_kernel, dim3(grid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc,
-                   counter);
+                   counter, split_item0);
     } else {
         uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * 8);
         FDB_LAUNCH(deflate_stored_kernel, dim3(grid), dim3(STORED_THREADS), 0, st, b, counter);
@@ -444,7 +497,8 @@ static int deflate_device(fdb_ctx* ctx, int kind, const void* d_in_base, const u
     b.out_len = d_out_len;
     b.status = d_status;
     b.n = (uint32_t)n;
-    return launch_deflate(ctx, kind, b, ctx->d_counters + 3, (cudaStream_t)cuda_stream);
+    return launch_deflate(ctx, kind, b, ctx->d_counters + 3, (cudaStream_t)cuda_stream, false,
+                          ctx->split_large ? &ctx->dsplit : nullptr);
 }
 
 extern "C" int fdb_deflate_ultrafast_batch_device(fdb_ctx* ctx, const void* d_in_base, const uint64_t* d_in_off,
@@ -634,7 +688,11 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             db.out_len = h_out_len + a;
             db.status = h_status + a;
             db.n = (uint32_t)(b - a);
-            if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st, dense))) return rr;
+            uint64_t max_len = 0;
+            for (size_t i = a; i < b; i++) max_len = std::max(max_len, in_len[i]);
+            if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st, dense,
+                                     max_len >= DF_SPLIT_MIN_BYTES ? &ln.dsplit : nullptr)))
+                return rr;
         }
         mark(k, 2, ln.st);
         FDB_TRY(cudaEventRecord(ctx->ev_res[k], ln.st));

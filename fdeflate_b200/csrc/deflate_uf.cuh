@@ -169,10 +169,37 @@ FDB_DEVICE uint4 load16_guarded(const uint8_t* in, uint64_t g, uint64_t n, bool 
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// One stream, one warp.  Returns the encoded length, or 0 with *status != ST_OK.
-FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok, const uint32_t* header,
-                                      uint32_t* stg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap,
-                                      int32_t* status) {
+// ---- segments: a long input encoded by several warps ------------------------------------------
+// An input of many 64 KiB SEGMENTS is encoded in three passes.  COUNT: every segment finds the run that
+// is pending where it starts (the zero bytes just before it: the reference's `run` counter at a chunk
+// boundary is exactly their number), walks its warp steps without packing anything and reports how many
+// bits it will emit, plus its adler32 partial sums.  A prefix sum over the segments of a stream turns the
+// bit counts into bit offsets (split_scan_kernel, which also knows the final length and checksum then).
+// WRITE: every segment encodes again, at its offset; the one word it shares with the segment before and
+// the one it shares with the segment after are merged with atomicOr into words the scan has zeroed, every
+// other word is stored exactly once as in the one-warp encoder.  DF_WHOLE is that one-warp encoder.
+enum : int { DF_WHOLE = 0, DF_COUNT = 1, DF_WRITE = 2 };
+static const uint64_t DF_SEG_BYTES = 64u << 10;              // multiple of the 512-byte warp step
+static const uint64_t DF_SPLIT_MIN_BYTES = 4 * DF_SEG_BYTES;  // inputs of >= 4 segments are split
+static const uint32_t DF_NO_ITEM = 0xffffffffu;
+
+struct DfSpan {
+    uint64_t begin, end;  // input bytes of the segment: begin is a multiple of 512, end = n for the last one
+    uint64_t bit_off;     // DF_WRITE: stream bit (0 = first bit of the zlib header) where the segment's tokens start
+    uint32_t run_in;      // pending run entering the segment, in bytes
+    uint32_t first, last; // the stream's first / last segment (header / end of block + checksum)
+    uint32_t adler;       // DF_WRITE, last: the stream's checksum
+};
+struct DfSpanOut {
+    uint64_t bits;        // DF_COUNT: bits of the segment's tokens
+    uint64_t s1, s2;      // DF_COUNT: adler32 partial sums of the segment's bytes (s2 mod 65521)
+};
+
+// DF_WHOLE: one stream, one warp; returns the encoded length, or 0 with *status != ST_OK.
+template <int MODE>
+FDB_DEVICE uint64_t deflate_uf_run(const uint2* lit, const uint32_t* tail_tok, const uint32_t* header,
+                                   uint32_t* stg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap,
+                                   int32_t* status, const DfSpan* sp, DfSpanOut* so) {
     const unsigned lane = simt::lane_id();
     const simt::saddr stg_s = simt::smem_addr(stg);
     const uint32_t oab = (uint32_t)((uintptr_t)out & 3u);  // out's offset inside its aligned word
@@ -200,7 +227,13 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok
     // ---- header (ultrafast.rs:81-91): 53 bytes + the low 5 bits of byte 53 ----
     uint64_t vbit = 8ull * oab + UF_HEADER_BITS;  // virtual bit cursor (bit 0 = bit 0 of obase[0])
     uint32_t wcarry = 0;                          // bits of the incomplete word below the cursor
-    {
+    // DF_WRITE: the first word this segment completes also holds the last bits of the segment before
+    bool merge_first = false;
+    if (MODE == DF_WRITE && !sp->first) {
+        vbit = 8ull * oab + sp->bit_off;
+        merge_first = true;
+    }
+    if (MODE == DF_WHOLE || (MODE == DF_WRITE && sp->first)) {
         uint32_t hw = 0;  // virtual word `lane` of the header
         if (lane < 16) {
             for (uint32_t j = 0; j < 4; j++) {
@@ -215,13 +248,15 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok
 
     // ---- data (ultrafast.rs:94-167) ----
     AdlerAcc ad = {0, 0};
-    uint32_t run_carry = 0;
-    const uint64_t iters = (n + 511) >> 9;
+    uint32_t run_carry = MODE == DF_WHOLE ? 0u : sp->run_in;
+    const uint64_t iters = (n + 511) >> 9;                                   // warp steps of the whole stream
+    const uint64_t it_begin = MODE == DF_WHOLE ? 0 : sp->begin >> 9;         // ... and of this call
+    const uint64_t it_end = MODE == DF_WHOLE ? iters : (sp->end + 511) >> 9;
     uint4 nxt = make_uint4(0, 0, 0, 0);
-    if (iters > 0) nxt = load16_guarded(in, (uint64_t)lane * 16, n, in_aligned);
+    if (it_begin < it_end) nxt = load16_guarded(in, (it_begin << 9) + (uint64_t)lane * 16, n, in_aligned);
     // "is the first byte of the next step zero": needed by lane 31 long before that step's data, so it
     // is fetched one step earlier than the data itself
-    uint32_t nfb_next = iters > 1 ? simt::ldg8(in + 512) : 1u;  // (the raw byte: compared when it is used)
+    uint32_t nfb_next = it_begin + 1 < iters ? simt::ldg8(in + ((it_begin + 1) << 9)) : 1u;  // (the raw byte: compared when it is used)
     // One 512-byte warp step.  FULL: every chunk of the step is a whole chunk inside the run-logic prefix
     // (all steps of a stream but the last one or two), which removes every end-of-input test.
     auto step = [&](uint64_t it, auto full_tag) {
@@ -234,7 +269,8 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok
         if (it + 2 < iters) nfb_next = simt::ldg8(in + base + 1024);
 
         // adler partial sums
-        if (FULL || g + 16 <= n) {
+        if (MODE == DF_WRITE) {
+        } else if (FULL || g + 16 <= n) {
             adler_add16(ad, q, g);
             if ((it & 63) == 63) adler_fold(ad);
         } else if (g < n) {
@@ -298,6 +334,10 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok
                                  ((p[6].n + p[7].n + t0.head_n) + (t0.tail_n + t1.head_n + t1.tail_n));
         const uint32_t incl_bits = simt::scan_incl_add(my_bits);
         const uint32_t total_bits = simt::shfl(incl_bits, 31);
+        if (MODE == DF_COUNT) {
+            vbit += total_bits;
+            return;
+        }
         const uint64_t o = vbit + (incl_bits - my_bits);
         const uint64_t wbase = vbit >> 5;
 
@@ -357,22 +397,37 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok
             uint32_t* const dst = obase + wbase;
             if (fit < nwords) overflow = true;
             // a step normally completes ~55 words: two straight-line rounds, then a loop for the rest
-            if (lane < fit) dst[lane] = simt::lds32(stg_s + 4u * lane);
+            if (MODE == DF_WRITE && merge_first && fit > 0) {
+                if (lane == 0) simt::atomic_or(dst, simt::lds32(stg_s));
+                else if (lane < fit) dst[lane] = simt::lds32(stg_s + 4u * lane);
+                merge_first = false;
+            } else if (lane < fit) dst[lane] = simt::lds32(stg_s + 4u * lane);
             if (lane + 32 < fit) dst[lane + 32] = simt::lds32(stg_s + 4u * lane + 128u);
 #pragma unroll 1
             for (uint32_t k = lane + 64; k < fit; k += 32) dst[k] = simt::lds32(stg_s + 4u * k);
         }
         simt::syncwarp();
     };
-    for (uint64_t it = 0; it < iters; it++) {
+    for (uint64_t it = it_begin; it < it_end; it++) {
         if ((it << 9) + 512 <= n8)
             step(it, std::true_type{});
         else
             step(it, std::false_type{});
     }
+    if (MODE == DF_COUNT) {
+        so->bits = vbit - (8ull * oab + UF_HEADER_BITS);
+        so->s1 = simt::reduce_add(ad.s1);
+        so->s2 = simt::reduce_add(ad.s2 % ADLER_MOD) % ADLER_MOD;
+        return 0;
+    }
+    if (MODE == DF_WRITE && !sp->last) {
+        // the word under the cursor is shared with the next segment: merge my bits into it
+        if (lane == 0 && (vbit & 31) && ((vbit >> 5) + 1) * 4 - oab <= cap) simt::atomic_or(obase + (vbit >> 5), wcarry);
+        return 0;
+    }
 
     // ---- finish (ultrafast.rs:170-181): EOB, pad to a byte, adler32 big-endian ----
-    const uint32_t adler = adler_finish_warp(ad, n);
+    const uint32_t adler = MODE == DF_WRITE ? sp->adler : adler_finish_warp(ad, n);
     overflow = simt::any(overflow);
     uint64_t total_len = 0;
     {
@@ -401,8 +456,14 @@ FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok
     return overflow ? 0 : total_len;
 }
 
+FDB_DEVICE uint64_t deflate_uf_stream(const uint2* lit, const uint32_t* tail_tok, const uint32_t* header,
+                                      uint32_t* stg, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap,
+                                      int32_t* status) {
+    return deflate_uf_run<DF_WHOLE>(lit, tail_tok, header, stg, in, n, out, cap, status, nullptr, nullptr);
+}
+
 FDB_GLOBAL void FDB_LAUNCH_BOUNDS(DEFLATE_WARPS * 32, DEFLATE_MIN_CTAS)
-    deflate_uf_kernel(DeflateBatch b, const UfEncTables* tables, uint32_t* next) {
+    deflate_uf_kernel(DeflateBatch b, const UfEncTables* tables, uint32_t* next, const uint32_t* split_item0) {
     FDB_SHARED DeflateSmem s;
     for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) s.lit[i] = tables->lit[i];
     for (uint32_t i = threadIdx.x; i < 258; i += blockDim.x) s.tail_tok[i] = tables->tail_tok[i];
@@ -415,6 +476,7 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(DEFLATE_WARPS * 32, DEFLATE_MIN_CTAS)
         if (lane == 0) i = simt::atomic_add(next, 1u);
         i = simt::shfl(i, 0);
         if (i >= b.n) break;
+        if (split_item0 && split_item0[i] != DF_NO_ITEM) continue;  // encoded segment by segment (below)
         int32_t st = ST_OK;
         uint64_t len = deflate_uf_stream(s.lit, s.tail_tok, s.header, stg, b.in_base + b.in_off[i], b.in_len[i],
                                          b.out_base + b.out_off[i], b.out_cap[i], &st);
@@ -422,6 +484,209 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(DEFLATE_WARPS * 32, DEFLATE_MIN_CTAS)
             b.out_len[i] = len;
             b.status[i] = st;
         }
+    }
+}
+
+// ---- segment path ------------------------------------------------------------------------------
+struct DfItem {
+    uint32_t stream, j;
+    uint32_t run_in;   // count pass
+    uint32_t skip;     // scan: the stream does not fit its slot, nothing is written
+    uint64_t bits;     // count pass
+    uint64_t s1, s2;   // count pass
+    uint64_t bit_off;  // scan
+};
+struct DfSplit {
+    DfItem* items;
+    uint32_t item_cap;
+    uint32_t* n_items;
+    uint32_t* item0;    // [n] first item of stream i, or DF_NO_ITEM
+    uint32_t* nseg;     // [n]
+    uint32_t* adler;    // [n] scan: checksum of the whole input
+    uint32_t* next_count;
+    uint32_t* next_scan;
+    uint32_t* next_write;
+};
+
+FDB_GLOBAL void deflate_uf_plan_kernel(DeflateBatch b, DfSplit sp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    sp.item0[i] = DF_NO_ITEM;
+    sp.nseg[i] = 0;
+    const uint64_t n = b.in_len[i];
+    if (n < DF_SPLIT_MIN_BYTES) return;
+    const uint64_t S = n / DF_SEG_BYTES;  // the last segment also takes the remainder
+    if (S > 0x7fffffffull) return;
+    const uint32_t base = simt::atomic_add(sp.n_items, (uint32_t)S);
+    if ((uint64_t)base + S > sp.item_cap) return;  // scratch exhausted: one warp encodes this stream
+    sp.item0[i] = base;
+    sp.nseg[i] = (uint32_t)S;
+    for (uint32_t j = 0; j < (uint32_t)S; j++) {
+        sp.items[base + j].stream = i;
+        sp.items[base + j].j = j;
+        sp.items[base + j].skip = 1;
+    }
+}
+FDB_DEVICE uint32_t df_item_count(const DfSplit& sp) {
+    const uint32_t c = *sp.n_items;
+    return c < sp.item_cap ? c : sp.item_cap;
+}
+FDB_DEVICE bool df_item_live(const DfSplit& sp, uint32_t idx, const DfItem& it, uint32_t n) {
+    return it.stream < n && sp.item0[it.stream] != DF_NO_ITEM && sp.item0[it.stream] + it.j == idx;
+}
+FDB_DEVICE void df_span_of(DfSpan& span, uint32_t j, uint32_t S, uint64_t n) {
+    span.begin = (uint64_t)j * DF_SEG_BYTES;
+    span.end = j + 1 == S ? n : span.begin + DF_SEG_BYTES;
+    span.first = j == 0;
+    span.last = j + 1 == S;
+    span.bit_off = 0;
+    span.run_in = 0;
+    span.adler = 0;
+}
+
+// The run pending at byte `pos` (a multiple of 512): the zero bytes just before it.  The reference's
+// counter (ultrafast.rs:97-131) is `run + 8` over an all-zero chunk and the chunk's trailing zeros
+// otherwise, i.e. at a chunk boundary it is the length of the zero suffix of everything before.
+FDB_DEVICE uint32_t pending_run_before(const uint8_t* in, uint64_t pos, bool in_aligned) {
+    const unsigned lane = simt::lane_id();
+    uint64_t x = 0;
+    while (pos > 0) {  // (pos stays a multiple of 512)
+        const uint64_t g = pos - 16u * (lane + 1u);  // lane 0 holds the 16 bytes just before pos
+        const uint4 q = in_aligned ? simt::ldg128((const uint4*)(in + g)) : load16_guarded(in, g, pos, false);
+        const bool nz = (q.x | q.y | q.z | q.w) != 0;
+        const uint32_t m = simt::ballot(nz);
+        if (m) {
+            const uint32_t l = simt::ffs(m) - 1u;
+            const uint32_t w3 = simt::shfl(q.w, l), w2 = simt::shfl(q.z, l), w1 = simt::shfl(q.y, l), w0 = simt::shfl(q.x, l);
+            const uint32_t tz = w3 ? simt::clz(w3) >> 3 : w2 ? 4u + (simt::clz(w2) >> 3) : w1 ? 8u + (simt::clz(w1) >> 3) : 12u + (simt::clz(w0) >> 3);
+            x += 16u * l + tz;
+            break;
+        }
+        x += 512;
+        pos -= 512;
+    }
+    // all the encoder ever uses of a run length is "mod 258" and "> 0" (chunk_plan): keep those, stay small
+    return (uint32_t)(x % 258u) + (x >= 258u ? 258u : 0u);
+}
+
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(DEFLATE_WARPS * 32, DEFLATE_MIN_CTAS)
+    deflate_uf_split_count_kernel(DeflateBatch b, const UfEncTables* tables, DfSplit sp) {
+    FDB_SHARED DeflateSmem s;
+    const uint32_t count = df_item_count(sp);
+    if (count == 0) return;
+    for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) s.lit[i] = tables->lit[i];
+    for (uint32_t i = threadIdx.x; i < 258; i += blockDim.x) s.tail_tok[i] = tables->tail_tok[i];
+    for (uint32_t i = threadIdx.x; i < 14; i += blockDim.x) s.header[i] = tables->header[i];
+    simt::syncthreads();
+    const unsigned lane = simt::lane_id();
+    uint32_t* stg = s.stg[simt::warp_in_block()];
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = simt::atomic_add(sp.next_count, 1u);
+        idx = simt::shfl(idx, 0);
+        if (idx >= count) break;
+        DfItem& it = sp.items[idx];
+        if (!df_item_live(sp, idx, it, b.n)) continue;
+        const uint32_t i = it.stream;
+        const uint8_t* in = b.in_base + b.in_off[i];
+        const uint64_t n = b.in_len[i];
+        DfSpan span;
+        df_span_of(span, it.j, sp.nseg[i], n);
+        span.run_in = pending_run_before(in, span.begin, ((uintptr_t)in & 15u) == 0);
+        DfSpanOut so;
+        int32_t st = ST_OK;
+        deflate_uf_run<DF_COUNT>(s.lit, s.tail_tok, s.header, stg, in, n, b.out_base + b.out_off[i], b.out_cap[i], &st, &span, &so);
+        if (lane == 0) {
+            it.run_in = span.run_in;
+            it.bits = so.bits;
+            it.s1 = so.s1;
+            it.s2 = so.s2;
+        }
+        simt::syncwarp();
+    }
+}
+
+// One warp per split stream: bit offsets of its segments, final length, checksum, status; zeroes the
+// words two segments share.
+FDB_GLOBAL void deflate_uf_split_scan_kernel(DeflateBatch b, DfSplit sp) {
+    const unsigned lane = simt::lane_id();
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = simt::atomic_add(sp.next_scan, 1u);
+        i = simt::shfl(i, 0);
+        if (i >= b.n) break;
+        const uint32_t base = sp.item0[i];
+        if (base == DF_NO_ITEM) continue;
+        const uint32_t S = sp.nseg[i];
+        const uint64_t n = b.in_len[i];
+        uint8_t* out = b.out_base + b.out_off[i];
+        const uint32_t oab = (uint32_t)((uintptr_t)out & 3u);
+        uint64_t carry = UF_HEADER_BITS, t1 = 0, t2 = 0;
+        for (uint32_t g = 0; g < S; g += 32) {
+            const uint32_t j = g + lane;
+            const bool have = j < S;
+            const uint64_t bits = have ? sp.items[base + j].bits : 0ull;
+            if (have) {
+                t1 += sp.items[base + j].s1;
+                t2 += sp.items[base + j].s2;
+            }
+            const uint64_t incl = simt::scan_incl_add(bits);
+            if (have) sp.items[base + j].bit_off = carry + incl - bits;
+            carry += simt::shfl(incl, 31);
+        }
+        // end of block (12 bits), pad to a byte, adler32 (ultrafast.rs:170-181)
+        const uint64_t total_len = (carry + 12 + 7) / 8 + 4;
+        const bool fits = total_len <= b.out_cap[i];
+        t1 = simt::reduce_add(t1);
+        t2 = simt::reduce_add(t2 % ADLER_MOD) % ADLER_MOD;
+        const uint32_t s1m = (uint32_t)(t1 % ADLER_MOD), s2m = (uint32_t)t2, nm = (uint32_t)(n % ADLER_MOD);
+        const uint32_t A = (1u + s1m) % ADLER_MOD;
+        const uint32_t B = (uint32_t)(((uint64_t)nm + (uint64_t)nm * s1m % ADLER_MOD + ADLER_MOD - s2m) % ADLER_MOD);
+        for (uint32_t j = lane; j < S; j += 32) {
+            sp.items[base + j].skip = fits ? 0u : 1u;
+            if (fits && j > 0) {  // the word segments j-1 and j share
+                const uint64_t k = (8ull * oab + sp.items[base + j].bit_off) >> 5;
+                *(uint32_t*)(out - oab + 4 * k) = 0u;
+            }
+        }
+        if (lane == 0) {
+            sp.adler[i] = (B << 16) | A;
+            b.out_len[i] = fits ? total_len : 0;
+            b.status[i] = fits ? ST_OK : ST_OUTPUT_BUFFER_TOO_SMALL;
+        }
+        simt::syncwarp();
+    }
+}
+
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(DEFLATE_WARPS * 32, DEFLATE_MIN_CTAS)
+    deflate_uf_split_write_kernel(DeflateBatch b, const UfEncTables* tables, DfSplit sp) {
+    FDB_SHARED DeflateSmem s;
+    const uint32_t count = df_item_count(sp);
+    if (count == 0) return;
+    for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) s.lit[i] = tables->lit[i];
+    for (uint32_t i = threadIdx.x; i < 258; i += blockDim.x) s.tail_tok[i] = tables->tail_tok[i];
+    for (uint32_t i = threadIdx.x; i < 14; i += blockDim.x) s.header[i] = tables->header[i];
+    simt::syncthreads();
+    const unsigned lane = simt::lane_id();
+    uint32_t* stg = s.stg[simt::warp_in_block()];
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = simt::atomic_add(sp.next_write, 1u);
+        idx = simt::shfl(idx, 0);
+        if (idx >= count) break;
+        const DfItem& it = sp.items[idx];
+        if (!df_item_live(sp, idx, it, b.n) || it.skip) continue;
+        const uint32_t i = it.stream;
+        const uint8_t* in = b.in_base + b.in_off[i];
+        const uint64_t n = b.in_len[i];
+        DfSpan span;
+        df_span_of(span, it.j, sp.nseg[i], n);
+        span.run_in = it.run_in;
+        span.bit_off = it.bit_off;
+        span.adler = sp.adler[i];
+        int32_t st = ST_OK;
+        deflate_uf_run<DF_WRITE>(s.lit, s.tail_tok, s.header, stg, in, n, b.out_base + b.out_off[i], b.out_cap[i], &st, &span, nullptr);
+        simt::syncwarp();
     }
 }
 

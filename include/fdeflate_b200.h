@@ -137,6 +137,11 @@ uint64_t fdb_launch_count(const fdb_ctx* ctx);
 /* how many streams of the most recent inflate batch on this context were declined by the
  * ultra-fast-format fast path and decoded by the general kernel.  Synchronises `cuda_stream`. */
 int64_t fdb_last_general_count(fdb_ctx* ctx, void* cuda_stream);
+/* Device-pointer calls only (the host-buffer calls decide by themselves, they see the sizes): when on,
+ * ultra-fast-format streams of >= 256 KiB are inflated span by span and inputs of >= 256 KiB are
+ * ultra-fast-deflated segment by segment, each by many warps, at the price of a few extra small launches
+ * per batch.  Results are identical either way.  Off by default. */
+int fdb_set_split_large(fdb_ctx* ctx, int on);
 /* how many spans the long streams of the most recent inflate batch on this context were cut into
  * (0 = every stream was decoded by one warp).  Synchronises `cuda_stream`. */
 int64_t fdb_last_split_spans(fdb_ctx* ctx, void* cuda_stream);

@@ -201,3 +201,51 @@ def test_inflate_long_streams_span_by_span(emul_ctx, emul_lib, oracle):
         dmg.append((bytes(b), n))
     parity.check_inflate(emul_ctx, dmg, 0)
     parity.check_inflate(emul_ctx, dmg[::2], FLAG_IGNORE_ADLER32)
+
+
+def _long_deflate_inputs(lib, seed):
+    """inputs of >= 256 KiB for the segment-by-segment deflate path: zero runs that start before, end after
+    and span whole 64 KiB segments, run lengths around the 258-byte token limit at the boundaries, lengths
+    that are and are not multiples of 8 / 512 / 64 KiB"""
+    from fdeflate_b200 import synth_tiles_host
+
+    rng = random.Random(seed)
+    seg = 65536
+    noise = bytes(rng.getrandbits(8) for _ in range(5 * seg + 77))
+    tile = synth_tiles_host(9, 1, 1024, 100, 5, lib)[0].tobytes()
+    a = bytearray(rng.getrandbits(8) | 1 for _ in range(6 * seg))
+    for b0, ln in ((seg - 5, 10), (2 * seg - 300, 258 + 300), (3 * seg - 1, 1), (3 * seg + 0, 9), (4 * seg - 258, 258 * 2 + 1),
+                   (5 * seg - 8, 8), (5 * seg + 512 - 3, 700)):
+        a[b0:b0 + ln] = bytes(ln)
+    zeros_mid = noise[:seg + 11] + bytes(3 * seg + 5) + noise[:seg]          # a run that covers whole segments
+    all_zero = bytes(4 * seg + 3)
+    tail_zero = noise[:2 * seg] + bytes(2 * seg + 100)                        # the run is still pending at the end
+    exact = noise[:4 * seg]                                                   # no remainder segment
+    return [noise, tile, bytes(a), zeros_mid, all_zero, tail_zero, exact, cases.sparse_bytes(rng, 5 * seg + 1000)]
+
+
+def test_deflate_long_inputs_segment_by_segment(emul_ctx, emul_lib, oracle):
+    """Inputs of >= 256 KiB are encoded by many warps (count pass, prefix sum of bit counts, write pass with
+    atomicOr on the words two segments share); the bytes must equal the oracle's single sequential pass."""
+    inputs = _long_deflate_inputs(emul_lib, 11)
+    parity.check_deflate_ultrafast(emul_ctx, inputs, align=16)
+    parity.check_deflate_ultrafast(emul_ctx, inputs[:4], align=1)
+    small = cases.compress_inputs(3, 6, [10, 3000])
+    l0 = emul_ctx.launch_count
+    parity.check_deflate_ultrafast(emul_ctx, small[:5] + inputs[2:5] + small[5:10], align=16)
+    assert emul_ctx.launch_count - l0 == 5  # plan, count, scan, write + the one-warp-per-stream kernel
+    _check_deflate_slot_sizes(emul_ctx, oracle, inputs[2])
+
+
+def _check_deflate_slot_sizes(ctx, oracle, data):
+    """a slot of exactly the encoded size works, one byte less gives OutputBufferTooSmall and length 0"""
+    import numpy as np
+
+    ref = oracle.compress_ultra_fast(data)
+    src = np.frombuffer(data, dtype=np.uint8).copy()
+    for cap, want in ((len(ref), 0), (len(ref) - 1, 18), (len(ref) // 2, 18)):
+        out = np.zeros(len(ref) + 64, dtype=np.uint8)
+        ln, st = ctx.deflate_ultrafast_packed(src, [0], [len(data)], out, [0], [cap])
+        assert st[0] == want and ln[0] == (len(ref) if want == 0 else 0)
+        if want == 0:
+            assert out[:len(ref)].tobytes() == ref

@@ -293,3 +293,19 @@ def test_config5_ragged_large_streams_roundtrip(gpu_ctx, oracle):
         assert o == d and k == len(s)
     for d, s in zip(datas, comp):
         assert zlib.adler32(d) == int.from_bytes(s[-4:], "big")
+
+
+def test_deflate_long_inputs_segment_by_segment(gpu_ctx, oracle):
+    """GPU twin of the emulator test: inputs of >= 256 KiB encoded by many warps must be byte-identical to
+    the oracle's single sequential pass (real concurrency: the words two segments share are merged with
+    atomicOr)."""
+    from test_emul_kernels import _check_deflate_slot_sizes, _long_deflate_inputs
+
+    inputs = _long_deflate_inputs(gpu_ctx.lib, 11) + _long_deflate_inputs(gpu_ctx.lib, 12)
+    for _ in range(3):  # scheduling differs from run to run
+        parity.check_deflate_ultrafast(gpu_ctx, inputs, align=16)
+    parity.check_deflate_ultrafast(gpu_ctx, inputs, align=1)
+    small = cases.compress_inputs(3, 30, [10, 3000, 70000])
+    parity.check_deflate_ultrafast(gpu_ctx, small[:40] + inputs[2:9] + small[40:80], align=16)
+    _check_deflate_slot_sizes(gpu_ctx, oracle, inputs[2])
+    _check_deflate_slot_sizes(gpu_ctx, oracle, inputs[4])

@@ -43,7 +43,16 @@ def run(order_name, heights):
         for _ in range(reps): f()
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
-    ms_d = timed(deflate); ms_i1 = timed(lambda: inflate(0))
+    ms_d1 = timed(deflate)
+    ref_len = c_len.clone(); ref_comp = comp.clone()
+    ctx.set_split_large(True); comp.zero_()
+    ms_d = timed(deflate)
+    ctx.set_split_large(False)
+    assert int(c_st.abs().sum()) == 0 and torch.equal(c_len, ref_len)
+    for i in range(0, n, max(1, n // 64)):  # (bytes past a stream's length are unspecified)
+        a = int(coffs[i]); assert torch.equal(comp[a:a + int(c_len[i])], ref_comp[a:a + int(c_len[i])]), "segment path differs"
+    del ref_comp
+    ms_i1 = timed(lambda: inflate(0))
     assert int(o_st.abs().sum()) == 0
     out.zero_()
     ms_i = timed(inflate)
@@ -53,7 +62,7 @@ def run(order_name, heights):
     for i in range(0, n, max(1, n // 16)):
         a = int(offs[i]); assert torch.equal(out[a:a + int(lens[i])], raw[a:a + int(lens[i])])
     unc = int(lens.sum())
-    print(f"{order_name:14s} {n} streams, {unc/1e9:.2f} GB, ratio {int(c_len.sum())/unc:.3f}: deflate {ms_d:8.2f} ms = {unc/ms_d/1e6:7.1f} GB/s   "
+    print(f"{order_name:14s} {n} streams, {unc/1e9:.2f} GB, ratio {int(c_len.sum())/unc:.3f}: deflate one warp/stream {ms_d1:8.2f} ms = {unc/ms_d1/1e6:6.1f} GB/s, segment by segment {ms_d:8.2f} ms = {unc/ms_d/1e6:7.1f} GB/s   "
           f"inflate one warp/stream {ms_i1:8.2f} ms = {unc/ms_i1/1e6:6.1f} GB/s, span by span ({spans} spans) {ms_i:8.2f} ms = {unc/ms_i/1e6:7.1f} GB/s   (largest stream {lens.max()/1e6:.1f} MB)")
     del raw, comp, out
     torch.cuda.empty_cache()
