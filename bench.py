@@ -226,6 +226,7 @@ def ours(args, rank: int, local_rank: int, world: int):
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = F.Context(local_rank)  # raises without the CUDA library / a GPU: there is no fallback

@@ -58,29 +58,66 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(STORED_THREADS, 1) deflate_stored_kernel(Defla
                 h[0] = 0x03; h[1] = 0x00;
             }
         }
-        // payload: input byte p lands at 2 + 5 * (p / 65535 + 1) + p
+        // payload: block k's bytes move from in + 65535 k to out + 2 + 65540 k + 5.  Source and destination are
+        // misaligned against each other by a different amount in every block, so each block is copied as: a few
+        // head bytes up to the first 16-byte boundary of the DESTINATION, then whole vectors (two aligned
+        // 16-byte loads funnel-shifted into one aligned 16-byte streaming store), then the tail bytes.
+        // adler32 rides along on the bytes in registers.
         AdlerAcc ad = {0, 0};
-        const bool aligned = ((uintptr_t)in & 15u) == 0;
-        const uint64_t nvec = aligned ? (n >> 4) : 0;
-        for (uint64_t v = tid; v < nvec; v += STORED_THREADS) {
-            uint4 q = simt::ldg128((const uint4*)in + v);
-            uint64_t p = v << 4;
-            adler_add16(ad, q, p);
-            adler_fold(ad);
-            uint32_t w[4] = {q.x, q.y, q.z, q.w};
-            uint64_t blk = p / 65535;
-            uint64_t next_edge = (blk + 1) * 65535;
-            uint64_t d = 2 + 5 * (blk + 1) + p;
-#pragma unroll
-            for (uint32_t j = 0; j < 16; j++) {
-                if (p + j == next_edge) d += 5;
-                out[d + j] = (uint8_t)(w[j >> 2] >> (8u * (j & 3u)));
+        const uint64_t nblocks = full + (rem ? 1 : 0);
+        for (uint64_t k = 0; k < nblocks; k++) {
+            const uint64_t p0 = k * 65535;
+            const uint32_t len = k < full ? 65535u : (uint32_t)rem;
+            const uint8_t* src = in + p0;
+            uint8_t* dst = out + 2 + k * 65540 + 5;
+            uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+            if (head > len) head = len;
+            const uint32_t nvec = (len - head) >> 4;
+            const uint32_t tail0 = head + (nvec << 4);
+            if (tid < head) {
+                const uint8_t v = simt::ldg8(src + tid);
+                adler_add1(ad, v, p0 + tid);
+                dst[tid] = v;
             }
-        }
-        for (uint64_t p = (nvec << 4) + tid; p < n; p += STORED_THREADS) {
-            uint8_t v = simt::ldg8(in + p);
-            adler_add1(ad, v, p);
-            out[2 + 5 * (p / 65535 + 1) + p] = v;
+            if (tid >= 32 && tid - 32 < len - tail0) {  // (another warp than the head's)
+                const uint32_t q = tail0 + (tid - 32);
+                const uint8_t v = simt::ldg8(src + q);
+                adler_add1(ad, v, p0 + q);
+                dst[q] = v;
+            }
+            const uint8_t* sh_src = src + head;
+            const uint32_t sh = (uint32_t)((uintptr_t)sh_src & 15u);
+            const uint4* a0 = (const uint4*)(sh_src - sh);
+            uint4* d0 = (uint4*)(dst + head);
+            const uint32_t s4 = sh >> 2, sb = 8u * (sh & 3u);
+            for (uint32_t v = tid; v < nvec; v += STORED_THREADS) {
+                const uint4 lo = simt::ldg128(a0 + v);
+                uint4 r = lo;
+                if (sh) {
+                    const uint4 hi = simt::ldg128(a0 + v + 1);
+                    switch (s4) {  // (uniform over the block)
+                        case 0:
+                            r = make_uint4(simt::funnel_r(lo.x, lo.y, sb), simt::funnel_r(lo.y, lo.z, sb),
+                                           simt::funnel_r(lo.z, lo.w, sb), simt::funnel_r(lo.w, hi.x, sb));
+                            break;
+                        case 1:
+                            r = make_uint4(simt::funnel_r(lo.y, lo.z, sb), simt::funnel_r(lo.z, lo.w, sb),
+                                           simt::funnel_r(lo.w, hi.x, sb), simt::funnel_r(hi.x, hi.y, sb));
+                            break;
+                        case 2:
+                            r = make_uint4(simt::funnel_r(lo.z, lo.w, sb), simt::funnel_r(lo.w, hi.x, sb),
+                                           simt::funnel_r(hi.x, hi.y, sb), simt::funnel_r(hi.y, hi.z, sb));
+                            break;
+                        default:
+                            r = make_uint4(simt::funnel_r(lo.w, hi.x, sb), simt::funnel_r(hi.x, hi.y, sb),
+                                           simt::funnel_r(hi.y, hi.z, sb), simt::funnel_r(hi.z, hi.w, sb));
+                            break;
+                    }
+                }
+                adler_add16(ad, r, p0 + head + ((uint64_t)v << 4));
+                simt::stcs128(d0 + v, r);
+            }
+            adler_fold(ad);
         }
         // block-wide adler reduction
         uint64_t s1 = simt::reduce_add(ad.s1);
