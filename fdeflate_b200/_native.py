@@ -20,7 +20,7 @@ EXPORTS = [
     "fdb_deflate_ultrafast_bound", "fdb_deflate_ultrafast_batch_device", "fdb_deflate_ultrafast_batch",
     "fdb_deflate_stored_bound", "fdb_deflate_stored_batch_device", "fdb_deflate_stored_batch",
     "fdb_synth_tile_bytes", "fdb_synth_tiles_host", "fdb_synth_tiles_device", "fdb_launch_count", "fdb_last_general_count",
-    "fdb_set_pipeline_chunk", "fdb_last_split_spans", "fdb_set_split_large",
+    "fdb_set_pipeline_chunk", "fdb_last_split_spans", "fdb_set_split_large", "fdb_set_split_threshold",
 ]
 
 FLAG_IGNORE_ADLER32 = 1
@@ -80,6 +80,8 @@ class NativeLib:
         L.fdb_last_general_count.argtypes = [vp, vp]
         L.fdb_set_split_large.restype = C.c_int
         L.fdb_set_split_large.argtypes = [vp, C.c_int]
+        L.fdb_set_split_threshold.restype = C.c_int
+        L.fdb_set_split_threshold.argtypes = [vp, sz, sz]
         L.fdb_last_split_spans.restype = C.c_int64
         L.fdb_last_split_spans.argtypes = [vp, vp]
 

@@ -115,6 +115,11 @@ class Context:
         """device-pointer calls: decode / encode long streams with many warps each (see fdeflate_b200.h)"""
         self._check(self.lib.L.fdb_set_split_large(self._h, 1 if on else 0), "fdb_set_split_large")
 
+    def set_split_threshold(self, inflate_stream_bytes: int = 0, deflate_input_bytes: int = 0):
+        """sizes from which a stream is decoded / encoded by many warps (0 = default: 256 KiB / 1 MiB)"""
+        self._check(self.lib.L.fdb_set_split_threshold(self._h, inflate_stream_bytes, deflate_input_bytes),
+                    "fdb_set_split_threshold")
+
     def last_split_spans(self, stream: int = 0) -> int:
         """spans the long streams of the most recent inflate batch were cut into (0 = one warp per stream)"""
         return int(self.lib.L.fdb_last_split_spans(self._h, stream))

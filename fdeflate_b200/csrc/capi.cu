@@ -78,6 +78,8 @@ struct fdb_ctx {
     fdb_split_scratch split;
     fdb_dsplit_scratch dsplit;
     int split_large = 0;            // device-pointer calls: long streams by many warps (fdb_set_split_large)
+    uint64_t inflate_split_min = K4_SPLIT_MIN_BYTES;  // fdb_set_split_threshold
+    uint64_t deflate_split_min = DF_SPLIT_MIN_BYTES;
     UfEncTables* d_enc = nullptr;
     UfDecTables* d_dec = nullptr;
     // host-API staging (grow-only)
@@ -181,6 +183,13 @@ extern "C" int64_t fdb_last_general_count(fdb_ctx* ctx, void* cuda_stream) {
 extern "C" int fdb_set_split_large(fdb_ctx* ctx, int on) {
     if (!ctx) return -1;
     ctx->split_large = on ? 1 : 0;
+    return 0;
+}
+
+extern "C" int fdb_set_split_threshold(fdb_ctx* ctx, size_t inflate_bytes, size_t deflate_bytes) {
+    if (!ctx) return -1;
+    ctx->inflate_split_min = inflate_bytes ? inflate_bytes : K4_SPLIT_MIN_BYTES;
+    ctx->deflate_split_min = deflate_bytes ? deflate_bytes : DF_SPLIT_MIN_BYTES;
     return 0;
 }
 
@@ -362,6 +371,7 @@ static int launch_inflate(fdb_ctx* ctx, const InflateBatch& b, uint32_t* counter
         sp.next_count = counters + 5;
         sp.next_scan = counters + 6;
         sp.next_write = counters + 7;
+        sp.min_bytes = ctx->inflate_split_min;
         split_item0 = sp.item0;
         FDB_LAUNCH(inflate_uf_plan_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0, st, b, (const UfDecTables*)ctx->d_dec, sp);
         FDB_LAUNCH(inflate_uf_split_count_kernel, dim3(sms), dim3(K4_WARPS * 32), sizeof(K4Smem), st, b,
@@ -453,6 +463,7 @@ static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_
         sp.next_count = c8 + 1;
         sp.next_scan = c8 + 2;
         sp.next_write = c8 + 3;
+        sp.min_bytes = ctx->deflate_split_min;
         split_item0 = sp.item0;
         const uint32_t pgrid = sms * DEFLATE_MIN_CTAS;
         FDB_LAUNCH(deflate_uf_plan_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0, st, b, sp);
@@ -672,7 +683,7 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             ib.status = h_status + a;
             ib.n = (uint32_t)(b - a);
             ib.flags = flags;
-            if (max_in >= K4_SPLIT_MIN_BYTES) ib.flags |= FDB_FLAG_SPLIT_LARGE;  // long streams: many warps each
+            if (max_in >= ctx->inflate_split_min) ib.flags |= FDB_FLAG_SPLIT_LARGE;  // long streams: many warps each
             ib.general_out = h_general + k;
             ib.split_out = h_split + k;
             if ((rr = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, dense, &ln.split)))
@@ -691,7 +702,7 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             uint64_t max_len = 0;
             for (size_t i = a; i < b; i++) max_len = std::max(max_len, in_len[i]);
             if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st, dense,
-                                     max_len >= DF_SPLIT_MIN_BYTES ? &ln.dsplit : nullptr)))
+                                     max_len >= ctx->deflate_split_min ? &ln.dsplit : nullptr)))
                 return rr;
         }
         mark(k, 2, ln.st);

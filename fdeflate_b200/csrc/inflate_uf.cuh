@@ -278,7 +278,7 @@ static const uint32_t K4_SPAN_SEGS = 64;                            // segments 
 static const uint64_t K4_SPAN_WORDS = (uint64_t)K4_SPAN_SEGS * 32 * K4_SUBW;
 enum : uint32_t { SP_EOB = 1, SP_FIRSTRUN = 2, SP_LASTNZ = 4, SP_DEAD = 8, SP_SKIP = 16, SP_SYNCFAIL = 32 };
 static const uint32_t K4_NO_ITEM = 0xffffffffu;
-static const uint64_t K4_SPLIT_MIN_BYTES = 4ull * K4_SPAN_WORDS * 4;  // streams of >= 4 spans (256 KiB) are split
+static const uint64_t K4_SPLIT_MIN_BYTES = 4ull * K4_SPAN_WORDS * 4;  // default: streams of >= 4 spans (256 KiB) are split
 
 // One span of one split stream (device scratch, filled by the three passes in turn).
 struct K4Item {
@@ -302,6 +302,7 @@ struct K4Split {
     uint32_t* next_count;  // work counters of the three persistent passes
     uint32_t* next_scan;
     uint32_t* next_write;
+    uint64_t min_bytes;    // streams at least this long are split
 };
 
 struct K4Span {
@@ -786,7 +787,7 @@ FDB_GLOBAL void inflate_uf_plan_kernel(InflateBatch b, const UfDecTables* tables
     sp.done[i] = 0;
     sp.failed[i] = 0;
     const uint64_t n = b.in_len[i];
-    if (n < K4_SPLIT_MIN_BYTES) return;
+    if (n < sp.min_bytes) return;
     const uint8_t* in = b.in_base + b.in_off[i];
     for (uint32_t j = 0; j < 54; j++) {  // the constant header (ultrafast.rs:82-91)
         uint32_t want = (tables->header[j >> 2] >> (8u * (j & 3u))) & 0xffu;

@@ -302,10 +302,16 @@ def test_deflate_long_inputs_segment_by_segment(gpu_ctx, oracle):
     from test_emul_kernels import _check_deflate_slot_sizes, _long_deflate_inputs
 
     inputs = _long_deflate_inputs(gpu_ctx.lib, 11) + _long_deflate_inputs(gpu_ctx.lib, 12)
-    for _ in range(3):  # scheduling differs from run to run
-        parity.check_deflate_ultrafast(gpu_ctx, inputs, align=16)
-    parity.check_deflate_ultrafast(gpu_ctx, inputs, align=1)
-    small = cases.compress_inputs(3, 30, [10, 3000, 70000])
-    parity.check_deflate_ultrafast(gpu_ctx, small[:40] + inputs[2:9] + small[40:80], align=16)
-    _check_deflate_slot_sizes(gpu_ctx, oracle, inputs[2])
-    _check_deflate_slot_sizes(gpu_ctx, oracle, inputs[4])
+    try:
+        gpu_ctx.set_split_threshold(0, 4 * 65536)  # (default 1 MiB)
+        for _ in range(3):  # scheduling differs from run to run
+            l0 = gpu_ctx.launch_count
+            parity.check_deflate_ultrafast(gpu_ctx, inputs, align=16)
+            assert gpu_ctx.launch_count - l0 == 5
+        parity.check_deflate_ultrafast(gpu_ctx, inputs, align=1)
+        small = cases.compress_inputs(3, 30, [10, 3000, 70000])
+        parity.check_deflate_ultrafast(gpu_ctx, small[:40] + inputs[2:9] + small[40:80], align=16)
+        _check_deflate_slot_sizes(gpu_ctx, oracle, inputs[2])
+        _check_deflate_slot_sizes(gpu_ctx, oracle, inputs[4])
+    finally:
+        gpu_ctx.set_split_threshold(0, 0)
