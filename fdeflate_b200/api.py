@@ -28,7 +28,7 @@ STATUS_NAMES = [
     "InvalidHlit", "InvalidHdist", "InvalidCodeLengthRepeat", "BadCodeLengthHuffmanTree",
     "BadLiteralLengthHuffmanTree", "BadDistanceHuffmanTree", "InvalidLiteralLengthCode", "InvalidDistanceCode",
     "InputStartsWithRun", "DistanceTooFarBack", "WrongChecksum", "ExtraInput", "OutputTooLarge",
-    "OutputBufferTooSmall",
+    "OutputBufferTooSmall", "PngBadFilterType", "PngBadGeometry",
 ]
 ST_OK, ST_INSUFFICIENT_INPUT, ST_OUTPUT_TOO_LARGE = 0, 2, 17
 
@@ -232,6 +232,53 @@ class Context:
         rc = self.lib.L.fdb_deflate_stored_batch_device(self._h, d_in, d_in_off, d_in_len, d_out, d_out_off,
                                                         d_out_cap, d_out_len, d_status, n, stream)
         self._check(rc, "fdb_deflate_stored_batch_device")
+
+    # ---- PNG row filters (png_filter.cuh) ------------------------------------------------------
+    def png_unfilter_device(self, d_filtered, d_filtered_off, d_raw, d_raw_off, d_height, d_stride, d_bpp, d_status,
+                            n: int, stream: int = 0):
+        rc = self.lib.L.fdb_png_unfilter_batch_device(self._h, d_filtered, d_filtered_off, d_raw, d_raw_off, d_height,
+                                                      d_stride, d_bpp, d_status, n, stream)
+        self._check(rc, "fdb_png_unfilter_batch_device")
+
+    def png_filter_device(self, d_raw, d_raw_off, d_filtered, d_filtered_off, d_height, d_stride, d_bpp, mode: int,
+                          d_status, n: int, stream: int = 0):
+        rc = self.lib.L.fdb_png_filter_batch_device(self._h, d_raw, d_raw_off, d_filtered, d_filtered_off, d_height,
+                                                    d_stride, d_bpp, mode, d_status, n, stream)
+        self._check(rc, "fdb_png_filter_batch_device")
+
+    def _png_batch(self, unfilter: bool, images: Sequence[bytes], geometry: Sequence[tuple], mode: int = 0):
+        """images[i] with geometry[i] = (height, stride, bpp) -> (status[n], list of bytes)"""
+        n = len(images)
+        h = np.array([g[0] for g in geometry], dtype=np.uint32)
+        s = np.array([g[1] for g in geometry], dtype=np.uint32)
+        b = np.array([g[2] for g in geometry], dtype=np.uint32)
+        filt = h.astype(np.uint64) * (1 + s.astype(np.uint64))
+        raw = h.astype(np.uint64) * s.astype(np.uint64)
+        in_sz, out_sz = (filt, raw) if unfilter else (raw, filt)
+        for i, im in enumerate(images):
+            if len(im) != int(in_sz[i]):
+                raise ValueError(f"image {i}: {len(im)} bytes, geometry says {int(in_sz[i])}")
+        in_base, in_off, _ = self._pack(images)
+        out_off = np.zeros(n, dtype=np.uint64)
+        if n > 1:
+            out_off[1:] = np.cumsum((out_sz[:-1] + np.uint64(15)) & ~np.uint64(15))
+        out_base = np.zeros(int(out_off[-1] + out_sz[-1]) + 16 if n else 16, dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int32)
+        if unfilter:
+            rc = self.lib.L.fdb_png_unfilter_batch(self._h, _ptr(in_base), _ptr(in_off), _ptr(out_base), _ptr(out_off),
+                                                   _ptr(h), _ptr(s), _ptr(b), _ptr(status), n)
+        else:
+            rc = self.lib.L.fdb_png_filter_batch(self._h, _ptr(in_base), _ptr(in_off), _ptr(out_base), _ptr(out_off),
+                                                 _ptr(h), _ptr(s), _ptr(b), mode, _ptr(status), n)
+        self._check(rc, "fdb_png_*_batch")
+        outs = [out_base[int(out_off[i]): int(out_off[i]) + int(out_sz[i])].tobytes() for i in range(n)]
+        return status, outs
+
+    def png_unfilter_batch(self, filtered: Sequence[bytes], geometry: Sequence[tuple]):
+        return self._png_batch(True, filtered, geometry)
+
+    def png_filter_batch(self, raw: Sequence[bytes], geometry: Sequence[tuple], mode: int = 4):
+        return self._png_batch(False, raw, geometry, mode)
 
     def synth_tiles_device(self, d_out: int, first_tile: int, n_tiles: int, width: int, height: int, seed: int,
                            stream: int = 0):

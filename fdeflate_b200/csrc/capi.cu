@@ -23,6 +23,7 @@
 #include "deflate_uf.cuh"
 #include "deflate_stored.cuh"
 #include "synth.cuh"
+#include "png_filter.cuh"
 
 using namespace fdb;
 
@@ -87,6 +88,8 @@ struct fdb_ctx {
     size_t d_in_cap = 0;
     uint8_t* d_out = nullptr;
     size_t d_out_cap = 0;
+    uint8_t* d_mid = nullptr;    // filtered images between the two steps of fdb_png_{decode,encode}_batch
+    size_t d_mid_cap = 0;
     uint64_t* d_meta = nullptr;  // in_off | in_len | out_off | out_cap | out_len | consumed | status(int32)
     size_t d_meta_cap = 0;
     uint64_t launches = 0;
@@ -305,6 +308,7 @@ extern "C" void fdb_destroy(fdb_ctx* ctx) {
     cudaFree(ctx->d_dec);
     cudaFree(ctx->d_in);
     cudaFree(ctx->d_out);
+    cudaFree(ctx->d_mid);
     cudaFree(ctx->d_meta);
     delete ctx;
 }
@@ -781,6 +785,246 @@ extern "C" int fdb_deflate_stored_batch(fdb_ctx* ctx, const uint8_t* in_base, co
                                         const uint64_t* in_len, uint8_t* out_base, const uint64_t* out_off,
                                         const uint64_t* out_cap, uint64_t* out_len, int32_t* status, size_t n) {
     return host_batch(ctx, 2, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, nullptr, status, n, 0);
+}
+
+// ---- PNG row filters --------------------------------------------------------------------------
+static int png_launch(fdb_ctx* ctx, bool unfilter, const void* d_in_base, const uint64_t* d_in_off, void* d_out_base,
+                      const uint64_t* d_out_off, const uint32_t* d_height, const uint32_t* d_stride, const uint32_t* d_bpp,
+                      uint32_t mode, int32_t* d_status, size_t n, void* cuda_stream) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (n > 0xffffffffull || !d_in_off || !d_out_off || !d_height || !d_stride || !d_bpp || !d_status)
+        return fail(ctx, "fdb_png_*_batch_device", cudaSuccess);
+    FDB_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    PngBatch b;
+    b.in_base = (const uint8_t*)d_in_base;
+    b.in_off = d_in_off;
+    b.out_base = (uint8_t*)d_out_base;
+    b.out_off = d_out_off;
+    b.height = d_height;
+    b.stride = d_stride;
+    b.bpp = d_bpp;
+    b.status = d_status;
+    b.n = (uint32_t)n;
+    b.mode = mode;
+    uint32_t* counter = ctx->d_counters + 12;
+    FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+    const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
+    if (unfilter) {
+        // a warp per image, persistent
+        uint32_t grid = (uint32_t)std::min<size_t>((n + PNG_UNFILTER_WARPS - 1) / PNG_UNFILTER_WARPS, (size_t)sms * 4);
+        FDB_LAUNCH(png_unfilter_kernel, dim3(grid), dim3(PNG_UNFILTER_WARPS * 32), 0, st, b, counter);
+    } else {
+        uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * 4);
+        FDB_LAUNCH(png_filter_kernel, dim3(grid), dim3(PNG_FILTER_WARPS * 32), 0, st, b, counter);
+    }
+    ctx->launches++;
+    FDB_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int fdb_png_unfilter_batch_device(fdb_ctx* ctx, const void* d_in_base, const uint64_t* d_in_off, void* d_out_base,
+                                             const uint64_t* d_out_off, const uint32_t* d_height, const uint32_t* d_stride,
+                                             const uint32_t* d_bpp, int32_t* d_status, size_t n, void* cuda_stream) {
+    return png_launch(ctx, true, d_in_base, d_in_off, d_out_base, d_out_off, d_height, d_stride, d_bpp, 0, d_status, n,
+                      cuda_stream);
+}
+extern "C" int fdb_png_filter_batch_device(fdb_ctx* ctx, const void* d_in_base, const uint64_t* d_in_off, void* d_out_base,
+                                           const uint64_t* d_out_off, const uint32_t* d_height, const uint32_t* d_stride,
+                                           const uint32_t* d_bpp, uint32_t mode, int32_t* d_status, size_t n,
+                                           void* cuda_stream) {
+    return png_launch(ctx, false, d_in_base, d_in_off, d_out_base, d_out_off, d_height, d_stride, d_bpp, mode, d_status, n,
+                      cuda_stream);
+}
+
+// host-buffer variants: stage through the context's device buffers on its first lane (one copy up, the kernel,
+// one copy back; these calls are not pipelined)
+static int png_host(fdb_ctx* ctx, bool unfilter, const uint8_t* in_base, const uint64_t* in_off, uint8_t* out_base,
+                    const uint64_t* out_off, const uint32_t* height, const uint32_t* stride, const uint32_t* bpp, uint32_t mode,
+                    int32_t* status, size_t n) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (n > 0xffffffffull || !in_off || !out_off || !height || !stride || !bpp || !status)
+        return fail(ctx, "fdb_png_*_batch", cudaSuccess);
+    FDB_TRY(cudaSetDevice(ctx->device));
+    uint64_t in_span = 0, out_span = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t filtered = (uint64_t)height[i] * (1ull + stride[i]), raw = (uint64_t)height[i] * stride[i];
+        in_span = std::max(in_span, in_off[i] + (unfilter ? filtered : raw));
+        out_span = std::max(out_span, out_off[i] + (unfilter ? raw : filtered));
+    }
+    int r;
+    if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, in_span + 64))) return r;
+    if ((r = grow(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, out_span + 64))) return r;
+    if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, 5 * n * sizeof(uint64_t)))) return r;
+    cudaStream_t st = ctx->lanes[0].st;
+    uint64_t* d_in_off = ctx->d_meta;
+    uint64_t* d_out_off = d_in_off + n;
+    uint32_t* d_h = (uint32_t*)(d_out_off + n);
+    uint32_t* d_s = d_h + n;
+    uint32_t* d_b = d_s + n;
+    int32_t* d_status = (int32_t*)(d_b + n);
+    FDB_TRY(cudaMemcpyAsync(d_in_off, in_off, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_out_off, out_off, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_h, height, n * 4, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_s, stride, n * 4, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_b, bpp, n * 4, cudaMemcpyHostToDevice, st));
+    if (in_span) FDB_TRY(cudaMemcpyAsync(ctx->d_in, in_base, in_span, cudaMemcpyHostToDevice, st));
+    if ((r = png_launch(ctx, unfilter, ctx->d_in, d_in_off, ctx->d_out, d_out_off, d_h, d_s, d_b, mode, d_status, n, st))) return r;
+    if (out_span) FDB_TRY(cudaMemcpyAsync(out_base, ctx->d_out, out_span, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+extern "C" int fdb_png_unfilter_batch(fdb_ctx* ctx, const uint8_t* filtered_base, const uint64_t* filtered_off,
+                                      uint8_t* raw_base, const uint64_t* raw_off, const uint32_t* height,
+                                      const uint32_t* stride, const uint32_t* bpp, int32_t* status, size_t n) {
+    return png_host(ctx, true, filtered_base, filtered_off, raw_base, raw_off, height, stride, bpp, 0, status, n);
+}
+extern "C" int fdb_png_filter_batch(fdb_ctx* ctx, const uint8_t* raw_base, const uint64_t* raw_off, uint8_t* filtered_base,
+                                    const uint64_t* filtered_off, const uint32_t* height, const uint32_t* stride,
+                                    const uint32_t* bpp, uint32_t mode, int32_t* status, size_t n) {
+    return png_host(ctx, false, raw_base, raw_off, filtered_base, filtered_off, height, stride, bpp, mode, status, n);
+}
+
+// ---- PNG image data: zlib stream <-> raw pixels, the intermediate filtered image never leaves the device ----
+// decode: IDAT payloads up, inflate (fast path / spans / general kernel as the streams require) into a device
+// buffer of filtered images, unfilter into a second one, raw pixels back.  status = the inflate status if it is
+// not Ok, else the unfilter status; a stream that inflates to anything but height * (1 + stride) bytes is
+// reported as InsufficientInput / OutputTooLarge by the inflate step (slot = exactly that size).
+extern "C" int fdb_png_decode_batch(fdb_ctx* ctx, const uint8_t* idat_base, const uint64_t* idat_off, const uint64_t* idat_len,
+                                    uint8_t* raw_base, const uint64_t* raw_off, const uint32_t* height, const uint32_t* stride,
+                                    const uint32_t* bpp, int32_t* status, size_t n) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (n > 0xffffffffull || !idat_off || !idat_len || !raw_off || !height || !stride || !bpp || !status)
+        return fail(ctx, "fdb_png_decode_batch", cudaSuccess);
+    FDB_TRY(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> m(4 * n);  // filtered_off | filtered_cap | (spare) | (spare)
+    uint64_t in_span = 0, raw_span = 0, filt_span = 0, max_in = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t filtered = (uint64_t)height[i] * (1ull + stride[i]);
+        in_span = std::max(in_span, idat_off[i] + idat_len[i]);
+        max_in = std::max(max_in, idat_len[i]);
+        raw_span = std::max(raw_span, raw_off[i] + (uint64_t)height[i] * stride[i]);
+        m[i] = filt_span;
+        m[n + i] = filtered;
+        filt_span += (filtered + 15) & ~15ull;
+    }
+    int r;
+    if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, in_span + 64))) return r;
+    if ((r = grow(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, raw_span + 64))) return r;
+    if ((r = grow(ctx, (void**)&ctx->d_mid, &ctx->d_mid_cap, filt_span + 64))) return r;
+    // idat_off | idat_len | filt_off | filt_cap | raw_off | out_len | consumed | h,s,b (u32) | status x2 (i32)
+    if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, 10 * n * sizeof(uint64_t)))) return r;
+    cudaStream_t st = ctx->lanes[0].st;
+    uint64_t* d = ctx->d_meta;
+    uint64_t *d_idat_off = d, *d_idat_len = d + n, *d_filt_off = d + 2 * n, *d_filt_cap = d + 3 * n, *d_raw_off = d + 4 * n,
+             *d_out_len = d + 5 * n, *d_consumed = d + 6 * n;
+    uint32_t* d_h = (uint32_t*)(d + 7 * n);
+    uint32_t *d_s = d_h + n, *d_b = d_s + n;
+    int32_t* d_st1 = (int32_t*)(d_b + n);
+    int32_t* d_st2 = d_st1 + n;
+    FDB_TRY(cudaMemcpyAsync(d_idat_off, idat_off, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_idat_len, idat_len, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_filt_off, m.data(), 2 * n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_raw_off, raw_off, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_h, height, n * 4, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_s, stride, n * 4, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_b, bpp, n * 4, cudaMemcpyHostToDevice, st));
+    if (in_span) FDB_TRY(cudaMemcpyAsync(ctx->d_in, idat_base, in_span, cudaMemcpyHostToDevice, st));
+    InflateBatch ib;
+    ib.in_base = ctx->d_in;
+    ib.in_off = d_idat_off;
+    ib.in_len = d_idat_len;
+    ib.out_base = ctx->d_mid;
+    ib.out_off = d_filt_off;
+    ib.out_cap = d_filt_cap;
+    ib.out_len = d_out_len;
+    ib.consumed = d_consumed;
+    ib.status = d_st1;
+    ib.n = (uint32_t)n;
+    ib.flags = max_in >= ctx->inflate_split_min ? FDB_FLAG_SPLIT_LARGE : 0u;
+    ctx->last_general_host = -1;
+    ctx->last_split_host = -1;
+    if ((r = launch_inflate(ctx, ib, ctx->d_counters, &ctx->d_worklist, &ctx->worklist_cap, st, false, &ctx->split))) return r;
+    if ((r = png_launch(ctx, true, ctx->d_mid, d_filt_off, ctx->d_out, d_raw_off, d_h, d_s, d_b, 0, d_st2, n, st))) return r;
+    std::vector<int32_t> st12(2 * n);
+    std::vector<uint64_t> olen(n);
+    if (raw_span) FDB_TRY(cudaMemcpyAsync(raw_base, ctx->d_out, raw_span, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaMemcpyAsync(st12.data(), d_st1, 2 * n * 4, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaMemcpyAsync(olen.data(), d_out_len, n * 8, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; i++) {
+        int32_t s1 = st12[i];
+        if (s1 == ST_OK && olen[i] != m[n + i]) s1 = ST_INSUFFICIENT_INPUT;  // the stream ended before the image was complete
+        status[i] = s1 != ST_OK ? s1 : st12[n + i];
+    }
+    return 0;
+}
+
+// encode: raw pixels up, filter, ultra-fast deflate, zlib streams back (slots of fdb_deflate_ultrafast_bound).
+extern "C" int fdb_png_encode_batch(fdb_ctx* ctx, const uint8_t* raw_base, const uint64_t* raw_off, const uint32_t* height,
+                                    const uint32_t* stride, const uint32_t* bpp, uint32_t mode, uint8_t* out_base,
+                                    const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, int32_t* status,
+                                    size_t n) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (n > 0xffffffffull || !raw_off || !height || !stride || !bpp || !out_off || !out_cap || !out_len || !status)
+        return fail(ctx, "fdb_png_encode_batch", cudaSuccess);
+    FDB_TRY(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> m(2 * n);  // filtered_off | filtered_len
+    uint64_t raw_span = 0, filt_span = 0, out_span = 0, max_len = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t filtered = (uint64_t)height[i] * (1ull + stride[i]);
+        raw_span = std::max(raw_span, raw_off[i] + (uint64_t)height[i] * stride[i]);
+        out_span = std::max(out_span, out_off[i] + out_cap[i]);
+        max_len = std::max(max_len, filtered);
+        m[i] = filt_span;
+        m[n + i] = filtered;
+        filt_span += (filtered + 15) & ~15ull;
+    }
+    int r;
+    if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, raw_span + 64))) return r;
+    if ((r = grow(ctx, (void**)&ctx->d_mid, &ctx->d_mid_cap, filt_span + 64))) return r;
+    if ((r = grow(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, out_span + 64))) return r;
+    if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, 10 * n * sizeof(uint64_t)))) return r;
+    cudaStream_t st = ctx->lanes[0].st;
+    uint64_t* d = ctx->d_meta;
+    uint64_t *d_raw_off = d, *d_filt_off = d + n, *d_filt_len = d + 2 * n, *d_out_off = d + 3 * n, *d_out_cap = d + 4 * n,
+             *d_out_len = d + 5 * n;
+    uint32_t* d_h = (uint32_t*)(d + 6 * n);
+    uint32_t *d_s = d_h + n, *d_b = d_s + n;
+    int32_t* d_st1 = (int32_t*)(d_b + n);
+    int32_t* d_st2 = d_st1 + n;
+    FDB_TRY(cudaMemcpyAsync(d_raw_off, raw_off, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_filt_off, m.data(), 2 * n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_out_off, out_off, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_out_cap, out_cap, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_h, height, n * 4, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_s, stride, n * 4, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_b, bpp, n * 4, cudaMemcpyHostToDevice, st));
+    if (raw_span) FDB_TRY(cudaMemcpyAsync(ctx->d_in, raw_base, raw_span, cudaMemcpyHostToDevice, st));
+    if ((r = png_launch(ctx, false, ctx->d_in, d_raw_off, ctx->d_mid, d_filt_off, d_h, d_s, d_b, mode, d_st1, n, st))) return r;
+    DeflateBatch db;
+    db.in_base = ctx->d_mid;
+    db.in_off = d_filt_off;
+    db.in_len = d_filt_len;
+    db.out_base = ctx->d_out;
+    db.out_off = d_out_off;
+    db.out_cap = d_out_cap;
+    db.out_len = d_out_len;
+    db.status = d_st2;
+    db.n = (uint32_t)n;
+    if ((r = launch_deflate(ctx, 0, db, ctx->d_counters + 3, st, false, max_len >= ctx->deflate_split_min ? &ctx->dsplit : nullptr)))
+        return r;
+    std::vector<int32_t> st12(2 * n);
+    if (out_span) FDB_TRY(cudaMemcpyAsync(out_base, ctx->d_out, out_span, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaMemcpyAsync(st12.data(), d_st1, 2 * n * 4, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaMemcpyAsync(out_len, d_out_len, n * 8, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; i++) status[i] = st12[i] != ST_OK ? st12[i] : st12[n + i];
+    return 0;
 }
 
 // ---- synthetic tiles --------------------------------------------------------------------------

@@ -29,6 +29,9 @@ enum Status : int32_t {
     // compress side only: caller's slot is smaller than the encoded stream (the reference writes
     // into a growing Vec and cannot hit this)
     ST_OUTPUT_BUFFER_TOO_SMALL = 18,
+    // PNG row filters (png_filter.cuh): a row's filter-type byte is not 0..4; bpp outside 1..8 or an unknown mode
+    ST_PNG_BAD_FILTER_TYPE = 19,
+    ST_PNG_BAD_GEOMETRY = 20,
     // internal: ultra-fast-format fast path declined the stream; the general kernel redoes it
     ST_PENDING_GENERAL = -1,
 };

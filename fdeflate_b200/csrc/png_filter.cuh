@@ -1,0 +1,176 @@
+// png_filter.cuh -- K8 / K9: the PNG row filters either side of the zlib path.
+//
+// Not part of image-rs/fdeflate (the `png` crate does this step around its fdeflate calls); the algorithm is
+// the PNG specification's section 9: a filtered image is h rows of (1 filter-type byte + stride bytes), filter
+// types 0..4 = None, Sub, Up, Average, Paeth, "left" = the byte bpp positions back, bytes outside the image
+// are 0.  Checked against oracle/png_filter_oracle.c, which is pinned by golden PNG files from two independent
+// encoders (tests/golden/png).
+//
+// K8 png_unfilter_kernel -- reconstruction is a recurrence (left, up, up-left), so one image is decoded by
+// ONE WARP as a diagonal wavefront: with bpp bytes per pixel, lane (r, c) owns byte channel c of row y0 + r of
+// a block of R = 32 / bpp rows, and row r runs one pixel behind row r - 1.  At step t lane (r, c) handles pixel
+// x = t - r: `left` is the lane's own previous result, `up` is what lane (r - 1, c) produced one step earlier
+// (one shuffle), `up-left` is the `up` of the step before -- the recurrence lives in registers; only the first
+// row of a block reads its `up` row from memory (written by the block before).  All five predictors are
+// computed branch-free and selected by the row's type.
+//
+// K9 png_filter_kernel -- the forward direction has no recurrence (every predictor reads the RAW image): one
+// CTA per image, one warp per row.  mode 0..4 = that type on every row; mode 5 = per row the type with the
+// smallest sum of |signed filtered byte| (PNG 12.8), lowest type on ties: two passes over the row, the first
+// accumulates the five sums.
+#pragma once
+#include "simt.h"
+#include "fdb_common.h"
+
+namespace fdb {
+
+struct PngBatch {
+    const uint8_t* in_base;
+    const uint64_t* in_off;   // [n]
+    uint8_t* out_base;
+    const uint64_t* out_off;  // [n]
+    const uint32_t* height;   // [n] rows
+    const uint32_t* stride;   // [n] bytes per raw row
+    const uint32_t* bpp;      // [n] bytes per complete pixel, 1..8
+    int32_t* status;          // [n] ST_OK / ST_PNG_BAD_FILTER_TYPE / ST_PNG_BAD_GEOMETRY
+    uint32_t n;
+    uint32_t mode;            // K9 only
+};
+
+FDB_DEVICE uint32_t png_paeth(uint32_t a, uint32_t b, uint32_t c) {  // PNG 9.4
+    const int32_t p = (int32_t)a + (int32_t)b - (int32_t)c;
+    int32_t pa = p - (int32_t)a, pb = p - (int32_t)b, pc = p - (int32_t)c;
+    pa = pa < 0 ? -pa : pa;
+    pb = pb < 0 ? -pb : pb;
+    pc = pc < 0 ? -pc : pc;
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+FDB_DEVICE uint32_t png_predict(uint32_t type, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t avg = (a + b) >> 1, pae = png_paeth(a, b, c);
+    uint32_t p = 0;
+    p = type == 1 ? a : p;
+    p = type == 2 ? b : p;
+    p = type == 3 ? avg : p;
+    p = type == 4 ? pae : p;
+    return p;
+}
+
+static const int PNG_UNFILTER_WARPS = 8;
+
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_UNFILTER_WARPS * 32, 4) png_unfilter_kernel(PngBatch b, uint32_t* next) {
+    const unsigned lane = simt::lane_id();
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = simt::atomic_add(next, 1u);
+        i = simt::shfl(i, 0);
+        if (i >= b.n) break;
+        const uint32_t h = b.height[i], stride = b.stride[i], bpp = b.bpp[i];
+        if (bpp < 1 || bpp > 8) {
+            if (lane == 0) b.status[i] = ST_PNG_BAD_GEOMETRY;
+            continue;
+        }
+        const uint8_t* in = b.in_base + b.in_off[i];
+        uint8_t* out = b.out_base + b.out_off[i];
+        const uint32_t R = 32u / bpp;              // rows per block
+        const uint32_t r = lane / bpp, c = lane - r * bpp;
+        const bool lane_on = r < R;
+        const uint32_t W = (stride + bpp - 1) / bpp;  // pixel steps per row
+        const uint64_t in_pitch = 1ull + stride;
+        int32_t st = ST_OK;
+        for (uint32_t y0 = 0; y0 < h && st == ST_OK; y0 += R) {
+            const uint32_t y = y0 + r;
+            const bool row_on = lane_on && y < h;
+            const uint32_t type = row_on ? (uint32_t)simt::ldg8(in + y * in_pitch) : 0u;
+            if (simt::any(type > 4u)) {
+                st = ST_PNG_BAD_FILTER_TYPE;
+                break;
+            }
+            const uint8_t* src = in + y * in_pitch + 1 + c;
+            uint8_t* dst = out + (uint64_t)y * stride + c;
+            const uint8_t* above = out + (uint64_t)(y0 - 1) * stride + c;  // (row 0 of the block only, y0 > 0)
+            uint32_t cur = 0, up = 0;
+            const uint32_t steps = W + R - 1;
+            for (uint32_t t = 0; t < steps; t++) {
+                const uint32_t x = t - r;  // (wraps for t < r: then x >= W)
+                const uint32_t xb = x * bpp;
+                const bool on = row_on && x < W && xb + c < stride;
+                const uint32_t from_lane = simt::shfl_up(cur, bpp);  // row r - 1, same pixel, produced one step ago
+                const uint32_t upleft = up;
+                uint32_t upv = from_lane;
+                if (r == 0) upv = (on && y0 > 0) ? (uint32_t)simt::ldcg8(above + xb) : 0u;
+                up = on ? upv : 0u;
+                const uint32_t f = on ? (uint32_t)simt::ldg8(src + xb) : 0u;
+                const uint32_t v = (f + png_predict(type, cur, up, upleft)) & 0xffu;
+                cur = on ? v : 0u;
+                if (on) dst[xb] = (uint8_t)v;
+            }
+            simt::syncwarp();  // the next block's first row reads this block's last row
+        }
+        if (lane == 0) b.status[i] = st;
+    }
+}
+
+static const int PNG_FILTER_WARPS = 8;
+
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_FILTER_WARPS * 32, 4) png_filter_kernel(PngBatch b, uint32_t* next) {
+    FDB_SHARED uint32_t cur_img;
+    const unsigned lane = simt::lane_id(), warp = simt::warp_in_block();
+    for (;;) {
+        if (threadIdx.x == 0) cur_img = simt::atomic_add(next, 1u);
+        simt::syncthreads();
+        const uint32_t i = cur_img;
+        simt::syncthreads();
+        if (i >= b.n) break;
+        const uint32_t h = b.height[i], stride = b.stride[i], bpp = b.bpp[i];
+        if (bpp < 1 || bpp > 8 || b.mode > 5) {
+            if (threadIdx.x == 0) b.status[i] = ST_PNG_BAD_GEOMETRY;
+            continue;
+        }
+        const uint8_t* in = b.in_base + b.in_off[i];
+        uint8_t* out = b.out_base + b.out_off[i];
+        for (uint32_t y = warp; y < h; y += PNG_FILTER_WARPS) {
+            const uint8_t* cur = in + (uint64_t)y * stride;
+            const uint8_t* up = cur - stride;  // (y > 0 only)
+            uint8_t* dst = out + (uint64_t)y * (1ull + stride);
+            uint32_t type = b.mode;
+            if (b.mode == 5) {
+                uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+                for (uint32_t x = lane; x < stride; x += 32) {
+                    const uint32_t v = simt::ldg8(cur + x);
+                    const uint32_t a = x >= bpp ? (uint32_t)simt::ldg8(cur + x - bpp) : 0u;
+                    const uint32_t bb = y ? (uint32_t)simt::ldg8(up + x) : 0u;
+                    const uint32_t cc = (y && x >= bpp) ? (uint32_t)simt::ldg8(up + x - bpp) : 0u;
+                    const uint32_t f0 = v, f1 = (v - a) & 0xffu, f2 = (v - bb) & 0xffu, f3 = (v - ((a + bb) >> 1)) & 0xffu,
+                                   f4 = (v - png_paeth(a, bb, cc)) & 0xffu;
+                    s0 += f0 < 128u ? f0 : 256u - f0;
+                    s1 += f1 < 128u ? f1 : 256u - f1;
+                    s2 += f2 < 128u ? f2 : 256u - f2;
+                    s3 += f3 < 128u ? f3 : 256u - f3;
+                    s4 += f4 < 128u ? f4 : 256u - f4;
+                }
+                s0 = simt::reduce_add(s0);
+                s1 = simt::reduce_add(s1);
+                s2 = simt::reduce_add(s2);
+                s3 = simt::reduce_add(s3);
+                s4 = simt::reduce_add(s4);
+                uint32_t best = s0;
+                type = 0;
+                if (s1 < best) { best = s1; type = 1; }
+                if (s2 < best) { best = s2; type = 2; }
+                if (s3 < best) { best = s3; type = 3; }
+                if (s4 < best) { best = s4; type = 4; }
+            }
+            if (lane == 0) dst[0] = (uint8_t)type;
+            for (uint32_t x = lane; x < stride; x += 32) {
+                const uint32_t v = simt::ldg8(cur + x);
+                const uint32_t a = x >= bpp ? (uint32_t)simt::ldg8(cur + x - bpp) : 0u;
+                const uint32_t bb = y ? (uint32_t)simt::ldg8(up + x) : 0u;
+                const uint32_t cc = (y && x >= bpp) ? (uint32_t)simt::ldg8(up + x - bpp) : 0u;
+                dst[1 + x] = (uint8_t)(v - png_predict(type, a, bb, cc));
+            }
+        }
+        if (threadIdx.x == 0) b.status[i] = ST_OK;
+    }
+}
+
+}  // namespace fdb

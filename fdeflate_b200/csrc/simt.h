@@ -73,6 +73,8 @@ FDB_DEVICE void threadfence() { __threadfence(); }
 FDB_DEVICE uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
 FDB_DEVICE uint4 ldg128(const uint4* p) { return __ldg(p); }
 FDB_DEVICE uint8_t ldg8(const uint8_t* p) { return __ldg(p); }
+// L2-coherent byte load (bypasses L1): data another lane of this warp stored earlier in the kernel
+FDB_DEVICE uint8_t ldcg8(const uint8_t* p) { return __ldcg(p); }
 // hint: bring the 128-byte line at p into L2 (no register, no dependency)
 FDB_DEVICE void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // streaming (evict-first) 16-byte store: output bytes are written once and never re-read by us

@@ -116,6 +116,44 @@ int fdb_deflate_stored_batch(fdb_ctx* ctx, const uint8_t* in_base, const uint64_
                              uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
                              int32_t* status, size_t n);
 
+/* ---- PNG row filters (the step either side of the zlib path in a PNG codec) ----
+ * Not part of image-rs/fdeflate: the `png` crate applies them around its fdeflate calls.  Semantics are the PNG
+ * specification's section 9.  A FILTERED image is `height` rows of (1 filter-type byte + stride bytes) -- exactly
+ * what inflating a non-interlaced IDAT stream yields -- a RAW image is `height` rows of stride bytes; bpp = bytes
+ * per complete pixel (1..8).  All pointers are device pointers; image i sits at base + off[i].
+ *   unfilter: filtered -> raw.  status 19 = a row's filter type is not 0..4, 20 = bpp out of range.
+ *   filter  : raw -> filtered.  mode 0..4 = None/Sub/Up/Average/Paeth on every row, 5 = per row the type with the
+ *             smallest sum of absolute signed differences (PNG 12.8), lowest type on ties. */
+int fdb_png_unfilter_batch_device(fdb_ctx* ctx, const void* d_filtered_base, const uint64_t* d_filtered_off,
+                                  void* d_raw_base, const uint64_t* d_raw_off, const uint32_t* d_height,
+                                  const uint32_t* d_stride, const uint32_t* d_bpp, int32_t* d_status, size_t n,
+                                  void* cuda_stream);
+int fdb_png_filter_batch_device(fdb_ctx* ctx, const void* d_raw_base, const uint64_t* d_raw_off, void* d_filtered_base,
+                                const uint64_t* d_filtered_off, const uint32_t* d_height, const uint32_t* d_stride,
+                                const uint32_t* d_bpp, uint32_t mode, int32_t* d_status, size_t n, void* cuda_stream);
+
+/* the same with host buffers (staged through the context; every array is a host array) */
+int fdb_png_unfilter_batch(fdb_ctx* ctx, const uint8_t* filtered_base, const uint64_t* filtered_off, uint8_t* raw_base,
+                           const uint64_t* raw_off, const uint32_t* height, const uint32_t* stride, const uint32_t* bpp,
+                           int32_t* status, size_t n);
+int fdb_png_filter_batch(fdb_ctx* ctx, const uint8_t* raw_base, const uint64_t* raw_off, uint8_t* filtered_base,
+                         const uint64_t* filtered_off, const uint32_t* height, const uint32_t* stride, const uint32_t* bpp,
+                         uint32_t mode, int32_t* status, size_t n);
+
+/* PNG image data in one call, host buffers, the filtered image stays on the device:
+ *   decode: n zlib streams (the concatenated IDAT payload of one non-interlaced image each) -> raw pixels at
+ *           raw_base + raw_off[i] (height[i] * stride[i] bytes).  status[i] = the inflate status if not Ok (a stream
+ *           that ends before height * (1 + stride) bytes is InsufficientInput, one that goes on is OutputTooLarge),
+ *           else the unfilter status.
+ *   encode: raw pixels -> filter (mode as above) -> ultra-fast deflate; slot i needs
+ *           fdb_deflate_ultrafast_bound(height[i] * (1 + stride[i])) bytes. */
+int fdb_png_decode_batch(fdb_ctx* ctx, const uint8_t* idat_base, const uint64_t* idat_off, const uint64_t* idat_len,
+                         uint8_t* raw_base, const uint64_t* raw_off, const uint32_t* height, const uint32_t* stride,
+                         const uint32_t* bpp, int32_t* status, size_t n);
+int fdb_png_encode_batch(fdb_ctx* ctx, const uint8_t* raw_base, const uint64_t* raw_off, const uint32_t* height,
+                         const uint32_t* stride, const uint32_t* bpp, uint32_t mode, uint8_t* out_base,
+                         const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, int32_t* status, size_t n);
+
 /* ---- synthetic PNG-filtered RGBA tiles (benchmark / test input) -----------------
  * Tile t is width x height RGBA8, row 0 Sub-filtered, other rows Paeth-filtered; each row is
  * 1 filter-type byte + 4*width residual bytes, so a tile is height*(1+4*width) bytes, laid out

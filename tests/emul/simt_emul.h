@@ -217,6 +217,7 @@ static inline void threadfence() {}
 static inline uint32_t ldg32(const uint32_t* p) { return *p; }
 static inline uint4 ldg128(const uint4* p) { return *p; }
 static inline uint8_t ldg8(const uint8_t* p) { return *p; }
+static inline uint8_t ldcg8(const uint8_t* p) { return *(const volatile uint8_t*)p; }
 static inline void stcs128(uint4* p, uint4 v) { *p = v; }
 static inline void prefetch_l2(const void*) {}
 // explicit shared-window addressing: plain host pointers here

@@ -56,11 +56,15 @@ def lib(native: bool = False) -> C.CDLL:
     if native in _LIBS:
         return _LIBS[native]
     path = ORACLE_DIR / ("libfdeflate_oracle_native.so" if native else "libfdeflate_oracle.so")
-    src_m = max(os.path.getmtime(ORACLE_DIR / f) for f in ("fdeflate_oracle.c", "fdeflate_oracle.h"))
+    src_m = max(os.path.getmtime(ORACLE_DIR / f) for f in ("fdeflate_oracle.c", "fdeflate_oracle.h", "png_filter_oracle.c"))
     if not path.exists() or os.path.getmtime(path) < src_m:
         build(native)
     L = C.CDLL(str(path))
     sz = C.c_size_t
+    L.fdo_png_unfilter.restype = sz
+    L.fdo_png_unfilter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.fdo_png_filter.restype = None
+    L.fdo_png_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.fdo_adler32.restype = C.c_uint32
     L.fdo_adler32.argtypes = [C.c_uint32, C.c_void_p, sz]
     L.fdo_inflate_into.restype = C.c_int
@@ -277,3 +281,21 @@ def compress_ultra_fast_batch(in_base: np.ndarray, in_off, in_len, out_base: np.
                                                      out_base.ctypes.data, out_off.ctypes.data, out_cap.ctypes.data,
                                                      out_len.ctypes.data, n, nthreads)
     return secs, out_len
+
+
+# ---- PNG row filters (oracle/png_filter_oracle.c; PNG specification section 9) -------------------
+def png_unfilter(filtered, h: int, stride: int, bpp: int):
+    """-> (bad_row, raw bytes): bad_row = 0, or 1 + index of the first row with a filter type > 4"""
+    src = np.frombuffer(bytes(filtered), dtype=np.uint8)
+    assert src.size == h * (1 + stride)
+    raw = np.zeros(h * stride, dtype=np.uint8)
+    bad = lib().fdo_png_unfilter(raw.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), h, stride, bpp)
+    return int(bad), raw.tobytes()
+
+
+def png_filter(raw, h: int, stride: int, bpp: int, mode: int) -> bytes:
+    src = np.frombuffer(bytes(raw), dtype=np.uint8)
+    assert src.size == h * stride
+    out = np.zeros(h * (1 + stride), dtype=np.uint8)
+    lib().fdo_png_filter(out.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), h, stride, bpp, mode)
+    return out.tobytes()

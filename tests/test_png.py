@@ -1,0 +1,194 @@
+"""PNG row filters and the PNG image-data path.
+
+CPU part: the oracle (oracle/png_filter_oracle.c, PNG specification section 9) is pinned against golden PNG files
+written by two independent encoders -- Pillow and OpenCV/libpng (tools/make_png_golden.py, tests/golden/png) --
+whose decoded pixels are recorded in manifest.json; the kernels run on the SIMT emulator against the oracle.
+GPU part (-m gpu): the same through libfdeflate_b200.so, plus files written by our encoder decoded by Pillow when
+it is installed."""
+import hashlib
+import json
+import random
+import zlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLD = Path(__file__).resolve().parent / "golden" / "png"
+MANIFEST = json.loads((GOLD / "manifest.json").read_text())
+
+
+def _pixels_hash(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_oracle_unfilter_matches_independent_decoders(oracle):
+    """zlib (system) inflates the IDAT stream, the oracle undoes the filters: the pixels must be the ones Pillow /
+    OpenCV decoded from the same file.  All five filter types occur in the fixtures."""
+    from fdeflate_b200 import png
+
+    types = set()
+    for name, want in sorted(MANIFEST.items()):
+        info, z = png.parse((GOLD / name).read_bytes())
+        filtered = zlib.decompress(z)
+        assert len(filtered) == info.height * (1 + info.stride)
+        types |= {filtered[y * (1 + info.stride)] for y in range(info.height)}
+        bad, raw = oracle.png_unfilter(filtered, info.height, info.stride, info.bpp)
+        assert bad == 0
+        a = png._to_array(info, np.frombuffer(raw, dtype=np.uint8))
+        assert list(a.shape) == want["shape"] and str(a.dtype) == want["dtype"], name
+        assert _pixels_hash(a) == want["sha256"], name
+    assert types == {0, 1, 2, 3, 4}
+
+
+def _random_images(seed, count):
+    rng = random.Random(seed)
+    out = []
+    for k in range(count):
+        bpp = rng.choice((1, 2, 3, 4, 6, 8))
+        w = rng.choice((1, 2, 3, 7, 31, 32, 33, 100))
+        h = rng.choice((1, 2, 5, 31, 32, 33, 40))
+        stride = w * bpp if k % 5 else max(1, w * bpp - rng.randrange(bpp))  # (sub-byte depths: stride % bpp != 0)
+        kind = k % 3
+        if kind == 0:
+            raw = bytes(rng.getrandbits(8) for _ in range(h * stride))
+        elif kind == 1:
+            raw = bytes((3 * (i % stride) + 5 * (i // stride)) & 0xff for i in range(h * stride))
+        else:
+            raw = bytes(rng.choice((0, 0, 0, 1, 255, 7)) for _ in range(h * stride))
+        out.append((raw, (h, stride, bpp)))
+    return out
+
+
+def test_oracle_filter_roundtrip_all_modes(oracle):
+    for raw, (h, stride, bpp) in _random_images(1, 40):
+        for mode in range(6):
+            f = oracle.png_filter(raw, h, stride, bpp, mode)
+            assert len(f) == h * (1 + stride)
+            if mode < 5:
+                assert all(f[y * (1 + stride)] == mode for y in range(h))
+            assert oracle.png_unfilter(f, h, stride, bpp) == (0, raw)
+
+
+def _check_filters(ctx, oracle, images):
+    geo = [g for _, g in images]
+    for mode in range(6):
+        st, outs = ctx.png_filter_batch([r for r, _ in images], geo, mode)
+        assert (st == 0).all()
+        for (raw, (h, s, b)), o in zip(images, outs):
+            assert o == oracle.png_filter(raw, h, s, b, mode), f"filter mode {mode} differs from the oracle ({h}x{s} bpp {b})"
+        st, back = ctx.png_unfilter_batch(outs, geo)
+        assert (st == 0).all()
+        assert back == [r for r, _ in images]
+    # a filter-type byte out of range
+    raw, (h, s, b) = images[3]
+    f = bytearray(oracle.png_filter(raw, h, s, b, 1))
+    f[(h - 1) * (1 + s)] = 5
+    st, _ = ctx.png_unfilter_batch([bytes(f)], [(h, s, b)])
+    assert st[0] == 19
+    st, _ = ctx.png_unfilter_batch([bytes(f)], [(h, s, 9)])
+    assert st[0] == 20
+
+
+@pytest.mark.emul
+def test_filter_kernels_on_emulator(emul_ctx, oracle):
+    _check_filters(emul_ctx, oracle, _random_images(2, 24))
+
+
+def _golden_files():
+    return [(name, (GOLD / name).read_bytes()) for name in sorted(MANIFEST)]
+
+
+def _check_decode_golden(ctx, files):
+    from fdeflate_b200 import png
+
+    arrays = png.decode_batch([d for _, d in files], ctx)
+    for (name, _), a in zip(files, arrays):
+        want = MANIFEST[name]
+        assert list(a.shape) == want["shape"] and str(a.dtype) == want["dtype"], name
+        assert _pixels_hash(a) == want["sha256"], name
+    return arrays
+
+
+@pytest.mark.emul
+def test_png_decode_golden_on_emulator(emul_ctx):
+    _check_decode_golden(emul_ctx, _golden_files()[::4])
+
+
+def _check_encode_roundtrip(ctx, arrays):
+    from fdeflate_b200 import png
+
+    for mode in (0, 4, 5):
+        files = png.encode_batch(arrays, ctx, filter_mode=mode)
+        for f, a in zip(files, arrays):
+            info, z = png.parse(f)
+            assert z[:2] == b"\x78\x01" and zlib.decompress(z)[0] == (mode if mode < 5 else zlib.decompress(z)[0])
+        back = png.decode_batch(files, ctx)
+        for a, b in zip(arrays, back):
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+    return files
+
+
+@pytest.mark.emul
+def test_png_encode_roundtrip_on_emulator(emul_ctx):
+    rng = np.random.default_rng(3)
+    arrays = [rng.integers(0, 256, (9, 13, 4), dtype=np.uint8), rng.integers(0, 256, (33, 5), dtype=np.uint8),
+              rng.integers(0, 65536, (4, 6, 3), dtype=np.uint16), np.zeros((40, 40, 3), dtype=np.uint8)]
+    _check_encode_roundtrip(emul_ctx, arrays)
+
+
+def test_png_container_errors():
+    from fdeflate_b200 import png
+
+    good = (GOLD / sorted(MANIFEST)[0]).read_bytes()
+    with pytest.raises(png.PngError):
+        png.parse(b"not a png")
+    with pytest.raises(png.PngError):
+        png.parse(good[:-5])
+    bad = bytearray(good)
+    bad[40] ^= 1  # inside a chunk: its CRC no longer matches
+    with pytest.raises(png.PngError):
+        png.parse(bytes(bad))
+
+
+# ---- GPU ------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_filter_kernels_on_gpu(gpu_ctx, oracle):
+    _check_filters(gpu_ctx, oracle, _random_images(2, 120))
+    # tile-sized images, every mode, against the oracle
+    from fdeflate_b200 import synth_tiles_host
+
+    rng = np.random.default_rng(4)
+    big = [(rng.integers(0, 256, 256 * 1024, dtype=np.uint8).tobytes(), (256, 1024, 4)),
+           (bytes(300 * 999), (300, 999, 3)), (rng.integers(0, 3, 128 * 4096, dtype=np.uint8).tobytes(), (128, 4096, 8))]
+    _check_filters(gpu_ctx, oracle, big + _random_images(5, 4))
+    tiles = synth_tiles_host(0, 8, 256, 256, 1, gpu_ctx.lib)  # already PNG-filtered rows (Sub / Paeth)
+    st, raws = gpu_ctx.png_unfilter_batch([t.tobytes() for t in tiles], [(256, 1024, 4)] * 8)
+    assert (st == 0).all()
+    for t, r in zip(tiles, raws):
+        assert oracle.png_unfilter(t.tobytes(), 256, 1024, 4) == (0, r)
+
+
+@pytest.mark.gpu
+def test_png_decode_golden_on_gpu(gpu_ctx):
+    _check_decode_golden(gpu_ctx, _golden_files())
+
+
+@pytest.mark.gpu
+def test_png_encode_roundtrip_on_gpu(gpu_ctx):
+    rng = np.random.default_rng(3)
+    y, x = np.mgrid[0:300, 0:517]
+    photo = np.stack([(x + y) % 256, (2 * x) % 256, (x * y >> 5) % 256, np.full_like(x, 255)], -1).astype(np.uint8)
+    arrays = [rng.integers(0, 256, (9, 13, 4), dtype=np.uint8), rng.integers(0, 256, (33, 5), dtype=np.uint8),
+              rng.integers(0, 65536, (40, 60, 3), dtype=np.uint16), np.zeros((400, 400, 3), dtype=np.uint8), photo,
+              rng.integers(0, 256, (1024, 1024, 4), dtype=np.uint8), photo[..., :2].copy()]
+    files = _check_encode_roundtrip(gpu_ctx, arrays)
+    try:
+        import io
+
+        from PIL import Image
+    except ImportError:
+        return
+    for f, a in zip(files, arrays):
+        if a.dtype == np.uint8:  # an independent decoder reads what we wrote
+            assert np.array_equal(np.asarray(Image.open(io.BytesIO(f))), a)
