@@ -56,6 +56,7 @@ FDB_DEVICE uint32_t png_predict(uint32_t type, uint32_t a, uint32_t b, uint32_t 
 }
 
 static const int PNG_UNFILTER_WARPS = 8;
+static const uint32_t PNG_AHEAD = 8;  // steps whose memory reads are issued together
 
 FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_UNFILTER_WARPS * 32, 4) png_unfilter_kernel(PngBatch b, uint32_t* next) {
     const unsigned lane = simt::lane_id();
@@ -90,19 +91,32 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_UNFILTER_WARPS * 32, 4) png_unfilter_kerne
             const uint8_t* above = out + (uint64_t)(y0 - 1) * stride + c;  // (row 0 of the block only, y0 > 0)
             uint32_t cur = 0, up = 0;
             const uint32_t steps = W + R - 1;
-            for (uint32_t t = 0; t < steps; t++) {
-                const uint32_t x = t - r;  // (wraps for t < r: then x >= W)
-                const uint32_t xb = x * bpp;
-                const bool on = row_on && x < W && xb + c < stride;
-                const uint32_t from_lane = simt::shfl_up(cur, bpp);  // row r - 1, same pixel, produced one step ago
-                const uint32_t upleft = up;
-                uint32_t upv = from_lane;
-                if (r == 0) upv = (on && y0 > 0) ? (uint32_t)simt::ldcg8(above + xb) : 0u;
-                up = on ? upv : 0u;
-                const uint32_t f = on ? (uint32_t)simt::ldg8(src + xb) : 0u;
-                const uint32_t v = (f + png_predict(type, cur, up, upleft)) & 0xffu;
-                cur = on ? v : 0u;
-                if (on) dst[xb] = (uint8_t)v;
+            // The bytes a step reads from memory (its filtered byte, and for the block's first row the byte above) do
+            // not depend on the recurrence, so they are fetched PNG_AHEAD steps at a time before the dependent chain of
+            // those steps runs: the loads' latency overlaps instead of adding up step by step.
+            for (uint32_t t0 = 0; t0 < steps; t0 += PNG_AHEAD) {
+                uint32_t fv[PNG_AHEAD], av[PNG_AHEAD];
+#pragma unroll
+                for (uint32_t k = 0; k < PNG_AHEAD; k++) {
+                    const uint32_t x = t0 + k - r;  // (wraps for t < r: then x >= W)
+                    const uint32_t xb = x * bpp;
+                    const bool on = row_on && x < W && xb + c < stride;
+                    fv[k] = on ? (uint32_t)simt::ldg8(src + xb) : 0u;
+                    av[k] = (on && r == 0 && y0 > 0) ? (uint32_t)above[xb] : 0u;  // (stored by this warp one block ago)
+                }
+#pragma unroll
+                for (uint32_t k = 0; k < PNG_AHEAD; k++) {
+                    const uint32_t x = t0 + k - r;
+                    const uint32_t xb = x * bpp;
+                    const bool on = row_on && x < W && xb + c < stride;
+                    const uint32_t from_lane = simt::shfl_up(cur, bpp);  // row r - 1, same pixel, produced one step ago
+                    const uint32_t upleft = up;
+                    const uint32_t upv = r == 0 ? av[k] : from_lane;
+                    up = on ? upv : 0u;
+                    const uint32_t v = (fv[k] + png_predict(type, cur, up, upleft)) & 0xffu;
+                    cur = on ? v : 0u;
+                    if (on) dst[xb] = (uint8_t)v;
+                }
             }
             simt::syncwarp();  // the next block's first row reads this block's last row
         }
@@ -161,6 +175,26 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_FILTER_WARPS * 32, 4) png_filter_kernel(Pn
                 if (s4 < best) { best = s4; type = 4; }
             }
             if (lane == 0) dst[0] = (uint8_t)type;
+            if (b.mode != 5 && bpp == 4 && (stride & 3u) == 0 && ((uintptr_t)in & 3u) == 0) {
+                // four bytes (one RGBA pixel) per lane from aligned words: the pixel, the one to its left, the one
+                // above and the one above-left
+                const uint32_t* cw = (const uint32_t*)cur;
+                const uint32_t* uw = (const uint32_t*)up;
+                for (uint32_t p = lane; p < (stride >> 2); p += 32) {
+                    const uint32_t v = simt::ldg32(cw + p);
+                    const uint32_t a = p ? simt::ldg32(cw + p - 1) : 0u;
+                    const uint32_t bb = y ? simt::ldg32(uw + p) : 0u;
+                    const uint32_t cc = (y && p) ? simt::ldg32(uw + p - 1) : 0u;
+                    uint8_t* d = dst + 1 + 4 * p;
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; k++) {
+                        const uint32_t sh = 8u * k;
+                        d[k] = (uint8_t)(((v >> sh) & 0xffu) -
+                                         png_predict(type, (a >> sh) & 0xffu, (bb >> sh) & 0xffu, (cc >> sh) & 0xffu));
+                    }
+                }
+                continue;
+            }
             for (uint32_t x = lane; x < stride; x += 32) {
                 const uint32_t v = simt::ldg8(cur + x);
                 const uint32_t a = x >= bpp ? (uint32_t)simt::ldg8(cur + x - bpp) : 0u;
