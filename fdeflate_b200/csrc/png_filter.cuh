@@ -55,6 +55,31 @@ FDB_DEVICE uint32_t png_predict(uint32_t type, uint32_t a, uint32_t b, uint32_t 
     return p;
 }
 
+// four byte channels at once (one RGBA pixel per 32-bit word)
+FDB_DEVICE uint32_t png_add4(uint32_t x, uint32_t y) {  // per-byte x + y mod 256
+    return ((x & 0x7f7f7f7fu) + (y & 0x7f7f7f7fu)) ^ ((x ^ y) & 0x80808080u);
+}
+FDB_DEVICE uint32_t png_avg4(uint32_t a, uint32_t b) {  // per-byte floor((a + b) / 2)
+    return (a & b) + (((a ^ b) & 0xfefefefeu) >> 1);
+}
+FDB_DEVICE uint32_t png_paeth4(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+        const uint32_t sh = 8u * k;
+        r |= png_paeth((a >> sh) & 0xffu, (b >> sh) & 0xffu, (c >> sh) & 0xffu) << sh;
+    }
+    return r;
+}
+FDB_DEVICE uint32_t png_predict4(uint32_t type, uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t p = 0;
+    p = type == 1 ? a : p;
+    p = type == 2 ? b : p;
+    p = type == 3 ? png_avg4(a, b) : p;
+    p = type == 4 ? png_paeth4(a, b, c) : p;
+    return p;
+}
+
 static const int PNG_UNFILTER_WARPS = 8;
 static const uint32_t PNG_AHEAD = 8;  // steps whose memory reads are issued together
 
@@ -72,6 +97,62 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_UNFILTER_WARPS * 32, 4) png_unfilter_kerne
         }
         const uint8_t* in = b.in_base + b.in_off[i];
         uint8_t* out = b.out_base + b.out_off[i];
+        if (bpp == 4 && (stride & 3u) == 0 && ((uintptr_t)out & 3u) == 0) {
+            // RGBA8 rows: LANE = ROW of a block of 32 rows, one whole pixel (a 32-bit word) per lane and step; row r
+            // runs one pixel behind row r - 1, `up` is one shuffle away, `left` and `up-left` are last step's values.
+            // The filtered row starts one byte after a row boundary, so a pixel is the funnel shift of two aligned
+            // words of the row; the raw row is word aligned and stored as such.
+            const uint32_t W = stride >> 2;
+            const uint64_t pitch = 1ull + stride;
+            int32_t st = ST_OK;
+            for (uint32_t y0 = 0; y0 < h && st == ST_OK; y0 += 32) {
+                const uint32_t y = y0 + lane;
+                const bool row_on = y < h;
+                const uint32_t type = row_on ? (uint32_t)simt::ldg8(in + y * pitch) : 0u;
+                if (simt::any(type > 4u)) {
+                    st = ST_PNG_BAD_FILTER_TYPE;
+                    break;
+                }
+                const uint8_t* srow = in + y * pitch + 1;
+                const uint32_t m = (uint32_t)((uintptr_t)srow & 3u);
+                const uint32_t* sw = (const uint32_t*)(srow - m);
+                const uint32_t sh = 8u * m;
+                uint32_t* drow = (uint32_t*)(out + (uint64_t)y * stride);
+                const uint32_t* arow = (const uint32_t*)(out + (uint64_t)(y0 - 1) * stride);  // (lane 0, y0 > 0)
+                uint32_t cur = 0, up = 0;
+                const uint32_t steps = W + 31;
+                for (uint32_t t0 = 0; t0 < steps; t0 += PNG_AHEAD) {
+                    uint32_t wv[PNG_AHEAD + 1], av[PNG_AHEAD];
+#pragma unroll
+                    for (uint32_t k = 0; k <= PNG_AHEAD; k++) {
+                        const uint32_t x = t0 + k - lane;  // (wraps for t < lane: then x > W)
+                        // word x holds the first bytes of pixel x; pixel W - 1 also needs word W unless the row is aligned
+                        wv[k] = (row_on && (x < W || (x == W && m != 0))) ? simt::ldg32(sw + x) : 0u;
+                    }
+#pragma unroll
+                    for (uint32_t k = 0; k < PNG_AHEAD; k++) {
+                        const uint32_t x = t0 + k - lane;
+                        av[k] = (lane == 0 && y0 > 0 && row_on && x < W) ? arow[x] : 0u;  // (stored by this warp one block ago)
+                    }
+#pragma unroll
+                    for (uint32_t k = 0; k < PNG_AHEAD; k++) {
+                        const uint32_t x = t0 + k - lane;
+                        const bool on = row_on && x < W;
+                        const uint32_t f = simt::funnel_r(wv[k], wv[k + 1], sh);
+                        const uint32_t from_lane = simt::shfl_up(cur, 1);
+                        const uint32_t upleft = up;
+                        const uint32_t upv = lane == 0 ? av[k] : from_lane;
+                        up = on ? upv : 0u;
+                        const uint32_t v = png_add4(f, png_predict4(type, cur, up, upleft));
+                        cur = on ? v : 0u;
+                        if (on) drow[x] = v;
+                    }
+                }
+                simt::syncwarp();  // the next block's first row reads this block's last row
+            }
+            if (lane == 0) b.status[i] = st;
+            continue;
+        }
         const uint32_t R = 32u / bpp;              // rows per block
         const uint32_t r = lane / bpp, c = lane - r * bpp;
         const bool lane_on = r < R;
