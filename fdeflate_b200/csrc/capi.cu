@@ -813,7 +813,7 @@ static int png_launch(fdb_ctx* ctx, bool unfilter, const void* d_in_base, const 
     const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
     if (unfilter) {
         // a warp per image, persistent
-        uint32_t grid = (uint32_t)std::min<size_t>((n + PNG_UNFILTER_WARPS - 1) / PNG_UNFILTER_WARPS, (size_t)sms * 4);
+        uint32_t grid = (uint32_t)std::min<size_t>((n + PNG_UNFILTER_WARPS - 1) / PNG_UNFILTER_WARPS, (size_t)sms * 6);
         FDB_LAUNCH(png_unfilter_kernel, dim3(grid), dim3(PNG_UNFILTER_WARPS * 32), 0, st, b, counter);
     } else {
         uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * 4);

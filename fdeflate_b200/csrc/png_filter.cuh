@@ -59,6 +59,14 @@ FDB_DEVICE uint32_t png_predict(uint32_t type, uint32_t a, uint32_t b, uint32_t 
 FDB_DEVICE uint32_t png_add4(uint32_t x, uint32_t y) {  // per-byte x + y mod 256
     return ((x & 0x7f7f7f7fu) + (y & 0x7f7f7f7fu)) ^ ((x ^ y) & 0x80808080u);
 }
+FDB_DEVICE uint32_t png_sub4(uint32_t x, uint32_t y) {  // per-byte x - y mod 256
+    return ((x | 0x80808080u) - (y & 0x7f7f7f7fu)) ^ ((x ^ ~y) & 0x80808080u);
+}
+FDB_DEVICE uint32_t png_abs4(uint32_t f) {  // per byte: f < 128 ? f : 256 - f   (128 stays 128)
+    const uint32_t neg = (f >> 7) & 0x01010101u;  // 1 in the bytes that are "negative"
+    const uint32_t mask = neg * 0xffu;            // 0xff in those bytes
+    return png_add4(f ^ mask, neg);               // two's complement of the negative bytes
+}
 FDB_DEVICE uint32_t png_avg4(uint32_t a, uint32_t b) {  // per-byte floor((a + b) / 2)
     return (a & b) + (((a ^ b) & 0xfefefefeu) >> 1);
 }
@@ -80,10 +88,13 @@ FDB_DEVICE uint32_t png_predict4(uint32_t type, uint32_t a, uint32_t b, uint32_t
     return p;
 }
 
-static const int PNG_UNFILTER_WARPS = 8;
+static const int PNG_UNFILTER_WARPS = 4;
 static const uint32_t PNG_AHEAD = 8;  // steps whose memory reads are issued together
+static const uint32_t PNG_ROW_WORDS = 34;                  // chunk buffer: 32 pixel words per row + 2 of padding
+static const uint32_t PNG_BUF_WORDS = 32 * PNG_ROW_WORDS;  // one chunk of 32 rows
 
-FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_UNFILTER_WARPS * 32, 4) png_unfilter_kernel(PngBatch b, uint32_t* next) {
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_UNFILTER_WARPS * 32, 6) png_unfilter_kernel(PngBatch b, uint32_t* next) {
+    FDB_SHARED uint32_t chunk_buf[PNG_UNFILTER_WARPS][2 * PNG_BUF_WORDS];  // RGBA fast path: two chunks per warp
     const unsigned lane = simt::lane_id();
     for (;;) {
         uint32_t i = 0;
@@ -100,9 +111,15 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_UNFILTER_WARPS * 32, 4) png_unfilter_kerne
         if (bpp == 4 && (stride & 3u) == 0 && ((uintptr_t)out & 3u) == 0) {
             // RGBA8 rows: LANE = ROW of a block of 32 rows, one whole pixel (a 32-bit word) per lane and step; row r
             // runs one pixel behind row r - 1, `up` is one shuffle away, `left` and `up-left` are last step's values.
-            // The filtered row starts one byte after a row boundary, so a pixel is the funnel shift of two aligned
-            // words of the row; the raw row is word aligned and stored as such.
-            const uint32_t W = stride >> 2;
+            // A lane walking its own row would touch 32 different lines per load / store (measured: bound by L1
+            // wavefronts), so the rows travel through shared memory in CHUNKS of 32 pixels: a chunk is loaded with
+            // one coalesced 128-byte read per row (the byte-misaligned filtered row becomes aligned pixel words on the
+            // way: two aligned words and a funnel shift), unfiltered in place, and leaves with one coalesced
+            // 128-byte store per row.  In phase p (steps 32p .. 32p+31) the rows are spread over chunks p-1 and p, so
+            // two chunk buffers alternate.  Row stride 34 words: lane r reads word 34 r + (t - r) -> bank (r + t) % 32.
+            uint32_t* const buf = &chunk_buf[simt::warp_in_block()][0];
+            const simt::saddr buf_s = simt::smem_addr(buf);
+            const uint32_t W = stride >> 2, NC = (W + 31) >> 5;
             const uint64_t pitch = 1ull + stride;
             int32_t st = ST_OK;
             for (uint32_t y0 = 0; y0 < h && st == ST_OK; y0 += 32) {
@@ -113,41 +130,59 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_UNFILTER_WARPS * 32, 4) png_unfilter_kerne
                     st = ST_PNG_BAD_FILTER_TYPE;
                     break;
                 }
-                const uint8_t* srow = in + y * pitch + 1;
-                const uint32_t m = (uint32_t)((uintptr_t)srow & 3u);
-                const uint32_t* sw = (const uint32_t*)(srow - m);
-                const uint32_t sh = 8u * m;
-                uint32_t* drow = (uint32_t*)(out + (uint64_t)y * stride);
+                const uint32_t rows = h - y0 < 32u ? h - y0 : 32u;
                 const uint32_t* arow = (const uint32_t*)(out + (uint64_t)(y0 - 1) * stride);  // (lane 0, y0 > 0)
+                auto flush_chunk = [&](uint32_t c) {
+                    const uint32_t x = 32u * c + lane;
+                    for (uint32_t r = 0; r < rows; r++) {
+                        const uint32_t v = simt::lds32(buf_s + 4u * ((c & 1u) * PNG_BUF_WORDS + r * PNG_ROW_WORDS + lane));
+                        if (x < W) ((uint32_t*)(out + (uint64_t)(y0 + r) * stride))[x] = v;
+                    }
+                };
+                auto load_chunk = [&](uint32_t c) {
+                    const uint32_t x = 32u * c + lane;
+#pragma unroll 4
+                    for (uint32_t r = 0; r < rows; r++) {
+                        const uint8_t* srow = in + (uint64_t)(y0 + r) * pitch + 1;
+                        const uint32_t m = (uint32_t)((uintptr_t)srow & 3u);
+                        const uint32_t* sw = (const uint32_t*)(srow - m);
+                        // word x holds the first bytes of pixel x; the last pixel of a row also needs word W unless aligned
+                        const uint32_t lo = x < W ? simt::ldg32(sw + x) : 0u;
+                        const uint32_t hi = (x < W && m != 0) ? simt::ldg32(sw + x + 1) : 0u;
+                        simt::sts32(buf_s + 4u * ((c & 1u) * PNG_BUF_WORDS + r * PNG_ROW_WORDS + lane), simt::funnel_r(lo, hi, 8u * m));
+                    }
+                };
                 uint32_t cur = 0, up = 0;
-                const uint32_t steps = W + 31;
-                for (uint32_t t0 = 0; t0 < steps; t0 += PNG_AHEAD) {
-                    uint32_t wv[PNG_AHEAD + 1], av[PNG_AHEAD];
+                for (uint32_t p = 0; p <= NC; p++) {
+                    simt::syncwarp();
+                    if (p >= 2) flush_chunk(p - 2);
+                    if (p < NC) load_chunk(p);
+                    simt::syncwarp();
+                    for (uint32_t s0 = 0; s0 < 32; s0 += PNG_AHEAD) {
+                        uint32_t av[PNG_AHEAD];
 #pragma unroll
-                    for (uint32_t k = 0; k <= PNG_AHEAD; k++) {
-                        const uint32_t x = t0 + k - lane;  // (wraps for t < lane: then x > W)
-                        // word x holds the first bytes of pixel x; pixel W - 1 also needs word W unless the row is aligned
-                        wv[k] = (row_on && (x < W || (x == W && m != 0))) ? simt::ldg32(sw + x) : 0u;
-                    }
+                        for (uint32_t k = 0; k < PNG_AHEAD; k++) {
+                            const uint32_t x = 32u * p + s0 + k;  // (lane 0: x = t)
+                            av[k] = (lane == 0 && y0 > 0 && x < W) ? arow[x] : 0u;  // (stored by this warp one block ago)
+                        }
 #pragma unroll
-                    for (uint32_t k = 0; k < PNG_AHEAD; k++) {
-                        const uint32_t x = t0 + k - lane;
-                        av[k] = (lane == 0 && y0 > 0 && row_on && x < W) ? arow[x] : 0u;  // (stored by this warp one block ago)
-                    }
-#pragma unroll
-                    for (uint32_t k = 0; k < PNG_AHEAD; k++) {
-                        const uint32_t x = t0 + k - lane;
-                        const bool on = row_on && x < W;
-                        const uint32_t f = simt::funnel_r(wv[k], wv[k + 1], sh);
-                        const uint32_t from_lane = simt::shfl_up(cur, 1);
-                        const uint32_t upleft = up;
-                        const uint32_t upv = lane == 0 ? av[k] : from_lane;
-                        up = on ? upv : 0u;
-                        const uint32_t v = png_add4(f, png_predict4(type, cur, up, upleft));
-                        cur = on ? v : 0u;
-                        if (on) drow[x] = v;
+                        for (uint32_t k = 0; k < PNG_AHEAD; k++) {
+                            const uint32_t x = 32u * p + s0 + k - lane;  // (wraps for t < lane: then x >= W)
+                            const bool on = row_on && x < W;
+                            const simt::saddr cell = buf_s + 4u * (((x >> 5) & 1u) * PNG_BUF_WORDS + lane * PNG_ROW_WORDS + (x & 31u));
+                            const uint32_t f = on ? simt::lds32(cell) : 0u;
+                            const uint32_t from_lane = simt::shfl_up(cur, 1);
+                            const uint32_t upleft = up;
+                            const uint32_t upv = lane == 0 ? av[k] : from_lane;
+                            up = on ? upv : 0u;
+                            const uint32_t v = png_add4(f, png_predict4(type, cur, up, upleft));
+                            cur = on ? v : 0u;
+                            if (on) simt::sts32(cell, v);
+                        }
                     }
                 }
+                simt::syncwarp();
+                if (NC >= 1) flush_chunk(NC - 1);
                 simt::syncwarp();  // the next block's first row reads this block's last row
             }
             if (lane == 0) b.status[i] = st;
@@ -228,9 +263,26 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_FILTER_WARPS * 32, 4) png_filter_kernel(Pn
             const uint8_t* up = cur - stride;  // (y > 0 only)
             uint8_t* dst = out + (uint64_t)y * (1ull + stride);
             uint32_t type = b.mode;
+            const bool words = bpp == 4 && (stride & 3u) == 0 && ((uintptr_t)in & 3u) == 0;  // RGBA rows, aligned words
             if (b.mode == 5) {
                 uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
-                for (uint32_t x = lane; x < stride; x += 32) {
+                if (words) {
+                    const uint32_t* cw = (const uint32_t*)cur;
+                    const uint32_t* uw = (const uint32_t*)up;
+                    for (uint32_t p = lane; p < (stride >> 2); p += 32) {
+                        const uint32_t v = simt::ldg32(cw + p);
+                        const uint32_t a = p ? simt::ldg32(cw + p - 1) : 0u;
+                        const uint32_t bb = y ? simt::ldg32(uw + p) : 0u;
+                        const uint32_t cc = (y && p) ? simt::ldg32(uw + p - 1) : 0u;
+                        // |signed byte| summed over the four channels: per-byte abs, then a dot product with ones
+                        s0 = simt::dp4a_u(png_abs4(v), 0x01010101u, s0);
+                        s1 = simt::dp4a_u(png_abs4(png_sub4(v, a)), 0x01010101u, s1);
+                        s2 = simt::dp4a_u(png_abs4(png_sub4(v, bb)), 0x01010101u, s2);
+                        s3 = simt::dp4a_u(png_abs4(png_sub4(v, png_avg4(a, bb))), 0x01010101u, s3);
+                        s4 = simt::dp4a_u(png_abs4(png_sub4(v, png_paeth4(a, bb, cc))), 0x01010101u, s4);
+                    }
+                }
+                for (uint32_t x = words ? stride : lane; x < stride; x += 32) {
                     const uint32_t v = simt::ldg8(cur + x);
                     const uint32_t a = x >= bpp ? (uint32_t)simt::ldg8(cur + x - bpp) : 0u;
                     const uint32_t bb = y ? (uint32_t)simt::ldg8(up + x) : 0u;
@@ -256,7 +308,7 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_FILTER_WARPS * 32, 4) png_filter_kernel(Pn
                 if (s4 < best) { best = s4; type = 4; }
             }
             if (lane == 0) dst[0] = (uint8_t)type;
-            if (b.mode != 5 && bpp == 4 && (stride & 3u) == 0 && ((uintptr_t)in & 3u) == 0) {
+            if (words) {
                 // four bytes (one RGBA pixel) per lane from aligned words: the pixel, the one to its left, the one
                 // above and the one above-left
                 const uint32_t* cw = (const uint32_t*)cur;
