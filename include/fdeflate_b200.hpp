@@ -65,6 +65,11 @@ public:
     void check(int rc, const char* what) const {
         if (rc != 0) throw std::runtime_error(std::string(what) + ": " + fdb_last_error(h_));
     }
+    // long streams by many warps each, for device-pointer calls (host-buffer calls decide by themselves)
+    void set_split_large(bool on) { check(fdb_set_split_large(h_, on ? 1 : 0), "fdb_set_split_large"); }
+    void set_split_threshold(size_t inflate_stream_bytes, size_t deflate_input_bytes) {
+        check(fdb_set_split_threshold(h_, inflate_stream_bytes, deflate_input_bytes), "fdb_set_split_threshold");
+    }
 
 private:
     fdb_ctx* h_ = nullptr;
