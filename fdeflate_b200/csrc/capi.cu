@@ -790,7 +790,7 @@ extern "C" int fdb_deflate_stored_batch(fdb_ctx* ctx, const uint8_t* in_base, co
 // ---- PNG row filters --------------------------------------------------------------------------
 static int png_launch(fdb_ctx* ctx, bool unfilter, const void* d_in_base, const uint64_t* d_in_off, void* d_out_base,
                       const uint64_t* d_out_off, const uint32_t* d_height, const uint32_t* d_stride, const uint32_t* d_bpp,
-                      uint32_t mode, int32_t* d_status, size_t n, void* cuda_stream) {
+                      uint32_t mode, int32_t* d_status, size_t n, void* cuda_stream, uint32_t* counter = nullptr) {
     if (!ctx) return -1;
     if (n == 0) return 0;
     if (n > 0xffffffffull || !d_in_off || !d_out_off || !d_height || !d_stride || !d_bpp || !d_status)
@@ -808,7 +808,7 @@ static int png_launch(fdb_ctx* ctx, bool unfilter, const void* d_in_base, const 
     b.status = d_status;
     b.n = (uint32_t)n;
     b.mode = mode;
-    uint32_t* counter = ctx->d_counters + 12;
+    if (!counter) counter = ctx->d_counters + 12;
     FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
     const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
     if (unfilter) {
@@ -900,13 +900,16 @@ extern "C" int fdb_png_decode_batch(fdb_ctx* ctx, const uint8_t* idat_base, cons
     if (n > 0xffffffffull || !idat_off || !idat_len || !raw_off || !height || !stride || !bpp || !status)
         return fail(ctx, "fdb_png_decode_batch", cudaSuccess);
     FDB_TRY(cudaSetDevice(ctx->device));
-    std::vector<uint64_t> m(4 * n);  // filtered_off | filtered_cap | (spare) | (spare)
-    uint64_t in_span = 0, raw_span = 0, filt_span = 0, max_in = 0;
+    std::vector<uint64_t> m(2 * n);  // filtered_off | filtered_cap
+    uint64_t in_span = 0, raw_span = 0, filt_span = 0;
+    bool ascending = true;
     for (size_t i = 0; i < n; i++) {
         const uint64_t filtered = (uint64_t)height[i] * (1ull + stride[i]);
         in_span = std::max(in_span, idat_off[i] + idat_len[i]);
-        max_in = std::max(max_in, idat_len[i]);
         raw_span = std::max(raw_span, raw_off[i] + (uint64_t)height[i] * stride[i]);
+        if (i && (idat_off[i] < idat_off[i - 1] + idat_len[i - 1] ||
+                  raw_off[i] < raw_off[i - 1] + (uint64_t)height[i - 1] * stride[i - 1]))
+            ascending = false;
         m[i] = filt_span;
         m[n + i] = filtered;
         filt_span += (filtered + 15) & ~15ull;
@@ -915,50 +918,81 @@ extern "C" int fdb_png_decode_batch(fdb_ctx* ctx, const uint8_t* idat_base, cons
     if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, in_span + 64))) return r;
     if ((r = grow(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, raw_span + 64))) return r;
     if ((r = grow(ctx, (void**)&ctx->d_mid, &ctx->d_mid_cap, filt_span + 64))) return r;
-    // idat_off | idat_len | filt_off | filt_cap | raw_off | out_len | consumed | h,s,b (u32) | status x2 (i32)
-    if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, 10 * n * sizeof(uint64_t)))) return r;
-    cudaStream_t st = ctx->lanes[0].st;
+    // idat_off | idat_len | filt_off | filt_cap | raw_off | consumed | h,s,b (u32)
+    if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, 8 * n * sizeof(uint64_t)))) return r;
+    // per-image results, written by the kernels straight into pinned host memory (as in host_batch)
+    const size_t res_bytes = n * (8 + 4 + 4) + 64;
+    if (res_bytes > ctx->h_res_cap) {
+        if (ctx->h_res) FDB_TRY(cudaFreeHost(ctx->h_res));
+        ctx->h_res = nullptr;
+        ctx->h_res_cap = 0;
+        FDB_TRY(cudaMallocHost((void**)&ctx->h_res, res_bytes + res_bytes / 4));
+        ctx->h_res_cap = res_bytes + res_bytes / 4;
+    }
+    uint64_t* h_out_len = (uint64_t*)ctx->h_res;
+    int32_t* h_st1 = (int32_t*)(h_out_len + n);
+    int32_t* h_st2 = h_st1 + n;
+    cudaStream_t hs = ctx->h2d_st, ds = ctx->d2h_st;
     uint64_t* d = ctx->d_meta;
     uint64_t *d_idat_off = d, *d_idat_len = d + n, *d_filt_off = d + 2 * n, *d_filt_cap = d + 3 * n, *d_raw_off = d + 4 * n,
-             *d_out_len = d + 5 * n, *d_consumed = d + 6 * n;
-    uint32_t* d_h = (uint32_t*)(d + 7 * n);
+             *d_consumed = d + 5 * n;
+    uint32_t* d_h = (uint32_t*)(d + 6 * n);
     uint32_t *d_s = d_h + n, *d_b = d_s + n;
-    int32_t* d_st1 = (int32_t*)(d_b + n);
-    int32_t* d_st2 = d_st1 + n;
-    FDB_TRY(cudaMemcpyAsync(d_idat_off, idat_off, n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_idat_len, idat_len, n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_filt_off, m.data(), 2 * n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_raw_off, raw_off, n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_h, height, n * 4, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_s, stride, n * 4, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_b, bpp, n * 4, cudaMemcpyHostToDevice, st));
-    if (in_span) FDB_TRY(cudaMemcpyAsync(ctx->d_in, idat_base, in_span, cudaMemcpyHostToDevice, st));
-    InflateBatch ib;
-    ib.in_base = ctx->d_in;
-    ib.in_off = d_idat_off;
-    ib.in_len = d_idat_len;
-    ib.out_base = ctx->d_mid;
-    ib.out_off = d_filt_off;
-    ib.out_cap = d_filt_cap;
-    ib.out_len = d_out_len;
-    ib.consumed = d_consumed;
-    ib.status = d_st1;
-    ib.n = (uint32_t)n;
-    ib.flags = max_in >= ctx->inflate_split_min ? FDB_FLAG_SPLIT_LARGE : 0u;
+    FDB_TRY(cudaMemcpyAsync(d_idat_off, idat_off, n * 8, cudaMemcpyHostToDevice, hs));
+    FDB_TRY(cudaMemcpyAsync(d_idat_len, idat_len, n * 8, cudaMemcpyHostToDevice, hs));
+    FDB_TRY(cudaMemcpyAsync(d_filt_off, m.data(), 2 * n * 8, cudaMemcpyHostToDevice, hs));
+    FDB_TRY(cudaMemcpyAsync(d_raw_off, raw_off, n * 8, cudaMemcpyHostToDevice, hs));
+    FDB_TRY(cudaMemcpyAsync(d_h, height, n * 4, cudaMemcpyHostToDevice, hs));
+    FDB_TRY(cudaMemcpyAsync(d_s, stride, n * 4, cudaMemcpyHostToDevice, hs));
+    FDB_TRY(cudaMemcpyAsync(d_b, bpp, n * 4, cudaMemcpyHostToDevice, hs));
+    // chunks of streams: streams up | inflate + unfilter | pixels back overlap.  Nothing the host does depends on
+    // a chunk's results (the pixel ranges are known from the geometry), so every chunk is queued at once.
+    size_t nchunk = 1;
+    if (ascending) nchunk = (size_t)std::min<uint64_t>(std::min<uint64_t>((in_span + raw_span) / ctx->chunk_bytes, FDB_MAX_CHUNKS), n);
+    if (nchunk < 1) nchunk = 1;
+    const size_t per = (n + nchunk - 1) / nchunk;
+    nchunk = (n + per - 1) / per;
+    const int L = ctx->n_lanes;
     ctx->last_general_host = -1;
     ctx->last_split_host = -1;
-    if ((r = launch_inflate(ctx, ib, ctx->d_counters, &ctx->d_worklist, &ctx->worklist_cap, st, false, &ctx->split))) return r;
-    if ((r = png_launch(ctx, true, ctx->d_mid, d_filt_off, ctx->d_out, d_raw_off, d_h, d_s, d_b, 0, d_st2, n, st))) return r;
-    std::vector<int32_t> st12(2 * n);
-    std::vector<uint64_t> olen(n);
-    if (raw_span) FDB_TRY(cudaMemcpyAsync(raw_base, ctx->d_out, raw_span, cudaMemcpyDeviceToHost, st));
-    FDB_TRY(cudaMemcpyAsync(st12.data(), d_st1, 2 * n * 4, cudaMemcpyDeviceToHost, st));
-    FDB_TRY(cudaMemcpyAsync(olen.data(), d_out_len, n * 8, cudaMemcpyDeviceToHost, st));
-    FDB_TRY(cudaStreamSynchronize(st));
+    for (size_t k = 0; k < nchunk; k++) {
+        const size_t a = k * per, b = std::min(n, a + per);
+        fdb_lane& ln = ctx->lanes[k % L];
+        uint64_t max_in = 0;
+        for (size_t i = a; i < b; i++) max_in = std::max(max_in, idat_len[i]);
+        const uint64_t in_lo = nchunk == 1 ? 0 : idat_off[a], in_hi = nchunk == 1 ? in_span : idat_off[b - 1] + idat_len[b - 1];
+        if (in_hi > in_lo) FDB_TRY(cudaMemcpyAsync(ctx->d_in + in_lo, idat_base + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, hs));
+        FDB_TRY(cudaEventRecord(ctx->ev_in[k], hs));
+        FDB_TRY(cudaStreamWaitEvent(ln.st, ctx->ev_in[k], 0));
+        InflateBatch ib;
+        ib.in_base = ctx->d_in;
+        ib.in_off = d_idat_off + a;
+        ib.in_len = d_idat_len + a;
+        ib.out_base = ctx->d_mid;
+        ib.out_off = d_filt_off + a;
+        ib.out_cap = d_filt_cap + a;
+        ib.out_len = h_out_len + a;
+        ib.consumed = d_consumed + a;
+        ib.status = h_st1 + a;
+        ib.n = (uint32_t)(b - a);
+        ib.flags = max_in >= ctx->inflate_split_min ? FDB_FLAG_SPLIT_LARGE : 0u;
+        if ((r = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, nchunk > 1, &ln.split))) return r;
+        if ((r = png_launch(ctx, true, ctx->d_mid, d_filt_off + a, ctx->d_out, d_raw_off + a, d_h + a, d_s + a, d_b + a, 0,
+                            h_st2 + a, b - a, ln.st, ln.d_counters + 12)))
+            return r;
+        FDB_TRY(cudaEventRecord(ctx->ev_res[k], ln.st));
+        FDB_TRY(cudaStreamWaitEvent(ds, ctx->ev_res[k], 0));
+        const uint64_t out_lo = nchunk == 1 ? 0 : raw_off[a];
+        const uint64_t out_hi = nchunk == 1 ? raw_span : raw_off[b - 1] + (uint64_t)height[b - 1] * stride[b - 1];
+        if (out_hi > out_lo) FDB_TRY(cudaMemcpyAsync(raw_base + out_lo, ctx->d_out + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, ds));
+    }
+    FDB_TRY(cudaStreamSynchronize(ds));
+    FDB_TRY(cudaStreamSynchronize(hs));
+    for (int l = 0; l < L; l++) FDB_TRY(cudaStreamSynchronize(ctx->lanes[l].st));
     for (size_t i = 0; i < n; i++) {
-        int32_t s1 = st12[i];
-        if (s1 == ST_OK && olen[i] != m[n + i]) s1 = ST_INSUFFICIENT_INPUT;  // the stream ended before the image was complete
-        status[i] = s1 != ST_OK ? s1 : st12[n + i];
+        int32_t s1 = h_st1[i];
+        if (s1 == ST_OK && h_out_len[i] != m[n + i]) s1 = ST_INSUFFICIENT_INPUT;  // the stream ended before the image was complete
+        status[i] = s1 != ST_OK ? s1 : h_st2[i];
     }
     return 0;
 }

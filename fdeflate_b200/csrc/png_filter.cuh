@@ -21,6 +21,7 @@
 #pragma once
 #include "simt.h"
 #include "fdb_common.h"
+#include <type_traits>
 
 namespace fdb {
 
@@ -79,12 +80,14 @@ FDB_DEVICE uint32_t png_paeth4(uint32_t a, uint32_t b, uint32_t c) {
     }
     return r;
 }
+// PAETH = false: no row of the warp's block uses the Paeth predictor (it is three quarters of the arithmetic)
+template <bool PAETH>
 FDB_DEVICE uint32_t png_predict4(uint32_t type, uint32_t a, uint32_t b, uint32_t c) {
     uint32_t p = 0;
     p = type == 1 ? a : p;
     p = type == 2 ? b : p;
     p = type == 3 ? png_avg4(a, b) : p;
-    p = type == 4 ? png_paeth4(a, b, c) : p;
+    if (PAETH) p = type == 4 ? png_paeth4(a, b, c) : p;
     return p;
 }
 
@@ -152,35 +155,42 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_UNFILTER_WARPS * 32, 6) png_unfilter_kerne
                         simt::sts32(buf_s + 4u * ((c & 1u) * PNG_BUF_WORDS + r * PNG_ROW_WORDS + lane), simt::funnel_r(lo, hi, 8u * m));
                     }
                 };
-                uint32_t cur = 0, up = 0;
-                for (uint32_t p = 0; p <= NC; p++) {
-                    simt::syncwarp();
-                    if (p >= 2) flush_chunk(p - 2);
-                    if (p < NC) load_chunk(p);
-                    simt::syncwarp();
-                    for (uint32_t s0 = 0; s0 < 32; s0 += PNG_AHEAD) {
-                        uint32_t av[PNG_AHEAD];
-#pragma unroll
-                        for (uint32_t k = 0; k < PNG_AHEAD; k++) {
-                            const uint32_t x = 32u * p + s0 + k;  // (lane 0: x = t)
-                            av[k] = (lane == 0 && y0 > 0 && x < W) ? arow[x] : 0u;  // (stored by this warp one block ago)
-                        }
-#pragma unroll
-                        for (uint32_t k = 0; k < PNG_AHEAD; k++) {
-                            const uint32_t x = 32u * p + s0 + k - lane;  // (wraps for t < lane: then x >= W)
-                            const bool on = row_on && x < W;
-                            const simt::saddr cell = buf_s + 4u * (((x >> 5) & 1u) * PNG_BUF_WORDS + lane * PNG_ROW_WORDS + (x & 31u));
-                            const uint32_t f = on ? simt::lds32(cell) : 0u;
-                            const uint32_t from_lane = simt::shfl_up(cur, 1);
-                            const uint32_t upleft = up;
-                            const uint32_t upv = lane == 0 ? av[k] : from_lane;
-                            up = on ? upv : 0u;
-                            const uint32_t v = png_add4(f, png_predict4(type, cur, up, upleft));
-                            cur = on ? v : 0u;
-                            if (on) simt::sts32(cell, v);
+                auto run_block = [&](auto paeth_tag) {
+                    constexpr bool PAETH = decltype(paeth_tag)::value;
+                    uint32_t cur = 0, up = 0;
+                    for (uint32_t p = 0; p <= NC; p++) {
+                        simt::syncwarp();
+                        if (p >= 2) flush_chunk(p - 2);
+                        if (p < NC) load_chunk(p);
+                        simt::syncwarp();
+                        for (uint32_t s0 = 0; s0 < 32; s0 += PNG_AHEAD) {
+                            uint32_t av[PNG_AHEAD];
+    #pragma unroll
+                            for (uint32_t k = 0; k < PNG_AHEAD; k++) {
+                                const uint32_t x = 32u * p + s0 + k;  // (lane 0: x = t)
+                                av[k] = (lane == 0 && y0 > 0 && x < W) ? arow[x] : 0u;  // (stored by this warp one block ago)
+                            }
+    #pragma unroll
+                            for (uint32_t k = 0; k < PNG_AHEAD; k++) {
+                                const uint32_t x = 32u * p + s0 + k - lane;  // (wraps for t < lane: then x >= W)
+                                const bool on = row_on && x < W;
+                                const simt::saddr cell = buf_s + 4u * (((x >> 5) & 1u) * PNG_BUF_WORDS + lane * PNG_ROW_WORDS + (x & 31u));
+                                const uint32_t f = on ? simt::lds32(cell) : 0u;
+                                const uint32_t from_lane = simt::shfl_up(cur, 1);
+                                const uint32_t upleft = up;
+                                const uint32_t upv = lane == 0 ? av[k] : from_lane;
+                                up = on ? upv : 0u;
+                                const uint32_t v = png_add4(f, png_predict4<PAETH>(type, cur, up, upleft));
+                                cur = on ? v : 0u;
+                                if (on) simt::sts32(cell, v);
+                            }
                         }
                     }
-                }
+                };
+                if (simt::any(type == 4u))
+                    run_block(std::true_type{});
+                else
+                    run_block(std::false_type{});
                 simt::syncwarp();
                 if (NC >= 1) flush_chunk(NC - 1);
                 simt::syncwarp();  // the next block's first row reads this block's last row
@@ -319,12 +329,11 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(PNG_FILTER_WARPS * 32, 4) png_filter_kernel(Pn
                     const uint32_t bb = y ? simt::ldg32(uw + p) : 0u;
                     const uint32_t cc = (y && p) ? simt::ldg32(uw + p - 1) : 0u;
                     uint8_t* d = dst + 1 + 4 * p;
+                    // (the row's type is uniform over the warp: only its predictor is evaluated)
+                    const uint32_t pred = type == 4 ? png_paeth4(a, bb, cc) : png_predict4<false>(type, a, bb, cc);
+                    const uint32_t f = png_sub4(v, pred);
 #pragma unroll
-                    for (uint32_t k = 0; k < 4; k++) {
-                        const uint32_t sh = 8u * k;
-                        d[k] = (uint8_t)(((v >> sh) & 0xffu) -
-                                         png_predict(type, (a >> sh) & 0xffu, (bb >> sh) & 0xffu, (cc >> sh) & 0xffu));
-                    }
+                    for (uint32_t k = 0; k < 4; k++) d[k] = (uint8_t)(f >> (8u * k));
                 }
                 continue;
             }

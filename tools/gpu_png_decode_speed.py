@@ -20,8 +20,14 @@ z_len = np.zeros(n, np.uint64); status = np.zeros(n, np.int32)
 def encode():
     rc = ctx.lib.L.fdb_png_encode_batch(ctx._h, _ptr(raw), _ptr(raw_off), _ptr(h), _ptr(s), _ptr(b), 4, _ptr(z), _ptr(z_off), _ptr(z_cap), _ptr(z_len), _ptr(status), n)
     assert rc == 0 and (status == 0).all()
+packed = {}
 def decode():
-    rc = ctx.lib.L.fdb_png_decode_batch(ctx._h, _ptr(z), _ptr(z_off), _ptr(z_len), _ptr(raw2), _ptr(raw_off), _ptr(h), _ptr(s), _ptr(b), _ptr(status), n)
+    if not packed:  # the streams back to back, as they sit in PNG files
+        off = np.zeros(n, np.uint64); off[1:] = np.cumsum((z_len[:-1] + np.uint64(15)) & ~np.uint64(15))
+        buf = pin(int(off[-1] + z_len[-1]) + 16)
+        for i in range(n): buf[int(off[i]):int(off[i]) + int(z_len[i])] = z[int(z_off[i]):int(z_off[i]) + int(z_len[i])]
+        packed["off"], packed["buf"] = off, buf
+    rc = ctx.lib.L.fdb_png_decode_batch(ctx._h, _ptr(packed["buf"]), _ptr(packed["off"]), _ptr(z_len), _ptr(raw2), _ptr(raw_off), _ptr(h), _ptr(s), _ptr(b), _ptr(status), n)
     assert rc == 0 and (status == 0).all()
 for name, f in (("encode (filter Paeth + ultra-fast deflate)", encode), ("decode (inflate + unfilter)", decode)):
     f(); t0 = time.perf_counter()
