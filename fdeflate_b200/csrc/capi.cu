@@ -589,9 +589,21 @@ static int copy_rows(fdb_ctx* ctx, uint8_t* dst_base, const uint8_t* src_base, c
 // small copy of its per-stream results; the host picks the results up in order and they decide how much
 // payload goes back on the device-to-host stream.  Both directions of the (full duplex) link therefore
 // stay busy from the first chunk to the last, and a call costs about max(H2D, D2H) + one chunk.
+static int png_launch(fdb_ctx* ctx, bool unfilter, const void* d_in_base, const uint64_t* d_in_off, void* d_out_base,
+                      const uint64_t* d_out_off, const uint32_t* d_height, const uint32_t* d_stride, const uint32_t* d_bpp,
+                      uint32_t mode, int32_t* d_status, size_t n, void* cuda_stream, uint32_t* counter = nullptr);
+
+// PNG encode rides the same pipeline: the inputs are raw images, and between "input landed" and the deflate
+// kernels a filter kernel writes the filtered images into a second device buffer, which is what gets compressed.
+struct PngPre {
+    const uint32_t *height, *stride, *bpp;
+    uint32_t mode;
+    int32_t* filter_status;  // [n] host array
+};
+
 static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
                       uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
-                      uint64_t* consumed, int32_t* status, size_t n, uint32_t flags) {
+                      uint64_t* consumed, int32_t* status, size_t n, uint32_t flags, const PngPre* png = nullptr) {
     if (!ctx) return -1;
     if (n == 0) return 0;
     if (n > 0xffffffffull || !in_off || !in_len || !out_off || !out_cap || !out_len || !status)
@@ -601,10 +613,28 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     int r;
     if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, sp.in_span + 64))) return r;
     if ((r = grow(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, sp.out_span + 64))) return r;
-    const size_t meta_words = 4 * n;
+    const size_t meta_words = 8 * n;
     if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, meta_words * sizeof(uint64_t)))) return r;
     uint64_t* m = ctx->d_meta;
     uint64_t *d_in_off = m, *d_in_len = m + n, *d_out_off = m + 2 * n, *d_out_cap = m + 3 * n;
+    // PNG encode: filtered_off | filtered_len | height, stride, bpp (u32) | filter status (i32)
+    uint64_t *d_filt_off = m + 4 * n, *d_filt_len = m + 5 * n;
+    uint32_t* d_geo = (uint32_t*)(m + 6 * n);
+    int32_t* d_fst = (int32_t*)(d_geo + 3 * n);
+    std::vector<uint64_t> filt;
+    uint64_t max_filtered = 0;
+    if (png) {
+        filt.resize(2 * n);
+        uint64_t span = 0;
+        for (size_t i = 0; i < n; i++) {
+            const uint64_t f = (uint64_t)png->height[i] * (1ull + png->stride[i]);
+            filt[i] = span;
+            filt[n + i] = f;
+            max_filtered = std::max(max_filtered, f);
+            span += (f + 15) & ~15ull;
+        }
+        if ((r = grow(ctx, (void**)&ctx->d_mid, &ctx->d_mid_cap, span + 64))) return r;
+    }
 
     // chunking needs slots laid out in ascending order (what every packer produces); anything else is one chunk
     bool ascending = true;
@@ -660,6 +690,12 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     FDB_TRY(cudaMemcpyAsync(d_in_len, in_len, n * 8, cudaMemcpyHostToDevice, hs));
     FDB_TRY(cudaMemcpyAsync(d_out_off, out_off, n * 8, cudaMemcpyHostToDevice, hs));
     FDB_TRY(cudaMemcpyAsync(d_out_cap, out_cap, n * 8, cudaMemcpyHostToDevice, hs));
+    if (png) {
+        FDB_TRY(cudaMemcpyAsync(d_filt_off, filt.data(), 2 * n * 8, cudaMemcpyHostToDevice, hs));
+        FDB_TRY(cudaMemcpyAsync(d_geo, png->height, n * 4, cudaMemcpyHostToDevice, hs));
+        FDB_TRY(cudaMemcpyAsync(d_geo + n, png->stride, n * 4, cudaMemcpyHostToDevice, hs));
+        FDB_TRY(cudaMemcpyAsync(d_geo + 2 * n, png->bpp, n * 4, cudaMemcpyHostToDevice, hs));
+    }
     const bool dense = nchunk > 1;
 
     auto issue = [&](size_t k) -> int {  // input, kernels and results of chunk k
@@ -697,13 +733,22 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             db.in_base = ctx->d_in;
             db.in_off = d_in_off + a;
             db.in_len = d_in_len + a;
+            if (png) {
+                if ((rr = png_launch(ctx, false, ctx->d_in, d_in_off + a, ctx->d_mid, d_filt_off + a, d_geo + a, d_geo + n + a,
+                                     d_geo + 2 * n + a, png->mode, d_fst + a, b - a, ln.st, ln.d_counters + 12)))
+                    return rr;
+                FDB_TRY(cudaMemcpyAsync(png->filter_status + a, d_fst + a, (b - a) * 4, cudaMemcpyDeviceToHost, ln.st));
+                db.in_base = ctx->d_mid;
+                db.in_off = d_filt_off + a;
+                db.in_len = d_filt_len + a;
+            }
             db.out_base = ctx->d_out;
             db.out_off = d_out_off + a;
             db.out_cap = d_out_cap + a;
             db.out_len = h_out_len + a;
             db.status = h_status + a;
             db.n = (uint32_t)(b - a);
-            uint64_t max_len = 0;
+            uint64_t max_len = png ? max_filtered : 0;
             for (size_t i = a; i < b; i++) max_len = std::max(max_len, in_len[i]);
             if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st, dense,
                                      max_len >= ctx->deflate_split_min ? &ln.dsplit : nullptr)))
@@ -790,7 +835,7 @@ extern "C" int fdb_deflate_stored_batch(fdb_ctx* ctx, const uint8_t* in_base, co
 // ---- PNG row filters --------------------------------------------------------------------------
 static int png_launch(fdb_ctx* ctx, bool unfilter, const void* d_in_base, const uint64_t* d_in_off, void* d_out_base,
                       const uint64_t* d_out_off, const uint32_t* d_height, const uint32_t* d_stride, const uint32_t* d_bpp,
-                      uint32_t mode, int32_t* d_status, size_t n, void* cuda_stream, uint32_t* counter = nullptr) {
+                      uint32_t mode, int32_t* d_status, size_t n, void* cuda_stream, uint32_t* counter) {
     if (!ctx) return -1;
     if (n == 0) return 0;
     if (n > 0xffffffffull || !d_in_off || !d_out_off || !d_height || !d_stride || !d_bpp || !d_status)
@@ -997,7 +1042,8 @@ extern "C" int fdb_png_decode_batch(fdb_ctx* ctx, const uint8_t* idat_base, cons
     return 0;
 }
 
-// encode: raw pixels up, filter, ultra-fast deflate, zlib streams back (slots of fdb_deflate_ultrafast_bound).
+// encode: raw pixels up, filter, ultra-fast deflate, zlib streams back (slots of fdb_deflate_ultrafast_bound), on
+// the pipeline of the host-buffer deflate call.
 extern "C" int fdb_png_encode_batch(fdb_ctx* ctx, const uint8_t* raw_base, const uint64_t* raw_off, const uint32_t* height,
                                     const uint32_t* stride, const uint32_t* bpp, uint32_t mode, uint8_t* out_base,
                                     const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, int32_t* status,
@@ -1006,58 +1052,17 @@ extern "C" int fdb_png_encode_batch(fdb_ctx* ctx, const uint8_t* raw_base, const
     if (n == 0) return 0;
     if (n > 0xffffffffull || !raw_off || !height || !stride || !bpp || !out_off || !out_cap || !out_len || !status)
         return fail(ctx, "fdb_png_encode_batch", cudaSuccess);
-    FDB_TRY(cudaSetDevice(ctx->device));
-    std::vector<uint64_t> m(2 * n);  // filtered_off | filtered_len
-    uint64_t raw_span = 0, filt_span = 0, out_span = 0, max_len = 0;
-    for (size_t i = 0; i < n; i++) {
-        const uint64_t filtered = (uint64_t)height[i] * (1ull + stride[i]);
-        raw_span = std::max(raw_span, raw_off[i] + (uint64_t)height[i] * stride[i]);
-        out_span = std::max(out_span, out_off[i] + out_cap[i]);
-        max_len = std::max(max_len, filtered);
-        m[i] = filt_span;
-        m[n + i] = filtered;
-        filt_span += (filtered + 15) & ~15ull;
-    }
-    int r;
-    if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, raw_span + 64))) return r;
-    if ((r = grow(ctx, (void**)&ctx->d_mid, &ctx->d_mid_cap, filt_span + 64))) return r;
-    if ((r = grow(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, out_span + 64))) return r;
-    if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, 10 * n * sizeof(uint64_t)))) return r;
-    cudaStream_t st = ctx->lanes[0].st;
-    uint64_t* d = ctx->d_meta;
-    uint64_t *d_raw_off = d, *d_filt_off = d + n, *d_filt_len = d + 2 * n, *d_out_off = d + 3 * n, *d_out_cap = d + 4 * n,
-             *d_out_len = d + 5 * n;
-    uint32_t* d_h = (uint32_t*)(d + 6 * n);
-    uint32_t *d_s = d_h + n, *d_b = d_s + n;
-    int32_t* d_st1 = (int32_t*)(d_b + n);
-    int32_t* d_st2 = d_st1 + n;
-    FDB_TRY(cudaMemcpyAsync(d_raw_off, raw_off, n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_filt_off, m.data(), 2 * n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_out_off, out_off, n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_out_cap, out_cap, n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_h, height, n * 4, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_s, stride, n * 4, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_b, bpp, n * 4, cudaMemcpyHostToDevice, st));
-    if (raw_span) FDB_TRY(cudaMemcpyAsync(ctx->d_in, raw_base, raw_span, cudaMemcpyHostToDevice, st));
-    if ((r = png_launch(ctx, false, ctx->d_in, d_raw_off, ctx->d_mid, d_filt_off, d_h, d_s, d_b, mode, d_st1, n, st))) return r;
-    DeflateBatch db;
-    db.in_base = ctx->d_mid;
-    db.in_off = d_filt_off;
-    db.in_len = d_filt_len;
-    db.out_base = ctx->d_out;
-    db.out_off = d_out_off;
-    db.out_cap = d_out_cap;
-    db.out_len = d_out_len;
-    db.status = d_st2;
-    db.n = (uint32_t)n;
-    if ((r = launch_deflate(ctx, 0, db, ctx->d_counters + 3, st, false, max_len >= ctx->deflate_split_min ? &ctx->dsplit : nullptr)))
-        return r;
-    std::vector<int32_t> st12(2 * n);
-    if (out_span) FDB_TRY(cudaMemcpyAsync(out_base, ctx->d_out, out_span, cudaMemcpyDeviceToHost, st));
-    FDB_TRY(cudaMemcpyAsync(st12.data(), d_st1, 2 * n * 4, cudaMemcpyDeviceToHost, st));
-    FDB_TRY(cudaMemcpyAsync(out_len, d_out_len, n * 8, cudaMemcpyDeviceToHost, st));
-    FDB_TRY(cudaStreamSynchronize(st));
-    for (size_t i = 0; i < n; i++) status[i] = st12[i] != ST_OK ? st12[i] : st12[n + i];
+    std::vector<uint64_t> raw_len(n);
+    std::vector<int32_t> fst(n, 0);
+    for (size_t i = 0; i < n; i++) raw_len[i] = (uint64_t)height[i] * stride[i];
+    PngPre pre = {height, stride, bpp, mode, fst.data()};
+    int r = host_batch(ctx, 1, raw_base, raw_off, raw_len.data(), out_base, out_off, out_cap, out_len, nullptr, status, n, 0, &pre);
+    if (r) return r;
+    for (size_t i = 0; i < n; i++)
+        if (fst[i] != ST_OK) {
+            status[i] = fst[i];
+            out_len[i] = 0;
+        }
     return 0;
 }
 
