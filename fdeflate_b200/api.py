@@ -280,6 +280,17 @@ class Context:
     def png_filter_batch(self, raw: Sequence[bytes], geometry: Sequence[tuple], mode: int = 4):
         return self._png_batch(False, raw, geometry, mode)
 
+    def crc32_batch(self, items: Sequence[bytes], seed: int = 0) -> np.ndarray:
+        """CRC-32 (zlib's crc32) of every item, continued from `seed`, computed on the device -> uint32[n]"""
+        n = len(items)
+        if n == 0:
+            return np.zeros(0, dtype=np.uint32)
+        base, off, lens = self._pack(items)
+        crc = np.zeros(n, dtype=np.uint32)
+        rc = self.lib.L.fdb_crc32_batch(self._h, _ptr(base), _ptr(off), _ptr(lens), seed & 0xffffffff, _ptr(crc), n)
+        self._check(rc, "fdb_crc32_batch")
+        return crc
+
     def synth_tiles_device(self, d_out: int, first_tile: int, n_tiles: int, width: int, height: int, seed: int,
                            stream: int = 0):
         rc = self.lib.L.fdb_synth_tiles_device(self._h, d_out, first_tile, n_tiles, width, height, seed, stream)

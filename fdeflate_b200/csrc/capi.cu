@@ -24,6 +24,7 @@
 #include "deflate_stored.cuh"
 #include "synth.cuh"
 #include "png_filter.cuh"
+#include "crc32.cuh"
 
 using namespace fdb;
 
@@ -83,6 +84,7 @@ struct fdb_ctx {
     uint64_t deflate_split_min = DF_SPLIT_MIN_BYTES;
     UfEncTables* d_enc = nullptr;
     UfDecTables* d_dec = nullptr;
+    CrcTables* d_crc = nullptr;
     // host-API staging (grow-only)
     uint8_t* d_in = nullptr;
     size_t d_in_cap = 0;
@@ -264,6 +266,12 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
     if ((e = cudaMalloc((void**)&ctx->d_dec, sizeof(UfDecTables))) != cudaSuccess) return bail(e);
     if ((e = cudaMemcpy(ctx->d_enc, &enc, sizeof enc, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
     if ((e = cudaMemcpy(ctx->d_dec, &dec, sizeof dec, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
+    {
+        CrcTables crc;
+        build_crc_tables(crc);
+        if ((e = cudaMalloc((void**)&ctx->d_crc, sizeof(CrcTables))) != cudaSuccess) return bail(e);
+        if ((e = cudaMemcpy(ctx->d_crc, &crc, sizeof crc, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
+    }
     if ((e = cudaFuncSetAttribute(inflate_uf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem))) != cudaSuccess)
         return bail(e);
     if ((e = cudaFuncSetAttribute(inflate_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem))) != cudaSuccess)
@@ -306,6 +314,7 @@ extern "C" void fdb_destroy(fdb_ctx* ctx) {
     cudaFree(ctx->dsplit.per_stream);
     cudaFree(ctx->d_enc);
     cudaFree(ctx->d_dec);
+    cudaFree(ctx->d_crc);
     cudaFree(ctx->d_in);
     cudaFree(ctx->d_out);
     cudaFree(ctx->d_mid);
@@ -1063,6 +1072,54 @@ extern "C" int fdb_png_encode_batch(fdb_ctx* ctx, const uint8_t* raw_base, const
             status[i] = fst[i];
             out_len[i] = 0;
         }
+    return 0;
+}
+
+// ---- CRC-32 of a batch of byte ranges (PNG chunk CRCs) ------------------------------------------------
+extern "C" int fdb_crc32_batch_device(fdb_ctx* ctx, const void* d_base, const uint64_t* d_off, const uint64_t* d_len,
+                                      uint32_t seed, uint32_t* d_crc, size_t n, void* cuda_stream) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (n > 0xffffffffull || !d_off || !d_len || !d_crc) return fail(ctx, "fdb_crc32_batch_device", cudaSuccess);
+    FDB_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CrcBatch b;
+    b.base = (const uint8_t*)d_base;
+    b.off = d_off;
+    b.len = d_len;
+    b.crc = d_crc;
+    b.n = (uint32_t)n;
+    b.seed = seed;
+    uint32_t* counter = ctx->d_counters + 13;
+    FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+    const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
+    uint32_t grid = (uint32_t)std::min<size_t>((n + CRC_WARPS - 1) / CRC_WARPS, (size_t)sms * 4);
+    FDB_LAUNCH(crc32_kernel, dim3(grid), dim3(CRC_WARPS * 32), 0, st, b, (const CrcTables*)ctx->d_crc, counter);
+    ctx->launches++;
+    FDB_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int fdb_crc32_batch(fdb_ctx* ctx, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t seed,
+                               uint32_t* crc, size_t n) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (n > 0xffffffffull || !off || !len || !crc) return fail(ctx, "fdb_crc32_batch", cudaSuccess);
+    FDB_TRY(cudaSetDevice(ctx->device));
+    uint64_t span = 0;
+    for (size_t i = 0; i < n; i++) span = std::max(span, off[i] + len[i]);
+    int r;
+    if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, span + 64))) return r;
+    if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, 3 * n * sizeof(uint64_t)))) return r;
+    cudaStream_t st = ctx->lanes[0].st;
+    uint64_t* d_off = ctx->d_meta;
+    uint64_t* d_len = d_off + n;
+    uint32_t* d_crc = (uint32_t*)(d_len + n);
+    FDB_TRY(cudaMemcpyAsync(d_off, off, n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_len, len, n * 8, cudaMemcpyHostToDevice, st));
+    if (span) FDB_TRY(cudaMemcpyAsync(ctx->d_in, base, span, cudaMemcpyHostToDevice, st));
+    if ((r = fdb_crc32_batch_device(ctx, ctx->d_in, d_off, d_len, seed, d_crc, n, st))) return r;
+    FDB_TRY(cudaMemcpyAsync(crc, d_crc, n * 4, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaStreamSynchronize(st));
     return 0;
 }
 

@@ -47,9 +47,10 @@ class PngInfo:
         return (self.width * self.channels * self.bit_depth + 7) // 8
 
 
-def parse(png: bytes) -> tuple[PngInfo, bytes]:
+def parse(png: bytes, crc_todo: list | None = None) -> tuple[PngInfo, bytes]:
     """-> (IHDR fields, the zlib stream = all IDAT payloads concatenated).  Checks the signature, the chunk CRCs,
-    the chunk order IHDR .. IDAT .. IEND and the IHDR values."""
+    the chunk order IHDR .. IDAT .. IEND and the IHDR values.  With `crc_todo` the chunk CRCs are not computed
+    here: (type + body, stored CRC, chunk type) is appended for every chunk, to be checked in one device batch."""
     if png[:8] != SIGNATURE:
         raise PngError("not a PNG file")
     pos, info, idat, seen_end = 8, None, [], False
@@ -61,7 +62,9 @@ def parse(png: bytes) -> tuple[PngInfo, bytes]:
         if len(body) != length or pos + 12 + length > len(png):
             raise PngError("truncated chunk")
         (crc,) = struct.unpack(">I", png[pos + 8 + length:pos + 12 + length])
-        if binascii.crc32(ctype + body) & 0xffffffff != crc:
+        if crc_todo is not None:
+            crc_todo.append((png[pos + 4:pos + 8 + length], crc, ctype))
+        elif binascii.crc32(ctype + body) & 0xffffffff != crc:
             raise PngError(f"bad CRC in {ctype!r} chunk")
         pos += 12 + length
         if info is None:
@@ -97,13 +100,23 @@ def _to_array(info: PngInfo, raw: np.ndarray) -> np.ndarray:
     return raw.reshape(info.height, info.stride)  # packed sub-byte samples, as stored
 
 
-def decode_batch(pngs: Sequence[bytes], ctx: Context | None = None) -> list[np.ndarray]:
-    """PNG files -> pixel arrays (h, w[, channels]) uint8 / uint16; sub-byte depths come back as packed rows."""
+def decode_batch(pngs: Sequence[bytes], ctx: Context | None = None, crc: str = "device") -> list[np.ndarray]:
+    """PNG files -> pixel arrays (h, w[, channels]) uint8 / uint16; sub-byte depths come back as packed rows.
+    crc = "device": all chunk CRCs of the batch in one fdb_crc32_batch call; "host": binascii while parsing;
+    "skip": not checked."""
     ctx = ctx or default_context()
-    infos, streams = zip(*(parse(p) for p in pngs)) if pngs else ((), ())
+    if crc not in ("device", "host", "skip"):
+        raise ValueError("crc must be 'device', 'host' or 'skip'")
+    todo: list | None = None if crc == "host" else []
+    infos, streams = zip(*(parse(p, todo) for p in pngs)) if pngs else ((), ())
     n = len(infos)
     if n == 0:
         return []
+    if crc == "device" and todo:
+        got = ctx.crc32_batch([t[0] for t in todo])
+        for (_, want, ctype), g in zip(todo, got):
+            if int(g) != want:
+                raise PngError(f"bad CRC in {ctype!r} chunk")
     idat_base, idat_off, idat_len = ctx._pack(streams)
     h = np.array([i.height for i in infos], dtype=np.uint32)
     s = np.array([i.stride for i in infos], dtype=np.uint32)
@@ -155,11 +168,15 @@ def encode_batch(images: Sequence[np.ndarray], ctx: Context | None = None, filte
     rc = ctx.lib.L.fdb_png_encode_batch(ctx._h, _ptr(raw_base), _ptr(raw_off), _ptr(h), _ptr(s), _ptr(b), filter_mode,
                                         _ptr(out), _ptr(out_off), _ptr(caps), _ptr(out_len), _ptr(status), n)
     ctx._check(rc, "fdb_png_encode_batch")
-    files = []
-    for i, info in enumerate(infos):
+    for i in range(n):
         if status[i] != 0:
             raise FdbError(f"image {i}: status {int(status[i])}")
+    zs = [out[int(out_off[i]): int(out_off[i]) + int(out_len[i])].tobytes() for i in range(n)]
+    # the IDAT chunk CRCs (over "IDAT" + payload) in one device batch; IHDR / IEND are a few bytes each
+    crcs = ctx.crc32_batch(zs, seed=binascii.crc32(b"IDAT"))
+    files = []
+    for info, z, c in zip(infos, zs, crcs):
         ihdr = struct.pack(">IIBBBBB", info.width, info.height, info.bit_depth, info.color_type, 0, 0, 0)
-        z = out[int(out_off[i]): int(out_off[i]) + int(out_len[i])].tobytes()
-        files.append(SIGNATURE + _chunk(b"IHDR", ihdr) + _chunk(b"IDAT", z) + _chunk(b"IEND", b""))
+        idat = struct.pack(">I", len(z)) + b"IDAT" + z + struct.pack(">I", int(c))
+        files.append(SIGNATURE + _chunk(b"IHDR", ihdr) + idat + _chunk(b"IEND", b""))
     return files

@@ -154,6 +154,14 @@ int fdb_png_encode_batch(fdb_ctx* ctx, const uint8_t* raw_base, const uint64_t* 
                          const uint32_t* stride, const uint32_t* bpp, uint32_t mode, uint8_t* out_base,
                          const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, int32_t* status, size_t n);
 
+/* ---- CRC-32 of a batch of byte ranges (PNG chunk CRCs; polynomial 0xEDB88320, the value zlib's crc32() gives) ----
+ * crc[i] = CRC-32 of base[off[i] .. off[i] + len[i]) continued from `seed` = the CRC of whatever precedes every
+ * range (0 = nothing; e.g. crc32("IDAT") for the payloads of IDAT chunks).  One warp per range. */
+int fdb_crc32_batch_device(fdb_ctx* ctx, const void* d_base, const uint64_t* d_off, const uint64_t* d_len, uint32_t seed,
+                           uint32_t* d_crc, size_t n, void* cuda_stream);
+int fdb_crc32_batch(fdb_ctx* ctx, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint32_t seed,
+                    uint32_t* crc, size_t n);
+
 /* ---- synthetic PNG-filtered RGBA tiles (benchmark / test input) -----------------
  * Tile t is width x height RGBA8, row 0 Sub-filtered, other rows Paeth-filtered; each row is
  * 1 filter-type byte + 4*width residual bytes, so a tile is height*(1+4*width) bytes, laid out

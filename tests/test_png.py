@@ -137,6 +137,45 @@ def test_png_encode_roundtrip_on_emulator(emul_ctx):
     _check_encode_roundtrip(emul_ctx, arrays)
 
 
+def _check_crc32(ctx):
+    rng = random.Random(9)
+    items = [b"", b"a", b"123456789", bytes(2047), bytes(rng.getrandbits(8) for _ in range(2048)),
+             bytes(rng.getrandbits(8) for _ in range(2049)), bytes(rng.getrandbits(8) for _ in range(70001)), bytes(300000)]
+    got = ctx.crc32_batch(items)
+    assert int(got[2]) == 0xcbf43926  # the check value of CRC-32/ISO-HDLC
+    assert [int(x) for x in got] == [zlib.crc32(i) for i in items]
+    seed = zlib.crc32(b"IDAT")
+    assert [int(x) for x in ctx.crc32_batch(items, seed)] == [zlib.crc32(i, seed) for i in items]
+
+
+def _check_crc_detection(ctx):
+    from fdeflate_b200 import png
+
+    name = max(MANIFEST, key=lambda k: (GOLD / k).stat().st_size)
+    good = (GOLD / name).read_bytes()
+    png.decode_batch([good], ctx, crc="device")
+    bad = bytearray(good)
+    bad[good.index(b"IDAT") + 40] ^= 4  # inside the IDAT payload
+    for mode in ("device", "host"):
+        with pytest.raises(png.PngError, match="bad CRC"):
+            png.decode_batch([good, bytes(bad)], ctx, crc=mode)
+
+
+@pytest.mark.emul
+def test_crc32_on_emulator(emul_ctx):
+    _check_crc32(emul_ctx)
+    _check_crc_detection(emul_ctx)
+
+
+@pytest.mark.gpu
+def test_crc32_on_gpu(gpu_ctx):
+    _check_crc32(gpu_ctx)
+    _check_crc_detection(gpu_ctx)
+    rng = np.random.default_rng(2)
+    items = [rng.integers(0, 256, int(n), dtype=np.uint8).tobytes() for n in rng.integers(0, 3_000_000, 40)]
+    assert [int(x) for x in gpu_ctx.crc32_batch(items)] == [zlib.crc32(i) for i in items]
+
+
 def test_png_container_errors():
     from fdeflate_b200 import png
 
