@@ -28,7 +28,7 @@ STATUS_NAMES = [
     "InvalidHlit", "InvalidHdist", "InvalidCodeLengthRepeat", "BadCodeLengthHuffmanTree",
     "BadLiteralLengthHuffmanTree", "BadDistanceHuffmanTree", "InvalidLiteralLengthCode", "InvalidDistanceCode",
     "InputStartsWithRun", "DistanceTooFarBack", "WrongChecksum", "ExtraInput", "OutputTooLarge",
-    "OutputBufferTooSmall", "PngBadFilterType", "PngBadGeometry",
+    "OutputBufferTooSmall", "PngBadFilterType", "PngBadGeometry", "PngBadFile", "PngBadCrc", "PngUnsupported",
 ]
 ST_OK, ST_INSUFFICIENT_INPUT, ST_OUTPUT_TOO_LARGE = 0, 2, 17
 

@@ -1123,6 +1123,256 @@ extern "C" int fdb_crc32_batch(fdb_ctx* ctx, const uint8_t* base, const uint64_t
     return 0;
 }
 
+// ---- PNG files: container walk on the host (C++), everything per byte on the device -------------------
+// PNG (Third Edition) 5.2-5.3 (signature, chunk layout), 11.2.2 (IHDR), 5.6 (chunk ordering: IHDR first, IDAT chunks
+// consecutive, IEND last).  Only the 8 header bytes of each chunk are read here; payload bytes are touched on the
+// device only (CRC-32, gather of the IDAT payloads, inflate, unfilter).
+struct PngChunkRef {
+    uint64_t off;  // of the chunk's type field, relative to the batch base (the CRC covers type + payload)
+    uint32_t len;  // payload length
+    uint32_t crc;  // stored CRC
+    uint32_t file;
+    bool idat;
+};
+struct PngFileInfo {
+    uint32_t width = 0, height = 0, depth = 0, color = 0, bpp = 0, stride = 0;
+    int32_t status = ST_PNG_BAD_FILE;
+    size_t first_chunk = 0, n_chunks = 0, n_idat = 0;
+    uint64_t idat_bytes = 0;
+};
+static uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+static void png_walk(const uint8_t* base, uint64_t off, uint64_t n, uint32_t file, PngFileInfo& fi, std::vector<PngChunkRef>* chunks) {
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    const uint8_t* f = base + off;
+    fi.status = ST_PNG_BAD_FILE;
+    if (chunks) fi.first_chunk = chunks->size();
+    if (n < 8 + 25 || memcmp(f, sig, 8) != 0) return;
+    uint64_t pos = 8;
+    bool have_ihdr = false, seen_idat = false, idat_closed = false, seen_end = false;
+    while (pos + 12 <= n) {
+        const uint32_t len = be32(f + pos);
+        const uint8_t* type = f + pos + 4;
+        if ((uint64_t)len + 12 > n - pos) return;  // truncated chunk
+        const bool is_idat = memcmp(type, "IDAT", 4) == 0;
+        if (!have_ihdr) {
+            if (memcmp(type, "IHDR", 4) != 0 || len != 13) return;
+            const uint8_t* d = f + pos + 8;
+            fi.width = be32(d);
+            fi.height = be32(d + 4);
+            fi.depth = d[8];
+            fi.color = d[9];
+            const uint32_t comp = d[10], filt = d[11], interlace = d[12];
+            uint32_t channels = 0;
+            bool depth_ok = false;
+            switch (fi.color) {  // PNG table 11.1
+                case 0: channels = 1; depth_ok = fi.depth == 1 || fi.depth == 2 || fi.depth == 4 || fi.depth == 8 || fi.depth == 16; break;
+                case 2: channels = 3; depth_ok = fi.depth == 8 || fi.depth == 16; break;
+                case 3: channels = 1; depth_ok = fi.depth == 1 || fi.depth == 2 || fi.depth == 4 || fi.depth == 8; break;
+                case 4: channels = 2; depth_ok = fi.depth == 8 || fi.depth == 16; break;
+                case 6: channels = 4; depth_ok = fi.depth == 8 || fi.depth == 16; break;
+                default: break;
+            }
+            if (!channels || !depth_ok || !fi.width || !fi.height || comp || filt || interlace > 1) return;
+            if ((uint64_t)fi.width * channels * fi.depth > 0x7fffffffull * 8) return;
+            fi.bpp = std::max(1u, channels * fi.depth / 8);
+            fi.stride = (uint32_t)(((uint64_t)fi.width * channels * fi.depth + 7) / 8);
+            have_ihdr = true;
+            if (interlace) {  // a valid file, but Adam7 passes are not decoded here
+                fi.status = ST_PNG_UNSUPPORTED;
+                return;
+            }
+        } else if (is_idat) {
+            if (idat_closed) return;  // IDAT chunks must be consecutive
+            seen_idat = true;
+            fi.n_idat++;
+            fi.idat_bytes += len;
+        } else {
+            if (seen_idat) idat_closed = true;
+            if (memcmp(type, "IEND", 4) == 0) seen_end = true;
+        }
+        if (chunks) {
+            chunks->push_back({off + pos + 4, len, be32(f + pos + 8 + len), file, is_idat});
+            fi.n_chunks++;
+        }
+        pos += 12 + (uint64_t)len;
+        if (seen_end) break;
+    }
+    if (have_ihdr && seen_idat && seen_end) fi.status = ST_OK;
+}
+
+extern "C" int fdb_png_probe_batch(const uint8_t* file_base, const uint64_t* file_off, const uint64_t* file_len, uint32_t* width,
+                                   uint32_t* height, uint32_t* bit_depth, uint32_t* color_type, uint32_t* stride,
+                                   int32_t* status, size_t n) {
+    if (n && (!file_base || !file_off || !file_len || !status)) return -1;
+    for (size_t i = 0; i < n; i++) {
+        PngFileInfo fi;
+        png_walk(file_base, file_off[i], file_len[i], (uint32_t)i, fi, nullptr);
+        if (width) width[i] = fi.width;
+        if (height) height[i] = fi.height;
+        if (bit_depth) bit_depth[i] = fi.depth;
+        if (color_type) color_type[i] = fi.color;
+        if (stride) stride[i] = fi.stride;
+        status[i] = fi.status;
+    }
+    return 0;
+}
+
+// files -> raw pixels.  raw_off[i] must leave room for height * stride bytes (fdb_png_probe_batch gives both).
+extern "C" int fdb_png_decode_files_batch(fdb_ctx* ctx, const uint8_t* file_base, const uint64_t* file_off,
+                                          const uint64_t* file_len, uint8_t* raw_base, const uint64_t* raw_off,
+                                          int32_t* status, size_t n) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (n > 0xffffffffull || !file_base || !file_off || !file_len || !raw_base || !raw_off || !status)
+        return fail(ctx, "fdb_png_decode_files_batch", cudaSuccess);
+    FDB_TRY(cudaSetDevice(ctx->device));
+    std::vector<PngFileInfo> fi(n);
+    std::vector<PngChunkRef> chunks;
+    chunks.reserve(4 * n);
+    uint64_t lo = ~0ull, hi = 0;
+    for (size_t i = 0; i < n; i++) {
+        png_walk(file_base, file_off[i], file_len[i], (uint32_t)i, fi[i], &chunks);
+        lo = std::min(lo, file_off[i]);
+        hi = std::max(hi, file_off[i] + file_len[i]);
+    }
+    if (hi <= lo) lo = hi = 0;
+    // streams: a file with one IDAT chunk is inflated where it lies; several chunks are gathered into one stream
+    std::vector<uint64_t> m(6 * n);  // idat_off | idat_len | filt_off | filt_cap | raw_off | (spare)
+    std::vector<uint32_t> geo(3 * n);
+    std::vector<GatherItem> items;
+    std::vector<uint64_t> crc_off, crc_len;
+    uint64_t gather_span = 0, filt_span = 0, raw_span = 0;
+    const uint64_t in_span = hi - lo;  // device copy of the files: d_in[0 .. in_span), gathered streams behind it
+    for (size_t i = 0; i < n; i++) {
+        const PngFileInfo& f = fi[i];
+        const bool ok = f.status == ST_OK;
+        const uint64_t filtered = ok ? (uint64_t)f.height * (1ull + f.stride) : 0;
+        geo[i] = ok ? f.height : 0;
+        geo[n + i] = ok ? f.stride : 0;
+        geo[2 * n + i] = ok ? f.bpp : 1;
+        m[2 * n + i] = filt_span;
+        m[3 * n + i] = filtered;
+        filt_span += (filtered + 15) & ~15ull;
+        m[4 * n + i] = raw_off[i];
+        if (ok) raw_span = std::max(raw_span, raw_off[i] + (uint64_t)f.height * f.stride);
+        m[i] = 0;
+        m[n + i] = 0;
+        if (!ok) continue;
+        uint64_t dst = (in_span + 15 & ~15ull) + gather_span;
+        bool first = true;
+        for (size_t c = f.first_chunk; c < f.first_chunk + f.n_chunks; c++) {
+            const PngChunkRef& ch = chunks[c];
+            crc_off.push_back(ch.off - lo);
+            crc_len.push_back((uint64_t)ch.len + 4);
+            if (!ch.idat) continue;
+            if (f.n_idat == 1) {
+                m[i] = ch.off + 4 - lo;
+                m[n + i] = ch.len;
+            } else {
+                if (first) m[i] = dst;
+                first = false;
+                if (ch.len) items.push_back({ch.off + 4 - lo, dst, ch.len});
+                dst += ch.len;
+                m[n + i] += ch.len;
+            }
+        }
+        if (f.n_idat != 1) gather_span += (f.idat_bytes + 15) & ~15ull;
+    }
+    const size_t n_crc = crc_off.size();
+    int r;
+    if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, ((in_span + 15) & ~15ull) + gather_span + 64))) return r;
+    if ((r = grow(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, raw_span + 64))) return r;
+    if ((r = grow(ctx, (void**)&ctx->d_mid, &ctx->d_mid_cap, filt_span + 64))) return r;
+    const size_t meta_bytes = 7 * n * 8 + 3 * n * 4 + 2 * n * 4 + n_crc * (8 + 8 + 4) + items.size() * sizeof(GatherItem) + 64;
+    if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, meta_bytes))) return r;
+    cudaStream_t st = ctx->lanes[0].st;
+    uint64_t* d = ctx->d_meta;
+    uint64_t *d_idat_off = d, *d_idat_len = d + n, *d_filt_off = d + 2 * n, *d_filt_cap = d + 3 * n, *d_raw_off = d + 4 * n,
+             *d_out_len = d + 5 * n, *d_consumed = d + 6 * n;
+    uint64_t* d_crc_off = d + 7 * n;
+    uint64_t* d_crc_len = d_crc_off + n_crc;
+    GatherItem* d_items = (GatherItem*)(d_crc_len + n_crc);
+    uint32_t* d_geo = (uint32_t*)(d_items + items.size());
+    int32_t* d_st1 = (int32_t*)(d_geo + 3 * n);
+    int32_t* d_st2 = d_st1 + n;
+    uint32_t* d_crc = (uint32_t*)(d_st2 + n);
+    FDB_TRY(cudaMemcpyAsync(d, m.data(), 5 * n * 8, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d_geo, geo.data(), 3 * n * 4, cudaMemcpyHostToDevice, st));
+    if (n_crc) {
+        FDB_TRY(cudaMemcpyAsync(d_crc_off, crc_off.data(), n_crc * 8, cudaMemcpyHostToDevice, st));
+        FDB_TRY(cudaMemcpyAsync(d_crc_len, crc_len.data(), n_crc * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (!items.empty()) FDB_TRY(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(GatherItem), cudaMemcpyHostToDevice, st));
+    if (in_span) FDB_TRY(cudaMemcpyAsync(ctx->d_in, file_base + lo, in_span, cudaMemcpyHostToDevice, st));
+    if (n_crc && (r = fdb_crc32_batch_device(ctx, ctx->d_in, d_crc_off, d_crc_len, 0, d_crc, n_crc, st))) return r;
+    if (!items.empty()) {
+        uint32_t* counter = ctx->d_counters + 14;
+        FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+        const uint32_t grid = (uint32_t)std::min<size_t>((items.size() + 7) / 8, (size_t)std::max(ctx->sm_count, 1) * 8);
+        FDB_LAUNCH(gather_kernel, dim3(grid), dim3(256), 0, st, (const uint8_t*)ctx->d_in, ctx->d_in, (const GatherItem*)d_items,
+                   (uint32_t)items.size(), counter);
+        ctx->launches++;
+        FDB_TRY(cudaGetLastError());
+    }
+    InflateBatch ib;
+    ib.in_base = ctx->d_in;
+    ib.in_off = d_idat_off;
+    ib.in_len = d_idat_len;
+    ib.out_base = ctx->d_mid;
+    ib.out_off = d_filt_off;
+    ib.out_cap = d_filt_cap;
+    ib.out_len = d_out_len;
+    ib.consumed = d_consumed;
+    ib.status = d_st1;
+    ib.n = (uint32_t)n;
+    uint64_t max_in = 0;
+    for (size_t i = 0; i < n; i++) max_in = std::max(max_in, m[n + i]);
+    ib.flags = max_in >= ctx->inflate_split_min ? FDB_FLAG_SPLIT_LARGE : 0u;
+    ctx->last_general_host = -1;
+    ctx->last_split_host = -1;
+    if ((r = launch_inflate(ctx, ib, ctx->d_counters, &ctx->d_worklist, &ctx->worklist_cap, st, false, &ctx->split))) return r;
+    if ((r = png_launch(ctx, true, ctx->d_mid, d_filt_off, ctx->d_out, d_raw_off, d_geo, d_geo + n, d_geo + 2 * n, 0, d_st2, n, st)))
+        return r;
+    std::vector<int32_t> st12(2 * n);
+    std::vector<uint64_t> olen(n);
+    std::vector<uint32_t> crc(n_crc);
+    // pixels back: image by image when the caller's layout has gaps, else in one piece
+    // (images that follow each other with less than 16 bytes of padding travel in one copy, padding included)
+    for (size_t i = 0; i < n;) {
+        if (fi[i].status != ST_OK) {
+            i++;
+            continue;
+        }
+        const uint64_t begin = raw_off[i];
+        uint64_t end = begin + (uint64_t)fi[i].height * fi[i].stride;
+        size_t j = i + 1;
+        while (j < n && fi[j].status == ST_OK && raw_off[j] >= end && raw_off[j] - end < 16) {
+            end = raw_off[j] + (uint64_t)fi[j].height * fi[j].stride;
+            j++;
+        }
+        FDB_TRY(cudaMemcpyAsync(raw_base + begin, ctx->d_out + begin, end - begin, cudaMemcpyDeviceToHost, st));
+        i = j;
+    }
+    FDB_TRY(cudaMemcpyAsync(st12.data(), d_st1, 2 * n * 4, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaMemcpyAsync(olen.data(), d_out_len, n * 8, cudaMemcpyDeviceToHost, st));
+    if (n_crc) FDB_TRY(cudaMemcpyAsync(crc.data(), d_crc, n_crc * 4, cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaStreamSynchronize(st));
+    size_t k = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (fi[i].status != ST_OK) {
+            status[i] = fi[i].status;
+            continue;
+        }
+        bool crc_ok = true;
+        for (size_t c = fi[i].first_chunk; c < fi[i].first_chunk + fi[i].n_chunks; c++, k++) crc_ok = crc_ok && crc[k] == chunks[c].crc;
+        int32_t s1 = st12[i];
+        if (s1 == ST_OK && olen[i] != m[3 * n + i]) s1 = ST_INSUFFICIENT_INPUT;
+        status[i] = !crc_ok ? ST_PNG_BAD_CRC : s1 != ST_OK ? s1 : st12[n + i];
+    }
+    return 0;
+}
+
 // ---- synthetic tiles --------------------------------------------------------------------------
 extern "C" size_t fdb_synth_tile_bytes(uint32_t width, uint32_t height) {
     return (size_t)height * (1u + 4u * (size_t)width);

@@ -116,4 +116,34 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(CRC_WARPS * 32, 4) crc32_kernel(CrcBatch b, co
     }
 }
 
+// ---- gather: byte ranges copied to new places (IDAT payloads of one file -> one contiguous zlib stream) ----
+struct GatherItem {
+    uint64_t src, dst, len;  // offsets into src_base / dst_base
+};
+FDB_GLOBAL void gather_kernel(const uint8_t* src_base, uint8_t* dst_base, const GatherItem* items, uint32_t n, uint32_t* next) {
+    const unsigned lane = simt::lane_id();
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = simt::atomic_add(next, 1u);
+        i = simt::shfl(i, 0);
+        if (i >= n) break;
+        const uint8_t* s = src_base + items[i].src;
+        uint8_t* d = dst_base + items[i].dst;
+        uint64_t len = items[i].len;
+        if ((((uintptr_t)s ^ (uintptr_t)d) & 3u) == 0) {  // same alignment: whole words in the middle
+            uint64_t head = (4u - (uint32_t)((uintptr_t)d & 3u)) & 3u;
+            if (head > len) head = len;
+            if (lane < head) d[lane] = simt::ldg8(s + lane);
+            const uint64_t words = (len - head) >> 2;
+            const uint32_t* sw = (const uint32_t*)(s + head);
+            uint32_t* dw = (uint32_t*)(d + head);
+            for (uint64_t k = lane; k < words; k += 32) dw[k] = simt::ldg32(sw + k);
+            const uint64_t done = head + (words << 2);
+            if (done + lane < len) d[done + lane] = simt::ldg8(s + done + lane);
+        } else {
+            for (uint64_t k = lane; k < len; k += 32) d[k] = simt::ldg8(s + k);
+        }
+    }
+}
+
 }  // namespace fdb

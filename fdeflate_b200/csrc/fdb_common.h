@@ -32,6 +32,11 @@ enum Status : int32_t {
     // PNG row filters (png_filter.cuh): a row's filter-type byte is not 0..4; bpp outside 1..8 or an unknown mode
     ST_PNG_BAD_FILTER_TYPE = 19,
     ST_PNG_BAD_GEOMETRY = 20,
+    // PNG files (fdb_png_probe_batch / fdb_png_decode_files_batch): not a PNG / broken chunk structure / invalid IHDR,
+    // a chunk whose CRC-32 does not match, a valid file of a kind that is not decoded here (interlaced)
+    ST_PNG_BAD_FILE = 21,
+    ST_PNG_BAD_CRC = 22,
+    ST_PNG_UNSUPPORTED = 23,
     // internal: ultra-fast-format fast path declined the stream; the general kernel redoes it
     ST_PENDING_GENERAL = -1,
 };

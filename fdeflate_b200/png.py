@@ -180,3 +180,37 @@ def encode_batch(images: Sequence[np.ndarray], ctx: Context | None = None, filte
         idat = struct.pack(">I", len(z)) + b"IDAT" + z + struct.pack(">I", int(c))
         files.append(SIGNATURE + _chunk(b"IHDR", ihdr) + idat + _chunk(b"IEND", b""))
     return files
+
+
+def decode_files_batch(pngs: Sequence[bytes], ctx: Context | None = None) -> list[np.ndarray]:
+    """Same result as decode_batch, but the container is handled by the library too (`fdb_png_probe_batch` +
+    `fdb_png_decode_files_batch`: chunk walk in C++, chunk CRCs / IDAT gathering / inflate / unfilter on the device),
+    so nothing per file or per byte happens in Python."""
+    ctx = ctx or default_context()
+    n = len(pngs)
+    if n == 0:
+        return []
+    base, off, lens = ctx._pack(pngs, align=1)
+    w, h, depth, color, stride = (np.zeros(n, dtype=np.uint32) for _ in range(5))
+    status = np.zeros(n, dtype=np.int32)
+    rc = ctx.lib.L.fdb_png_probe_batch(_ptr(base), _ptr(off), _ptr(lens), _ptr(w), _ptr(h), _ptr(depth), _ptr(color),
+                                       _ptr(stride), _ptr(status), n)
+    if rc != 0:
+        raise FdbError("fdb_png_probe_batch failed")
+    for i in range(n):
+        if status[i] != 0:
+            raise PngError(f"image {i}: {STATUS_NAMES[status[i]]}")
+    raw_sz = h.astype(np.uint64) * stride.astype(np.uint64)
+    raw_off = np.zeros(n, dtype=np.uint64)
+    raw_off[1:] = np.cumsum((raw_sz[:-1] + np.uint64(15)) & ~np.uint64(15))
+    raw = np.zeros(int(raw_off[-1] + raw_sz[-1]) + 16, dtype=np.uint8)
+    rc = ctx.lib.L.fdb_png_decode_files_batch(ctx._h, _ptr(base), _ptr(off), _ptr(lens), _ptr(raw), _ptr(raw_off),
+                                              _ptr(status), n)
+    ctx._check(rc, "fdb_png_decode_files_batch")
+    out = []
+    for i in range(n):
+        if status[i] != 0:
+            raise PngError(f"image {i}: {STATUS_NAMES[status[i]] if status[i] < len(STATUS_NAMES) else status[i]}")
+        info = PngInfo(int(w[i]), int(h[i]), int(depth[i]), int(color[i]))
+        out.append(_to_array(info, raw[int(raw_off[i]): int(raw_off[i]) + int(raw_sz[i])].copy()))
+    return out

@@ -154,6 +154,19 @@ int fdb_png_encode_batch(fdb_ctx* ctx, const uint8_t* raw_base, const uint64_t* 
                          const uint32_t* stride, const uint32_t* bpp, uint32_t mode, uint8_t* out_base,
                          const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, int32_t* status, size_t n);
 
+/* PNG FILES in one call.  The chunk structure is walked on the host (signature, IHDR, chunk order, lengths: PNG 5.2-5.6,
+ * 11.2.2; only chunk headers are read); chunk CRCs, the gathering of several IDAT payloads into one zlib stream,
+ * inflate and unfilter run on the device.  status: 0, an inflate / unfilter status, or 21 = not a PNG / broken chunk
+ * structure / invalid IHDR, 22 = a chunk's CRC-32 does not match, 23 = valid but not decoded here (interlaced).
+ *   probe : host only, no context: geometry of every file (stride = bytes per raw row; pixels need height * stride).
+ *   decode: raw pixels of file i to raw_base + raw_off[i].  Images whose slots follow each other with less than
+ *           16 bytes of padding are copied back in one piece, padding included. */
+int fdb_png_probe_batch(const uint8_t* file_base, const uint64_t* file_off, const uint64_t* file_len, uint32_t* width,
+                        uint32_t* height, uint32_t* bit_depth, uint32_t* color_type, uint32_t* stride, int32_t* status,
+                        size_t n);
+int fdb_png_decode_files_batch(fdb_ctx* ctx, const uint8_t* file_base, const uint64_t* file_off, const uint64_t* file_len,
+                               uint8_t* raw_base, const uint64_t* raw_off, int32_t* status, size_t n);
+
 /* ---- CRC-32 of a batch of byte ranges (PNG chunk CRCs; polynomial 0xEDB88320, the value zlib's crc32() gives) ----
  * crc[i] = CRC-32 of base[off[i] .. off[i] + len[i]) continued from `seed` = the CRC of whatever precedes every
  * range (0 = nothing; e.g. crc32("IDAT") for the payloads of IDAT chunks).  One warp per range. */

@@ -176,6 +176,56 @@ def test_crc32_on_gpu(gpu_ctx):
     assert [int(x) for x in gpu_ctx.crc32_batch(items)] == [zlib.crc32(i) for i in items]
 
 
+def _check_decode_files(ctx):
+    """the library's own container walk: same pixels as the recorded ones; broken files get the right status"""
+    from fdeflate_b200 import png
+
+    files = _golden_files()
+    arrays = png.decode_files_batch([d for _, d in files], ctx)
+    for (name, _), a in zip(files, arrays):
+        want = MANIFEST[name]
+        assert list(a.shape) == want["shape"] and str(a.dtype) == want["dtype"] and _pixels_hash(a) == want["sha256"], name
+    # a file cut into many small IDAT chunks (what libpng writes) must give the same pixels: gather path
+    name, good = max(files, key=lambda f: len(f[1]))
+    info, z = png.parse(good)
+    ihdr_end = 8 + 12 + 13
+    pieces = [z[i:i + 97] for i in range(0, len(z), 97)] + [b""]
+    multi = good[:ihdr_end] + b"".join(png._chunk(b"IDAT", p) for p in pieces) + png._chunk(b"tEXt", b"k\0v") + png._chunk(b"IEND", b"")
+    a = png.decode_files_batch([multi, good], ctx)
+    assert _pixels_hash(a[0]) == MANIFEST[name]["sha256"] and _pixels_hash(a[1]) == MANIFEST[name]["sha256"]
+    # statuses through the C ABI
+    import numpy as np
+    from fdeflate_b200.api import _ptr
+
+    bad_crc = bytearray(good); bad_crc[good.index(b"IDAT") + 40] ^= 4
+    interlaced = bytearray(good); interlaced[8 + 8 + 12] = 1
+    import binascii, struct
+    interlaced[8 + 8 + 13:8 + 8 + 17] = struct.pack(">I", binascii.crc32(bytes(interlaced[12:8 + 8 + 13])))
+    split_idat = good[:ihdr_end] + png._chunk(b"IDAT", z[:50]) + png._chunk(b"tEXt", b"k\0v") + png._chunk(b"IDAT", z[50:]) + png._chunk(b"IEND", b"")
+    cases_ = [good, bytes(bad_crc), bytes(interlaced), b"not a png at all, but long enough to look at", good[:-12], split_idat,
+              good[:ihdr_end] + png._chunk(b"IEND", b"")]
+    base, off, lens = ctx._pack(cases_, align=1)
+    n = len(cases_)
+    w, h, d, c, s_ = (np.zeros(n, dtype=np.uint32) for _ in range(5))
+    st = np.zeros(n, dtype=np.int32)
+    assert ctx.lib.L.fdb_png_probe_batch(_ptr(base), _ptr(off), _ptr(lens), _ptr(w), _ptr(h), _ptr(d), _ptr(c), _ptr(s_), _ptr(st), n) == 0
+    assert list(st) == [0, 0, 23, 21, 21, 21, 21]
+    raw_off = np.arange(n, dtype=np.uint64) * np.uint64(int(h[0]) * int(s_[0]) + 64)
+    raw = np.zeros(int(raw_off[-1]) + int(h[0]) * int(s_[0]) + 64, dtype=np.uint8)
+    assert ctx.lib.L.fdb_png_decode_files_batch(ctx._h, _ptr(base), _ptr(off), _ptr(lens), _ptr(raw), _ptr(raw_off), _ptr(st), n) == 0
+    assert list(st) == [0, 22, 23, 21, 21, 21, 21]
+
+
+@pytest.mark.emul
+def test_png_decode_files_on_emulator(emul_ctx):
+    _check_decode_files(emul_ctx)
+
+
+@pytest.mark.gpu
+def test_png_decode_files_on_gpu(gpu_ctx):
+    _check_decode_files(gpu_ctx)
+
+
 def test_png_container_errors():
     from fdeflate_b200 import png
 

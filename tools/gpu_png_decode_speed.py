@@ -35,3 +35,30 @@ for name, f in (("encode (filter Paeth + ultra-fast deflate)", encode), ("decode
     dt = (time.perf_counter() - t0) / 3
     print(f"{name}: {dt*1e3:.1f} ms per {n} tiles = {n*H*S/dt/1e9:.1f} GB/s of pixels (host buffers)")
 assert (raw2 == raw).all()
+# ---- whole PNG files through the library's own container walk (fdb_png_probe_batch + fdb_png_decode_files_batch)
+import struct, binascii
+def chunk(t, b): return struct.pack(">I", len(b)) + t + b + struct.pack(">I", binascii.crc32(t + b) & 0xffffffff)
+ihdr = chunk(b"IHDR", struct.pack(">IIBBBBB", 256, 256, 8, 6, 0, 0, 0)); iend = chunk(b"IEND", b"")
+sig = b"\x89PNG\r\n\x1a\n"
+for label, piece in (("one IDAT chunk per file", 1 << 30), ("8 KiB IDAT chunks (gather)", 8192)):
+    files = []
+    for i in range(n):
+        zi = z[int(z_off[i]):int(z_off[i]) + int(z_len[i])].tobytes()
+        files.append(sig + ihdr + b"".join(chunk(b"IDAT", zi[k:k + piece]) for k in range(0, len(zi), piece)) + iend)
+    lens = np.array([len(f) for f in files], np.uint64); offs = np.zeros(n, np.uint64); offs[1:] = np.cumsum(lens[:-1])
+    fbuf = pin(int(lens.sum()) + 16)
+    for i, f in enumerate(files): fbuf[int(offs[i]):int(offs[i]) + len(f)] = np.frombuffer(f, np.uint8)
+    w_, h_, d_, c_, s_ = (np.zeros(n, np.uint32) for _ in range(5))
+    t0 = time.perf_counter()
+    assert ctx.lib.L.fdb_png_probe_batch(_ptr(fbuf), _ptr(offs), _ptr(lens), _ptr(w_), _ptr(h_), _ptr(d_), _ptr(c_), _ptr(s_), _ptr(status), n) == 0
+    t_probe = time.perf_counter() - t0
+    assert (status == 0).all() and (h_ == 256).all() and (s_ == 1024).all()
+    raw2[:] = 0
+    def decode_files():
+        rc = ctx.lib.L.fdb_png_decode_files_batch(ctx._h, _ptr(fbuf), _ptr(offs), _ptr(lens), _ptr(raw2), _ptr(raw_off), _ptr(status), n)
+        assert rc == 0 and (status == 0).all()
+    decode_files(); t0 = time.perf_counter()
+    for _ in range(3): decode_files()
+    dt = (time.perf_counter() - t0) / 3
+    assert (raw2 == raw).all()
+    print(f"decode PNG files, {label}: probe {t_probe*1e3:.1f} ms, decode {dt*1e3:.1f} ms per {n} files = {n*H*S/dt/1e9:.1f} GB/s of pixels")
