@@ -207,7 +207,7 @@ def reference_arm(args, rank: int, world: int):
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "inflate_gbs": round(nbytes / t_inf / 1e9, 3), "deflate_gbs": round(nbytes / t_def / 1e9, 3),
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -226,7 +226,6 @@ def ours(args, rank: int, local_rank: int, world: int):
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = F.Context(local_rank)  # raises without the CUDA library / a GPU: there is no fallback
@@ -418,13 +417,29 @@ def ours(args, rank: int, local_rank: int, world: int):
                 line["cpu_baseline"] = cpu_baseline_measure()
             except Exception as e:  # the GPU numbers stand on their own
                 line["cpu_baseline"] = {"error": repr(e)}
-        print(json.dumps(line))
+        emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """the one JSON line, on the process's original stdout"""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries the one JSON line and nothing else: whatever libraries print to file descriptor 1 (NCCL's
+    # version banner, for one) is sent to stderr, and the line itself goes to a duplicate of the original descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
