@@ -591,15 +591,15 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                     } else {
                         // exact stores: the byte after this lane's last one belongs to the next lane
                         simt::sts8(wptr, e1);
-                        if (k1 >= 2) simt::sts8(wptr + 1, e1 >> 8);
-                        if (k1 >= 3) simt::sts8(wptr + 2, e1 >> 16);
+                        simt::sts8_if(wptr + 1, e1 >> 8, k1 >= 2);
+                        simt::sts8_if(wptr + 2, e1 >> 16, k1 >= 3);
                         wptr += k1;
                         n = (e1 >> 24) & 15u;
                         const uint32_t e2 = wt_at(t, bits >> n);  // special: 0 bytes, 0 bits -> next trip
                         const uint32_t k2 = e2 >> 28;
-                        if (k2 >= 1) simt::sts8(wptr, e2);
-                        if (k2 >= 2) simt::sts8(wptr + 1, e2 >> 8);
-                        if (k2 >= 3) simt::sts8(wptr + 2, e2 >> 16);
+                        simt::sts8_if(wptr, e2, k2 >= 1);
+                        simt::sts8_if(wptr + 1, e2 >> 8, k2 >= 2);
+                        simt::sts8_if(wptr + 2, e2 >> 16, k2 >= 3);
                         wptr += k2;
                         n += (e2 >> 24) & 15u;
                     }

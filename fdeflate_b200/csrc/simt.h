@@ -113,6 +113,11 @@ FDB_DEVICE uint32_t lds32(saddr a) {
     return v;
 }
 FDB_DEVICE void sts8(saddr a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// predicated byte store: never a branch (the compiler turns `if (p) sts8(..)` into a divergent region with its
+// BSSY / BSYNC pair when several of them nest)
+FDB_DEVICE void sts8_if(saddr a, uint32_t v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u8 [%0], %1;\n\t}" ::"r"(a), "r"(v), "r"((uint32_t)p) : "memory");
+}
 FDB_DEVICE void sts32(saddr a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 }  // namespace simt
 #endif
