@@ -1076,8 +1076,14 @@ extern "C" int fdb_png_encode_batch(fdb_ctx* ctx, const uint8_t* raw_base, const
 }
 
 // ---- CRC-32 of a batch of byte ranges (PNG chunk CRCs) ------------------------------------------------
+static int crc_launch(fdb_ctx* ctx, const void* d_base, const uint64_t* d_off, const uint64_t* d_len, uint32_t seed,
+                      uint32_t* d_crc, size_t n, void* cuda_stream, uint32_t* counter);
 extern "C" int fdb_crc32_batch_device(fdb_ctx* ctx, const void* d_base, const uint64_t* d_off, const uint64_t* d_len,
                                       uint32_t seed, uint32_t* d_crc, size_t n, void* cuda_stream) {
+    return crc_launch(ctx, d_base, d_off, d_len, seed, d_crc, n, cuda_stream, nullptr);
+}
+static int crc_launch(fdb_ctx* ctx, const void* d_base, const uint64_t* d_off, const uint64_t* d_len, uint32_t seed,
+                      uint32_t* d_crc, size_t n, void* cuda_stream, uint32_t* counter) {
     if (!ctx) return -1;
     if (n == 0) return 0;
     if (n > 0xffffffffull || !d_off || !d_len || !d_crc) return fail(ctx, "fdb_crc32_batch_device", cudaSuccess);
@@ -1090,7 +1096,7 @@ extern "C" int fdb_crc32_batch_device(fdb_ctx* ctx, const void* d_base, const ui
     b.crc = d_crc;
     b.n = (uint32_t)n;
     b.seed = seed;
-    uint32_t* counter = ctx->d_counters + 13;
+    if (!counter) counter = ctx->d_counters + 13;
     FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
     const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
     uint32_t grid = (uint32_t)std::min<size_t>((n + CRC_WARPS - 1) / CRC_WARPS, (size_t)sms * 4);
@@ -1242,6 +1248,7 @@ extern "C" int fdb_png_decode_files_batch(fdb_ctx* ctx, const uint8_t* file_base
     std::vector<uint32_t> geo(3 * n);
     std::vector<GatherItem> items;
     std::vector<uint64_t> crc_off, crc_len;
+    std::vector<size_t> crc_first(n + 1, 0), item_first(n + 1, 0);  // per file: where its entries start in the two lists
     uint64_t gather_span = 0, filt_span = 0, raw_span = 0;
     const uint64_t in_span = hi - lo;  // device copy of the files: d_in[0 .. in_span), gathered streams behind it
     for (size_t i = 0; i < n; i++) {
@@ -1258,8 +1265,10 @@ extern "C" int fdb_png_decode_files_batch(fdb_ctx* ctx, const uint8_t* file_base
         if (ok) raw_span = std::max(raw_span, raw_off[i] + (uint64_t)f.height * f.stride);
         m[i] = 0;
         m[n + i] = 0;
+        crc_first[i] = crc_off.size();
+        item_first[i] = items.size();
         if (!ok) continue;
-        uint64_t dst = (in_span + 15 & ~15ull) + gather_span;
+        uint64_t dst = ((in_span + 15) & ~15ull) + gather_span;
         bool first = true;
         for (size_t c = f.first_chunk; c < f.first_chunk + f.n_chunks; c++) {
             const PngChunkRef& ch = chunks[c];
@@ -1280,13 +1289,15 @@ extern "C" int fdb_png_decode_files_batch(fdb_ctx* ctx, const uint8_t* file_base
         if (f.n_idat != 1) gather_span += (f.idat_bytes + 15) & ~15ull;
     }
     const size_t n_crc = crc_off.size();
+    crc_first[n] = n_crc;
+    item_first[n] = items.size();
     int r;
     if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, ((in_span + 15) & ~15ull) + gather_span + 64))) return r;
     if ((r = grow(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, raw_span + 64))) return r;
     if ((r = grow(ctx, (void**)&ctx->d_mid, &ctx->d_mid_cap, filt_span + 64))) return r;
     const size_t meta_bytes = 7 * n * 8 + 3 * n * 4 + 2 * n * 4 + n_crc * (8 + 8 + 4) + items.size() * sizeof(GatherItem) + 64;
     if ((r = grow(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, meta_bytes))) return r;
-    cudaStream_t st = ctx->lanes[0].st;
+    cudaStream_t hs = ctx->h2d_st, ds = ctx->d2h_st;
     uint64_t* d = ctx->d_meta;
     uint64_t *d_idat_off = d, *d_idat_len = d + n, *d_filt_off = d + 2 * n, *d_filt_cap = d + 3 * n, *d_raw_off = d + 4 * n,
              *d_out_len = d + 5 * n, *d_consumed = d + 6 * n;
@@ -1297,67 +1308,92 @@ extern "C" int fdb_png_decode_files_batch(fdb_ctx* ctx, const uint8_t* file_base
     int32_t* d_st1 = (int32_t*)(d_geo + 3 * n);
     int32_t* d_st2 = d_st1 + n;
     uint32_t* d_crc = (uint32_t*)(d_st2 + n);
-    FDB_TRY(cudaMemcpyAsync(d, m.data(), 5 * n * 8, cudaMemcpyHostToDevice, st));
-    FDB_TRY(cudaMemcpyAsync(d_geo, geo.data(), 3 * n * 4, cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(d, m.data(), 5 * n * 8, cudaMemcpyHostToDevice, hs));
+    FDB_TRY(cudaMemcpyAsync(d_geo, geo.data(), 3 * n * 4, cudaMemcpyHostToDevice, hs));
     if (n_crc) {
-        FDB_TRY(cudaMemcpyAsync(d_crc_off, crc_off.data(), n_crc * 8, cudaMemcpyHostToDevice, st));
-        FDB_TRY(cudaMemcpyAsync(d_crc_len, crc_len.data(), n_crc * 8, cudaMemcpyHostToDevice, st));
+        FDB_TRY(cudaMemcpyAsync(d_crc_off, crc_off.data(), n_crc * 8, cudaMemcpyHostToDevice, hs));
+        FDB_TRY(cudaMemcpyAsync(d_crc_len, crc_len.data(), n_crc * 8, cudaMemcpyHostToDevice, hs));
     }
-    if (!items.empty()) FDB_TRY(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(GatherItem), cudaMemcpyHostToDevice, st));
-    if (in_span) FDB_TRY(cudaMemcpyAsync(ctx->d_in, file_base + lo, in_span, cudaMemcpyHostToDevice, st));
-    if (n_crc && (r = fdb_crc32_batch_device(ctx, ctx->d_in, d_crc_off, d_crc_len, 0, d_crc, n_crc, st))) return r;
-    if (!items.empty()) {
-        uint32_t* counter = ctx->d_counters + 14;
-        FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
-        const uint32_t grid = (uint32_t)std::min<size_t>((items.size() + 7) / 8, (size_t)std::max(ctx->sm_count, 1) * 8);
-        FDB_LAUNCH(gather_kernel, dim3(grid), dim3(256), 0, st, (const uint8_t*)ctx->d_in, ctx->d_in, (const GatherItem*)d_items,
-                   (uint32_t)items.size(), counter);
-        ctx->launches++;
-        FDB_TRY(cudaGetLastError());
-    }
-    InflateBatch ib;
-    ib.in_base = ctx->d_in;
-    ib.in_off = d_idat_off;
-    ib.in_len = d_idat_len;
-    ib.out_base = ctx->d_mid;
-    ib.out_off = d_filt_off;
-    ib.out_cap = d_filt_cap;
-    ib.out_len = d_out_len;
-    ib.consumed = d_consumed;
-    ib.status = d_st1;
-    ib.n = (uint32_t)n;
-    uint64_t max_in = 0;
-    for (size_t i = 0; i < n; i++) max_in = std::max(max_in, m[n + i]);
-    ib.flags = max_in >= ctx->inflate_split_min ? FDB_FLAG_SPLIT_LARGE : 0u;
+    if (!items.empty()) FDB_TRY(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(GatherItem), cudaMemcpyHostToDevice, hs));
+    // chunks of files (files and pixel slots in ascending order, what every packer produces; else one chunk):
+    // files up | CRCs, gather, inflate, unfilter | pixels back overlap, every chunk queued at once
+    bool ascending = true;
+    for (size_t i = 1; i < n && ascending; i++)
+        ascending = file_off[i] >= file_off[i - 1] + file_len[i - 1] &&
+                    raw_off[i] >= raw_off[i - 1] + (fi[i - 1].status == ST_OK ? (uint64_t)fi[i - 1].height * fi[i - 1].stride : 0);
+    size_t nchunk = 1;
+    if (ascending) nchunk = (size_t)std::min<uint64_t>(std::min<uint64_t>((in_span + raw_span) / ctx->chunk_bytes, FDB_MAX_CHUNKS), n);
+    if (nchunk < 1) nchunk = 1;
+    const size_t per = (n + nchunk - 1) / nchunk;
+    nchunk = (n + per - 1) / per;
+    const int L = ctx->n_lanes;
     ctx->last_general_host = -1;
     ctx->last_split_host = -1;
-    if ((r = launch_inflate(ctx, ib, ctx->d_counters, &ctx->d_worklist, &ctx->worklist_cap, st, false, &ctx->split))) return r;
-    if ((r = png_launch(ctx, true, ctx->d_mid, d_filt_off, ctx->d_out, d_raw_off, d_geo, d_geo + n, d_geo + 2 * n, 0, d_st2, n, st)))
-        return r;
+    for (size_t kc = 0; kc < nchunk; kc++) {
+        const size_t a = kc * per, b = std::min(n, a + per);
+        fdb_lane& ln = ctx->lanes[kc % L];
+        const uint64_t f_lo = nchunk == 1 ? lo : file_off[a], f_hi = nchunk == 1 ? hi : file_off[b - 1] + file_len[b - 1];
+        if (f_hi > f_lo) FDB_TRY(cudaMemcpyAsync(ctx->d_in + (f_lo - lo), file_base + f_lo, f_hi - f_lo, cudaMemcpyHostToDevice, hs));
+        FDB_TRY(cudaEventRecord(ctx->ev_in[kc], hs));
+        FDB_TRY(cudaStreamWaitEvent(ln.st, ctx->ev_in[kc], 0));
+        const size_t c0 = crc_first[a], c1 = crc_first[b], g0 = item_first[a], g1 = item_first[b];
+        if (c1 > c0 && (r = crc_launch(ctx, ctx->d_in, d_crc_off + c0, d_crc_len + c0, 0, d_crc + c0, c1 - c0, ln.st, ln.d_counters + 13)))
+            return r;
+        if (g1 > g0) {
+            uint32_t* counter = ln.d_counters + 14;
+            FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), ln.st));
+            const uint32_t grid = (uint32_t)std::min<size_t>((g1 - g0 + 7) / 8, (size_t)std::max(ctx->sm_count, 1) * 8);
+            FDB_LAUNCH(gather_kernel, dim3(grid), dim3(256), 0, ln.st, (const uint8_t*)ctx->d_in, ctx->d_in,
+                       (const GatherItem*)(d_items + g0), (uint32_t)(g1 - g0), counter);
+            ctx->launches++;
+            FDB_TRY(cudaGetLastError());
+        }
+        InflateBatch ib;
+        ib.in_base = ctx->d_in;
+        ib.in_off = d_idat_off + a;
+        ib.in_len = d_idat_len + a;
+        ib.out_base = ctx->d_mid;
+        ib.out_off = d_filt_off + a;
+        ib.out_cap = d_filt_cap + a;
+        ib.out_len = d_out_len + a;
+        ib.consumed = d_consumed + a;
+        ib.status = d_st1 + a;
+        ib.n = (uint32_t)(b - a);
+        uint64_t max_in = 0;
+        for (size_t i = a; i < b; i++) max_in = std::max(max_in, m[n + i]);
+        ib.flags = max_in >= ctx->inflate_split_min ? FDB_FLAG_SPLIT_LARGE : 0u;
+        if ((r = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, nchunk > 1, &ln.split))) return r;
+        if ((r = png_launch(ctx, true, ctx->d_mid, d_filt_off + a, ctx->d_out, d_raw_off + a, d_geo + a, d_geo + n + a,
+                            d_geo + 2 * n + a, 0, d_st2 + a, b - a, ln.st, ln.d_counters + 12)))
+            return r;
+        FDB_TRY(cudaEventRecord(ctx->ev_res[kc], ln.st));
+        FDB_TRY(cudaStreamWaitEvent(ds, ctx->ev_res[kc], 0));
+        // pixels back (images that follow each other with less than 16 bytes of padding travel in one copy, padding included)
+        for (size_t i = a; i < b;) {
+            if (fi[i].status != ST_OK) {
+                i++;
+                continue;
+            }
+            const uint64_t begin = raw_off[i];
+            uint64_t end = begin + (uint64_t)fi[i].height * fi[i].stride;
+            size_t j = i + 1;
+            while (j < b && fi[j].status == ST_OK && raw_off[j] >= end && raw_off[j] - end < 16) {
+                end = raw_off[j] + (uint64_t)fi[j].height * fi[j].stride;
+                j++;
+            }
+            FDB_TRY(cudaMemcpyAsync(raw_base + begin, ctx->d_out + begin, end - begin, cudaMemcpyDeviceToHost, ds));
+            i = j;
+        }
+    }
     std::vector<int32_t> st12(2 * n);
     std::vector<uint64_t> olen(n);
     std::vector<uint32_t> crc(n_crc);
-    // pixels back: image by image when the caller's layout has gaps, else in one piece
-    // (images that follow each other with less than 16 bytes of padding travel in one copy, padding included)
-    for (size_t i = 0; i < n;) {
-        if (fi[i].status != ST_OK) {
-            i++;
-            continue;
-        }
-        const uint64_t begin = raw_off[i];
-        uint64_t end = begin + (uint64_t)fi[i].height * fi[i].stride;
-        size_t j = i + 1;
-        while (j < n && fi[j].status == ST_OK && raw_off[j] >= end && raw_off[j] - end < 16) {
-            end = raw_off[j] + (uint64_t)fi[j].height * fi[j].stride;
-            j++;
-        }
-        FDB_TRY(cudaMemcpyAsync(raw_base + begin, ctx->d_out + begin, end - begin, cudaMemcpyDeviceToHost, st));
-        i = j;
-    }
-    FDB_TRY(cudaMemcpyAsync(st12.data(), d_st1, 2 * n * 4, cudaMemcpyDeviceToHost, st));
-    FDB_TRY(cudaMemcpyAsync(olen.data(), d_out_len, n * 8, cudaMemcpyDeviceToHost, st));
-    if (n_crc) FDB_TRY(cudaMemcpyAsync(crc.data(), d_crc, n_crc * 4, cudaMemcpyDeviceToHost, st));
-    FDB_TRY(cudaStreamSynchronize(st));
+    for (int l = 0; l < L; l++) FDB_TRY(cudaStreamSynchronize(ctx->lanes[l].st));
+    FDB_TRY(cudaMemcpyAsync(st12.data(), d_st1, 2 * n * 4, cudaMemcpyDeviceToHost, ds));
+    FDB_TRY(cudaMemcpyAsync(olen.data(), d_out_len, n * 8, cudaMemcpyDeviceToHost, ds));
+    if (n_crc) FDB_TRY(cudaMemcpyAsync(crc.data(), d_crc, n_crc * 4, cudaMemcpyDeviceToHost, ds));
+    FDB_TRY(cudaStreamSynchronize(ds));
+    FDB_TRY(cudaStreamSynchronize(hs));
     size_t k = 0;
     for (size_t i = 0; i < n; i++) {
         if (fi[i].status != ST_OK) {
