@@ -82,6 +82,7 @@ struct fdb_ctx {
     int split_large = 0;            // device-pointer calls: long streams by many warps (fdb_set_split_large)
     uint64_t inflate_split_min = K4_SPLIT_MIN_BYTES;  // fdb_set_split_threshold
     uint64_t deflate_split_min = DF_SPLIT_MIN_BYTES;
+    uint64_t deflate_auto_min = DF_AUTO_SPLIT_BYTES;  // host-buffer deflate: a chunk with an input this long takes the segment path
     UfEncTables* d_enc = nullptr;
     UfDecTables* d_dec = nullptr;
     CrcTables* d_crc = nullptr;
@@ -195,6 +196,7 @@ extern "C" int fdb_set_split_threshold(fdb_ctx* ctx, size_t inflate_bytes, size_
     if (!ctx) return -1;
     ctx->inflate_split_min = inflate_bytes ? inflate_bytes : K4_SPLIT_MIN_BYTES;
     ctx->deflate_split_min = deflate_bytes ? deflate_bytes : DF_SPLIT_MIN_BYTES;
+    ctx->deflate_auto_min = deflate_bytes ? deflate_bytes : DF_AUTO_SPLIT_BYTES;
     return 0;
 }
 
@@ -243,7 +245,7 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e);
     if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail(e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(uint32_t))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc((void**)&ctx->d_counters, 32 * sizeof(uint32_t))) != cudaSuccess) return bail(e);
     if ((e = xfer_acquire(device, &ctx->h2d_st, &ctx->d2h_st)) != cudaSuccess) return bail(e);
     for (int k = 0; k < FDB_MAX_CHUNKS; k++) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
@@ -260,7 +262,7 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
     ctx->lanes[0].st = ctx->stream;
     for (int l = 0; l < ctx->n_lanes; l++) {
         if (l && (e = cudaStreamCreateWithFlags(&ctx->lanes[l].st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
-        if ((e = cudaMalloc((void**)&ctx->lanes[l].d_counters, 16 * sizeof(uint32_t))) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc((void**)&ctx->lanes[l].d_counters, 32 * sizeof(uint32_t))) != cudaSuccess) return bail(e);
     }
     if ((e = cudaMalloc((void**)&ctx->d_enc, sizeof(UfEncTables))) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc((void**)&ctx->d_dec, sizeof(UfDecTables))) != cudaSuccess) return bail(e);
@@ -477,13 +479,18 @@ static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_
         sp.next_scan = c8 + 2;
         sp.next_write = c8 + 3;
         sp.min_bytes = ctx->deflate_split_min;
+        uint64_t* total = (uint64_t*)(counter + 15);  // counters[18..19]
+        FDB_TRY(cudaMemsetAsync(total, 0, sizeof(uint64_t), st));
+        FDB_LAUNCH(batch_total_kernel, dim3((uint32_t)std::min<size_t>((n + 255) / 256, 64)), dim3(256), 0, st, b.in_len, b.n, total);
+        sp.total = total;
+        sp.slots = sms * 32u;
         split_item0 = sp.item0;
         const uint32_t pgrid = sms * DEFLATE_MIN_CTAS;
         FDB_LAUNCH(deflate_uf_plan_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0, st, b, sp);
         FDB_LAUNCH(deflate_uf_split_count_kernel, dim3(pgrid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc, sp);
         FDB_LAUNCH(deflate_uf_split_scan_kernel, dim3((uint32_t)std::min<size_t>((n + 7) / 8, (size_t)sms * 4)), dim3(256), 0, st, b, sp);
         FDB_LAUNCH(deflate_uf_split_write_kernel, dim3(pgrid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc, sp);
-        ctx->launches += 4;
+        ctx->launches += 5;
         FDB_TRY(cudaGetLastError());
     }
     if (kind == 0) {
@@ -760,7 +767,7 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             uint64_t max_len = png ? max_filtered : 0;
             for (size_t i = a; i < b; i++) max_len = std::max(max_len, in_len[i]);
             if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st, dense,
-                                     max_len >= ctx->deflate_split_min ? &ln.dsplit : nullptr)))
+                                     max_len >= ctx->deflate_auto_min ? &ln.dsplit : nullptr)))
                 return rr;
         }
         mark(k, 2, ln.st);

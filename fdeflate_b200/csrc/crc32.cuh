@@ -116,6 +116,14 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(CRC_WARPS * 32, 4) crc32_kernel(CrcBatch b, co
     }
 }
 
+// ---- sum of a batch's stream lengths (input of the span / segment planners) ----
+FDB_GLOBAL void batch_total_kernel(const uint64_t* len, uint32_t n, uint64_t* total) {
+    uint64_t s = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += len[i];
+    s = simt::reduce_add(s);
+    if (simt::lane_id() == 0 && s) simt::atomic_add(total, s);
+}
+
 // ---- gather: byte ranges copied to new places (IDAT payloads of one file -> one contiguous zlib stream) ----
 struct GatherItem {
     uint64_t src, dst, len;  // offsets into src_base / dst_base

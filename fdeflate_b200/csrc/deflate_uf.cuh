@@ -180,7 +180,8 @@ FDB_DEVICE uint4 load16_guarded(const uint8_t* in, uint64_t g, uint64_t n, bool 
 // other word is stored exactly once as in the one-warp encoder.  DF_WHOLE is that one-warp encoder.
 enum : int { DF_WHOLE = 0, DF_COUNT = 1, DF_WRITE = 2 };
 static const uint64_t DF_SEG_BYTES = 64u << 10;              // multiple of the 512-byte warp step
-static const uint64_t DF_SPLIT_MIN_BYTES = 16 * DF_SEG_BYTES;  // default: inputs of >= 1 MiB are split (never < 2 segments)
+static const uint64_t DF_SPLIT_MIN_BYTES = 4 * DF_SEG_BYTES;   // default: inputs of >= 256 KiB are split (never < 2 segments)
+static const uint64_t DF_AUTO_SPLIT_BYTES = 16 * DF_SEG_BYTES;  // host-buffer calls turn the segment path on for a chunk that holds an input this long
 static const uint32_t DF_NO_ITEM = 0xffffffffu;
 
 struct DfSpan {
@@ -506,7 +507,9 @@ struct DfSplit {
     uint32_t* next_count;
     uint32_t* next_scan;
     uint32_t* next_write;
-    uint64_t min_bytes;  // inputs at least this long are split
+    uint64_t min_bytes;  // inputs at least this long are split ...
+    const uint64_t* total;  // ... if they are also long against the batch: sum of the batch's input lengths
+    uint32_t slots;         // warps the device runs at once
 };
 
 FDB_GLOBAL void deflate_uf_plan_kernel(DeflateBatch b, DfSplit sp) {
@@ -515,7 +518,7 @@ FDB_GLOBAL void deflate_uf_plan_kernel(DeflateBatch b, DfSplit sp) {
     sp.item0[i] = DF_NO_ITEM;
     sp.nseg[i] = 0;
     const uint64_t n = b.in_len[i];
-    if (n < sp.min_bytes || n < 2 * DF_SEG_BYTES) return;
+    if (n < deflate_split_threshold(sp.min_bytes, *sp.total, b.n, sp.slots) || n < 2 * DF_SEG_BYTES) return;
     const uint64_t S = n / DF_SEG_BYTES;  // the last segment also takes the remainder
     if (S > 0x7fffffffull) return;
     const uint32_t base = simt::atomic_add(sp.n_items, (uint32_t)S);

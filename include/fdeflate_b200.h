@@ -197,11 +197,13 @@ uint64_t fdb_launch_count(const fdb_ctx* ctx);
  * ultra-fast-format fast path and decoded by the general kernel.  Synchronises `cuda_stream`. */
 int64_t fdb_last_general_count(fdb_ctx* ctx, void* cuda_stream);
 /* Long streams, many warps each.  An ultra-fast-format stream of >= 256 KiB is inflated span by span and an
- * input of >= 1 MiB is ultra-fast-deflated segment by segment (64 KiB units, three passes),
- * so that a batch of few or very uneven streams still fills the GPU.  Results are identical either way.
- * The host-buffer calls turn this on by themselves for a batch (chunk) that holds such a stream; for the
- * device-pointer calls, which do not see the sizes, it is off unless fdb_set_split_large(ctx, 1) (costs a few
- * extra small launches per batch).  fdb_set_split_threshold changes the two sizes (0 = default). */
+ * input of >= 256 KiB is ultra-fast-deflated segment by segment (64 KiB units, three passes),
+ * so that a batch of few or very uneven streams still fills the GPU.  A deflate batch with more inputs than the device
+ * runs warps only cuts an input that holds an eighth of the batch's bytes (the work counter balances the rest).
+ * Results are identical either way.  The host-buffer calls turn this on by themselves for a batch
+ * (chunk) that holds a stream of >= 256 KiB (inflate) or an input of >= 1 MiB (deflate); for the device-pointer
+ * calls, which do not see the sizes, it is off unless fdb_set_split_large(ctx, 1) (costs a few extra small
+ * launches per batch).  fdb_set_split_threshold changes the two sizes (0 = default). */
 int fdb_set_split_large(fdb_ctx* ctx, int on);
 int fdb_set_split_threshold(fdb_ctx* ctx, size_t inflate_stream_bytes, size_t deflate_input_bytes);
 /* how many spans the long streams of the most recent inflate batch on this context were cut into

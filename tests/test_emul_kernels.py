@@ -229,13 +229,13 @@ def test_deflate_long_inputs_segment_by_segment(emul_ctx, emul_lib, oracle):
     atomicOr on the words two segments share); the bytes must equal the oracle's single sequential pass."""
     inputs = _long_deflate_inputs(emul_lib, 11)
     try:
-        emul_ctx.set_split_threshold(0, 4 * 65536)  # (default 1 MiB: keep the emulator run short)
+        emul_ctx.set_split_threshold(0, 4 * 65536)  # (host-buffer calls switch at 1 MiB by default: keep the emulator run short)
         parity.check_deflate_ultrafast(emul_ctx, inputs, align=16)
         parity.check_deflate_ultrafast(emul_ctx, inputs[:4], align=1)
         small = cases.compress_inputs(3, 6, [10, 3000])
         l0 = emul_ctx.launch_count
         parity.check_deflate_ultrafast(emul_ctx, small[:5] + inputs[2:5] + small[5:10], align=16)
-        assert emul_ctx.launch_count - l0 == 5  # plan, count, scan, write + the one-warp-per-stream kernel
+        assert emul_ctx.launch_count - l0 == 6  # total, plan, count, scan, write + the one-warp-per-stream kernel
         _check_deflate_slot_sizes(emul_ctx, oracle, inputs[2])
     finally:
         emul_ctx.set_split_threshold(0, 0)
