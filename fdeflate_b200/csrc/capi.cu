@@ -37,7 +37,7 @@ struct fdb_split_scratch {
     uint32_t* per_stream = nullptr;  // item0 | nspans | need | done | failed, n words each
     size_t per_stream_bytes = 0;
 };
-static const uint32_t FDB_SPLIT_ITEMS = 1u << 18;  // spans per batch (16 GiB of compressed input)
+static const uint32_t FDB_SPLIT_ITEMS = 1u << 20;  // spans per batch (64 GiB of compressed input); scratch is allocated on first use
 // ... and of the segment-by-segment deflate path
 struct fdb_dsplit_scratch {
     DfItem* items = nullptr;
