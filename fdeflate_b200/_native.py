@@ -20,7 +20,7 @@ EXPORTS = [
     "fdb_deflate_ultrafast_bound", "fdb_deflate_ultrafast_batch_device", "fdb_deflate_ultrafast_batch",
     "fdb_deflate_stored_bound", "fdb_deflate_stored_batch_device", "fdb_deflate_stored_batch",
     "fdb_synth_tile_bytes", "fdb_synth_tiles_host", "fdb_synth_tiles_device", "fdb_launch_count", "fdb_last_general_count",
-    "fdb_set_pipeline_chunk", "fdb_last_split_spans", "fdb_set_split_large", "fdb_set_split_threshold", "fdb_png_unfilter_batch_device", "fdb_png_filter_batch_device", "fdb_png_unfilter_batch", "fdb_png_filter_batch", "fdb_png_decode_batch", "fdb_png_encode_batch", "fdb_crc32_batch_device", "fdb_crc32_batch", "fdb_png_probe_batch", "fdb_png_decode_files_batch",
+    "fdb_set_pipeline_chunk", "fdb_last_split_spans", "fdb_set_split_large", "fdb_set_split_threshold", "fdb_png_unfilter_batch_device", "fdb_png_filter_batch_device", "fdb_png_unfilter_batch", "fdb_png_filter_batch", "fdb_png_decode_batch", "fdb_png_encode_batch", "fdb_crc32_batch_device", "fdb_crc32_batch", "fdb_png_probe_batch", "fdb_png_decode_files_batch", "fdb_png_file_bound", "fdb_png_encode_files_batch",
 ]
 
 FLAG_IGNORE_ADLER32 = 1
@@ -100,6 +100,10 @@ class NativeLib:
         L.fdb_png_probe_batch.argtypes = [vp] * 9 + [sz]
         L.fdb_png_decode_files_batch.restype = C.c_int
         L.fdb_png_decode_files_batch.argtypes = [vp] * 7 + [sz]
+        L.fdb_png_file_bound.restype = sz
+        L.fdb_png_file_bound.argtypes = [C.c_uint32] * 4
+        L.fdb_png_encode_files_batch.restype = C.c_int
+        L.fdb_png_encode_files_batch.argtypes = [vp] * 7 + [C.c_uint32] + [vp] * 5 + [sz]
         L.fdb_set_split_threshold.restype = C.c_int
         L.fdb_set_split_threshold.argtypes = [vp, sz, sz]
         L.fdb_last_split_spans.restype = C.c_int64

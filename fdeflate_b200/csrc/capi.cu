@@ -609,12 +609,16 @@ static int png_launch(fdb_ctx* ctx, bool unfilter, const void* d_in_base, const 
                       const uint64_t* d_out_off, const uint32_t* d_height, const uint32_t* d_stride, const uint32_t* d_bpp,
                       uint32_t mode, int32_t* d_status, size_t n, void* cuda_stream, uint32_t* counter = nullptr);
 
+static int crc_launch(fdb_ctx* ctx, const void* d_base, const uint64_t* d_off, const uint64_t* d_len, uint32_t seed,
+                      uint32_t* d_crc, size_t n, void* cuda_stream, uint32_t* counter);
+
 // PNG encode rides the same pipeline: the inputs are raw images, and between "input landed" and the deflate
 // kernels a filter kernel writes the filtered images into a second device buffer, which is what gets compressed.
 struct PngPre {
     const uint32_t *height, *stride, *bpp;
     uint32_t mode;
     int32_t* filter_status;  // [n] host array
+    uint32_t* idat_crc;      // [n] host array or null: CRC-32 of "IDAT" + the compressed stream, computed on the device
 };
 
 static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
@@ -681,7 +685,7 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     // The per-stream results live in pinned host memory and the kernels write them there directly (mapped
     // memory: a few bytes per stream over PCIe), so no copy stands between "kernels done" and the host
     // knowing how much payload to fetch.
-    const size_t res_bytes = n * (8 + 8 + 4) + nchunk * 8 + 64;
+    const size_t res_bytes = n * (8 + 8 + 4 + 4) + nchunk * 8 + 64;
     if (res_bytes > ctx->h_res_cap) {
         if (ctx->h_res) FDB_TRY(cudaFreeHost(ctx->h_res));
         ctx->h_res = nullptr;
@@ -694,6 +698,7 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     int32_t* h_status = (int32_t*)(h_consumed + n);
     uint32_t* h_general = (uint32_t*)(h_status + n);
     uint32_t* h_split = h_general + nchunk;
+    uint32_t* h_crc = h_split + nchunk;  // PNG encode: chunk CRCs, written by the device like the other results
     memset(h_split, 0, nchunk * sizeof(uint32_t));
 
     uint64_t in_stride = 0, out_stride = 0;
@@ -769,6 +774,12 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st, dense,
                                      max_len >= ctx->deflate_auto_min ? &ln.dsplit : nullptr)))
                 return rr;
+            // the CRC of each IDAT chunk ("IDAT" + stream): the stream lengths are read where the deflate kernel
+            // wrote them (mapped host memory)
+            if (png && png->idat_crc &&
+                (rr = crc_launch(ctx, ctx->d_out, d_out_off + a, h_out_len + a, 0x35af061eu /* crc32("IDAT") */, h_crc + a, b - a,
+                                 ln.st, ln.d_counters + 13)))
+                return rr;
         }
         mark(k, 2, ln.st);
         FDB_TRY(cudaEventRecord(ctx->ev_res[k], ln.st));
@@ -820,6 +831,7 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     }
     memcpy(out_len, h_out_len, n * 8);
     memcpy(status, h_status, n * 4);
+    if (png && png->idat_crc) memcpy(png->idat_crc, h_crc, n * 4);
     if (kind == 0) {
         if (consumed) memcpy(consumed, h_consumed, n * 8);
         int64_t g = 0;
@@ -1071,7 +1083,7 @@ extern "C" int fdb_png_encode_batch(fdb_ctx* ctx, const uint8_t* raw_base, const
     std::vector<uint64_t> raw_len(n);
     std::vector<int32_t> fst(n, 0);
     for (size_t i = 0; i < n; i++) raw_len[i] = (uint64_t)height[i] * stride[i];
-    PngPre pre = {height, stride, bpp, mode, fst.data()};
+    PngPre pre = {height, stride, bpp, mode, fst.data(), nullptr};
     int r = host_batch(ctx, 1, raw_base, raw_off, raw_len.data(), out_base, out_off, out_cap, out_len, nullptr, status, n, 0, &pre);
     if (r) return r;
     for (size_t i = 0; i < n; i++)
@@ -1079,6 +1091,100 @@ extern "C" int fdb_png_encode_batch(fdb_ctx* ctx, const uint8_t* raw_base, const
             status[i] = fst[i];
             out_len[i] = 0;
         }
+    return 0;
+}
+
+// raw pixels -> PNG files (signature, IHDR, one IDAT chunk, IEND) written straight into the caller's file slots:
+// the deflate kernel writes the zlib stream at its place inside the file, the IDAT CRC comes from the device, the 57
+// bytes around it (signature, IHDR chunk, IDAT length / type / CRC, IEND chunk) are written by the host.
+static uint32_t host_crc32(const uint8_t* p, size_t n) {
+    static CrcTables* t = [] {
+        CrcTables* c = new CrcTables();
+        build_crc_tables(*c);
+        return c;
+    }();
+    uint32_t r = 0xffffffffu;
+    for (size_t i = 0; i < n; i++) r = (r >> 8) ^ t->t[0][(r ^ p[i]) & 0xffu];
+    return ~r;
+}
+static void put_be32(uint8_t* p, uint32_t v) {
+    p[0] = (uint8_t)(v >> 24);
+    p[1] = (uint8_t)(v >> 16);
+    p[2] = (uint8_t)(v >> 8);
+    p[3] = (uint8_t)v;
+}
+static const size_t PNG_PRE = 8 + 25 + 8;   // signature + IHDR chunk + IDAT length and type
+static const size_t PNG_POST = 4 + 12;      // IDAT CRC + IEND chunk
+
+static bool png_geometry(uint32_t width, uint32_t height, uint32_t depth, uint32_t color, uint32_t* stride, uint32_t* bpp) {
+    uint32_t channels = color == 0 ? 1 : color == 2 ? 3 : color == 4 ? 2 : color == 6 ? 4 : 0;  // (no palette images: no PLTE here)
+    if (!channels || !width || !height || (depth != 8 && depth != 16)) return false;
+    if ((uint64_t)width * channels * depth / 8 > 0x7fffffffull) return false;
+    *bpp = channels * depth / 8;
+    *stride = width * *bpp;
+    return true;
+}
+extern "C" size_t fdb_png_file_bound(uint32_t width, uint32_t height, uint32_t bit_depth, uint32_t color_type) {
+    uint32_t stride = 0, bpp = 0;
+    if (!png_geometry(width, height, bit_depth, color_type, &stride, &bpp)) return 0;
+    return PNG_PRE + fdb_deflate_ultrafast_bound((size_t)height * (1 + (size_t)stride)) + PNG_POST;
+}
+extern "C" int fdb_png_encode_files_batch(fdb_ctx* ctx, const uint8_t* raw_base, const uint64_t* raw_off, const uint32_t* width,
+                                          const uint32_t* height, const uint32_t* bit_depth, const uint32_t* color_type,
+                                          uint32_t mode, uint8_t* file_base, const uint64_t* file_off, const uint64_t* file_cap,
+                                          uint64_t* file_len, int32_t* status, size_t n) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (n > 0xffffffffull || !raw_base || !raw_off || !width || !height || !bit_depth || !color_type || !file_base || !file_off ||
+        !file_cap || !file_len || !status)
+        return fail(ctx, "fdb_png_encode_files_batch", cudaSuccess);
+    std::vector<uint32_t> stride(n), bpp(n), h(n), crc(n);
+    std::vector<uint64_t> raw_len(n), z_off(n), z_cap(n), z_len(n);
+    std::vector<int32_t> fst(n, 0);
+    std::vector<bool> ok(n);
+    for (size_t i = 0; i < n; i++) {
+        ok[i] = png_geometry(width[i], height[i], bit_depth[i], color_type[i], &stride[i], &bpp[i]) && file_cap[i] > PNG_PRE + PNG_POST;
+        if (!ok[i]) {  // an empty job for the device: zero rows
+            stride[i] = 1;
+            bpp[i] = 1;
+        }
+        h[i] = ok[i] ? height[i] : 0;
+        raw_len[i] = (uint64_t)h[i] * stride[i];
+        z_off[i] = file_off[i] + PNG_PRE;
+        z_cap[i] = ok[i] ? file_cap[i] - PNG_PRE - PNG_POST : 64;
+    }
+    PngPre pre = {h.data(), stride.data(), bpp.data(), mode, fst.data(), crc.data()};
+    int r = host_batch(ctx, 1, raw_base, raw_off, raw_len.data(), file_base, z_off.data(), z_cap.data(), z_len.data(), nullptr, status,
+                       n, 0, &pre);
+    if (r) return r;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    for (size_t i = 0; i < n; i++) {
+        file_len[i] = 0;
+        if (!ok[i]) {
+            status[i] = ST_PNG_BAD_GEOMETRY;
+            continue;
+        }
+        if (fst[i] != ST_OK) status[i] = fst[i];
+        if (status[i] != ST_OK) continue;
+        uint8_t* f = file_base + file_off[i];
+        memcpy(f, sig, 8);
+        put_be32(f + 8, 13);
+        memcpy(f + 12, "IHDR", 4);
+        put_be32(f + 16, width[i]);
+        put_be32(f + 20, height[i]);
+        f[24] = (uint8_t)bit_depth[i];
+        f[25] = (uint8_t)color_type[i];
+        f[26] = f[27] = f[28] = 0;
+        put_be32(f + 29, host_crc32(f + 12, 17));
+        put_be32(f + 33, (uint32_t)z_len[i]);
+        memcpy(f + 37, "IDAT", 4);
+        uint8_t* t = f + PNG_PRE + z_len[i];
+        put_be32(t, crc[i]);
+        put_be32(t + 4, 0);
+        memcpy(t + 8, "IEND", 4);
+        put_be32(t + 12, 0xae426082u);  // crc32("IEND")
+        file_len[i] = PNG_PRE + z_len[i] + PNG_POST;
+    }
     return 0;
 }
 

@@ -167,6 +167,16 @@ int fdb_png_probe_batch(const uint8_t* file_base, const uint64_t* file_off, cons
 int fdb_png_decode_files_batch(fdb_ctx* ctx, const uint8_t* file_base, const uint64_t* file_off, const uint64_t* file_len,
                                uint8_t* raw_base, const uint64_t* raw_off, int32_t* status, size_t n);
 
+/* ... and the other way: raw pixels (8- or 16-bit gray, gray + alpha, RGB, RGBA; 16-bit samples big-endian as in the
+ * file) -> complete PNG files (signature, IHDR, one IDAT chunk holding an ultra-fast zlib stream, IEND) at
+ * file_base + file_off[i]; file_cap[i] >= fdb_png_file_bound(...).  Filter `mode` as in fdb_png_filter_batch.  The row
+ * filter, the deflate and the IDAT CRC run on the device, on the pipeline of the host-buffer deflate call. */
+size_t fdb_png_file_bound(uint32_t width, uint32_t height, uint32_t bit_depth, uint32_t color_type);
+int fdb_png_encode_files_batch(fdb_ctx* ctx, const uint8_t* raw_base, const uint64_t* raw_off, const uint32_t* width,
+                               const uint32_t* height, const uint32_t* bit_depth, const uint32_t* color_type, uint32_t mode,
+                               uint8_t* file_base, const uint64_t* file_off, const uint64_t* file_cap, uint64_t* file_len,
+                               int32_t* status, size_t n);
+
 /* ---- CRC-32 of a batch of byte ranges (PNG chunk CRCs; polynomial 0xEDB88320, the value zlib's crc32() gives) ----
  * crc[i] = CRC-32 of base[off[i] .. off[i] + len[i]) continued from `seed` = the CRC of whatever precedes every
  * range (0 = nothing; e.g. crc32("IDAT") for the payloads of IDAT chunks).  One warp per range. */
