@@ -1,31 +1,40 @@
 // inflate_uf.cuh -- K4: inflate of ultra-fast-format streams, ONE WARP PER STREAM with all 32
-// lanes decoding different parts of the SAME stream.
+// lanes decoding different parts of the SAME stream, every compressed bit decoded ONCE.
 //
 // A stream qualifies when its first 53 bytes + 5 bits equal the constant header the reference's
 // UltraFastCompressor writes (src/compress/ultrafast.rs:81-91): one dynamic block whose litlen code
 // is HUFFMAN_LENGTHS (src/tables.rs:7-20) and whose only distance code is "distance 1".  For such
 // streams the decode table is a constant (built once on the host, shared by the whole CTA) and every
-// match replicates the previous byte, so output positions are a pure prefix sum of per-token byte
+// match replicates the previous byte, so output positions are a pure prefix sum of per-lane byte
 // counts.  That is what makes intra-stream parallelism possible:
 //
 //   per segment of 32 x SUBW words of compressed bits
-//   1. stage   : coalesced 16-byte loads -> padded shared memory (conflict-free per-lane reads)
-//   2. count   : lane i starts WARM words BEFORE its sub-sequence at a guessed bit position, decodes
-//                single tokens until it crosses its boundary (Huffman codes self-synchronise within
-//                a few tokens), then counts the bytes of its own sub-sequence.  Lane 0 starts at the
-//                known true position.
-//   3. verify  : lane i's start must equal lane i-1's end; since lane 0 is exact this proves every
+//   1. stage   : coalesced 16-byte loads -> transposed shared-memory rows (conflict-free per-lane reads)
+//   2. warm-up : lane i starts WARM words BEFORE its sub-sequence at a guessed bit position and walks
+//                tokens until it crosses its boundary (Huffman codes self-synchronise within a few
+//                tokens).  Lane 0 starts at the known true position.
+//   3. decode  : every lane decodes its sub-sequence ONCE into a lane-private, transposed output row:
+//                literals are appended to a 32-bit accumulator with two funnel shifts and leave as
+//                whole words (conflict-free stores); zero runs go into the row as zeros while they
+//                fit, a run that does not fit becomes a GAP (position, length) in a small per-lane list.
+//   4. verify  : lane i's start must equal lane i-1's end; since lane 0 is exact this proves every
 //                lane.  A lane that had not synchronised is re-run from its predecessor's end
 //                (loop until consistent; normally zero rounds).
-//   4. scan    : exclusive prefix sum of byte counts -> output offsets; last-literal propagation
-//                gives every lane the byte its leading match replicates.
-//   5. write   : lanes decode again (two-literal table entries) and drop literals into a
-//                zero-initialised shared-memory window; zero runs are skipped, not written.  Full
-//                windows leave with 16-byte coalesced stores and feed adler32 on the way out.
+//   5. scan    : exclusive prefix sum of byte counts -> output offsets; last-byte propagation checks
+//                that every run follows a zero byte (the only matches the reference encoder emits).
+//   6. move    : each lane copies the pieces of its row (word-wise, funnel-shifted to the destination
+//                alignment) into a zeroed shared-memory window at its offset -- gaps are skipped, the
+//                window is already zero -- and finished 16-byte vectors leave with coalesced streaming
+//                stores, feeding adler32 on the way out.  The window shares its memory with the
+//                staging rows (they are never live together).
+//
+// (Until round 2 the lanes decoded twice: a count pass, then a write pass with byte stores into the
+// window; ncu showed every bit decoded 2.5 times and 2.9-way bank conflicts on those byte stores.)
 //
 // Anything irregular (foreign header, distance bit 1, truncation, output larger than the slot,
-// match at position 0) is not diagnosed here: the stream is appended to a work list and the general
-// kernel (K3) redoes it from scratch, which yields exactly the reference's status.
+// match at position 0, more gaps than a lane's list holds) is not diagnosed here: the stream is
+// appended to a work list and the general kernel (K3) redoes it from scratch, which yields exactly
+// the reference's status.
 //
 // Semantics replaced: reference src/decompress.rs:611-1018 (decode loop) + :306-326 (checksum) for
 // this stream class; results are identical to K3's and to the oracle's.
@@ -37,28 +46,49 @@
 namespace fdb {
 
 #ifndef K4_WARPS_PER_CTA
-#define K4_WARPS_PER_CTA 32
+#define K4_WARPS_PER_CTA 20
+#endif
+#ifndef K4_SUBW_WORDS
+#define K4_SUBW_WORDS 8
+#endif
+#ifndef K4_WIN_BYTES
+#define K4_WIN_BYTES 4096
 #endif
 static const int K4_WARPS = K4_WARPS_PER_CTA;  // warps per CTA (one CTA per SM; they share the 24 KiB of tables)
-static const uint32_t K4_SUBW = 8;     // 32-bit words of compressed data per lane per segment
+static const uint32_t K4_SUBW = K4_SUBW_WORDS;  // 32-bit words of compressed data per lane per segment (multiple of 4)
 static const uint32_t K4_WARM = 4;     // warm-up words before a lane's sub-sequence
 static const uint32_t K4_TAILW = 3;    // words after it (token overrun + two-word look-ahead)
-static const uint32_t K4_ROWW = K4_WARM + K4_SUBW + K4_TAILW;  // 15 words seen by one lane
+static const uint32_t K4_ROWW = K4_WARM + K4_SUBW + K4_TAILW;  // words seen by one lane
 static const uint32_t K4_ROWS_ALLOC = K4_ROWW + 1;             // +1: the look-ahead may touch one more
+static const uint32_t K4_VPR = K4_SUBW / 4;                    // 16-byte vectors per sub-sequence
 static const uint32_t K4_SEG_WORDS = K4_WARM + 32 * K4_SUBW + 4;  // words staged per segment (vectors of 4)
 static const uint32_t K4_LIM_LO = 32u * K4_WARM;               // a lane's sub-sequence, in bits of its row
 static const uint32_t K4_LIM_HI = 32u * (K4_WARM + K4_SUBW);
 static const uint32_t K4_PAIR = 24;    // two table entries consume at most 2 x 12 bits
-static const uint32_t K4_WIN = 4096;   // output window bytes (a segment normally expands to ~2.5 KiB)
+static const uint32_t K4_WIN = K4_WIN_BYTES;  // output window bytes (a segment of SUBW = 8 normally expands to ~2.5 KiB)
 static const uint32_t K4_INVALID = 0xffffffffu;
+// A lane's output row and its gap list share K4_OROWW words: the row grows up from word 0, gap g sits in word
+// OROWW - 1 - g.  A sub-sequence holds at most 16 * SUBW literals (2 bits each); a run is kept in the row (or a new
+// gap opened) only while the literals that can still follow fit as well, so the two never meet.
+static const uint32_t K4_OROWW = 4 * K4_SUBW + 8;
+static const uint32_t K4_ROW_SLACK = 3;
+static const uint32_t K4_GAP_POS_BITS = 9;  // gap word: [8:0] row position, [31:9] length
+static_assert(4 * K4_OROWW < (1u << K4_GAP_POS_BITS), "gap positions fit their field");
+static_assert(K4_SUBW % 4 == 0 && K4_WARM + K4_TAILW <= K4_SUBW, "staging scatter assumes a word lands in at most two rows");
+static_assert(K4_WIN % 16 == 0 && K4_WIN >= 4 * K4_ROWS_ALLOC * 32, "the window covers the staging rows it shares memory with");
 
 // Staging is TRANSPOSED and PRIVATE per lane: row i holds the words lane i can ever touch
 // (WARM words before its sub-sequence, the sub-sequence, TAILW after), word c of row i at
 // stg[c * 32 + i].  Every lane therefore reads bank == lane (never a conflict) and walks its row
 // with a constant +128-byte pointer step.  Overlapping words are simply stored twice.
+// The output rows are laid out the same way (word c of lane i's row at rows[c * 32 + i]).
 struct K4Warp {
-    uint32_t stg[K4_ROWS_ALLOC * 32];
-    uint8_t win[K4_WIN + 16];
+    union {
+        uint32_t stg[K4_ROWS_ALLOC * 32];  // compressed words, while the lanes decode
+        uint8_t win[K4_WIN];               // output window, while the rows are moved out
+    } u;
+    uint32_t rows[K4_OROWW * 32];  // word c of lane i's row at rows[c * 32 + i]; its gaps from the top down
+    uint4 carry;                   // the unfinished 16-byte vector between two segments
 };
 
 struct K4Smem {
@@ -122,16 +152,20 @@ struct LaneCount {
     uint32_t end;    // bit position (row-relative) where the lane stopped: first token boundary >= LIM_HI
     uint32_t cnt;    // bytes produced in [start, end)
     uint32_t flags;  // CF_*
+    uint32_t fill;   // decode_tokens only: bytes in the lane's output row (pieces + the padding between them)
+    uint32_t ngap;   // decode_tokens only: gaps in the lane's list
 };
 // CF_BAD: a token the fast path does not decode (distance bit 1, or a run that follows a non-zero
-// byte inside this lane).  CF_FIRSTRUN / CF_LASTNZ let the warp check the same across lanes.
+// byte inside this lane, or more gaps than the lane's row has room for).  CF_FIRSTRUN / CF_LASTNZ let the warp check the same
+// across lanes.
 enum : uint32_t { CF_EOB = 1, CF_BAD = 2, CF_FIRSTRUN = 4, CF_LASTNZ = 8 };
 
 // Count the bytes of the tokens in [start, LIM_HI); stop at the first token boundary >= LIM_HI or at
 // EOB (then end = position of the EOB code).  No early exits inside the loops, so lanes that still
-// iterate stay converged and the others wait at the loop exit.
+// iterate stay converged and the others wait at the loop exit.  (Used by the count pass of the span
+// path, which only needs sizes.)
 FDB_DEVICE LaneCount count_tokens(const UfTabs& t, simt::saddr row, uint32_t start, uint32_t active) {
-    LaneCount c = {K4_INVALID, 0, 0};
+    LaneCount c = {K4_INVALID, 0, 0, 0, 0};
     LaneBits b;
     lb_start(b, row, active ? start : 0u);
     uint32_t cnt = 0, flags = 0;
@@ -215,6 +249,146 @@ FDB_DEVICE LaneCount count_tokens(const UfTabs& t, simt::saddr row, uint32_t sta
     return c;
 }
 
+// Decode the tokens in [start, LIM_HI) ONCE into the lane's output row (transposed words at `orow`, gaps
+// from the top of the same words down); stop at the first token boundary >= LIM_HI or at EOB, exactly where
+// count_tokens stops.
+//
+// Literals: `acc` keeps the bytes that do not fill a word yet in its TOP bytes (s = 32 - 8 * pending), so
+// appending the k bytes of a table entry e (bytes in [23:0]) is
+//     word = (acc >> s) | (e << (32 - s))        one clamped funnel shift: pending bytes, then e's
+//     acc  = (acc >> 8k) | (e << (32 - 8k))      one funnel shift: e's k bytes enter at the top
+// and `word` is stored when s - 8k <= 0, i.e. when it is complete (then only bytes 0..3-pending of e are in it,
+// so the fields above e's bytes never reach memory).  The top byte of acc is the last LITERAL produced, which is
+// what a run token has to look at unless the token before it was a run as well.  A second-of-pair special entry
+// has k = 0, n = 0 and is a no-op.
+FDB_DEVICE LaneCount decode_tokens(const UfTabs& t, simt::saddr row, uint32_t start, uint32_t active, simt::saddr orow) {
+    LaneCount c = {K4_INVALID, 0, 0, 0, 0};
+    LaneBits b;
+    lb_start(b, row, active ? start : 0u);
+    uint32_t acc = 0;
+    int32_t s = 32;
+    simt::saddr rowp = orow;
+    uint32_t flags = 0, bad = 0;
+    uint32_t stop = active ? 0u : 1u;
+    uint32_t ngap = 0, gp = 0, gl = 0, gsum = 0;  // the open gap (gl != 0): row position, length; bytes in all gaps
+    uint32_t run_end = K4_INVALID;                // bit position behind the last run token
+    {  // does the lane open with a run token?
+        const uint32_t e = wt_at(t, lb_peek(b));
+        if ((e >> 28) == 0 && !(e & UW_EOB)) flags |= CF_FIRSTRUN;
+    }
+#define K4_APPEND(e, k8)                                   \
+    do {                                                   \
+        const uint32_t word_ = simt::funnel_rc(acc, (e), (uint32_t)s); \
+        acc = simt::funnel_r(acc, (e), (k8));              \
+        s -= (int32_t)(k8);                                \
+        if (s <= 0) {                                      \
+            simt::sts32(rowp, word_);                      \
+            rowp += 128u;                                  \
+            s += 32;                                       \
+        }                                                  \
+    } while (0)
+    // a length token: zeros into the row while the literals that can still follow fit behind them, else a gap
+    auto run_token = [&](uint32_t e, uint32_t bits) -> uint32_t {
+        uint32_t n, len, bd;
+        uf_long_run(e, bits, n, len, bd);
+        bad |= bd | (b.rp == run_end ? 0u : acc >> 24);  // distance bit 1, or the byte before the run is not a zero
+        run_end = b.rp + n;
+        const uint32_t f = (uint32_t)(32 - s) >> 3;
+        const uint32_t fill = ((uint32_t)(rowp - orow) >> 5) + f;
+        const uint32_t lits = run_end < K4_LIM_HI ? (K4_LIM_HI - run_end + 1u) >> 1 : 0u;  // literals that can still follow
+        // Room: a new gap needs a literal (>= 2 bits, one row byte) and a length token (>= 10 bits) since the last
+        // one, which frees 5 bytes of the literal reservation for the word it takes, so gaps alone can never use
+        // the row up, except for one or two near LIM_HI where the reservation is already gone: runs kept in the row
+        // leave K4_ROW_SLACK words for those.
+        if (((fill + len + lits + 3u) >> 2) + 1u + ngap + K4_ROW_SLACK <= K4_OROWW) {
+            const uint32_t tot = f + len;
+            if (tot < 4u) {
+                acc >>= 8u * len;
+                s -= (int32_t)(8u * len);
+            } else {
+                simt::sts32(rowp, s >= 32 ? 0u : acc >> s);
+                rowp += 128u;
+#pragma unroll 1
+                for (uint32_t z = (tot - 4u) >> 2; z; z--) {
+                    simt::sts32(rowp, 0u);
+                    rowp += 128u;
+                }
+                acc = 0;
+                s = 32 - 8 * (int32_t)((tot - 4u) & 3u);
+            }
+        } else if (gl != 0 && fill == gp) {
+            gl += len;  // sym-285 chains and their tail token: one gap
+            gsum += len;
+        } else {
+            if (gl != 0) simt::sts32(orow + 128u * (K4_OROWW - ngap), gp | (gl << K4_GAP_POS_BITS));
+            if (((fill + lits + 3u) >> 2) + 2u + ngap > K4_OROWW) {
+                bad |= 1u;  // no room for another gap (K3 decodes the stream)
+                gl = 0;
+            } else {
+                ngap++;
+                gp = fill;
+                gl = len;
+                gsum += len;
+            }
+        }
+        return n;
+    };
+    // main loop: two entries per 32-bit window; together they consume <= 24 bits, so neither can cross LIM_HI
+    while (!stop && b.rp <= K4_LIM_HI - K4_PAIR) {
+        const uint32_t bits = lb_peek(b);
+        const uint32_t e1 = wt_at(t, bits);
+        uint32_t n;
+        if ((e1 >> 28) == 0) {
+            if (e1 & UW_EOB) {
+                flags |= CF_EOB;
+                stop = 1;
+                n = 0;
+            } else {
+                n = run_token(e1, bits);
+            }
+        } else {
+            K4_APPEND(e1, (e1 >> 25) & 0x18u);
+            n = (e1 >> 24) & 15u;
+            const uint32_t e2 = wt_at(t, bits >> n);  // special: 0 bytes, 0 bits -> comes back as a first entry
+            K4_APPEND(e2, (e2 >> 25) & 0x18u);
+            n += (e2 >> 24) & 15u;
+        }
+        lb_advance(b, n);
+    }
+    // tail: single tokens up to the first token boundary >= LIM_HI
+    while (!stop && b.rp < K4_LIM_HI) {
+        const uint32_t bits = lb_peek(b);
+        const uint32_t e = wt_at(t, bits);
+        uint32_t n;
+        if ((e >> 28) == 0) {
+            if (e & UW_EOB) {
+                flags |= CF_EOB;
+                stop = 1;
+                n = 0;
+            } else {
+                n = run_token(e, bits);
+            }
+        } else {
+            const uint32_t lit = e & 0xffu;
+            K4_APPEND(lit, 8u);
+            n = (ct_at(t, bits) >> 7) & 15u;  // bits of the first token alone
+        }
+        lb_advance(b, n);
+    }
+#undef K4_APPEND
+    if (active) {
+        const uint32_t f = (uint32_t)(32 - s) >> 3;
+        if (f) simt::sts32(rowp, acc >> s);
+        if (gl != 0) simt::sts32(orow + 128u * (K4_OROWW - ngap), gp | (gl << K4_GAP_POS_BITS));
+        c.end = b.rp;
+        c.fill = ((uint32_t)(rowp - orow) >> 5) + f;
+        c.ngap = ngap;
+        c.cnt = c.fill + gsum;
+        c.flags = flags | (bad ? CF_BAD : 0u) | ((b.rp != run_end && (acc >> 24)) ? CF_LASTNZ : 0u);
+    }
+    return c;
+}
+
 // warm-up: tokens from a guessed start until the first boundary >= LIM_LO
 FDB_DEVICE uint32_t warm_up(const UfTabs& t, simt::saddr row, uint32_t active) {
     LaneBits b;
@@ -256,6 +430,38 @@ FDB_DEVICE uint32_t warm_up(const UfTabs& t, simt::saddr row, uint32_t active) {
     return (active && !dead) ? b.rp : K4_INVALID;
 }
 
+// Copy `len` bytes of the lane's output row, from byte `a`, to window position `d` (which may lie partly or
+// wholly outside the window [0, K4_WIN): only the part inside is written).  Word-wise: every destination
+// word is one funnel shift of two row words; the first and the last word of the piece are shared with the
+// neighbouring pieces and are written byte by byte.
+FDB_DEVICE void k4_copy_piece(simt::saddr orow, simt::saddr win_s, uint32_t a, uint32_t len, int32_t d) {
+    const int32_t lo = d < 0 ? 0 : d;
+    int32_t hi = d + (int32_t)len;
+    if (hi > (int32_t)K4_WIN) hi = (int32_t)K4_WIN;
+    if (hi <= lo) return;
+    const uint32_t sa = a + (uint32_t)(lo - d);
+    const uint32_t db = (uint32_t)lo & 3u;
+    const int32_t q = (int32_t)sa - (int32_t)db;  // row byte that lands on byte 0 of the first destination word (>= -3)
+    const uint32_t sh = ((uint32_t)q & 3u) * 8u;
+    const int32_t qw = q >> 2;                    // -1: that word starts before the row (its bytes are masked)
+    const simt::saddr sp = orow + (simt::saddr)(qw + 1) * 128u;  // the word after
+    const simt::saddr dp = win_s + ((uint32_t)lo & ~3u);
+    const uint32_t left = db + (uint32_t)(hi - lo);  // from the start of the first destination word to the end of the piece
+    uint32_t w_lo = qw >= 0 ? simt::lds32(sp - 128u) : 0u;
+    for (uint32_t j4 = 0; j4 < left; j4 += 4u) {
+        const uint32_t w_hi = simt::lds32(sp + j4 * 32u);
+        const uint32_t v = simt::funnel_r(w_lo, w_hi, sh);
+        w_lo = w_hi;
+        if (j4 >= db && j4 + 4u <= left) {
+            simt::sts32(dp + j4, v);
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++)
+                simt::sts8_if(dp + j4 + k, v >> (8u * k), j4 + k >= db && j4 + k < left);
+        }
+    }
+}
+
 struct K4Stream {
     const uint8_t* in;
     uint64_t n;
@@ -272,9 +478,10 @@ struct K4Stream {
 // equal the position where the span before it stopped, and span 0 starts at the exact first data bit, so
 // equality along the chain proves every span (split_scan_kernel; anything else sends the stream to K3).
 // A prefix sum of the byte counts gives every span its output offset, and a WRITE pass decodes the spans
-// again, each into its own part of the slot.  K4_WHOLE is the ordinary one-warp-per-stream decode.
+// (the single-pass decode above), each into its own part of the slot.  K4_WHOLE is the ordinary
+// one-warp-per-stream decode.
 enum : int { K4_WHOLE = 0, K4_COUNT = 1, K4_WRITE = 2 };
-static const uint32_t K4_SPAN_SEGS = 64;                            // segments per span (64 KiB of compressed data)
+static const uint32_t K4_SPAN_SEGS = 64;                            // segments per span (64 KiB of compressed data at SUBW = 8)
 static const uint64_t K4_SPAN_WORDS = (uint64_t)K4_SPAN_SEGS * 32 * K4_SUBW;
 enum : uint32_t { SP_EOB = 1, SP_FIRSTRUN = 2, SP_LASTNZ = 4, SP_DEAD = 8, SP_SKIP = 16, SP_SYNCFAIL = 32 };
 static const uint32_t K4_NO_ITEM = 0xffffffffu;
@@ -328,10 +535,11 @@ template <int MODE>
 FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& ws, const K4Stream& s, uint32_t flags,
                                   uint64_t* out_len, uint64_t* consumed, const K4Span* sp, K4SpanOut* so) {
     const unsigned lane = simt::lane_id();
-    uint32_t* stg = ws.stg;
-    const simt::saddr row = simt::smem_addr(ws.stg + lane);
-    uint8_t* win = ws.win;
-    const simt::saddr win_s = simt::smem_addr(ws.win);
+    uint32_t* stg = ws.u.stg;
+    const simt::saddr row = simt::smem_addr(ws.u.stg + lane);
+    uint8_t* win = ws.u.win;
+    const simt::saddr win_s = simt::smem_addr(ws.u.win);
+    const simt::saddr orow = simt::smem_addr(ws.rows + lane);
     if (MODE == K4_WHOLE) {
         *out_len = 0;
         *consumed = 0;
@@ -389,29 +597,27 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
         lo_vo = oalign + o0;
         win_vo = lo_vo & ~(uint64_t)15;
     }
+    if (MODE != K4_COUNT) {
+        simt::syncwarp();
+        if (lane == 0) ws.carry = make_uint4(0, 0, 0, 0);
+    }
 
-    // zero the output window
-    for (uint32_t v = lane; v < (K4_WIN + 16) / 16; v += 32) ((uint4*)win)[v] = make_uint4(0, 0, 0, 0);
-    simt::syncwarp();
-
-    // Store the finished vectors win[0 .. 16*nvec) at virtual position win_vo, feed adler32, and zero
-    // them again.  Bytes outside [oalign, stream_end_vo) (first / last vector of the stream) are masked.
+    // Store the finished vectors win[0 .. 16*nvec) at virtual position win_vo and feed adler32.
+    // Bytes outside [lo_vo, stream_end_vo) (first / last vector of the stream or span) are masked.
     auto flush_vectors = [&](uint32_t nvec, uint64_t stream_end_vo) {
         if (win_vo >= lo_vo && win_vo + 16ull * nvec <= stream_end_vo) {
             // every vector lies inside the stream (all segments but the first / last of a stream)
             uint8_t* const dst = obase + win_vo;
             const uint64_t pos0 = win_vo - oalign;
             for (uint32_t v = lane; v < nvec; v += 32) {
-                uint4 q = ((const uint4*)win)[v];
-                ((uint4*)win)[v] = make_uint4(0, 0, 0, 0);
+                const uint4 q = ((const uint4*)win)[v];
                 simt::stcs128((uint4*)(dst + 16u * v), q);
                 adler_add16(ad, q, pos0 + 16u * v);
             }
             return;
         }
         for (uint32_t v = lane; v < nvec; v += 32) {
-            uint4 q = ((const uint4*)win)[v];
-            ((uint4*)win)[v] = make_uint4(0, 0, 0, 0);
+            const uint4 q = ((const uint4*)win)[v];
             uint64_t vo = win_vo + 16ull * v;
             bool head_cut = vo < lo_vo;
             bool tail_cut = vo + 16 > stream_end_vo;
@@ -431,6 +637,15 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
             }
         }
     };
+    // the bytes produced so far that have not left yet (fewer than 16) are in ws.carry: store them
+    auto flush_carry = [&](uint64_t end_vo) {
+        const uint32_t left = (uint32_t)(end_vo - win_vo);
+        simt::syncwarp();
+        if (lane == 0) ((uint4*)win)[0] = ws.carry;
+        simt::syncwarp();
+        flush_vectors((left + 15) / 16, end_vo);
+        simt::syncwarp();
+    };
 
     for (;;) {
         if (MODE != K4_WHOLE && seg_word >= sp->stop_word) {
@@ -441,9 +656,7 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                 so->flags |= prev_nz ? SP_LASTNZ : 0u;
             }
             if (MODE == K4_WRITE) {
-                const uint32_t left = (uint32_t)(oalign + o0 - win_vo);
-                flush_vectors((left + 15) / 16, oalign + o0);
-                simt::syncwarp();
+                flush_carry(oalign + o0);
                 so->ad = ad;
             }
             return ST_OK;
@@ -453,16 +666,17 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
 
         // ---- 1. stage: coalesced 16-byte loads, every word scattered to the row(s) that can see it ----
         simt::syncwarp();
-        // (lane l takes vectors 2l, 2l+1, then 64+l: within one store instruction every lane writes a
-        // different row, i.e. a different bank)
+        // (lane l takes the VPR vectors of row l, then the vectors behind row 31: within one store
+        // instruction every lane writes a different row, i.e. a different bank)
         const bool seg_inside = (s0 << 2) >= first_byte && (s0 << 2) + 4ull * K4_SEG_WORDS <= end_byte;
         if (seg_inside) {
             // the next segment's lines are needed in a few thousand cycles: start them towards L2 now
             const uint64_t pf = (s0 << 2) + 4u * 32u * K4_SUBW + 128u * lane;
-            if (lane < 9 && pf < end_byte) simt::prefetch_l2(abase + pf);  // (only lines that hold stream bytes)
+            if (lane < (4u * 32u * K4_SUBW + 127u) / 128u + 1u && pf < end_byte) simt::prefetch_l2(abase + pf);  // (only lines that hold stream bytes)
         }
-        for (uint32_t it = 0; it < 3; it++) {
-            const uint32_t v = it < 2 ? 2u * lane + it : 64u + lane;
+#pragma unroll
+        for (uint32_t it = 0; it <= K4_VPR; it++) {
+            const uint32_t v = it < K4_VPR ? K4_VPR * lane + it : 32u * K4_VPR + lane;
             if (v >= K4_SEG_WORDS / 4) continue;
             uint64_t byte0 = (s0 << 2) + 16ull * v;  // relative to abase
             uint4 q = make_uint4(0, 0, 0, 0);
@@ -479,23 +693,24 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                     q = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
-            // staged word t = 4v + j is word (t & 7) of row (t >> 3) and word (t & 7) + 8 of the row before
-            const uint32_t r1 = v >> 1, c1 = (v & 1) * 4;
+            // staged word 4v + j is word c1 + j of row r1 and word c1 + j + SUBW of the row before
+            const uint32_t r1 = (4u * v) / K4_SUBW, c1 = (4u * v) % K4_SUBW;
             const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (uint32_t j = 0; j < 4; j++) {
                 if (r1 < 32) stg[(c1 + j) * 32 + r1] = w4[j];
-                if (r1 >= 1 && c1 + j + 8 < K4_ROWW) stg[(c1 + j + 8) * 32 + (r1 - 1)] = w4[j];
+                if (r1 >= 1 && c1 + j + K4_SUBW < K4_ROWW) stg[(c1 + j + K4_SUBW) * 32 + (r1 - 1)] = w4[j];
             }
         }
         simt::syncwarp();
 
-        // ---- 2. count ----
+        // ---- 2. / 3. warm up, then decode (the count pass of the span path only counts) ----
         uint32_t start = warm_up(t, row, lane != 0);
         if (lane == 0) start = (uint32_t)(p0 - (s0 << 5));
-        LaneCount c = count_tokens(t, row, start, start != K4_INVALID);
+        LaneCount c = MODE == K4_COUNT ? count_tokens(t, row, start, start != K4_INVALID)
+                                       : decode_tokens(t, row, start, start != K4_INVALID, orow);
 
-        // ---- 3. verify the chain: my start must be my predecessor's end (rows are 32*SUBW bits apart) ----
+        // ---- 4. verify the chain: my start must be my predecessor's end (rows are 32*SUBW bits apart) ----
         uint32_t eob_lane = 32;
         for (;;) {
             uint32_t prev_end = simt::shfl_up(c.end, 1);
@@ -514,7 +729,7 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
             // re-run the lanes whose start disagrees with their predecessor's end
             bool redo = mismatch && !(prev_flags & CF_EOB) && prev_end != K4_INVALID;
             if (mismatch) start = redo ? want : K4_INVALID;
-            LaneCount c2 = count_tokens(t, row, start, redo);
+            LaneCount c2 = MODE == K4_COUNT ? count_tokens(t, row, start, redo) : decode_tokens(t, row, start, redo, orow);
             if (mismatch) c = c2;  // (unresolved lanes get end = INVALID, cnt = 0, flags = 0)
         }
         if (lane > eob_lane) {
@@ -535,12 +750,11 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
         }
         if (simt::any((c.flags & CF_BAD) != 0)) return ST_PENDING_GENERAL;
 
-        // ---- 4. scan ----
+        // ---- 5. scan ----
         const uint32_t incl = simt::scan_incl_add(c.cnt);
         const uint64_t seg_bytes = simt::shfl(incl, 31);
         if (o0 + seg_bytes > s.cap) return ST_PENDING_GENERAL;  // K3 reports OutputTooLarge
-        uint64_t op = oalign + o0 + (incl - c.cnt);             // my virtual output position
-        const uint64_t my_end_vo = op + c.cnt;
+        const uint64_t op = oalign + o0 + (incl - c.cnt);       // my virtual output position
         {
             // a lane that opens with a run needs a zero byte before it: the last byte of the nearest
             // lane below that produced anything, else the last byte of the previous segment
@@ -559,120 +773,46 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
             if (has_mask) prev_nz = (nz_mask >> (31u - simt::clz(has_mask))) & 1u;
         }
 
-        // ---- 5. write ----
-        // The window base slides with the output: it is the 16-byte vector holding the first byte of
-        // this segment, so a segment whose output fits in K4_WIN is written by all lanes at once.
-        // Only literals are stored; runs are zeros and the window is zero-initialised.
+        // ---- 6. move the rows into the window, window by window ----
+        // The window base is the 16-byte vector holding the first byte of this segment, so a segment whose
+        // output fits in K4_WIN takes one pass.  The window is zero apart from the vector carried over from
+        // the previous segment; gaps (zero runs) are skipped.
         const uint64_t seg_end_vo = oalign + o0 + seg_bytes;
-        LaneBits b;
-        lb_start(b, row, start != K4_INVALID ? start : 0u);
-        uint32_t fin = (start == K4_INVALID || lane > eob_lane) ? 1u : 0u;  // no more tokens to decode
-        for (; MODE != K4_COUNT;) {
-            const uint64_t wend = win_vo + K4_WIN;
-            const bool mine = !fin && op < wend;
-            uint32_t wp = mine ? (uint32_t)(op - win_vo) : 0u;
-            if (mine && my_end_vo <= wend) {
-                // fast path: everything this lane still has to write fits in the window
-                simt::saddr wptr = win_s + wp;
-                while (!fin && b.rp <= K4_LIM_HI - K4_PAIR) {
-                    const uint32_t bits = lb_peek(b);
-                    const uint32_t e1 = wt_at(t, bits);
-                    const uint32_t k1 = e1 >> 28;
-                    uint32_t n;
-                    if (k1 == 0) {
-                        if (e1 & UW_EOB) {
-                            fin = 1;
-                            n = 0;
-                        } else {
-                            uint32_t len, bd;
-                            uf_long_run(e1, bits, n, len, bd);
-                            wptr += len;
-                        }
-                    } else {
-                        // exact stores: the byte after this lane's last one belongs to the next lane
-                        simt::sts8(wptr, e1);
-                        simt::sts8_if(wptr + 1, e1 >> 8, k1 >= 2);
-                        simt::sts8_if(wptr + 2, e1 >> 16, k1 >= 3);
-                        wptr += k1;
-                        n = (e1 >> 24) & 15u;
-                        const uint32_t e2 = wt_at(t, bits >> n);  // special: 0 bytes, 0 bits -> next trip
-                        const uint32_t k2 = e2 >> 28;
-                        simt::sts8_if(wptr, e2, k2 >= 1);
-                        simt::sts8_if(wptr + 1, e2 >> 8, k2 >= 2);
-                        simt::sts8_if(wptr + 2, e2 >> 16, k2 >= 3);
-                        wptr += k2;
-                        n += (e2 >> 24) & 15u;
-                    }
-                    lb_advance(b, n);
-                }
-                while (!fin && b.rp < K4_LIM_HI) {  // single tokens up to the first boundary >= LIM_HI
-                    const uint32_t bits = lb_peek(b);
-                    const uint32_t e = wt_at(t, bits);
-                    const uint32_t k = e >> 28;
-                    uint32_t n;
-                    if (k == 0) {
-                        if (e & UW_EOB) {
-                            fin = 1;
-                            n = 0;
-                        } else {
-                            uint32_t len, bd;
-                            uf_long_run(e, bits, n, len, bd);
-                            wptr += len;
-                        }
-                    } else {
-                        const uint32_t c1 = ct_at(t, bits);
-                        if (c1 & UC_RUN) {
-                            wptr += k;
-                            n = (e >> 24) & 15u;
-                        } else {
-                            simt::sts8(wptr, e);
-                            wptr += 1u;
-                            n = (c1 >> 7) & 15u;
+        if (MODE != K4_COUNT) {
+            const uint32_t npieces = c.cnt != 0 ? c.ngap + 1u : 0u;
+            simt::syncwarp();  // every lane is done with the staging rows
+            for (;;) {
+                const uint64_t wend = win_vo + K4_WIN;
+                const uint32_t need = seg_end_vo < wend ? (uint32_t)(seg_end_vo - win_vo) : K4_WIN;
+                for (uint32_t v = lane; v <= need / 16 && v < K4_WIN / 16; v += 32)
+                    ((uint4*)win)[v] = v == 0 ? ws.carry : make_uint4(0, 0, 0, 0);
+                simt::syncwarp();
+                {
+                    int32_t dpos = (int32_t)(int64_t)(op - win_vo);
+                    uint32_t a = 0;
+                    for (uint32_t g = 0; simt::any(g < npieces); g++) {
+                        if (g < npieces) {
+                            uint32_t pe = c.fill, gl = 0;
+                            if (g < c.ngap) {
+                                const uint32_t ge = simt::lds32(orow + 128u * (K4_OROWW - 1u - g));
+                                pe = ge & ((1u << K4_GAP_POS_BITS) - 1u);
+                                gl = ge >> K4_GAP_POS_BITS;
+                            }
+                            k4_copy_piece(orow, win_s, a, pe - a, dpos);
+                            dpos += (int32_t)(pe - a + gl);
+                            a = pe;
                         }
                     }
-                    lb_advance(b, n);
                 }
-                fin = 1;
-                wp = (uint32_t)(wptr - win_s);
-            } else if (mine) {
-                // careful path: this lane's output crosses the window end (long runs); single tokens,
-                // stop at the window end and resume after the flush
-                while (wp < K4_WIN && !fin) {
-                    const uint32_t bits = lb_peek(b);
-                    const uint32_t e = wt_at(t, bits);
-                    const uint32_t k = e >> 28;
-                    uint32_t n;
-                    if (k == 0) {
-                        if (e & UW_EOB) {
-                            fin = 1;
-                            n = 0;
-                        } else {
-                            uint32_t len, bd;
-                            uf_long_run(e, bits, n, len, bd);
-                            wp += len;
-                        }
-                    } else {
-                        const uint32_t c1 = ct_at(t, bits);
-                        if (c1 & UC_RUN) {
-                            wp += k;
-                            n = (e >> 24) & 15u;
-                        } else {
-                            simt::sts8(win_s + wp, e);
-                            wp += 1u;
-                            n = (c1 >> 7) & 15u;
-                        }
-                    }
-                    lb_advance(b, n);
-                    if (b.rp >= K4_LIM_HI) fin = 1;
-                }
+                simt::syncwarp();
+                if (seg_end_vo < wend) break;  // the rest of this segment is in the window
+                // the window is complete: flush all of it and slide by K4_WIN
+                flush_vectors(K4_WIN / 16, ~0ull);
+                win_vo = wend;
+                simt::syncwarp();
+                if (lane == 0) ws.carry = make_uint4(0, 0, 0, 0);
+                simt::syncwarp();
             }
-            if (mine) op = win_vo + wp;
-            simt::syncwarp();
-            if (seg_end_vo < wend) break;  // the rest of this segment fits: leave it in the window
-            // the window is complete: flush all of it and slide by K4_WIN
-            flush_vectors(K4_WIN / 16, ~0ull);
-            simt::syncwarp();
-            win_vo = wend;
         }
 
         // ---- next segment or finish ----
@@ -709,19 +849,12 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
             if (!(flags & FLAG_IGNORE_ADLER32) && got != stored) return ST_WRONG_CHECKSUM;
             return ST_OK;
         }
-        // flush the finished vectors of this segment and slide the window base to the vector that
-        // holds the next output byte (its already-written bytes move to win[0..16))
+        // store the finished vectors of this segment; the vector that holds the next output byte is carried
+        // over (the staging rows of the next segment take the window's memory)
         if (MODE != K4_COUNT) {
             const uint32_t nvec = (uint32_t)((seg_end_vo - win_vo) >> 4);
-            uint4 tail = ((const uint4*)win)[nvec];
-            simt::syncwarp();
             flush_vectors(nvec, ~0ull);
-            simt::syncwarp();
-            if (nvec > 0 && lane == 0) {
-                ((uint4*)win)[nvec] = make_uint4(0, 0, 0, 0);
-                ((uint4*)win)[0] = tail;
-            }
-            simt::syncwarp();
+            if (lane == 0) ws.carry = ((const uint4*)win)[nvec];
             win_vo += 16ull * nvec;
         }
         p0 = ((s0 + (uint64_t)K4_SUBW * 31) << 5) + simt::shfl(c.end, 31);

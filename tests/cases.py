@@ -144,3 +144,39 @@ def damaged(rng: random.Random, s: bytes, cap: int):
         b[rng.randrange(54, len(b))] ^= 1 << rng.randrange(8)
         out.append((bytes(b), cap + 100))
     return out
+
+
+def uf_row_cases(seed: int):
+    """Ultra-fast-format streams that stress the single-pass decoder's lane rows (inflate_uf.cuh): rows full of
+    2-bit literals, zero runs kept in the row, runs that become gaps, more gaps than a lane's list holds, run
+    chains, and mixtures.  -> (mixed, gap_heavy): lists of (stream, expected output); all stay on the fast path."""
+    rng = random.Random(seed)
+    lit = lambda: rng.choice([1, 2, 3, 254, 255, 7, 9, 130, rng.getrandbits(8) | 1])
+    fast, overflow = [], []
+    fast.append(uf_craft.encode([0] * 6000))                                   # 128 literals per lane
+    fast.append(uf_craft.encode([rng.choice([0, 0, 0, 1, 255]) for _ in range(9000)]))
+    t = []
+    for _ in range(1500):                                                     # short runs: zeros inside the rows
+        t += [lit() for _ in range(rng.randrange(0, 4))] + [0, ("m", rng.randrange(3, 41))]
+    fast.append(uf_craft.encode(t))
+    t = []
+    for _ in range(600):                                                      # a few long runs per lane: gaps
+        t += [lit() for _ in range(rng.randrange(10, 40))] + [0, ("m", rng.choice([150, 200, 257, 258]))]
+        if rng.random() < 0.3:
+            t += [("m", 258)] * rng.randrange(1, 4) + [("m", rng.randrange(3, 259))]
+    fast.append(uf_craft.encode(t))
+    t = []
+    for _ in range(2500):                                                     # anything goes
+        r = rng.random()
+        if r < 0.25:
+            t += [0, ("m", rng.choice([3, 4, 8, 12, 13, 31, 64, 100, 130, 258, rng.randrange(3, 259)]))]
+        elif r < 0.3:
+            t += [0] + [("m", 258)] * rng.randrange(1, 30)
+        else:
+            t += [rng.choice([0, 0, 1, 255, lit()]) for _ in range(rng.randrange(1, 30))]
+    fast.append(uf_craft.encode(t))
+    fast.append(uf_craft.encode([0] + [("m", 258)] * 3000 + [1, 2, 3]))          # one gap spanning many segments
+    # a long run behind every other literal: as many gaps as a lane can ever see (each takes a word of its row)
+    overflow.append(uf_craft.encode([x for _ in range(400) for x in (lit(), 0, ("m", 258))]))
+    overflow.append(uf_craft.encode([x for _ in range(900) for x in (0, ("m", 258), 1, 0, ("m", 200), 0)]))
+    return fast, overflow

@@ -71,6 +71,25 @@ def test_inflate_fast_path_foreign_token_sequences(emul_ctx, oracle):
     parity.check_inflate(emul_ctx, c, 0)
 
 
+def test_inflate_fast_path_rows_and_gaps(emul_ctx, oracle):
+    """The single-pass decoder's lane rows: literal-only rows, zero runs inside the rows, runs that become
+    gaps, a gap behind every other literal, exact-fit and short slots, unaligned slots."""
+    fast, overflow = cases.uf_row_cases(11)
+    for s, e in fast + overflow:
+        assert e is not None and oracle.inflate_into(s, len(e))[:2] == (0, e)
+    c = [(s, len(e)) for s, e in fast]
+    parity.check_inflate(emul_ctx, c, 0, expect_general=0)
+    parity.check_inflate(emul_ctx, c, 0, align=1, expect_general=0)
+    parity.check_inflate(emul_ctx, [(s, n + 5) for s, n in c], 0, expect_general=0)
+    parity.check_inflate(emul_ctx, [(s, n - 1) for s, n in c], 0)
+    parity.check_inflate(emul_ctx, [(s, len(e)) for s, e in overflow], 0, expect_general=0)
+    rng = random.Random(5)
+    dmg = []
+    for s, n in c:
+        dmg += cases.damaged(rng, s, n)
+    parity.check_inflate(emul_ctx, dmg, 0)
+
+
 def test_batch_composition_invariance(emul_ctx, oracle):
     """a stream's result must not depend on its neighbours or its position in the batch."""
     rng = random.Random(8)
