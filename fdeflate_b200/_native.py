@@ -99,7 +99,7 @@ class NativeLib:
         L.fdb_png_probe_batch.restype = C.c_int
         L.fdb_png_probe_batch.argtypes = [vp] * 9 + [sz]
         L.fdb_png_decode_files_batch.restype = C.c_int
-        L.fdb_png_decode_files_batch.argtypes = [vp] * 7 + [sz]
+        L.fdb_png_decode_files_batch.argtypes = [vp] * 8 + [sz]
         L.fdb_png_file_bound.restype = sz
         L.fdb_png_file_bound.argtypes = [C.c_uint32] * 4
         L.fdb_png_encode_files_batch.restype = C.c_int

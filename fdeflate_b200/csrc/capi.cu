@@ -584,17 +584,56 @@ static bool uniform_stride(const uint64_t* off, size_t n, uint64_t* stride) {
     return true;
 }
 
-// Copies rows [a, b) of a slot array between host and device: one 2-D copy of the used prefix of every
-// slot when the slots are evenly spaced and mostly empty, else the contiguous span.
-static int copy_rows(fdb_ctx* ctx, uint8_t* dst_base, const uint8_t* src_base, const uint64_t* off, size_t a, size_t b,
-                     uint64_t width, uint64_t last_extent, bool uniform, uint64_t stride, cudaMemcpyKind kind,
+// Copies the used part of rows [a, b) of a slot array between host and device.  ext[i] (clamped to cap[i] when
+// given) is what row i holds.  Evenly spaced, mostly empty slots: one 2-D copy moves the widest row's width of every
+// row BUT THE LAST (whose slot may end before that width does -- the caller's buffer ends with it), and a 1-D copy
+// moves the last row's own extent.  Anything else: one copy per run of adjacent slots (up to 64 runs, which covers
+// slots in any order), else one contiguous copy of the hull [min off, max off + ext).  Bytes between slots may be
+// copied along; nothing outside the hull is touched.
+static int copy_rows(fdb_ctx* ctx, uint8_t* dst_base, const uint8_t* src_base, const uint64_t* off, const uint64_t* ext,
+                     const uint64_t* cap, size_t a, size_t b, bool uniform, uint64_t stride, cudaMemcpyKind kind,
                      cudaStream_t st) {
+    uint64_t lo = ~0ull, hi = 0, width = 0;
+    auto extent = [&](size_t i) { return cap ? std::min(ext[i], cap[i]) : ext[i]; };
+    for (size_t i = a; i < b; i++) {
+        const uint64_t e = extent(i);
+        if (!e) continue;
+        lo = std::min(lo, off[i]);
+        hi = std::max(hi, off[i] + e);
+        width = std::max(width, e);
+    }
+    if (hi <= lo) return 0;
     const size_t rows = b - a;
-    const uint64_t span = off[b - 1] + last_extent - off[a];
-    if (uniform && rows > 1 && width <= stride && width * rows < span - span / 8) {
-        if (width) FDB_TRY(cudaMemcpy2DAsync(dst_base + off[a], stride, src_base + off[a], stride, width, rows, kind, st));
-    } else if (span) {
-        FDB_TRY(cudaMemcpyAsync(dst_base + off[a], src_base + off[a], span, kind, st));
+    const uint64_t span = hi - lo;
+    if (uniform && rows > 2 && width <= stride && width * rows < span - span / 8) {
+        FDB_TRY(cudaMemcpy2DAsync(dst_base + off[a], stride, src_base + off[a], stride, width, rows - 1, kind, st));
+        const uint64_t e = extent(b - 1);
+        if (e) FDB_TRY(cudaMemcpyAsync(dst_base + off[b - 1], src_base + off[b - 1], e, kind, st));
+    } else {
+        // runs of slots that follow each other (ascending, less than 256 bytes apart) travel in one copy each; if that
+        // makes too many copies (widely and unevenly spaced slots) the whole hull goes in one
+        struct Piece {
+            uint64_t lo, hi;
+        };
+        Piece pieces[64];
+        size_t np = 0;
+        bool ok = true;
+        for (size_t i = a; i < b && ok; i++) {
+            const uint64_t e = extent(i);
+            if (!e) continue;
+            if (np && off[i] >= pieces[np - 1].hi && off[i] - pieces[np - 1].hi < 256)
+                pieces[np - 1].hi = off[i] + e;
+            else if (np == 64)
+                ok = false;
+            else
+                pieces[np++] = {off[i], off[i] + e};
+        }
+        if (!ok) {
+            FDB_TRY(cudaMemcpyAsync(dst_base + lo, src_base + lo, span, kind, st));
+        } else {
+            for (size_t k = 0; k < np; k++)
+                FDB_TRY(cudaMemcpyAsync(dst_base + pieces[k].lo, src_base + pieces[k].lo, pieces[k].hi - pieces[k].lo, kind, st));
+        }
     }
     return 0;
 }
@@ -725,8 +764,7 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
         uint64_t max_in = 0;
         for (size_t i = a; i < b; i++) max_in = std::max(max_in, in_len[i]);
         mark(k, 0, hs);
-        int rr = copy_rows(ctx, ctx->d_in, in_base, in_off, a, b, max_in, in_len[b - 1], in_uniform, in_stride,
-                           cudaMemcpyHostToDevice, hs);
+        int rr = copy_rows(ctx, ctx->d_in, in_base, in_off, in_len, nullptr, a, b, in_uniform, in_stride, cudaMemcpyHostToDevice, hs);
         if (rr) return rr;
         mark(k, 1, hs);
         FDB_TRY(cudaEventRecord(ctx->ev_in[k], hs));
@@ -787,10 +825,8 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     };
     auto finish = [&](size_t k) -> int {  // the results (already on the host) decide how much payload comes back
         const size_t a = k * per, b = std::min(n, a + per);
-        uint64_t max_out = 0;
-        for (size_t i = a; i < b; i++) max_out = std::max(max_out, h_out_len[i]);
         mark(k, 3, ds);
-        int rr = copy_rows(ctx, out_base, ctx->d_out, out_off, a, b, max_out, h_out_len[b - 1], out_uniform, out_stride,
+        int rr = copy_rows(ctx, out_base, ctx->d_out, out_off, h_out_len, out_cap, a, b, out_uniform, out_stride,
                            cudaMemcpyDeviceToHost, ds);
         mark(k, 4, ds);
         return rr;
@@ -1138,33 +1174,45 @@ extern "C" int fdb_png_encode_files_batch(fdb_ctx* ctx, const uint8_t* raw_base,
     if (n > 0xffffffffull || !raw_base || !raw_off || !width || !height || !bit_depth || !color_type || !file_base || !file_off ||
         !file_cap || !file_len || !status)
         return fail(ctx, "fdb_png_encode_files_batch", cudaSuccess);
-    std::vector<uint32_t> stride(n), bpp(n), h(n), crc(n);
-    std::vector<uint64_t> raw_len(n), z_off(n), z_cap(n), z_len(n);
-    std::vector<int32_t> fst(n, 0);
-    std::vector<bool> ok(n);
-    for (size_t i = 0; i < n; i++) {
-        ok[i] = png_geometry(width[i], height[i], bit_depth[i], color_type[i], &stride[i], &bpp[i]) && file_cap[i] > PNG_PRE + PNG_POST;
-        if (!ok[i]) {  // an empty job for the device: zero rows
-            stride[i] = 1;
-            bpp[i] = 1;
-        }
-        h[i] = ok[i] ? height[i] : 0;
-        raw_len[i] = (uint64_t)h[i] * stride[i];
-        z_off[i] = file_off[i] + PNG_PRE;
-        z_cap[i] = ok[i] ? file_cap[i] - PNG_PRE - PNG_POST : 64;
-    }
-    PngPre pre = {h.data(), stride.data(), bpp.data(), mode, fst.data(), crc.data()};
-    int r = host_batch(ctx, 1, raw_base, raw_off, raw_len.data(), file_base, z_off.data(), z_cap.data(), z_len.data(), nullptr, status,
-                       n, 0, &pre);
-    if (r) return r;
-    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    // Only images with a valid geometry and a slot that can hold the framing go to the device (compacted, in
+    // their original order); the others get their status here and no byte of their slot is written.
+    std::vector<size_t> idx;
+    idx.reserve(n);
+    std::vector<uint32_t> stride(n), bpp(n);
     for (size_t i = 0; i < n; i++) {
         file_len[i] = 0;
-        if (!ok[i]) {
+        if (!png_geometry(width[i], height[i], bit_depth[i], color_type[i], &stride[i], &bpp[i]))
             status[i] = ST_PNG_BAD_GEOMETRY;
-            continue;
+        else if (file_cap[i] <= PNG_PRE + PNG_POST)
+            status[i] = ST_OUTPUT_BUFFER_TOO_SMALL;
+        else {
+            status[i] = ST_OK;
+            idx.push_back(i);
         }
-        if (fst[i] != ST_OK) status[i] = fst[i];
+    }
+    const size_t m = idx.size();
+    if (m == 0) return 0;
+    std::vector<uint32_t> c_stride(m), c_bpp(m), c_h(m), crc(m);
+    std::vector<uint64_t> c_raw_off(m), raw_len(m), z_off(m), z_cap(m), z_len(m);
+    std::vector<int32_t> fst(m, 0), zst(m, 0);
+    for (size_t k = 0; k < m; k++) {
+        const size_t i = idx[k];
+        c_stride[k] = stride[i];
+        c_bpp[k] = bpp[i];
+        c_h[k] = height[i];
+        c_raw_off[k] = raw_off[i];
+        raw_len[k] = (uint64_t)height[i] * stride[i];
+        z_off[k] = file_off[i] + PNG_PRE;
+        z_cap[k] = file_cap[i] - PNG_PRE - PNG_POST;
+    }
+    PngPre pre = {c_h.data(), c_stride.data(), c_bpp.data(), mode, fst.data(), crc.data()};
+    int r = host_batch(ctx, 1, raw_base, c_raw_off.data(), raw_len.data(), file_base, z_off.data(), z_cap.data(), z_len.data(), nullptr,
+                       zst.data(), m, 0, &pre);
+    if (r) return r;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    for (size_t k = 0; k < m; k++) {
+        const size_t i = idx[k];
+        status[i] = fst[k] != ST_OK ? fst[k] : zst[k];
         if (status[i] != ST_OK) continue;
         uint8_t* f = file_base + file_off[i];
         memcpy(f, sig, 8);
@@ -1176,14 +1224,14 @@ extern "C" int fdb_png_encode_files_batch(fdb_ctx* ctx, const uint8_t* raw_base,
         f[25] = (uint8_t)color_type[i];
         f[26] = f[27] = f[28] = 0;
         put_be32(f + 29, host_crc32(f + 12, 17));
-        put_be32(f + 33, (uint32_t)z_len[i]);
+        put_be32(f + 33, (uint32_t)z_len[k]);
         memcpy(f + 37, "IDAT", 4);
-        uint8_t* t = f + PNG_PRE + z_len[i];
-        put_be32(t, crc[i]);
+        uint8_t* t = f + PNG_PRE + z_len[k];
+        put_be32(t, crc[k]);
         put_be32(t + 4, 0);
         memcpy(t + 8, "IEND", 4);
         put_be32(t + 12, 0xae426082u);  // crc32("IEND")
-        file_len[i] = PNG_PRE + z_len[i] + PNG_POST;
+        file_len[i] = PNG_PRE + z_len[k] + PNG_POST;
     }
     return 0;
 }
@@ -1337,13 +1385,15 @@ extern "C" int fdb_png_probe_batch(const uint8_t* file_base, const uint64_t* fil
     return 0;
 }
 
-// files -> raw pixels.  raw_off[i] must leave room for height * stride bytes (fdb_png_probe_batch gives both).
+// files -> raw pixels.  Slot i holds raw_cap[i] bytes; a file whose IHDR asks for more (height * stride, see
+// fdb_png_probe_batch) gets status OutputTooLarge before anything is sized from it, so a hostile header can neither
+// overrun a slot nor make the batch's device buffers unallocatable.
 extern "C" int fdb_png_decode_files_batch(fdb_ctx* ctx, const uint8_t* file_base, const uint64_t* file_off,
                                           const uint64_t* file_len, uint8_t* raw_base, const uint64_t* raw_off,
-                                          int32_t* status, size_t n) {
+                                          const uint64_t* raw_cap, int32_t* status, size_t n) {
     if (!ctx) return -1;
     if (n == 0) return 0;
-    if (n > 0xffffffffull || !file_base || !file_off || !file_len || !raw_base || !raw_off || !status)
+    if (n > 0xffffffffull || !file_base || !file_off || !file_len || !raw_base || !raw_off || !raw_cap || !status)
         return fail(ctx, "fdb_png_decode_files_batch", cudaSuccess);
     FDB_TRY(cudaSetDevice(ctx->device));
     std::vector<PngFileInfo> fi(n);
@@ -1352,6 +1402,7 @@ extern "C" int fdb_png_decode_files_batch(fdb_ctx* ctx, const uint8_t* file_base
     uint64_t lo = ~0ull, hi = 0;
     for (size_t i = 0; i < n; i++) {
         png_walk(file_base, file_off[i], file_len[i], (uint32_t)i, fi[i], &chunks);
+        if (fi[i].status == ST_OK && (uint64_t)fi[i].height * fi[i].stride > raw_cap[i]) fi[i].status = ST_OUTPUT_TOO_LARGE;
         lo = std::min(lo, file_off[i]);
         hi = std::max(hi, file_off[i] + file_len[i]);
     }

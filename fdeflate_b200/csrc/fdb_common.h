@@ -132,11 +132,13 @@ FDB_HD uint32_t make_dist_entry(uint32_t sym, uint32_t nbits) {
 
 // ---- constant decode tables of the ultra-fast format (K4 only; index = the next 12 stream bits) ----
 // UW "write table", u32:
-//   literal  [23:0]  the 1..3 leading literals whose codes fit in the 12 bits together, in stream order
-//                    (unused bytes are 0)
-//            [27:24] bits consumed (2..12)      [29:28] bytes produced (1..3), bits 30, 31 = 0
+//   regular  [23:0]  up to three literal bytes in stream order (unused bytes are 0)
+//            [27:24] bits consumed (1..12)      [31:28] bytes produced (1..12)
+//            - literal entry: the 1..3 leading literals whose codes fit in the 12 bits together
+//            - short-run entry: ONE length token whose code + extra bits + distance bit ("0") fit in
+//              the 12 bits; bytes = 0, produced = the match length (3..12)
 //   special  [31:24] == 0:  [3:0] code bits  [6:4] extra-bit count  [7] end of block  [16:8] base length
-//            - end of block, or a length token (its extra bits and distance bit are read from the stream)
+//            - end of block, a length token longer than 12 bits, or a length token with distance bit 1
 // UC "count table", u16 (0 = special, see the write table):
 //   [3:0] bits consumed by the 1..6 leading literals / the one short run     [15:12] bytes they produce
 //   [4] RUN: the entry is a short-run token   [5] ENDNZ: its last byte is non-zero

@@ -134,13 +134,13 @@ static inline bool build_uf_host_tables(UfHostTables& t) {
         } else {
             const uint32_t xb = len_sym_extra((uint32_t)s), base = len_sym_base((uint32_t)s), tot = L + xb + 1u;
             const uint32_t len = base + ((idx >> L) & ((1u << xb) - 1u));  // (only meaningful when tot <= 12)
-            // every length token is a SPECIAL entry of the write table (the decoder appends literals with two
-            // funnel shifts and has no room for a run in that path); the count table keeps the short ones
-            t.wt[uf_slot(idx)] = L | (xb << 4) | (base << 8);
-            if (tot <= 12 && len <= 12 && ((idx >> (L + xb)) & 1u) == 0)  // (symbol 285 = 258 bytes stays special)
+            if (tot <= 12 && len <= 12 && ((idx >> (L + xb)) & 1u) == 0) {  // (symbol 285 = 258 bytes stays special)
+                t.wt[uf_slot(idx)] = (tot << 24) | (len << 28);
                 t.ct[uf_slot(idx)] = (uint16_t)(tot | UC_RUN | (tot << 7) | (len << 12));
-            else
+            } else {
+                t.wt[uf_slot(idx)] = L | (xb << 4) | (base << 8);
                 t.ct[uf_slot(idx)] = 0;
+            }
         }
     }
     return true;

@@ -182,7 +182,10 @@ def encode_batch(images: Sequence[np.ndarray], ctx: Context | None = None, filte
     return files
 
 
-def decode_files_batch(pngs: Sequence[bytes], ctx: Context | None = None) -> list[np.ndarray]:
+MAX_IMAGE_BYTES = 1 << 32  # decode_files_batch: largest raw image (height * stride from the untrusted IHDR) it allocates for
+
+
+def decode_files_batch(pngs: Sequence[bytes], ctx: Context | None = None, max_image_bytes: int = MAX_IMAGE_BYTES) -> list[np.ndarray]:
     """Same result as decode_batch, but the container is handled by the library too (`fdb_png_probe_batch` +
     `fdb_png_decode_files_batch`: chunk walk in C++, chunk CRCs / IDAT gathering / inflate / unfilter on the device),
     so nothing per file or per byte happens in Python."""
@@ -201,11 +204,14 @@ def decode_files_batch(pngs: Sequence[bytes], ctx: Context | None = None) -> lis
         if status[i] != 0:
             raise PngError(f"image {i}: {STATUS_NAMES[status[i]]}")
     raw_sz = h.astype(np.uint64) * stride.astype(np.uint64)
+    for i in range(n):
+        if int(raw_sz[i]) > max_image_bytes:
+            raise PngError(f"image {i}: {int(raw_sz[i])} bytes of pixels exceed max_image_bytes = {max_image_bytes}")
     raw_off = np.zeros(n, dtype=np.uint64)
     raw_off[1:] = np.cumsum((raw_sz[:-1] + np.uint64(15)) & ~np.uint64(15))
     raw = np.zeros(int(raw_off[-1] + raw_sz[-1]) + 16, dtype=np.uint8)
     rc = ctx.lib.L.fdb_png_decode_files_batch(ctx._h, _ptr(base), _ptr(off), _ptr(lens), _ptr(raw), _ptr(raw_off),
-                                              _ptr(status), n)
+                                              _ptr(raw_sz), _ptr(status), n)
     ctx._check(rc, "fdb_png_decode_files_batch")
     out = []
     for i in range(n):

@@ -20,7 +20,15 @@
  *     device memory owned by the context, and return when the results are in the caller's buffers.
  *   - device input buffers must be readable up to the next 16-byte boundary past the last stream
  *     (true for any cudaMalloc'ed buffer).
- *   - a context is bound to one GPU and is not re-entrant; use one context per host thread.
+ *   - slots may come in any order.  The host-buffer entry points move runs of adjacent slots (less than
+ *     256 bytes apart) and evenly spaced slots in one copy each, and a batch of more than 64 widely and
+ *     unevenly spaced slots per pipeline chunk as one range: bytes of out_base BETWEEN slots may therefore be
+ *     overwritten.  Nothing before the first slot or behind the end of the last one is ever touched, and
+ *     nothing outside in_base's [min in_off, max in_off + in_len) is read.
+ *   - a context is bound to one GPU and is not re-entrant; use one context per host thread.  The
+ *     *_device entry points share the context's work counters and scratch: at most ONE device-pointer
+ *     call per context may be in flight on the GPU at a time (enqueue the next one on the same stream, or
+ *     after the previous one has finished; use one context per concurrent stream).
  *   - there is no CPU fallback: without a CUDA device fdb_create fails.
  */
 #ifndef FDEFLATE_B200_H
@@ -159,13 +167,15 @@ int fdb_png_encode_batch(fdb_ctx* ctx, const uint8_t* raw_base, const uint64_t* 
  * inflate and unfilter run on the device.  status: 0, an inflate / unfilter status, or 21 = not a PNG / broken chunk
  * structure / invalid IHDR, 22 = a chunk's CRC-32 does not match, 23 = valid but not decoded here (interlaced).
  *   probe : host only, no context: geometry of every file (stride = bytes per raw row; pixels need height * stride).
- *   decode: raw pixels of file i to raw_base + raw_off[i].  Images whose slots follow each other with less than
- *           16 bytes of padding are copied back in one piece, padding included. */
+ *   decode: raw pixels of file i to raw_base + raw_off[i], a slot of raw_cap[i] bytes.  The sizes come from the
+ *           (untrusted) file: an image that needs more than raw_cap[i] bytes gets status 17 (OutputTooLarge), nothing
+ *           of it is written and the rest of the batch is unaffected.  Images whose slots follow each other with
+ *           less than 16 bytes of padding are copied back in one piece, padding included. */
 int fdb_png_probe_batch(const uint8_t* file_base, const uint64_t* file_off, const uint64_t* file_len, uint32_t* width,
                         uint32_t* height, uint32_t* bit_depth, uint32_t* color_type, uint32_t* stride, int32_t* status,
                         size_t n);
 int fdb_png_decode_files_batch(fdb_ctx* ctx, const uint8_t* file_base, const uint64_t* file_off, const uint64_t* file_len,
-                               uint8_t* raw_base, const uint64_t* raw_off, int32_t* status, size_t n);
+                               uint8_t* raw_base, const uint64_t* raw_off, const uint64_t* raw_cap, int32_t* status, size_t n);
 
 /* ... and the other way: raw pixels (8- or 16-bit gray, gray + alpha, RGB, RGBA; 16-bit samples big-endian as in the
  * file) -> complete PNG files (signature, IHDR, one IDAT chunk holding an ultra-fast zlib stream, IEND) at

@@ -181,29 +181,82 @@ inline std::vector<uint8_t> compress_to_vec_ultra_fast(Context& ctx, const std::
     return Batch(ctx).deflate_ultra_fast({input})[0];
 }
 
-// src/compress/ultrafast.rs:9-181.  W needs `void write(const uint8_t*, size_t)`.  Single write_data call
-// = compress_to_vec_ultra_fast; the Python mirror (fdeflate_b200/api.py) also reproduces the reference's
-// call-boundary-dependent output for several calls by splicing; this header keeps to one call.
+// src/compress/ultrafast.rs:9-181.  W needs `void write(const uint8_t*, size_t)`.
+// The reference's bytes depend on how the input is cut into write_data calls: its zero-run counter and its 8-byte
+// chunking restart with every call (:97-99).  Each call is therefore compressed as its own stream, all of them in ONE
+// device batch at finish(), and their token bits are spliced on the host behind one header: byte for byte what the
+// reference writes for the same call pattern (tests/cpp/test_cpp_api.cpp checks it against the oracle's
+// new / write_data / finish).
+namespace detail {
+// bits [from, to) of `src` (LSB first) appended to `dst` at bit position `pos`
+inline void append_bits(std::vector<uint8_t>& dst, uint64_t& pos, const std::vector<uint8_t>& src, uint64_t from, uint64_t to) {
+    dst.resize((pos + (to - from) + 7) / 8 + 8, 0);
+    for (uint64_t b = from; b < to;) {
+        const uint64_t take = std::min<uint64_t>(to - b, 8 - (b & 7));  // bits of one source byte
+        const uint32_t v = (uint32_t(src[b >> 3]) >> (b & 7)) & ((1u << take) - 1u);
+        const uint32_t sh = uint32_t(pos & 7);
+        dst[pos >> 3] |= uint8_t(v << sh);
+        if (sh + take > 8) dst[(pos >> 3) + 1] |= uint8_t(v >> (8 - sh));
+        pos += take;
+        b += take;
+    }
+}
+// RFC 1950 adler32, continued from `adler` (the checksum of a multi-call stream covers all calls in order)
+inline uint32_t adler32(uint32_t adler, const uint8_t* p, size_t n) {
+    uint32_t a = adler & 0xffffu, b = adler >> 16;
+    while (n) {
+        size_t k = std::min<size_t>(n, 5552);
+        n -= k;
+        while (k--) {
+            a += *p++;
+            b += a;
+        }
+        a %= 65521u;
+        b %= 65521u;
+    }
+    return (b << 16) | a;
+}
+}  // namespace detail
+
 template <class W>
 class UltraFastCompressor {
 public:
     UltraFastCompressor(Context& ctx, W writer) : ctx_(ctx), w_(std::move(writer)) {}
-    void write_data(const uint8_t* data, size_t n) {
-        if (called_) throw std::logic_error("UltraFastCompressor (C++ mirror): one write_data call per stream");
-        called_ = true;
-        buf_.assign(data, data + n);
-    }
+    void write_data(const uint8_t* data, size_t n) { calls_.emplace_back(data, data + n); }
     W finish() {
-        std::vector<uint8_t> z = compress_to_vec_ultra_fast(ctx_, buf_);
-        w_.write(z.data(), z.size());
+        if (calls_.empty()) calls_.emplace_back();
+        std::vector<std::vector<uint8_t>> z = Batch(ctx_).deflate_ultra_fast(calls_);
+        if (z.size() == 1) {
+            w_.write(z[0].data(), z[0].size());
+            return std::move(w_);
+        }
+        const uint64_t header_bits = 53 * 8 + 5;  // ultrafast.rs:87-88
+        std::vector<uint8_t> out;
+        uint64_t pos = 0;
+        detail::append_bits(out, pos, z[0], 0, header_bits);
+        uint32_t adler = 1;
+        for (size_t i = 0; i < z.size(); i++) {
+            // the stream body ends with the 12-bit end-of-block code 0x8ff, whose top bit is the highest set bit
+            // before the 4 checksum bytes (the padding behind it is zero)
+            size_t last = z[i].size() - 5;
+            while (z[i][last] == 0) last--;
+            uint64_t end = 8 * uint64_t(last) + 8;
+            for (uint8_t v = z[i][last]; !(v & 0x80); v = uint8_t(v << 1)) end--;
+            detail::append_bits(out, pos, z[i], header_bits, end - 12);
+            adler = detail::adler32(adler, calls_[i].data(), calls_[i].size());
+        }
+        const std::vector<uint8_t> eob = {0xff, 0x08};  // code 2303, 12 bits
+        detail::append_bits(out, pos, eob, 0, 12);
+        out.resize((pos + 7) / 8);
+        for (int k = 3; k >= 0; k--) out.push_back(uint8_t(adler >> (8 * k)));
+        w_.write(out.data(), out.size());
         return std::move(w_);
     }
 
 private:
     Context& ctx_;
     W w_;
-    std::vector<uint8_t> buf_;
-    bool called_ = false;
+    std::vector<std::vector<uint8_t>> calls_;
 };
 
 // src/compress/mod.rs:47-215 restricted to level 0 ("stored"): block boundaries do not depend on the

@@ -181,10 +181,24 @@ const uint8_t *fdo_length_to_len_extra(void) {
  * (decompress.rs:145,311,318,332; ultrafast.rs:72,95,176).
  * ---------------------------------------------------------------------------------------- */
 uint32_t fdo_adler32(uint32_t adler, const uint8_t *data, size_t len) {
+    /* Same arithmetic as the byte loop (a += d; b += a), regrouped per block of 32 bytes:
+     * b += 32 a + sum (32 - i) d[i]; a += sum d[i] -- two reductions gcc vectorises, so that the CPU baseline is not
+     * held back by a scalar checksum (the reference uses the SIMD crate simd-adler32, Cargo.toml:21). */
     uint32_t a = adler & 0xffff, b = adler >> 16;
     while (len > 0) {
-        size_t n = len < 5552 ? len : 5552; /* largest n with 255n(n+1)/2 + (n+1)(65520) < 2^32 */
+        size_t n = len < 5536 ? len : 5536; /* multiple of 32 below 5552, the largest n that cannot overflow 32 bits */
         len -= n;
+        while (n >= 32) {
+            uint32_t s = 0, w = 0;
+            for (unsigned i = 0; i < 32; i++) {
+                s += data[i];
+                w += (32u - i) * data[i];
+            }
+            b += 32u * a + w;
+            a += s;
+            data += 32;
+            n -= 32;
+        }
         while (n--) {
             a += *data++;
             b += a;
@@ -1231,22 +1245,35 @@ static unsigned lz_bytes(uint64_t v) { return (unsigned)__builtin_clzll(v) / 8; 
 
 size_t fdo_ultrafast_bound(size_t n) { return 54 + (n * 12 + 7) / 8 + 2 + 4 + 8; }
 
-/* compress/mod.rs:313-317 = UltraFastCompressor::new (ultrafast.rs:70-91) + write_data(whole input)
- * (ultrafast.rs:94-167) + finish (ultrafast.rs:170-181) */
-size_t fdo_compress_ultra_fast(const uint8_t *data, size_t n, uint8_t *out, size_t out_cap) {
+/* UltraFastCompressor, call by call (ultrafast.rs:9-181).  The zero-run counter and the 8-byte chunking are LOCAL to
+ * a write_data call (:97-99: `let mut run = 0; let mut chunks = data.chunks_exact(8)`), so the bytes produced depend on
+ * how the input is cut into calls; the bit buffer and the checksum carry over. */
+struct fdo_ultrafast {
+    uf_writer w;
+    uint32_t checksum;
+};
+
+/* new (:70-79) + write_headers (:81-91) */
+fdo_ultrafast *fdo_ultrafast_new(uint8_t *out, size_t out_cap) {
     ensure_init();
-    uf_writer w = {0, 0, out, out_cap, 0, 0};
+    fdo_ultrafast *c = (fdo_ultrafast *)calloc(1, sizeof *c);
+    if (!c) return NULL;
+    c->w.out = out;
+    c->w.cap = out_cap;
+    c->checksum = 1; /* Adler32::new() */
+    uf_write_all(&c->w, UF_HEADER, 53);
+    uf_write_bits(&c->w, UF_HEADER[53], 5);
+    return c;
+}
 
-    /* write_headers :81-91 */
-    uf_write_all(&w, UF_HEADER, 53);
-    uf_write_bits(&w, UF_HEADER[53], 5);
-
-    /* write_data :94-167 */
-    uint32_t checksum = fdo_adler32(1, data, n);
+/* write_data (:94-167) */
+void fdo_ultrafast_write_data(fdo_ultrafast *c, const uint8_t *data, size_t n) {
+    uf_writer *w = &c->w;
+    c->checksum = fdo_adler32(c->checksum, data, n); /* :95 */
     uint32_t run = 0;
     size_t nchunks = n / 8;
-    for (size_t c = 0; c < nchunks; c++) {
-        const uint8_t *chunk = data + 8 * c;
+    for (size_t k8 = 0; k8 < nchunks; k8++) {
+        const uint8_t *chunk = data + 8 * k8;
         uint64_t ichunk;
         memcpy(&ichunk, chunk, 8);
 
@@ -1255,12 +1282,12 @@ size_t fdo_compress_ultra_fast(const uint8_t *data, size_t n, uint8_t *out, size
             continue;
         } else if (run > 0) {
             uint32_t run_extra = tz_bytes(ichunk);
-            uf_write_run(&w, run + run_extra);
+            uf_write_run(w, run + run_extra);
             run = 0;
             if (run_extra > 0) {
                 run = lz_bytes(ichunk);
                 for (unsigned k = run_extra; k < 8 - run; k++)
-                    uf_write_bits(&w, HUFFMAN_CODES[chunk[k]], HUFFMAN_LENGTHS[chunk[k]]);
+                    uf_write_bits(w, HUFFMAN_CODES[chunk[k]], HUFFMAN_LENGTHS[chunk[k]]);
                 continue;
             }
         }
@@ -1268,7 +1295,7 @@ size_t fdo_compress_ultra_fast(const uint8_t *data, size_t n, uint8_t *out, size
         uint32_t run_start = lz_bytes(ichunk);
         if (run_start > 0) {
             for (unsigned k = 0; k < 8 - run_start; k++)
-                uf_write_bits(&w, HUFFMAN_CODES[chunk[k]], HUFFMAN_LENGTHS[chunk[k]]);
+                uf_write_bits(w, HUFFMAN_CODES[chunk[k]], HUFFMAN_LENGTHS[chunk[k]]);
             run = run_start;
             continue;
         }
@@ -1278,25 +1305,39 @@ size_t fdo_compress_ultra_fast(const uint8_t *data, size_t n, uint8_t *out, size
         uint64_t bits = (uint64_t)HUFFMAN_CODES[chunk[0]] | ((uint64_t)HUFFMAN_CODES[chunk[1]] << n0) |
                         ((uint64_t)HUFFMAN_CODES[chunk[2]] << (n0 + n1)) |
                         ((uint64_t)HUFFMAN_CODES[chunk[3]] << (n0 + n1 + n2));
-        uf_write_bits(&w, bits, (uint8_t)(n0 + n1 + n2 + n3));
+        uf_write_bits(w, bits, (uint8_t)(n0 + n1 + n2 + n3));
 
         uint8_t n4 = HUFFMAN_LENGTHS[chunk[4]], n5 = HUFFMAN_LENGTHS[chunk[5]];
         uint8_t n6 = HUFFMAN_LENGTHS[chunk[6]], n7 = HUFFMAN_LENGTHS[chunk[7]];
         uint64_t bits2 = (uint64_t)HUFFMAN_CODES[chunk[4]] | ((uint64_t)HUFFMAN_CODES[chunk[5]] << n4) |
                          ((uint64_t)HUFFMAN_CODES[chunk[6]] << (n4 + n5)) |
                          ((uint64_t)HUFFMAN_CODES[chunk[7]] << (n4 + n5 + n6));
-        uf_write_bits(&w, bits2, (uint8_t)(n4 + n5 + n6 + n7));
+        uf_write_bits(w, bits2, (uint8_t)(n4 + n5 + n6 + n7));
     }
-    if (run > 0) uf_write_run(&w, run);
-    for (size_t k = nchunks * 8; k < n; k++) uf_write_bits(&w, HUFFMAN_CODES[data[k]], HUFFMAN_LENGTHS[data[k]]);
+    if (run > 0) uf_write_run(w, run);
+    for (size_t k = nchunks * 8; k < n; k++) uf_write_bits(w, HUFFMAN_CODES[data[k]], HUFFMAN_LENGTHS[data[k]]);
+}
 
-    /* finish :170-181 */
-    uf_write_bits(&w, HUFFMAN_CODES[256], HUFFMAN_LENGTHS[256]);
-    uf_flush(&w);
-    uint8_t be[4] = {(uint8_t)(checksum >> 24), (uint8_t)(checksum >> 16), (uint8_t)(checksum >> 8),
-                     (uint8_t)checksum};
-    uf_write_all(&w, be, 4);
-    return w.overflow ? 0 : w.pos;
+/* finish (:170-181): end of block, pad to a byte, checksum big-endian.  Returns the stream length (0 = the
+ * buffer was too small) and frees the compressor. */
+size_t fdo_ultrafast_finish(fdo_ultrafast *c) {
+    uf_writer *w = &c->w;
+    uf_write_bits(w, HUFFMAN_CODES[256], HUFFMAN_LENGTHS[256]);
+    uf_flush(w);
+    uint8_t be[4] = {(uint8_t)(c->checksum >> 24), (uint8_t)(c->checksum >> 16), (uint8_t)(c->checksum >> 8),
+                     (uint8_t)c->checksum};
+    uf_write_all(w, be, 4);
+    size_t r = w->overflow ? 0 : w->pos;
+    free(c);
+    return r;
+}
+
+/* compress/mod.rs:313-317: new + write_data(whole input) + finish */
+size_t fdo_compress_ultra_fast(const uint8_t *data, size_t n, uint8_t *out, size_t out_cap) {
+    fdo_ultrafast *c = fdo_ultrafast_new(out, out_cap);
+    if (!c) return 0;
+    fdo_ultrafast_write_data(c, data, n);
+    return fdo_ultrafast_finish(c);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1363,7 +1404,7 @@ size_t fdo_compress_stored(const uint8_t *data, size_t n, uint8_t *out, size_t o
  * how a caller would spread independent streams over host cores).  Used as the CPU baseline.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
-    int kind; /* 0 inflate, 1 ultra-fast compress */
+    int kind; /* 0 inflate, 1 ultra-fast compress, 2 synthetic tiles */
     const uint8_t *in_base;
     const uint64_t *in_off, *in_len;
     uint8_t *out_base;
@@ -1372,33 +1413,63 @@ typedef struct {
     int32_t *status;
     size_t n;
     uint32_t flags;
-    size_t next;
-    pthread_mutex_t mu;
+    /* kind 2 */
+    uint64_t first_tile, seed;
+    uint32_t width, height;
 } batch_job;
 
-static void *batch_worker(void *arg) {
-    batch_job *j = (batch_job *)arg;
+static void synth_tile(uint8_t *out, uint64_t seed, uint64_t tile, uint32_t width, uint32_t height);
+
+static void batch_item(const batch_job *j, size_t i) {
+    if (j->kind == 0) {
+        size_t olen = 0, consumed = 0;
+        int st = fdo_inflate_into(j->in_base + j->in_off[i], (size_t)j->in_len[i], j->out_base + j->out_off[i],
+                                  (size_t)j->out_cap[i], j->flags, &olen, &consumed);
+        j->out_len[i] = olen;
+        if (j->status) j->status[i] = st;
+    } else if (j->kind == 1) {
+        j->out_len[i] = fdo_compress_ultra_fast(j->in_base + j->in_off[i], (size_t)j->in_len[i],
+                                                j->out_base + j->out_off[i], (size_t)j->out_cap[i]);
+    } else {
+        synth_tile(j->out_base + i * (size_t)j->height * (1u + 4u * (size_t)j->width), j->seed, j->first_tile + i,
+                   j->width, j->height);
+    }
+}
+
+/* A persistent pool of worker threads (created on first use, one set per thread count): a batch call posts its job,
+ * wakes the workers and waits; the timed region of the CPU baseline therefore holds no thread creation. */
+#define POOL_MAX 512
+static struct {
+    pthread_mutex_t mu;
+    pthread_cond_t wake, done;
+    pthread_t th[POOL_MAX];
+    int nthreads;            /* workers alive */
+    int want;                /* workers that take part in the current job */
+    const batch_job *job;
+    size_t next;             /* next item of the current job */
+    unsigned long generation;
+    int running;             /* workers still inside the current job */
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, 0, NULL, 0, 0, 0};
+
+static void *pool_worker(void *arg) {
+    const int id = (int)(intptr_t)arg;
+    unsigned long seen = 0;
+    pthread_mutex_lock(&g_pool.mu);
     for (;;) {
-        pthread_mutex_lock(&j->mu);
-        size_t i = j->next;
-        size_t end = i + 4 < j->n ? i + 4 : j->n;
-        j->next = end;
-        pthread_mutex_unlock(&j->mu);
-        if (i >= j->n) break;
-        for (; i < end; i++) {
-            if (j->kind == 0) {
-                size_t olen = 0, consumed = 0;
-                int st = fdo_inflate_into(j->in_base + j->in_off[i], (size_t)j->in_len[i],
-                                          j->out_base + j->out_off[i], (size_t)j->out_cap[i], j->flags, &olen,
-                                          &consumed);
-                j->out_len[i] = olen;
-                if (j->status) j->status[i] = st;
-            } else {
-                size_t olen = fdo_compress_ultra_fast(j->in_base + j->in_off[i], (size_t)j->in_len[i],
-                                                      j->out_base + j->out_off[i], (size_t)j->out_cap[i]);
-                j->out_len[i] = olen;
-            }
+        while (g_pool.generation == seen) pthread_cond_wait(&g_pool.wake, &g_pool.mu);
+        seen = g_pool.generation;
+        if (id >= g_pool.want) continue;
+        const batch_job *j = g_pool.job;
+        for (;;) {
+            size_t i = g_pool.next;
+            size_t end = i + 4 < j->n ? i + 4 : j->n;
+            g_pool.next = end;
+            if (i >= j->n) break;
+            pthread_mutex_unlock(&g_pool.mu);
+            for (; i < end; i++) batch_item(j, i);
+            pthread_mutex_lock(&g_pool.mu);
         }
+        if (--g_pool.running == 0) pthread_cond_signal(&g_pool.done);
     }
     return NULL;
 }
@@ -1412,30 +1483,116 @@ static double now_s(void) {
 static double run_batch(batch_job *j, int nthreads) {
     ensure_init();
     if (nthreads < 1) nthreads = 1;
-    pthread_mutex_init(&j->mu, NULL);
-    j->next = 0;
-    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    if (nthreads > POOL_MAX) nthreads = POOL_MAX;
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.nthreads < nthreads) {
+        if (pthread_create(&g_pool.th[g_pool.nthreads], NULL, pool_worker, (void *)(intptr_t)g_pool.nthreads) != 0) break;
+        pthread_detach(g_pool.th[g_pool.nthreads]);
+        g_pool.nthreads++;
+    }
+    if (nthreads > g_pool.nthreads) nthreads = g_pool.nthreads;
+    if (nthreads < 1) { /* no worker could be created: run inline */
+        pthread_mutex_unlock(&g_pool.mu);
+        double t0 = now_s();
+        for (size_t i = 0; i < j->n; i++) batch_item(j, i);
+        return now_s() - t0;
+    }
     double t0 = now_s();
-    for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, batch_worker, j);
-    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    g_pool.job = j;
+    g_pool.next = 0;
+    g_pool.want = nthreads;
+    g_pool.running = nthreads;
+    g_pool.generation++;
+    pthread_cond_broadcast(&g_pool.wake);
+    while (g_pool.running > 0) pthread_cond_wait(&g_pool.done, &g_pool.mu);
     double t1 = now_s();
-    free(th);
-    pthread_mutex_destroy(&j->mu);
+    pthread_mutex_unlock(&g_pool.mu);
     return t1 - t0;
 }
 
 double fdo_inflate_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len, uint8_t *out_base,
                          const uint64_t *out_off, const uint64_t *out_cap, uint64_t *out_len, int32_t *status,
                          size_t n, uint32_t flags, int nthreads) {
-    batch_job j = {0, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, flags, 0, {{0}}};
+    batch_job j = {0, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, flags, 0, 0, 0, 0};
     return run_batch(&j, nthreads);
 }
 
 double fdo_compress_ultra_fast_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
                                      uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
                                      uint64_t *out_len, size_t n, int nthreads) {
-    batch_job j = {1, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, NULL, n, 0, 0, {{0}}};
+    batch_job j = {1, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, NULL, n, 0, 0, 0, 0, 0};
     return run_batch(&j, nthreads);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic PNG-filtered RGBA tiles: the benchmark / test input of SURVEY.md 8d, restated here so that the CPU legs
+ * of bench.py need nothing but this file (the product library has the same generator in csrc/synth.cuh; the two are
+ * compared byte for byte in tests/test_oracle.py).  Integer-only, counter-based:
+ *   tile seed s = splitmix64(seed + tile); channel c of pixel (x, y) = (a_c x + b_c y + ((x y) >> 6) + noise) & 0xff
+ *   with a_c, b_c in [0, 3] per tile and noise = hash % 5 - 2; A = 255; two constant-colour rectangles of 96 x 64;
+ *   row 0 Sub-filtered (type 1), the others Paeth (type 4); a row is 1 type byte + 4 * width residual bytes.
+ * ---------------------------------------------------------------------------------------- */
+static uint64_t sm64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+typedef struct {
+    uint64_t s;
+    uint32_t a[3], b[3], rx[2], ry[2], col[2];
+} tile_par;
+static uint32_t synth_raw(const tile_par *p, uint32_t x, uint32_t y, uint32_t c, uint32_t width) {
+    if (c == 3) return 255u;
+    for (int k = 0; k < 2; k++)
+        if (x >= p->rx[k] && x < p->rx[k] + 96u && y >= p->ry[k] && y < p->ry[k] + 64u) return (p->col[k] >> (8u * c)) & 0xffu;
+    uint64_t h = sm64(p->s + ((uint64_t)(y * width + x) * 4u + c) * 0x9E3779B97F4A7C15ull);
+    int32_t noise = (int32_t)(h % 5u) - 2;
+    return (uint32_t)((int32_t)(p->a[c] * x + p->b[c] * y + ((x * y) >> 6)) + noise) & 0xffu;
+}
+static uint32_t synth_paeth(uint32_t a, uint32_t b, uint32_t c) {
+    int32_t pa = (int32_t)b - (int32_t)c, pb = (int32_t)a - (int32_t)c;
+    int32_t pc = pa + pb;
+    pa = pa < 0 ? -pa : pa;
+    pb = pb < 0 ? -pb : pb;
+    pc = pc < 0 ? -pc : pc;
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+static void synth_tile(uint8_t *out, uint64_t seed, uint64_t tile, uint32_t width, uint32_t height) {
+    tile_par p;
+    p.s = sm64(seed + tile);
+    uint64_t h = sm64(p.s ^ 0x1234567ull);
+    for (int c = 0; c < 3; c++) {
+        p.a[c] = (uint32_t)(h >> (4 * c)) & 3u;
+        p.b[c] = (uint32_t)(h >> (4 * c + 2)) & 3u;
+    }
+    for (int k = 0; k < 2; k++) {
+        uint64_t r = sm64(p.s ^ (0xABCDEFull + (uint64_t)k));
+        p.rx[k] = (uint32_t)(r & 0xffffu) % width;
+        p.ry[k] = (uint32_t)((r >> 16) & 0xffffu) % height;
+        p.col[k] = (uint32_t)(r >> 32) | 0xff000000u;
+    }
+    for (uint32_t y = 0; y < height; y++) {
+        uint8_t *row = out + (size_t)y * (1u + 4u * (size_t)width);
+        row[0] = y == 0 ? 1 : 4;
+        for (uint32_t x = 0; x < width; x++)
+            for (uint32_t c = 0; c < 4; c++) {
+                uint32_t cur = synth_raw(&p, x, y, c, width);
+                uint32_t left = x ? synth_raw(&p, x - 1, y, c, width) : 0u;
+                uint32_t pred = left;
+                if (y != 0) {
+                    uint32_t up = synth_raw(&p, x, y - 1, c, width);
+                    uint32_t ul = x ? synth_raw(&p, x - 1, y - 1, c, width) : 0u;
+                    pred = synth_paeth(left, up, ul);
+                }
+                row[1 + 4 * x + c] = (uint8_t)(cur - pred);
+            }
+    }
+}
+void fdo_synth_tiles(uint8_t *out, uint64_t first_tile, uint64_t n_tiles, uint32_t width, uint32_t height,
+                     uint64_t seed, int nthreads) {
+    batch_job j = {2, NULL, NULL, NULL, out, NULL, NULL, NULL, NULL, (size_t)n_tiles, 0, first_tile, seed, width, height};
+    run_batch(&j, nthreads);
 }
 
 int fdo_hardware_threads(void) {

@@ -92,6 +92,14 @@ size_t fdo_ultrafast_bound(size_t n);
 /* returns compressed length (always succeeds if out_cap >= fdo_ultrafast_bound(n)); 0 on overflow. */
 size_t fdo_compress_ultra_fast(const uint8_t *data, size_t n, uint8_t *out, size_t out_cap);
 
+/* UltraFastCompressor call by call (ultrafast.rs:70-181): new(writer) -> write_data(..)* -> finish.  The output
+ * depends on how the input is cut into write_data calls (the zero-run state and the 8-byte chunking restart with
+ * every call, :97-99).  `out` plays the writer; finish returns the stream length (0 = out_cap too small) and frees. */
+typedef struct fdo_ultrafast fdo_ultrafast;
+fdo_ultrafast *fdo_ultrafast_new(uint8_t *out, size_t out_cap);
+void fdo_ultrafast_write_data(fdo_ultrafast *c, const uint8_t *data, size_t n);
+size_t fdo_ultrafast_finish(fdo_ultrafast *c);
+
 /* ---- compress/mod.rs:69-101,126-156,194-214,241-268: Compressor::new(w, 0, true) +
  * one write_data(whole input) + finish ---- */
 size_t fdo_stored_bound(size_t n);
@@ -115,6 +123,11 @@ double fdo_compress_ultra_fast_batch(const uint8_t *in_base, const uint64_t *in_
                                      uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
                                      uint64_t *out_len, size_t n, int nthreads);
 int fdo_hardware_threads(void);
+
+/* ---- synthetic PNG-filtered RGBA tiles (the benchmark input, same bytes as the product library's
+ * fdb_synth_tiles_host): n_tiles tiles of height * (1 + 4 * width) bytes back to back, generated on nthreads ---- */
+void fdo_synth_tiles(uint8_t *out, uint64_t first_tile, uint64_t n_tiles, uint32_t width, uint32_t height,
+                     uint64_t seed, int nthreads);
 
 #ifdef __cplusplus
 }

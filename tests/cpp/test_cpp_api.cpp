@@ -70,6 +70,30 @@ int main() {
     fdeflate::UltraFastCompressor<VecWriter> uf(ctx, VecWriter{});
     uf.write_data(data.data(), data.size());
     CHECK(uf.finish().v == z);
+    // several write_data calls: the reference's bytes depend on the call pattern (ultrafast.rs:97-99); compare with
+    // the oracle's new / write_data / finish for a few patterns (cuts inside zero runs, empty calls, one-byte calls)
+    {
+        const size_t cut_sets[][6] = {{0, 1, 2, 3, 7000, 7001}, {8, 16, 4096, 4097, 12345, 19999}, {5, 5, 5, 20000, 20000, 20000},
+                                      {3333, 6666, 9999, 13332, 16665, 19998}};
+        for (const auto& cuts : cut_sets) {
+            fdeflate::UltraFastCompressor<VecWriter> m(ctx, VecWriter{});
+            std::vector<uint8_t> want(fdo_ultrafast_bound(data.size()) + 256);
+            fdo_ultrafast* o = fdo_ultrafast_new(want.data(), want.size());
+            size_t prev = 0;
+            for (int k = 0; k <= 6; k++) {
+                const size_t next = k < 6 ? cuts[k] : data.size();
+                m.write_data(data.data() + prev, next - prev);
+                fdo_ultrafast_write_data(o, data.data() + prev, next - prev);
+                prev = next;
+            }
+            want.resize(fdo_ultrafast_finish(o));
+            std::vector<uint8_t> got = m.finish().v;
+            CHECK(got == want);
+            CHECK(fdeflate::decompress_to_vec(ctx, got) == data);
+        }
+        fdeflate::UltraFastCompressor<VecWriter> none(ctx, VecWriter{});
+        CHECK(none.finish().v == oracle_uf({}));
+    }
     fdeflate::Compressor<VecWriter> st(ctx, VecWriter{}, 0, true);
     st.write_data(data.data(), 7000);
     st.write_data(data.data() + 7000, data.size() - 7000);

@@ -105,6 +105,14 @@ def lib(native: bool = False) -> C.CDLL:
     L.fdo_compress_ultra_fast_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, sz, C.c_int]
     L.fdo_hardware_threads.restype = C.c_int
+    L.fdo_ultrafast_new.restype = C.c_void_p
+    L.fdo_ultrafast_new.argtypes = [C.c_void_p, sz]
+    L.fdo_ultrafast_write_data.restype = None
+    L.fdo_ultrafast_write_data.argtypes = [C.c_void_p, C.c_void_p, sz]
+    L.fdo_ultrafast_finish.restype = sz
+    L.fdo_ultrafast_finish.argtypes = [C.c_void_p]
+    L.fdo_synth_tiles.restype = None
+    L.fdo_synth_tiles.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int]
     _LIBS[native] = L
     return L
 
@@ -149,6 +157,27 @@ def compress_ultra_fast(data) -> bytes:
     m = lib().fdo_compress_ultra_fast(p, n, C.c_void_p(out.ctypes.data), cap)
     assert m > 0
     return out[:m].tobytes()
+
+
+def compress_ultra_fast_calls(calls) -> bytes:
+    """UltraFastCompressor::new, one write_data per element of `calls`, finish (ultrafast.rs:70-181)."""
+    total = sum(len(c) for c in calls)
+    cap = lib().fdo_ultrafast_bound(total) + 16 * (len(calls) + 1)
+    out = np.zeros(cap, dtype=np.uint8)
+    h = lib().fdo_ultrafast_new(C.c_void_p(out.ctypes.data), cap)
+    for c in calls:
+        p, n, _keep = _buf(c)
+        lib().fdo_ultrafast_write_data(h, p, n)
+    m = lib().fdo_ultrafast_finish(h)
+    assert m > 0
+    return out[:m].tobytes()
+
+
+def synth_tiles(first_tile: int, n_tiles: int, width: int, height: int, seed: int, nthreads: int = 1, native: bool = False) -> np.ndarray:
+    """the synthetic PNG-filtered tiles of SURVEY 8d, generated by the oracle (uint8 [n_tiles, height * (1 + 4 * width)])"""
+    out = np.zeros((n_tiles, height * (1 + 4 * width)), dtype=np.uint8)
+    lib(native).fdo_synth_tiles(C.c_void_p(out.ctypes.data), first_tile, n_tiles, width, height, seed, nthreads)
+    return out
 
 
 def compress_stored(data) -> bytes:

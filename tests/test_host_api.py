@@ -99,6 +99,7 @@ def _suite(ctx, oracle):
         w.write_data(p)
     multi = w.finish().getvalue()
     assert zlib.decompress(multi) == data and F.decompress_to_vec(multi, ctx) == data
+    assert multi == oracle.compress_ultra_fast_calls(parts)  # the reference's bytes for this call pattern
     assert F.UltraFastCompressor(io.BytesIO(), ctx).finish().getvalue() == oracle.compress_ultra_fast(b"")
 
     # Compressor::new(w, 0, zlib): stored; other levels are out of scope
@@ -124,6 +125,14 @@ def test_multi_call_ultrafast_matches_reference_semantics(oracle):
     spliced = _splice_ultrafast(streams, calls)
     assert zlib.decompress(spliced) == b"".join(calls)
     assert _splice_ultrafast(streams[:1], calls[:1]) == streams[0]
+    # byte for byte against the oracle's call-by-call compressor (new / write_data / finish, ultrafast.rs:70-181)
+    assert spliced == oracle.compress_ultra_fast_calls(calls)
+    for _ in range(300):
+        d = cases.sparse_bytes(rng, rng.randrange(1, 3000))
+        cuts = sorted(rng.randrange(len(d) + 1) for _ in range(rng.randrange(1, 7)))
+        calls = [d[a:b] for a, b in zip([0] + cuts, cuts + [len(d)])]
+        streams = [oracle.compress_ultra_fast(c) for c in calls]
+        assert _splice_ultrafast(streams, calls) == oracle.compress_ultra_fast_calls(calls)
 
 
 @pytest.mark.emul

@@ -260,3 +260,91 @@ def test_chunking_invariance(oracle):
         k = rng.randrange(1, 9)
         split = oracle.decompress_by_chunks(stream, iter(lambda: k, 0))
         assert whole == bytewise == split
+
+
+def _adversarial_input(rng: random.Random, n: int) -> bytes:
+    """bytes whose zero runs start, end and straddle 8-byte chunk edges, with lengths around the multiples of 258"""
+    kind = rng.randrange(5)
+    if kind == 0:
+        return bytes(rng.choice([0, 0, 0, 1, 255, 7]) for _ in range(n))
+    if kind == 1:
+        return bytes(rng.getrandbits(8) for _ in range(n))
+    out = bytearray()
+    while len(out) < n:
+        r = rng.random()
+        if r < 0.45:
+            out += bytes(rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 23, 24, 25, 256, 257, 258, 259, 260, 261, 262, 263,
+                                     264, 265, 266, 267, 515, 516, 517, 518, 519, 520, 521, 522, 523, 524, 525,
+                                     rng.randrange(1, 1200)]))
+        elif r < 0.8:
+            out += bytes(rng.choice([1, 255, 2, 254, 128, 0]) for _ in range(rng.randrange(1, 12)))
+        else:
+            out += bytes([rng.getrandbits(8) | 1]) * rng.randrange(1, 20)
+    return bytes(out[:n])
+
+
+def test_ultrafast_second_restatement(oracle):
+    """the reference holds no vector for the ultra-fast encoder's bytes, so the C oracle is diffed
+    against an independent pure-Python transliteration of ultrafast.rs (tests/uf_reference_py.py) on >= 10^4 random
+    and adversarial inputs; every output must also inflate with zlib."""
+    import uf_reference_py as P
+
+    # the one table the transliteration derives itself: RFC 1951 3.2.5 against LENGTH_TO_SYMBOL / LENGTH_TO_LEN_EXTRA
+    ls, le = oracle.const_table("length_to_symbol", 256), oracle.const_table("length_to_len_extra", 256)
+    for length in range(3, 259):
+        sym, extra, _ = P._length_symbol(length)
+        assert (ls[length - 3], le[length - 3]) == (sym, extra)
+    rng = random.Random(2024)
+    count = 0
+    for size_hi, reps in ((40, 5000), (300, 4000), (3000, 1200), (30000, 60)):
+        for _ in range(reps):
+            d = _adversarial_input(rng, rng.randrange(size_hi + 1))
+            z = oracle.compress_ultra_fast(d)
+            assert z == P.compress_calls([d]), f"restatements disagree on a {len(d)}-byte input"
+            if count % 16 == 0:
+                assert zlib.decompress(z) == d
+            count += 1
+    assert count >= 10000
+
+
+def test_ultrafast_multi_call(oracle):
+    """write_data call boundaries change the bytes (ultrafast.rs:97-99: the run counter and the 8-byte chunking
+    restart with every call): the oracle's new / write_data / finish against the Python transliteration over random
+    call patterns, and against the single-call output where the two must agree (cuts on 8-byte edges outside zero
+    runs)."""
+    import uf_reference_py as P
+
+    rng = random.Random(77)
+    differ = 0
+    for _ in range(1500):
+        d = _adversarial_input(rng, rng.randrange(1, 2500))
+        cuts = sorted(rng.randrange(len(d) + 1) for _ in range(rng.randrange(0, 6)))
+        calls = [d[a:b] for a, b in zip([0] + cuts, cuts + [len(d)])]
+        z = oracle.compress_ultra_fast_calls(calls)
+        assert z == P.compress_calls(calls)
+        assert zlib.decompress(z) == d
+        differ += z != oracle.compress_ultra_fast(d)
+    assert differ > 100  # the call pattern really is visible in the output
+    d = bytes(rng.choice([1, 2, 3]) for _ in range(4096))
+    assert oracle.compress_ultra_fast_calls([d[:1024], d[1024:2048], d[2048:]]) == oracle.compress_ultra_fast(d)
+    assert oracle.compress_ultra_fast_calls([]) == oracle.compress_ultra_fast(b"")
+    assert oracle.compress_ultra_fast_calls([b"", b""]) == oracle.compress_ultra_fast(b"")
+
+
+def test_adler32_against_zlib(oracle):
+    """the blocked adler32 (the CPU baseline's checksum) is RFC 1950 arithmetic: zlib.adler32 on block edges"""
+    rng = random.Random(1)
+    for n in (0, 1, 31, 32, 33, 63, 64, 5535, 5536, 5537, 5551, 5552, 5553, 11072, 100003):
+        for d in (bytes(rng.getrandbits(8) for _ in range(n)), bytes([255]) * n):
+            assert oracle.adler32(d) == zlib.adler32(d)
+            assert oracle.adler32(d, 0xfff0fff0 % 65521 | (65520 << 16)) == zlib.adler32(d, 0xfff0fff0 % 65521 | (65520 << 16))
+
+
+def test_synth_tiles_match_product_generator(oracle, emul_lib):
+    """bench.py's CPU legs generate their input with the oracle's own tile generator; it must be the generator the
+    product uses on the device and on the host (csrc/synth.cuh), byte for byte"""
+    from fdeflate_b200 import synth_tiles_host
+
+    for first, n, w, h, seed in ((0, 3, 256, 256, 2024), (1000, 2, 1024, 37, 5), (7, 4, 5, 3, 1), (2 ** 40, 1, 300, 1, 99)):
+        a = synth_tiles_host(first, n, w, h, seed, emul_lib).reshape(n, -1)
+        assert np.array_equal(a, oracle.synth_tiles(first, n, w, h, seed, 3))

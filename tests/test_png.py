@@ -212,8 +212,23 @@ def _check_decode_files(ctx):
     assert list(st) == [0, 0, 23, 21, 21, 21, 21]
     raw_off = np.arange(n, dtype=np.uint64) * np.uint64(int(h[0]) * int(s_[0]) + 64)
     raw = np.zeros(int(raw_off[-1]) + int(h[0]) * int(s_[0]) + 64, dtype=np.uint8)
-    assert ctx.lib.L.fdb_png_decode_files_batch(ctx._h, _ptr(base), _ptr(off), _ptr(lens), _ptr(raw), _ptr(raw_off), _ptr(st), n) == 0
+    raw_cap = np.full(n, int(h[0]) * int(s_[0]), dtype=np.uint64)
+    assert ctx.lib.L.fdb_png_decode_files_batch(ctx._h, _ptr(base), _ptr(off), _ptr(lens), _ptr(raw), _ptr(raw_off), _ptr(raw_cap), _ptr(st), n) == 0
     assert list(st) == [0, 22, 23, 21, 21, 21, 21]
+    # a slot one byte short (or a header that claims more pixels than the slot holds): OutputTooLarge for that file only,
+    # and nothing is written to its slot
+    raw[:] = 0xAB
+    raw_cap[0] -= 1
+    assert ctx.lib.L.fdb_png_decode_files_batch(ctx._h, _ptr(base), _ptr(off), _ptr(lens), _ptr(raw), _ptr(raw_off), _ptr(raw_cap), _ptr(st), n) == 0
+    assert list(st) == [17, 22, 23, 21, 21, 21, 21]
+    assert (raw[: int(raw_off[1])] == 0xAB).all()
+    huge = bytearray(good); huge[16:24] = struct.pack(">II", 60000, 60000)  # a header that claims 14 GB of pixels
+    huge[29:33] = struct.pack(">I", binascii.crc32(bytes(huge[12:29])))
+    base2, off2, lens2 = ctx._pack([bytes(huge), good], align=1)
+    st2 = np.zeros(2, dtype=np.int32)
+    cap2 = np.full(2, int(h[0]) * int(s_[0]), dtype=np.uint64)
+    assert ctx.lib.L.fdb_png_decode_files_batch(ctx._h, _ptr(base2), _ptr(off2), _ptr(lens2), _ptr(raw), _ptr(raw_off), _ptr(cap2), _ptr(st2), 2) == 0
+    assert list(st2) == [17, 0]
 
 
 @pytest.mark.emul
