@@ -12,9 +12,14 @@ and outputs resident in HBM.  `e2e` is the same step through the host-buffer C-A
 Streams shard by index across ranks with no collective (weak scaling: every GPU gets `tiles` streams);
 torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the device time.
 
+The same invocation also runs BASELINE configs[4] at one GPU's share per GPU (`sweep` in the JSON line): ragged
+streams of 64 KiB..16 MiB, byte-balanced over the ranks by fdeflate_b200/shard.py, long streams cut into spans /
+segments, device-resident, both directions.
+
 `--impl reference` times the reference algorithm on the host cores (the C oracle, which is a
 line-by-line restatement of the Rust crate: no Rust toolchain exists in this image, so the crate
-itself cannot be built) on a bounded sample of the same workload.
+itself cannot be built) on a bounded sample of the same workload.  That arm loads nothing but the oracle:
+its input comes from the oracle's own tile generator.
 """
 from __future__ import annotations
 
@@ -35,8 +40,8 @@ TILE_W = TILE_H = 256
 TILE_BYTES = TILE_H * (1 + 4 * TILE_W)  # 262400
 
 
-def config_dict(tiles: int, n_gpus: int) -> dict:
-    return {
+def config_dict(tiles: int, n_gpus: int, extra: dict | None = None) -> dict:
+    d = {
         "workload": "BASELINE configs[1]+[2]: per GPU, batch inflate of %d ultra-fast zlib streams of 256x256 RGBA "
                     "PNG-filtered tiles, then batch ultra-fast deflate of the same %d tiles" % (tiles, tiles),
         "streams_per_gpu": tiles,
@@ -45,6 +50,9 @@ def config_dict(tiles: int, n_gpus: int) -> dict:
         "sharding": "by stream, no collective" if n_gpus > 1 else "single GPU",
         "cache": "inputs exceed L2 (%.2f GB per GPU per step vs 126 MB)" % (tiles * TILE_BYTES * 1.4 / 1e9),
     }
+    if extra:
+        d.update(extra)
+    return d
 
 
 def measured_peak():
@@ -114,14 +122,13 @@ class ClockSampler(threading.Thread):
 # CPU legs: the oracle (reference algorithm restated in C), all host threads, bounded sample
 # ------------------------------------------------------------------------------------------------
 def cpu_sample(sample_tiles: int, seed_tile: int = 0):
-    """host tiles + their ultra-fast streams for the CPU legs (generated by the library's host generator
-    and compressed by the oracle itself)"""
+    """host tiles + their ultra-fast streams for the CPU legs: generated by the oracle's own tile generator (the same
+    bytes as the product's, tests/test_oracle.py) and compressed by the oracle itself -- the product library is not
+    loaded on this path"""
     import numpy as np
 
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle_lib as O
-
-    import fdeflate_b200 as F
 
     try:
         O.lib(native=True)
@@ -130,7 +137,7 @@ def cpu_sample(sample_tiles: int, seed_tile: int = 0):
         O.lib(native=False)
         native = False
     threads = O.hardware_threads()
-    tiles = F.synth_tiles_host(seed_tile, sample_tiles, TILE_W, TILE_H, 2024).reshape(-1)
+    tiles = O.synth_tiles(seed_tile, sample_tiles, TILE_W, TILE_H, 2024, threads, native).reshape(-1)
     bound = (54 + TILE_BYTES * 12 // 8 + 16 + 15) // 16 * 16
     n = sample_tiles
     in_off = np.arange(n, dtype=np.uint64) * TILE_BYTES
@@ -196,7 +203,10 @@ def reference_arm(args, rank: int, world: int):
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * (t_inf + t_def) / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": config_dict(args.tiles, args.gpus),
+        "config": config_dict(args.tiles, args.gpus, {
+            "reference_sample_streams": s["n"],
+            "reference_sample": "each timed step of this arm runs %d of the %d streams (a bounded sample of the same "
+                                "workload; GB/s does not depend on the count)" % (s["n"], args.tiles)}),
         "cpu_baseline": {
             "value": round(value, 3), "unit": UNIT, "cores": s["threads"], "kind": "port",
             "sample": "each step = %d tiles (%.0f MB uncompressed): inflate + ultra-fast deflate with the C oracle%s "
@@ -208,6 +218,180 @@ def reference_arm(args, rank: int, world: int):
         "inflate_gbs": round(nbytes / t_inf / 1e9, 3), "deflate_gbs": round(nbytes / t_def / 1e9, 3),
     }
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: the stream-sharded sweep (ragged streams of 64 KiB..16 MiB), one GPU's share per GPU
+# ------------------------------------------------------------------------------------------------
+SWEEP_W = 1024
+SWEEP_ROW = 1 + 4 * SWEEP_W
+
+
+def sweep_sizes(total_streams: int):
+    """the batch every rank derives for itself: stream g has sweep_heights[g] rows of 1024 RGBA pixels (log-uniform
+    64 KiB..16 MiB, seeded), its content is tile 1000 + g of the synthetic generator"""
+    import numpy as np
+
+    rng = np.random.default_rng(5)
+    sizes = np.exp(rng.uniform(np.log(64 << 10), np.log(16 << 20), total_streams))
+    heights = np.maximum(1, (sizes / SWEEP_ROW).astype(np.int64))
+    return heights, heights * SWEEP_ROW
+
+
+def sweep(ctx, args, rank: int, world: int, dev, dist, stream, peak: float) -> dict | None:
+    import numpy as np
+    import torch
+
+    import fdeflate_b200 as F
+    from fdeflate_b200.shard import partition_lpt
+
+    per = args.sweep_streams
+    if per <= 0:
+        return None
+    total_n = per * world
+    heights, lens_all = sweep_sizes(total_n)
+    parts = partition_lpt(lens_all, world)  # byte-balanced, deterministic: every rank computes the same partition
+    mine = parts[rank]
+    n = int(mine.size)
+    lens = lens_all[mine]
+    i64 = torch.int64
+    offs = np.zeros(n, dtype=np.int64)
+    offs[1:] = np.cumsum((lens[:-1] + 15) & ~15)
+    total = int(offs[-1] + lens[-1])
+    raw = torch.empty(total + 16, dtype=torch.uint8, device=dev)
+    for k in range(n):
+        ctx.synth_tiles_device(raw.data_ptr() + int(offs[k]), 1000 + int(mine[k]), 1, SWEEP_W, int(heights[mine[k]]), 5, stream)
+    bounds = np.array([ctx.ultrafast_bound(int(l)) for l in lens], dtype=np.int64)
+    coffs = np.zeros(n, dtype=np.int64)
+    coffs[1:] = np.cumsum(bounds[:-1])
+    comp = torch.empty(int(coffs[-1] + bounds[-1]), dtype=torch.uint8, device=dev)
+    out = torch.empty(total + 16, dtype=torch.uint8, device=dev)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_off, d_len, d_coff, d_ccap = T(offs), T(lens), T(coffs), T(bounds)
+    c_len = torch.zeros(n, dtype=i64, device=dev)
+    c_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    o_len = torch.zeros(n, dtype=i64, device=dev)
+    o_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    ctx.set_split_large(True)  # long streams: spans (inflate) / segments (deflate, by the batch policy)
+
+    def deflate():
+        ctx.deflate_ultrafast_device(raw.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), comp.data_ptr(), d_coff.data_ptr(),
+                                     d_ccap.data_ptr(), c_len.data_ptr(), c_st.data_ptr(), n, stream)
+
+    def inflate():
+        ctx.inflate_device(comp.data_ptr(), d_coff.data_ptr(), c_len.data_ptr(), out.data_ptr(), d_off.data_ptr(), d_len.data_ptr(),
+                           o_len.data_ptr(), 0, o_st.data_ptr(), n, F.FLAG_SPLIT_LARGE, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(f, reps):
+        f()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            f()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / reps
+
+    launches0 = ctx.launch_count
+    ms_def = timed(deflate, args.sweep_steps)
+    ms_inf = timed(inflate, args.sweep_steps)
+    launches = ctx.launch_count - launches0
+    spans = ctx.last_split_spans(stream)
+    assert int(c_st.abs().sum()) == 0 and int(o_st.abs().sum()) == 0, "sweep: a stream failed"
+    assert ctx.last_general_count(stream) == 0, "sweep: ultra-fast streams left the fast path"
+    assert torch.equal(o_len, d_len)
+    pick = np.random.default_rng().choice(n, size=min(n, 24), replace=False)  # a fresh sample every run
+    for k in pick:
+        a = int(offs[k])
+        assert torch.equal(out[a:a + int(lens[k])], raw[a:a + int(lens[k])]), "sweep: inflate(deflate(x)) != x"
+    # ... and against the oracle (the checker), on the shortest of the sampled streams
+    checked = 0
+    try:
+        sys.path.insert(0, str(ROOT / "tests"))
+        import oracle_lib as O
+
+        for k in sorted(pick, key=lambda k: lens[k])[:3]:
+            a, c0, cl = int(offs[k]), int(coffs[k]), int(c_len[k])
+            src = raw[a:a + int(lens[k])].cpu().numpy().tobytes()
+            z = comp[c0:c0 + cl].cpu().numpy().tobytes()
+            assert z == O.compress_ultra_fast(src), "sweep: deflate output differs from the oracle"
+            assert O.inflate_into(z, len(src))[:2] == (0, src), "sweep: the oracle inflates the stream differently"
+            checked += 1
+    except ImportError:
+        pass
+    ctx.set_split_large(False)
+    unc = int(lens.sum())
+    cbytes = int(c_len.sum())
+    t = torch.tensor([ms_inf, ms_def], dtype=torch.float64, device=dev)
+    b = torch.tensor([float(unc), float(cbytes)], dtype=torch.float64, device=dev)
+    mx = torch.tensor([float(unc)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    ms_inf, ms_def = [float(x) for x in t.cpu()]
+    unc_all, comp_all = [float(x) for x in b.cpu()]
+    del raw, comp, out
+    torch.cuda.empty_cache()
+    alg = (unc_all + comp_all) / world  # per GPU and launch set, either direction
+    return {
+        "workload": "BASELINE configs[4] at one GPU's share per GPU (weak scaling): %d ultra-fast streams of 64 KiB..16 MiB "
+                    "(log-uniform) per GPU, %d in all, byte-balanced over the ranks (LPT, fdeflate_b200/shard.py), inflate "
+                    "with long streams cut into spans + ultra-fast deflate, device-resident" % (per, total_n),
+        "streams_per_gpu": per, "streams_total": total_n,
+        "uncompressed_bytes_total": int(unc_all), "compressed_ratio": round(comp_all / unc_all, 4),
+        "balance_max_over_mean": round(float(mx.cpu()[0]) / (unc_all / world), 4),
+        "value": round(2 * unc_all / ((ms_inf + ms_def) / 1e3) / 1e9, 2), "unit": UNIT,
+        "inflate_gbs": round(unc_all / (ms_inf / 1e3) / 1e9, 2), "deflate_gbs": round(unc_all / (ms_def / 1e3) / 1e9, 2),
+        "ms_inflate": round(ms_inf, 3), "ms_deflate": round(ms_def, 3), "steps": args.sweep_steps,
+        "roofline_frac_per_gpu": {"inflate": round(alg / (ms_inf / 1e3) / 1e9 / peak, 4),
+                                  "deflate": round(alg / (ms_def / 1e3) / 1e9 / peak, 4)},
+        "spans_rank0": int(spans), "gpu_launches": int(launches),
+        "verified": "every status Ok, lengths equal, %d random streams per rank byte-equal after inflate(deflate(x)), "
+                    "%d of them equal to the oracle's deflate bytes and inflated identically by the oracle" % (len(pick), checked),
+    }
+
+
+def link_ceiling(dev, dist) -> dict:
+    """what the host link of this box gives with every rank copying at once: 1 GiB pinned, both directions together"""
+    import torch
+
+    n = 1 << 30
+    h_a = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_b = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_a.fill_(1)
+    d_a = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_b = torch.zeros(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def both():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_a, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_b.copy_(d_b, non_blocking=True)
+
+    both()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    reps = 4
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        both()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    rate = torch.tensor([reps * n / dt / 1e9], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(rate, op=dist.ReduceOp.SUM)
+    return {"gbs_per_direction_all_gpus": round(float(rate.cpu()[0]), 1),
+            "how": "1 GiB pinned host buffers, cudaMemcpyAsync both directions at once on every rank, %d repetitions" % reps}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -296,6 +480,22 @@ def ours(args, rank: int, local_rank: int, world: int):
     assert ctx.last_general_count(stream) == 0, "ultra-fast streams left the fast path"
     assert torch.equal(out, tiles), "inflate(deflate(x)) != x"
     assert torch.equal(c_len2, c_len) and torch.equal(comp2, comp), "deflate output not reproducible"
+    # ... and a fresh random sample of the timed work against the oracle (the checker): the deflate bytes are the
+    # reference encoder's, and the reference's inflate reads them back to the tile
+    oracle_checked = 0
+    try:
+        sys.path.insert(0, str(ROOT / "tests"))
+        import oracle_lib as O
+
+        for i in np.random.default_rng().choice(n, size=min(n, 8), replace=False):
+            tile = tiles[int(i) * TILE_BYTES:(int(i) + 1) * TILE_BYTES].cpu().numpy().tobytes()
+            z = comp2[int(i) * bound:int(i) * bound + int(c_len2[int(i)])].cpu().numpy().tobytes()
+            assert z == O.compress_ultra_fast(tile), "deflate output differs from the oracle (stream %d)" % int(i)
+            assert O.inflate_into(z, TILE_BYTES)[:2] == (0, tile), "the oracle inflates stream %d differently" % int(i)
+            assert out[int(i) * TILE_BYTES:(int(i) + 1) * TILE_BYTES].cpu().numpy().tobytes() == tile
+            oracle_checked += 1
+    except ImportError:
+        pass
 
     # ---- end to end through the host-buffer C ABI: pinned host memory, copies inside the timed region ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -363,6 +563,10 @@ def ours(args, rank: int, local_rank: int, world: int):
     pool.shutdown()
     h2d = int(n * TILE_BYTES + int(clen.sum()) + 2 * 4 * 8 * n)
     d2h = int(n * TILE_BYTES + int(clen.sum()) + 2 * (8 + 8 + 4) * n)
+    del ctx2, h_comp2, h_packed, h_out, h_comp, h_tiles
+    link = link_ceiling(dev, dist)
+    peak, peak_src = measured_peak()
+    sweep_res = sweep(ctx, args, rank, world, dev, dist, stream, peak)
 
     # ---- reduce over ranks (max time), whole-job throughput ----
     t = torch.tensor([ms_total, ms_inf, ms_def, e2e_s], dtype=torch.float64, device=dev)
@@ -376,7 +580,6 @@ def ours(args, rank: int, local_rank: int, world: int):
     e2e_value = world * 2 * unc * e2e_steps / e2e_s / 1e9
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         alg_bytes = unc + comp_bytes  # per launch, both kernels: read once + written once
         inf_ms, def_ms = ms_inf / args.steps, ms_def / args.steps
         dominant = "inflate_uf_kernel" if inf_ms >= def_ms else "deflate_uf_kernel"
@@ -392,7 +595,8 @@ def ours(args, rank: int, local_rank: int, world: int):
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": config_dict(n, world),
+            "config": config_dict(n, world, {"workloads": ["configs[1]+[2] tiles (the headline: value, roofline, e2e)"] +
+                                             (["configs[4] sweep (key `sweep`)"] if sweep_res else [])}),
             "inflate_gbs": round(inflate_gbs, 2), "deflate_gbs": round(deflate_gbs, 2),
             "compressed_ratio": round(comp_bytes / unc, 4),
             "roofline": {
@@ -407,11 +611,19 @@ def ours(args, rank: int, local_rank: int, world: int):
             },
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "fdb_deflate_ultrafast_batch + fdb_inflate_batch, pinned host buffers, " +
-                           ("one call after the other" if args.e2e_serial else "the two calls issued concurrently on two contexts")},
+                           ("one call after the other" if args.e2e_serial else "the two calls issued concurrently on two contexts"),
+                    # the host link bounds this number: bytes that must cross it per step / what the link moves with all
+                    # ranks copying both ways at once (measured in this run)
+                    "link": link,
+                    "frac_of_link": round((world * max(h2d, d2h) / 1e9 / link["gbs_per_direction_all_gpus"]) / (e2e_s / e2e_steps), 3)
+                    if link["gbs_per_direction_all_gpus"] > 0 else None},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "verified": "inflate(deflate(x)) == x on all streams; re-encode byte-identical; fast path on 100% of streams",
+            "verified": "inflate(deflate(x)) == x on all streams; re-encode byte-identical; fast path on 100%% of streams; "
+                        "%d random streams of the timed work equal to the oracle's bytes in both directions" % oracle_checked,
         }
+        if sweep_res:
+            line["sweep"] = sweep_res
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline_measure()
@@ -448,6 +660,8 @@ def main():
     ap.add_argument("--tiles", type=int, default=4096, help="streams per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep-streams", type=int, default=8192, help="configs[4]: streams per GPU (0 = skip the sweep)")
+    ap.add_argument("--sweep-steps", type=int, default=2)
     ap.add_argument("--e2e-serial", action="store_true", help="end-to-end leg: deflate call, then inflate call (no overlap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
