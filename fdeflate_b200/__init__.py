@@ -13,6 +13,7 @@ from .api import (
     DecompressionError,
     Decompressor,
     FdbError,
+    MultiContext,
     UltraFastCompressor,
     compress_to_vec_stored,
     compress_to_vec_ultra_fast,
@@ -24,7 +25,7 @@ from .api import (
 
 __all__ = [
     "FLAG_GENERAL_ONLY", "FLAG_IGNORE_ADLER32", "FLAG_SPLIT_LARGE", "NativeLib", "NativeLibraryMissing", "STATUS_NAMES",
-    "BoundedDecompressionError", "Compressor", "Context", "DecompressionError", "Decompressor", "FdbError",
+    "BoundedDecompressionError", "Compressor", "Context", "DecompressionError", "Decompressor", "FdbError", "MultiContext",
     "UltraFastCompressor", "compress_to_vec_stored", "compress_to_vec_ultra_fast", "decompress_to_vec",
     "decompress_to_vec_bounded", "default_context", "synth_tiles_host",
 ]

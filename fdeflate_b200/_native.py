@@ -21,6 +21,9 @@ EXPORTS = [
     "fdb_deflate_stored_bound", "fdb_deflate_stored_batch_device", "fdb_deflate_stored_batch",
     "fdb_synth_tile_bytes", "fdb_synth_tiles_host", "fdb_synth_tiles_device", "fdb_launch_count", "fdb_last_general_count",
     "fdb_set_pipeline_chunk", "fdb_last_split_spans", "fdb_set_split_large", "fdb_set_split_threshold", "fdb_png_unfilter_batch_device", "fdb_png_filter_batch_device", "fdb_png_unfilter_batch", "fdb_png_filter_batch", "fdb_png_decode_batch", "fdb_png_encode_batch", "fdb_crc32_batch_device", "fdb_crc32_batch", "fdb_png_probe_batch", "fdb_png_decode_files_batch", "fdb_png_file_bound", "fdb_png_encode_files_batch",
+    "fdb_stream_open_batch", "fdb_stream_read_batch", "fdb_stream_close_batch",
+    "fdb_multi_create", "fdb_multi_destroy", "fdb_multi_device_count", "fdb_multi_last_error", "fdb_multi_inflate_batch",
+    "fdb_multi_deflate_ultrafast_batch", "fdb_multi_deflate_stored_batch", "fdb_multi_last_partition",
 ]
 
 FLAG_IGNORE_ADLER32 = 1
@@ -108,6 +111,28 @@ class NativeLib:
         L.fdb_set_split_threshold.argtypes = [vp, sz, sz]
         L.fdb_last_split_spans.restype = C.c_int64
         L.fdb_last_split_spans.argtypes = [vp, vp]
+        L.fdb_stream_open_batch.restype = C.c_int
+        L.fdb_stream_open_batch.argtypes = [vp, vp, sz]
+        L.fdb_stream_close_batch.restype = C.c_int
+        L.fdb_stream_close_batch.argtypes = [vp, vp, sz]
+        L.fdb_stream_read_batch.restype = C.c_int
+        L.fdb_stream_read_batch.argtypes = [vp] * 10 + [sz, u32]
+        L.fdb_multi_create.restype = C.c_int
+        L.fdb_multi_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.fdb_multi_destroy.restype = None
+        L.fdb_multi_destroy.argtypes = [vp]
+        L.fdb_multi_device_count.restype = C.c_int
+        L.fdb_multi_device_count.argtypes = [vp]
+        L.fdb_multi_last_error.restype = C.c_char_p
+        L.fdb_multi_last_error.argtypes = [vp]
+        L.fdb_multi_inflate_batch.restype = C.c_int
+        L.fdb_multi_inflate_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, u32]
+        for name in ("fdb_multi_deflate_ultrafast_batch", "fdb_multi_deflate_stored_batch"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, sz]
+        L.fdb_multi_last_partition.restype = C.c_int
+        L.fdb_multi_last_partition.argtypes = [vp, vp, sz]
 
     def version(self) -> str:
         return self.L.fdb_version().decode()

@@ -214,6 +214,39 @@ class Context:
     def deflate_stored_batch(self, inputs: Sequence[bytes], align: int = 16) -> list[bytes]:
         return self._deflate_batch(self.deflate_stored_packed, self.lib.L.fdb_deflate_stored_bound, inputs, align)
 
+    # ---- streaming decoders (fdb_stream_*): many in-flight Decompressor::read state machines, state on the device ----
+    def stream_open(self, n: int = 1) -> np.ndarray:
+        ids = np.zeros(n, dtype=np.uint32)
+        self._check(self.lib.L.fdb_stream_open_batch(self._h, _ptr(ids), n), "fdb_stream_open_batch")
+        return ids
+
+    def stream_close(self, ids) -> None:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        if self._h:
+            self._check(self.lib.L.fdb_stream_close_batch(self._h, _ptr(ids), len(ids)), "fdb_stream_close_batch")
+
+    def stream_read_packed(self, ids, in_base, in_off, in_len, out_base, out_off, out_room, flags: int = 0):
+        """one launch advances every decoder in `ids`; -> (produced uint64[n], status int32[n])"""
+        n = len(ids)
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        in_off, in_len, out_off, out_room = (np.ascontiguousarray(a, dtype=np.uint64) for a in (in_off, in_len, out_off, out_room))
+        produced = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        rc = self.lib.L.fdb_stream_read_batch(self._h, _ptr(ids), _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base),
+                                              _ptr(out_off), _ptr(out_room), _ptr(produced), _ptr(status), n, flags)
+        self._check(rc, "fdb_stream_read_batch")
+        return produced, status
+
+    def stream_read(self, ids, datas: Sequence[bytes], rooms: Sequence[int], flags: int = 0):
+        """-> (status int32[n], outputs list[bytes]) for one step of the decoders `ids`"""
+        in_base, in_off, in_len = self._pack(datas, 1)
+        rooms = np.asarray(rooms, dtype=np.uint64)
+        out_off = np.zeros(len(rooms), dtype=np.uint64)
+        out_off[1:] = np.cumsum(rooms[:-1])
+        out_base = np.zeros(max(int(rooms.sum()), 1), dtype=np.uint8)
+        produced, status = self.stream_read_packed(ids, in_base, in_off, in_len, out_base, out_off, rooms, flags)
+        return status, [out_base[int(o): int(o) + int(p)].tobytes() for o, p in zip(out_off, produced)]
+
     # ---- device-pointer calls (ints / torch data_ptr()); enqueue only -----------------------------
     def inflate_device(self, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_consumed, d_status,
                        n: int, flags: int = 0, stream: int = 0):
@@ -319,6 +352,69 @@ def synth_tiles_host(first_tile: int, n_tiles: int, width: int, height: int, see
 _default_ctx: dict[int, Context] = {}
 
 
+class MultiContext(Context):
+    """One fdb_multi: the GPUs of one box behind one handle (include/fdeflate_b200.h, fdb_multi_*).  Batches are
+    partitioned by stream (byte-balanced, no collective) and every device runs the ordinary host-buffer call on
+    its share from its own host thread; arguments and results are those of Context.  Only the host-buffer batch
+    calls exist on a device set."""
+
+    def __init__(self, devices: Sequence[int], lib: NativeLib | None = None):
+        self.lib = lib if lib is not None else _native.default_lib()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.L.fdb_multi_create(devs, len(devices), C.byref(h))
+        if rc != 0 or not h:
+            raise FdbError(f"fdb_multi_create(devices={list(devices)}) failed with code {rc}: no usable CUDA device "
+                           f"(fdeflate_b200 has no CPU fallback)")
+        self._m = h
+        self._h = None
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self.lib.L.fdb_multi_destroy(self._m)
+            self._m = None
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise FdbError(f"{what} failed ({rc}): {self.lib.L.fdb_multi_last_error(self._m).decode()}")
+
+    def inflate_packed(self, in_base, in_off, in_len, out_base, out_off, out_cap, flags: int = 0):
+        n = len(in_off)
+        in_off, in_len, out_off, out_cap = (np.ascontiguousarray(a, dtype=np.uint64) for a in (in_off, in_len, out_off, out_cap))
+        out_len = np.zeros(n, dtype=np.uint64)
+        consumed = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        rc = self.lib.L.fdb_multi_inflate_batch(self._m, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off),
+                                                _ptr(out_cap), _ptr(out_len), _ptr(consumed), _ptr(status), n, flags)
+        self._check(rc, "fdb_multi_inflate_batch")
+        return out_len, consumed, status
+
+    def _multi_deflate(self, fn, what, in_base, in_off, in_len, out_base, out_off, out_cap):
+        n = len(in_off)
+        in_off, in_len, out_off, out_cap = (np.ascontiguousarray(a, dtype=np.uint64) for a in (in_off, in_len, out_off, out_cap))
+        out_len = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        rc = fn(self._m, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off), _ptr(out_cap), _ptr(out_len),
+                _ptr(status), n)
+        self._check(rc, what)
+        return out_len, status
+
+    def deflate_ultrafast_packed(self, in_base, in_off, in_len, out_base, out_off, out_cap):
+        return self._multi_deflate(self.lib.L.fdb_multi_deflate_ultrafast_batch, "fdb_multi_deflate_ultrafast_batch", in_base, in_off,
+                                   in_len, out_base, out_off, out_cap)
+
+    def deflate_stored_packed(self, in_base, in_off, in_len, out_base, out_off, out_cap):
+        return self._multi_deflate(self.lib.L.fdb_multi_deflate_stored_batch, "fdb_multi_deflate_stored_batch", in_base, in_off,
+                                   in_len, out_base, out_off, out_cap)
+
+    def last_partition(self, n: int) -> np.ndarray:
+        owner = np.zeros(n, dtype=np.uint32)
+        if self.lib.L.fdb_multi_last_partition(self._m, _ptr(owner), n) != 0:
+            raise FdbError("fdb_multi_last_partition: no call of that size yet")
+        return owner
+
+
 def default_context(device: int = 0) -> Context:
     if device not in _default_ctx:
         _default_ctx[device] = Context(device)
@@ -365,17 +461,31 @@ def compress_to_vec_stored(data: bytes, ctx: Context | None = None) -> bytes:
 
 
 class Decompressor:
-    """Streaming facade with the reference's read() contract (src/decompress.rs:158-184) on top of the
-    whole-stream batch engine: input is buffered, and every call re-inflates the buffered prefix to
-    find the bytes that became available.  Chunking-invariant by construction; quadratic for
-    byte-wise feeding (the streaming row of SURVEY 8f is future work)."""
+    """The reference's streaming decoder (src/decompress.rs:96-342) with the read() contract of :158-184.  The state
+    machine lives on the device (fdb_stream_*, csrc/inflate_general.cuh: K3StreamState): every call resumes at the
+    token boundary the last one stopped at, so the work of a call is proportional to the bytes of that call whatever
+    the chunking (byte-wise feeding is linear in the stream length).  read() takes all of `data` (what cannot be parsed
+    yet is kept by the context) and returns (len(data), bytes written); when the output is full, call again with more
+    room (data may be empty).  Many decoders advance in one launch through Context.stream_read."""
 
     def __init__(self, ctx: Context | None = None):
         self._ctx = ctx or default_context()
-        self._buf = bytearray()
-        self._emitted = 0
+        self._id = self._ctx.stream_open(1)
         self._done = False
         self._flags = 0
+
+    def close(self):
+        if self._id is not None:
+            try:
+                self._ctx.stream_close(self._id)
+            finally:
+                self._id = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def ignore_adler32(self):
         self._flags |= FLAG_IGNORE_ADLER32
@@ -385,22 +495,22 @@ class Decompressor:
 
     def read(self, data: bytes, output: np.ndarray, output_position: int):
         if self._done:
-            return 0, 0
+            return 0, 0  # :185-187
         if output_position > output.size:
             raise IndexError("output_position out of bounds")  # the reference panics (:189)
-        self._buf += bytes(data)
+        data = bytes(data)
+        in_base = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, dtype=np.uint8)
         room = output.size - output_position
-        cap = self._emitted + room
-        status, outs, _ = self._ctx.inflate_batch([bytes(self._buf)], [cap], self._flags)
+        z = np.zeros(1, dtype=np.uint64)
+        produced, status = self._ctx.stream_read_packed(self._id, in_base, z, np.array([len(data)], dtype=np.uint64), output,
+                                                        np.array([output_position], dtype=np.uint64),
+                                                        np.array([room], dtype=np.uint64), self._flags)
         st = int(status[0])
-        if st not in (ST_OK, ST_INSUFFICIENT_INPUT, ST_OUTPUT_TOO_LARGE):
+        if st > 0:
             raise DecompressionError(st)
-        new = outs[0][self._emitted:]
-        output[output_position: output_position + len(new)] = np.frombuffer(new, dtype=np.uint8)
-        self._emitted += len(new)
         if st == ST_OK:
             self._done = True
-        return len(data), len(new)
+        return len(data), int(produced[0])
 
 
 class UltraFastCompressor:

@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <mutex>
 #include <new>
+#include <queue>
+#include <thread>
 #include <vector>
 
 #include "simt.h"
@@ -97,6 +99,21 @@ struct fdb_ctx {
     size_t d_meta_cap = 0;
     uint64_t launches = 0;
     char err[512] = {0};
+    // streaming decoders (fdb_stream_*): per-decoder device state + window buffer, host copy of the unparsed input tail
+    struct stream_slot {
+        bool open = false;
+        K3StreamState* d_state = nullptr;
+        uint8_t* d_buf = nullptr;
+        size_t buf_cap = 0;
+        uint64_t pos = 0, lo = 0;       // d_buf[lo .. pos) = the decoder's most recent output
+        std::vector<uint8_t> tail;      // input bytes the decoder has not parsed yet
+        uint32_t start_bit = 0;         // bits of tail[0] already consumed
+        bool finished = false;
+        int32_t final_status = 0;       // once finished: FDB_OK (stream complete) or the error
+    };
+    std::vector<stream_slot> streams;
+    K3StreamJob* d_jobs = nullptr;
+    size_t d_jobs_cap = 0;
 };
 
 // ---- optional timeline of the host pipeline (FDB_TRACE=<file>): one line per chunk with the device times
@@ -282,6 +299,8 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
         return bail(e);
     if ((e = cudaFuncSetAttribute(inflate_uf_split_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem))) != cudaSuccess)
         return bail(e);
+    if ((e = cudaFuncSetAttribute(inflate_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem))) != cudaSuccess)
+        return bail(e);
     *out = ctx;
     return 0;
 }
@@ -321,6 +340,11 @@ extern "C" void fdb_destroy(fdb_ctx* ctx) {
     cudaFree(ctx->d_out);
     cudaFree(ctx->d_mid);
     cudaFree(ctx->d_meta);
+    for (auto& sl : ctx->streams) {
+        cudaFree(sl.d_state);
+        cudaFree(sl.d_buf);
+    }
+    cudaFree(ctx->d_jobs);
     delete ctx;
 }
 
@@ -590,12 +614,16 @@ static bool uniform_stride(const uint64_t* off, size_t n, uint64_t* stride) {
 // moves the last row's own extent.  Anything else: one copy per run of adjacent slots (up to 64 runs, which covers
 // slots in any order), else one contiguous copy of the hull [min off, max off + ext).  Bytes between slots may be
 // copied along; nothing outside the hull is touched.
+// `exact` (device sets: the bytes between this call's slots may be another device's slots): a device-to-host copy
+// writes nothing outside the slots themselves -- the 2-D copy only when every slot holds the widest row, the runs only
+// over slots that touch, and as many runs as it takes.
 static int copy_rows(fdb_ctx* ctx, uint8_t* dst_base, const uint8_t* src_base, const uint64_t* off, const uint64_t* ext,
                      const uint64_t* cap, size_t a, size_t b, bool uniform, uint64_t stride, cudaMemcpyKind kind,
-                     cudaStream_t st) {
-    uint64_t lo = ~0ull, hi = 0, width = 0;
+                     cudaStream_t st, bool exact = false) {
+    uint64_t lo = ~0ull, hi = 0, width = 0, min_cap = ~0ull;
     auto extent = [&](size_t i) { return cap ? std::min(ext[i], cap[i]) : ext[i]; };
     for (size_t i = a; i < b; i++) {
+        if (cap) min_cap = std::min(min_cap, cap[i]);
         const uint64_t e = extent(i);
         if (!e) continue;
         lo = std::min(lo, off[i]);
@@ -605,6 +633,29 @@ static int copy_rows(fdb_ctx* ctx, uint8_t* dst_base, const uint8_t* src_base, c
     if (hi <= lo) return 0;
     const size_t rows = b - a;
     const uint64_t span = hi - lo;
+    const bool to_host = kind == cudaMemcpyDeviceToHost;
+    if (exact && to_host) {
+        if (uniform && rows > 2 && width <= stride && width <= min_cap && width * rows < span - span / 8) {
+            FDB_TRY(cudaMemcpy2DAsync(dst_base + off[a], stride, src_base + off[a], stride, width, rows - 1, kind, st));
+            const uint64_t e = extent(b - 1);
+            if (e) FDB_TRY(cudaMemcpyAsync(dst_base + off[b - 1], src_base + off[b - 1], e, kind, st));
+            return 0;
+        }
+        uint64_t p_lo = 0, p_hi = 0;
+        for (size_t i = a; i < b; i++) {
+            const uint64_t e = extent(i);
+            if (!e) continue;
+            if (p_hi > p_lo && off[i] == p_hi) {
+                p_hi = off[i] + e;
+                continue;
+            }
+            if (p_hi > p_lo) FDB_TRY(cudaMemcpyAsync(dst_base + p_lo, src_base + p_lo, p_hi - p_lo, kind, st));
+            p_lo = off[i];
+            p_hi = off[i] + e;
+        }
+        if (p_hi > p_lo) FDB_TRY(cudaMemcpyAsync(dst_base + p_lo, src_base + p_lo, p_hi - p_lo, kind, st));
+        return 0;
+    }
     if (uniform && rows > 2 && width <= stride && width * rows < span - span / 8) {
         FDB_TRY(cudaMemcpy2DAsync(dst_base + off[a], stride, src_base + off[a], stride, width, rows - 1, kind, st));
         const uint64_t e = extent(b - 1);
@@ -662,7 +713,8 @@ struct PngPre {
 
 static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
                       uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
-                      uint64_t* consumed, int32_t* status, size_t n, uint32_t flags, const PngPre* png = nullptr) {
+                      uint64_t* consumed, int32_t* status, size_t n, uint32_t flags, const PngPre* png = nullptr,
+                      bool exact = false) {
     if (!ctx) return -1;
     if (n == 0) return 0;
     if (n > 0xffffffffull || !in_off || !in_len || !out_off || !out_cap || !out_len || !status)
@@ -827,7 +879,7 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
         const size_t a = k * per, b = std::min(n, a + per);
         mark(k, 3, ds);
         int rr = copy_rows(ctx, out_base, ctx->d_out, out_off, h_out_len, out_cap, a, b, out_uniform, out_stride,
-                           cudaMemcpyDeviceToHost, ds);
+                           cudaMemcpyDeviceToHost, ds, exact);
         mark(k, 4, ds);
         return rr;
     };
@@ -1600,4 +1652,334 @@ extern "C" int fdb_synth_tiles_device(fdb_ctx* ctx, void* d_out, uint64_t first_
     ctx->launches++;
     FDB_TRY(cudaGetLastError());
     return 0;
+}
+
+// ---- streaming decoders ----------------------------------------------------------------------------------------
+// Decompressor::read (src/decompress.rs:158-219) for many in-flight decoders at once: every decoder keeps its state on
+// the device (inflate_general.cuh: K3StreamState), one launch advances all decoders of a call.
+static const uint64_t STREAM_WINDOW = 32768;  // matches reach back 32 KiB at most (RFC 1951)
+
+extern "C" int fdb_stream_open_batch(fdb_ctx* ctx, uint32_t* ids, size_t n) {
+    if (!ctx || (n && !ids)) return -1;
+    FDB_TRY(cudaSetDevice(ctx->device));
+    size_t scan = 0;
+    for (size_t k = 0; k < n; k++) {
+        while (scan < ctx->streams.size() && ctx->streams[scan].open) scan++;
+        if (scan == ctx->streams.size()) ctx->streams.emplace_back();
+        fdb_ctx::stream_slot& sl = ctx->streams[scan];
+        if (!sl.d_state) FDB_TRY(cudaMalloc((void**)&sl.d_state, sizeof(K3StreamState)));
+        FDB_TRY(cudaMemsetAsync(sl.d_state, 0, sizeof(K3StreamState), ctx->stream));
+        const uint32_t one = 1;  // adler32 starts at 1
+        FDB_TRY(cudaMemcpyAsync(&sl.d_state->adler_a, &one, sizeof one, cudaMemcpyHostToDevice, ctx->stream));
+        FDB_TRY(cudaStreamSynchronize(ctx->stream));
+        sl.open = true;
+        sl.pos = sl.lo = 0;
+        sl.tail.clear();
+        sl.start_bit = 0;
+        sl.finished = false;
+        sl.final_status = 0;
+        ids[k] = (uint32_t)scan;
+    }
+    return 0;
+}
+
+extern "C" int fdb_stream_close_batch(fdb_ctx* ctx, const uint32_t* ids, size_t n) {
+    if (!ctx || (n && !ids)) return -1;
+    for (size_t k = 0; k < n; k++) {
+        if (ids[k] >= ctx->streams.size() || !ctx->streams[ids[k]].open) return fail(ctx, "fdb_stream_close_batch: no such decoder", cudaSuccess);
+        fdb_ctx::stream_slot& sl = ctx->streams[ids[k]];
+        sl.open = false;
+        sl.tail.clear();
+        sl.tail.shrink_to_fit();
+        if (sl.buf_cap > (1u << 20)) {  // keep small window buffers for the next decoder in this slot
+            cudaFree(sl.d_buf);
+            sl.d_buf = nullptr;
+            sl.buf_cap = 0;
+        }
+    }
+    return 0;
+}
+
+extern "C" int fdb_stream_read_batch(fdb_ctx* ctx, const uint32_t* ids, const uint8_t* in_base, const uint64_t* in_off,
+                                     const uint64_t* in_len, uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_room,
+                                     uint64_t* produced, int32_t* status, size_t n, uint32_t flags) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (!ids || !in_off || !in_len || !out_off || !out_room || !produced || !status || n > 0xffffffffull)
+        return fail(ctx, "fdb_stream_read_batch", cudaSuccess);
+    FDB_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<K3StreamJob> jobs;
+    std::vector<size_t> owner;  // job -> index in the call
+    jobs.reserve(n);
+    uint64_t stage_bytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (ids[i] >= ctx->streams.size() || !ctx->streams[ids[i]].open) return fail(ctx, "fdb_stream_read_batch: no such decoder", cudaSuccess);
+        for (size_t j = 0; j < i; j++)
+            if (ids[j] == ids[i]) return fail(ctx, "fdb_stream_read_batch: a decoder appears twice in one call", cudaSuccess);
+        fdb_ctx::stream_slot& sl = ctx->streams[ids[i]];
+        produced[i] = 0;
+        if (sl.finished) {  // :185-187 (Done) -- or the error the stream ended with
+            status[i] = sl.final_status;
+            continue;
+        }
+        if (in_len[i]) sl.tail.insert(sl.tail.end(), in_base + in_off[i], in_base + in_off[i] + in_len[i]);
+        // room for the new output behind the window
+        const uint64_t room = out_room[i];
+        if (sl.pos + room + 64 > sl.buf_cap) {
+            const uint64_t keep = std::min<uint64_t>(sl.pos - sl.lo, STREAM_WINDOW);
+            if (sl.pos > keep) {  // drop everything but the window
+                FDB_LAUNCH(stream_compact_kernel, dim3(1), dim3(1024), 0, st, sl.d_buf, sl.pos, keep);
+                ctx->launches++;
+                FDB_TRY(cudaGetLastError());
+                sl.pos = keep;
+                sl.lo = 0;
+            }
+            if (sl.pos + room + 64 > sl.buf_cap) {
+                const size_t ncap = (size_t)(sl.pos + room + 64 + (64u << 10));
+                uint8_t* nb = nullptr;
+                FDB_TRY(cudaMalloc((void**)&nb, ncap));
+                if (sl.pos) FDB_TRY(cudaMemcpyAsync(nb, sl.d_buf, sl.pos, cudaMemcpyDeviceToDevice, st));
+                FDB_TRY(cudaStreamSynchronize(st));
+                cudaFree(sl.d_buf);
+                sl.d_buf = nb;
+                sl.buf_cap = ncap;
+            }
+        }
+        K3StreamJob jb;
+        memset(&jb, 0, sizeof jb);
+        jb.state = sl.d_state;
+        jb.in = nullptr;  // set below, once the staging buffer exists
+        jb.in_len = sl.tail.size();
+        jb.start_bit = sl.start_bit;
+        jb.flags = flags;
+        jb.buf = sl.d_buf;
+        jb.pos = sl.pos;
+        jb.lo = sl.lo;
+        jb.room = room;
+        jobs.push_back(jb);
+        owner.push_back(i);
+        stage_bytes += (sl.tail.size() + 15 + 16) & ~(uint64_t)15;
+    }
+    if (jobs.empty()) return 0;
+    int r;
+    if ((r = grow(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, stage_bytes + 64))) return r;
+    {
+        void* p = ctx->d_jobs;
+        size_t cap_bytes = ctx->d_jobs_cap * sizeof(K3StreamJob);
+        if ((r = grow(ctx, &p, &cap_bytes, jobs.size() * sizeof(K3StreamJob)))) return r;
+        ctx->d_jobs = (K3StreamJob*)p;
+        ctx->d_jobs_cap = cap_bytes / sizeof(K3StreamJob);
+    }
+    std::vector<uint8_t> stage((size_t)stage_bytes + 64, 0);
+    uint64_t so = 0;
+    for (size_t k = 0; k < jobs.size(); k++) {
+        const fdb_ctx::stream_slot& sl = ctx->streams[ids[owner[k]]];
+        if (!sl.tail.empty()) memcpy(stage.data() + so, sl.tail.data(), sl.tail.size());
+        jobs[k].in = ctx->d_in + so;
+        so += (sl.tail.size() + 15 + 16) & ~(uint64_t)15;
+    }
+    FDB_TRY(cudaMemcpyAsync(ctx->d_in, stage.data(), stage.size(), cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemcpyAsync(ctx->d_jobs, jobs.data(), jobs.size() * sizeof(K3StreamJob), cudaMemcpyHostToDevice, st));
+    FDB_TRY(cudaMemsetAsync(ctx->d_counters + 2, 0, sizeof(uint32_t), st));
+    const uint32_t grid = (uint32_t)std::min<size_t>(jobs.size(), (size_t)std::max(ctx->sm_count, 1) * 8);
+    FDB_LAUNCH(inflate_stream_kernel, dim3(grid), dim3(32), sizeof(K3Smem), st, ctx->d_jobs, (uint32_t)jobs.size(), ctx->d_counters + 2);
+    ctx->launches++;
+    FDB_TRY(cudaGetLastError());
+    FDB_TRY(cudaMemcpyAsync(jobs.data(), ctx->d_jobs, jobs.size() * sizeof(K3StreamJob), cudaMemcpyDeviceToHost, st));
+    FDB_TRY(cudaStreamSynchronize(st));
+    for (size_t k = 0; k < jobs.size(); k++) {
+        const size_t i = owner[k];
+        fdb_ctx::stream_slot& sl = ctx->streams[ids[i]];
+        const K3StreamJob& jb = jobs[k];
+        if (jb.produced) FDB_TRY(cudaMemcpyAsync(out_base + out_off[i], sl.d_buf + sl.pos, jb.produced, cudaMemcpyDeviceToHost, st));
+        produced[i] = jb.produced;
+        sl.pos += jb.produced;
+        const uint64_t whole = std::min<uint64_t>(jb.consumed_bits >> 3, sl.tail.size());
+        sl.tail.erase(sl.tail.begin(), sl.tail.begin() + (ptrdiff_t)whole);
+        sl.start_bit = (uint32_t)(jb.consumed_bits & 7);
+        status[i] = jb.status;
+        if (jb.status >= 0) {  // complete, or an error: the decoder takes no more input (bytes behind the checksum are ignored)
+            sl.finished = true;
+            sl.final_status = jb.status;
+            sl.tail.clear();
+        }
+    }
+    FDB_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- several GPUs behind one handle --------------------------------------------------------------------------
+// Streams are independent: the batch is partitioned by stream, byte-balanced, and every device runs the
+// ordinary host-buffer call on its share from its own host thread.  No collective, no peer access; the only shared
+// resource is the host link.
+struct fdb_multi {
+    std::vector<fdb_ctx*> ctx;
+    std::vector<uint32_t> owner;  // device index of every stream of the last call
+    char err[600] = {0};
+};
+
+extern "C" int fdb_multi_create(const int* devices, int n_devices, fdb_multi** out) {
+    if (!out) return -1;
+    *out = nullptr;
+    if (!devices || n_devices <= 0 || n_devices > 64) return -1;
+    fdb_multi* m = new (std::nothrow) fdb_multi();
+    if (!m) return -3;
+    for (int k = 0; k < n_devices; k++) {
+        fdb_ctx* c = nullptr;
+        int r = fdb_create(devices[k], &c);
+        if (r != 0) {
+            for (fdb_ctx* x : m->ctx) fdb_destroy(x);
+            delete m;
+            return r;
+        }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return 0;
+}
+extern "C" void fdb_multi_destroy(fdb_multi* m) {
+    if (!m) return;
+    for (fdb_ctx* c : m->ctx) fdb_destroy(c);
+    delete m;
+}
+extern "C" int fdb_multi_device_count(const fdb_multi* m) { return m ? (int)m->ctx.size() : 0; }
+extern "C" const char* fdb_multi_last_error(const fdb_multi* m) { return m ? m->err : "null handle"; }
+extern "C" int fdb_multi_last_partition(const fdb_multi* m, uint32_t* owner, size_t n) {
+    if (!m || !owner || n != m->owner.size()) return -1;
+    memcpy(owner, m->owner.data(), n * sizeof(uint32_t));
+    return 0;
+}
+
+// longest-processing-time greedy (the partition of fdeflate_b200/shard.py): streams by cost descending, ties by index,
+// each to the least loaded device (first minimum).  Every device's list comes out in ascending stream order, so a
+// packer's ascending slot layout stays ascending per device and the pipeline can still cut it into chunks.
+static void partition_lpt(const std::vector<uint64_t>& cost, size_t world, std::vector<uint32_t>& owner) {
+    const size_t n = cost.size();
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+    typedef std::pair<uint64_t, uint32_t> Load;  // (bytes, device): the smallest pair is the first minimum
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pq;
+    for (size_t d = 0; d < world; d++) pq.push(Load(0, (uint32_t)d));
+    owner.assign(n, 0);
+    for (uint32_t i : order) {
+        Load l = pq.top();
+        pq.pop();
+        owner[i] = l.second;
+        l.first += std::max<uint64_t>(cost[i], 1);
+        pq.push(l);
+    }
+}
+
+static int multi_batch(fdb_multi* m, int kind, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                       uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len, uint64_t* consumed,
+                       int32_t* status, size_t n, uint32_t flags) {
+    if (!m || m->ctx.empty()) return -1;
+    m->err[0] = 0;
+    if (n == 0) {
+        m->owner.clear();
+        return 0;
+    }
+    if (!in_off || !in_len || !out_off || !out_cap || !out_len || !status) {
+        snprintf(m->err, sizeof m->err, "fdb_multi_*: invalid argument");
+        return -1;
+    }
+    const size_t world = m->ctx.size();
+    std::vector<uint64_t> cost(n);
+    for (size_t i = 0; i < n; i++) cost[i] = in_len[i] + (kind == 0 ? out_cap[i] : 0);
+    partition_lpt(cost, world, m->owner);
+    // When cutting the batch into `world` CONTIGUOUS runs of streams balances (nearly) as well -- it does whenever there
+    // are many streams per device -- that partition is used instead: a packer's slots then stay one contiguous range
+    // per device, which the pipeline moves in large copies.  Otherwise the LPT shares interleave in the caller's
+    // buffers, and each device copies back exactly its own slots.
+    bool exact = true;
+    {
+        uint64_t total = 0;
+        for (uint64_t c : cost) total += std::max<uint64_t>(c, 1);
+        std::vector<uint64_t> load(world, 0);
+        for (size_t i = 0; i < n; i++) load[m->owner[i]] += std::max<uint64_t>(cost[i], 1);
+        const uint64_t lpt_max = *std::max_element(load.begin(), load.end());
+        std::vector<uint32_t> run(n);
+        std::vector<uint64_t> rload(world, 0);
+        uint64_t acc = 0;
+        for (size_t i = 0; i < n; i++) {
+            const uint64_t c = std::max<uint64_t>(cost[i], 1);
+            size_t d = (size_t)(((acc + c / 2) * world) / total);  // the device whose range holds the stream's midpoint
+            if (d >= world) d = world - 1;
+            run[i] = (uint32_t)d;
+            rload[d] += c;
+            acc += c;
+        }
+        bool ascending = true;
+        for (size_t i = 1; i < n && ascending; i++)
+            ascending = in_off[i] >= in_off[i - 1] + in_len[i - 1] && out_off[i] >= out_off[i - 1] + out_cap[i - 1];
+        const uint64_t run_max = *std::max_element(rload.begin(), rload.end());
+        if (ascending && run_max <= lpt_max + lpt_max / 32) {
+            m->owner = run;
+            exact = false;
+        }
+    }
+    struct Share {
+        std::vector<uint32_t> idx;
+        std::vector<uint64_t> in_off, in_len, out_off, out_cap, out_len, consumed;
+        std::vector<int32_t> status;
+        int rc = 0;
+    };
+    std::vector<Share> sh(world);
+    for (size_t i = 0; i < n; i++) sh[m->owner[i]].idx.push_back((uint32_t)i);
+    auto run = [&](size_t d) {
+        Share& s = sh[d];
+        const size_t k = s.idx.size();
+        if (k == 0) return;
+        s.in_off.resize(k), s.in_len.resize(k), s.out_off.resize(k), s.out_cap.resize(k), s.out_len.assign(k, 0);
+        s.consumed.assign(k, 0), s.status.assign(k, 0);
+        for (size_t j = 0; j < k; j++) {
+            const uint32_t i = s.idx[j];
+            s.in_off[j] = in_off[i], s.in_len[j] = in_len[i], s.out_off[j] = out_off[i], s.out_cap[j] = out_cap[i];
+        }
+        s.rc = host_batch(m->ctx[d], kind, in_base, s.in_off.data(), s.in_len.data(), out_base, s.out_off.data(), s.out_cap.data(),
+                          s.out_len.data(), kind == 0 ? s.consumed.data() : nullptr, s.status.data(), k, flags, nullptr, exact);
+    };
+#ifdef FDB_EMUL
+    for (size_t d = 0; d < world; d++) run(d);  // (the test-only emulator is single-threaded)
+#else
+    {
+        std::vector<std::thread> th;
+        for (size_t d = 1; d < world; d++) th.emplace_back(run, d);
+        run(0);
+        for (auto& t : th) t.join();
+    }
+#endif
+    int rc = 0;
+    for (size_t d = 0; d < world; d++) {
+        const Share& s = sh[d];
+        if (s.rc != 0 && rc == 0) {
+            rc = s.rc;
+            snprintf(m->err, sizeof m->err, "device %zu: %s", d, fdb_last_error(m->ctx[d]));
+        }
+        for (size_t j = 0; j < s.idx.size(); j++) {
+            const uint32_t i = s.idx[j];
+            out_len[i] = s.out_len[j];
+            status[i] = s.status[j];
+            if (consumed) consumed[i] = s.consumed[j];
+        }
+    }
+    return rc;
+}
+
+extern "C" int fdb_multi_inflate_batch(fdb_multi* m, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                                       uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                                       uint64_t* consumed, int32_t* status, size_t n, uint32_t flags) {
+    return multi_batch(m, 0, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, consumed, status, n, flags);
+}
+extern "C" int fdb_multi_deflate_ultrafast_batch(fdb_multi* m, const uint8_t* in_base, const uint64_t* in_off,
+                                                 const uint64_t* in_len, uint8_t* out_base, const uint64_t* out_off,
+                                                 const uint64_t* out_cap, uint64_t* out_len, int32_t* status, size_t n) {
+    return multi_batch(m, 1, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, nullptr, status, n, 0);
+}
+extern "C" int fdb_multi_deflate_stored_batch(fdb_multi* m, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                                              uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                                              int32_t* status, size_t n) {
+    return multi_batch(m, 2, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, nullptr, status, n, 0);
 }

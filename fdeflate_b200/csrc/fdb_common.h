@@ -39,6 +39,10 @@ enum Status : int32_t {
     ST_PNG_UNSUPPORTED = 23,
     // internal: ultra-fast-format fast path declined the stream; the general kernel redoes it
     ST_PENDING_GENERAL = -1,
+    // streaming decoders (fdb_stream_read_batch): the call stopped at a token boundary because the input given so
+    // far ends inside the next item / the caller's room is full; both are "call again", not errors
+    ST_STREAM_NEED_INPUT = -2,
+    ST_STREAM_OUTPUT_FULL = -3,
 };
 
 enum : uint32_t { FLAG_IGNORE_ADLER32 = 1u };

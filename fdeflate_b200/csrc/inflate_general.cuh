@@ -21,6 +21,8 @@
 // (the reference's nbits gates only bind when its reservoir holds every remaining bit):
 // see DESIGN.md "Inflate semantics".
 #pragma once
+#include <stddef.h>
+
 #include "simt.h"
 #include "fdb_common.h"
 #include "adler.cuh"
@@ -301,6 +303,14 @@ struct OutCursor {
     uint8_t* out;
     uint64_t pos;
     uint64_t cap;
+    uint64_t lo;  // first position that holds output (0 except for a streaming decoder that has dropped old history):
+                  // a distance reaches back to `lo` at most
+};
+
+// What a streaming decoder carries from one fdb_stream_read_batch call to the next besides its tables
+// (decode_block only; the block-level state is K3StreamState below).
+struct K3Resume {
+    uint32_t pend_len, pend_dist;  // the part of a match that did not fit the caller's room (reference QueuedOutput, :1066-1070)
 };
 
 // Matches are not executed one by one: the warp keeps decoding and parks up to 32 of them, one per
@@ -658,7 +668,7 @@ FDB_DEVICE bool decode_block_parallel(K3Smem& s, BitReader& r, OutCursor& o) {
                     o.out[o0 + rel] = (uint8_t)t.lit;
                     if (t.bytes == 2) o.out[o0 + rel + 1] = (uint8_t)(t.lit >> 8);
                 } else if (t.kind == GT_MATCH) {
-                    if ((uint64_t)t.dist > o0 + rel) bad = true;  // DistanceTooFarBack: the sequential decoder reports it
+                    if ((uint64_t)t.dist > o0 + rel - o.lo) bad = true;  // DistanceTooFarBack: the sequential decoder reports it
                     s.pmatch[mi] = make_uint2(rel, t.bytes | (t.dist << 16));
                     mi++;
                 } else {
@@ -805,7 +815,7 @@ FDB_DEVICE void decode_block_fast(K3Smem& s, BitReader& r, OutCursor& o, MatchQu
         if (!(de & DS_VALID)) break;  // long or invalid distance code
         const uint32_t dbits = de & 15u, dextra = (de >> 4) & 15u;
         const uint32_t dist = (de >> 16) + ((dbitsw >> dbits) & ((1u << dextra) - 1u));
-        if (dist > pos) break;  // DistanceTooFarBack, reported by the careful loop
+        if (dist > pos - o.lo) break;  // DistanceTooFarBack, reported by the careful loop
         if (lane == mq.qn) {
             mq.dst = pos;
             mq.len = length;
@@ -822,8 +832,12 @@ FDB_DEVICE void decode_block_fast(K3Smem& s, BitReader& r, OutCursor& o, MatchQu
     br_seek(r, r.pos + used);
 }
 
+// rs == nullptr: whole-buffer semantics (decompress_to_vec_bounded).  rs != nullptr: a streaming decoder -- where the
+// whole-buffer call would report InsufficientInput or OutputTooLarge, the reader goes back to the start of the token it
+// could not finish and returns ST_STREAM_NEED_INPUT / ST_STREAM_OUTPUT_FULL; the next call carries on from there with
+// more input / more room (what the reference's read() does with its bit reservoir and its QueuedOutput, :194-219).
 FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t eof_code, uint32_t eof_bits,
-                                bool* too_large) {
+                                bool* too_large, K3Resume* rs = nullptr) {
     const unsigned lane = simt::lane_id();
     const uint32_t eof_mask = (1u << eof_bits) - 1u;
     MatchQueue mq = {0, 0, 0, 0};
@@ -843,23 +857,38 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
 #endif
         br_refill(r);
         uint64_t avail = br_avail(r);
+        const uint64_t tok_pos = r.pos;  // where this token starts
+// the input ends inside this token
+#define K3_STARVED()                              \
+    do {                                          \
+        if (rs) {                                 \
+            br_seek(r, tok_pos);                  \
+            K3_RETURN(ST_STREAM_NEED_INPUT);      \
+        }                                         \
+        K3_RETURN(ST_INSUFFICIENT_INPUT);         \
+    } while (0)
         if (o.pos == o.cap) {
             // output exactly full: only an end-of-block code may follow (EOB peek, :1009-1015)
             if (avail >= 15 && (br_peek(r, 15) & eof_mask) == eof_code) {
                 br_consume(r, eof_bits);
                 K3_RETURN(ST_OK);
             }
+            if (rs) K3_RETURN(ST_STREAM_OUTPUT_FULL);
             *too_large = true;
             K3_RETURN(ST_OK);
         }
         uint32_t e = s.litlen[br_peek(r, 12)];
         uint32_t nbits = e & 15u;
         if (e & LL_LIT) {  // :846-877
-            if (avail < nbits) K3_RETURN(ST_INSUFFICIENT_INPUT);
+            if (avail < nbits) K3_STARVED();
             bool two = (e & LL_LIT2) != 0;
             if (lane == 0) o.out[o.pos] = (uint8_t)(e >> 8);
             if (two && o.pos + 1 == o.cap) {  // second literal does not fit (queued in the reference)
                 o.pos += 1;
+                if (rs) {  // take the first literal only; the second one is decoded again by the next call
+                    br_consume(r, (e >> 24) & 15u);
+                    K3_RETURN(ST_STREAM_OUTPUT_FULL);
+                }
                 br_consume(r, nbits);
                 *too_large = true;
                 K3_RETURN(ST_OK);
@@ -871,7 +900,7 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
         }
         uint32_t len_base, len_extra;
         if (e & LL_EOB) {  // :910-918 (includes the 286/287 quirk)
-            if (avail < nbits) K3_RETURN(ST_INSUFFICIENT_INPUT);
+            if (avail < nbits) K3_STARVED();
             br_consume(r, nbits);
             K3_RETURN(ST_OK);
         } else if (e & LL_LEN) {
@@ -881,7 +910,7 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
             uint32_t sym = 0;
             if (!canon_long_decode(s, 0, s.sorted_lit, br_peek(r, 15), 13, &sym, &nbits))
                 K3_RETURN(ST_INVALID_LITERAL_LENGTH_CODE);
-            if (avail < nbits) K3_RETURN(ST_INSUFFICIENT_INPUT);
+            if (avail < nbits) K3_STARVED();
             if (sym < 256) {
                 if (lane == 0) o.out[o.pos] = (uint8_t)sym;
                 o.pos += 1;
@@ -914,12 +943,12 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
             dextra = dist_sym_extra(dsym);
             dbase = dist_sym_base(dsym);
         } else {
-            K3_RETURN(ST_INSUFFICIENT_INPUT);  // `break` with the input exhausted
+            K3_STARVED();  // `break` with the input exhausted
         }
         uint32_t dd_bits = dbits + dextra;  // <= 28
         uint64_t dist = dbase + ((br_peek(r, dd_bits) >> dbits) & ((1u << dextra) - 1u));
-        if (avail < (uint64_t)le_bits + dd_bits) K3_RETURN(ST_INSUFFICIENT_INPUT);  // :961
-        if (dist > o.pos) K3_RETURN(ST_DISTANCE_TOO_FAR_BACK);                        // :963
+        if (avail < (uint64_t)le_bits + dd_bits) K3_STARVED();                          // :961
+        if (dist > o.pos - o.lo) K3_RETURN(ST_DISTANCE_TOO_FAR_BACK);                  // :963
         br_consume(r, dd_bits);
 
         uint64_t room = o.cap - o.pos;
@@ -932,12 +961,101 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
         mq.qn++;
         o.pos += n;
         if (n < length) {  // remainder would be queued (:797-801, :823-827) => output too large
+            if (rs) {
+                rs->pend_len = length - n;
+                rs->pend_dist = (uint32_t)dist;
+                K3_RETURN(ST_STREAM_OUTPUT_FULL);
+            }
             *too_large = true;
             K3_RETURN(ST_OK);
         }
         if (mq.qn == 32) mq_flush(o.out, mq);
     }
+#undef K3_STARVED
 #undef K3_RETURN
+}
+
+// The header of a dynamic block, its 3 type bits included (:415-434, :440-555): HLIT / HDIST / HCLEN, the code-length
+// code, the HLIT + HDIST code lengths into s.lens (litlen at 0..287, distance at 288..319).  ST_INSUFFICIENT_INPUT
+// when the input ends inside the header (a streaming decoder then parses it again from its first bit).
+FDB_DEVICE int32_t read_dynamic_header(K3Smem& s, BitReader& r, uint32_t* hlit_out) {
+    const unsigned lane = simt::lane_id();
+    if (br_avail(r) < 17) return ST_INSUFFICIENT_INPUT;
+    uint32_t hlit = (br_peek(r, 8) >> 3) + 257;
+    uint32_t hdist = (br_peek(r, 13) >> 8) + 1;
+    uint32_t hclen = (br_peek(r, 17) >> 13) + 4;
+    if (hlit > 286) return ST_INVALID_HLIT;
+    if (hdist > 30) return ST_INVALID_HDIST;
+    br_consume(r, 17);
+    if (br_avail(r) < 3ull * hclen) return ST_INSUFFICIENT_INPUT;
+    if (lane < 32) s.cl_lens[lane] = 0;
+    simt::syncwarp();
+    for (uint32_t i = 0; i < hclen; i++) {
+        br_refill(r);
+        // reference tables.rs:63-65 CLCL_ORDER, packed 5 bits per entry
+        const uint64_t order_lo = 0x22caa324e804a30ull;  // entries 0..11
+        const uint64_t order_hi = 0x3c2e1346cull;  // entries 12..18
+        uint32_t sym = (i < 12) ? (uint32_t)((order_lo >> (5 * i)) & 31u)
+                                : (uint32_t)((order_hi >> (5 * (i - 12))) & 31u);
+        if (lane == 0) s.cl_lens[sym] = (uint8_t)br_peek(r, 3);
+        br_consume(r, 3);
+    }
+    simt::syncwarp();
+    canon_setup(s, 2, s.cl_lens, 19, s.sorted_cl, 7);
+    if (!s.info[1]) return ST_BAD_CODE_LENGTH_HUFFMAN_TREE;  // :462-472
+    for (uint32_t idx = lane; idx < 128; idx += 32) {
+        uint32_t v = simt::brev(idx) >> 25;
+        uint32_t e = 0;
+        for (uint32_t L = 1; L <= 7; L++) {
+            if (v < s.lim[2][L]) {
+                uint32_t c = v >> (7 - L);
+                e = ((uint32_t)s.sorted_cl[s.off[2][L] + c - s.first[2][L]] << 3) | L;
+                break;
+            }
+        }
+        s.cl_table[idx] = (uint8_t)e;
+    }
+    simt::syncwarp();
+    // code lengths (:479-539)
+    uint32_t total = hlit + hdist, nread = 0;
+    while (nread < total) {
+        br_refill(r);
+        uint64_t avail = br_avail(r);
+        if (avail < 7) return ST_INSUFFICIENT_INPUT;
+        uint32_t ce = s.cl_table[br_peek(r, 7)];
+        uint32_t clen = ce & 7u, sym = ce >> 3;
+        if (sym <= 15) {
+            if (lane == 0) s.lens[nread] = (uint8_t)sym;
+            nread += 1;
+            br_consume(r, clen);
+        } else {
+            uint32_t base_repeat = sym == 18 ? 11u : 3u;
+            uint32_t extra = sym == 16 ? 2u : sym == 17 ? 3u : 7u;
+            if (avail < clen + extra) return ST_INSUFFICIENT_INPUT;
+            uint32_t value = 0;
+            if (sym == 16) {
+                if (nread == 0) return ST_INVALID_CODE_LENGTH_REPEAT;
+                simt::syncwarp();
+                value = s.lens[nread - 1];
+            }
+            uint32_t repeat = (br_peek(r, clen + extra) >> clen) + base_repeat;
+            if (nread + repeat > total) return ST_INVALID_CODE_LENGTH_REPEAT;
+            simt::syncwarp();
+            if (lane < repeat) s.lens[nread + lane] = (uint8_t)value;
+            for (uint32_t i = 32 + lane; i < repeat; i += 32) s.lens[nread + i] = (uint8_t)value;
+            nread += repeat;
+            br_consume(r, clen + extra);
+        }
+    }
+    simt::syncwarp();
+    // split into litlen[0..288) and dist[288..320) (:541-549); hdist <= 30 so no overlap issues
+    uint8_t dl = (lane < hdist) ? s.lens[hlit + lane] : (uint8_t)0;
+    simt::syncwarp();
+    for (uint32_t i = hlit + lane; i < 288; i += 32) s.lens[i] = 0;
+    s.lens[288 + lane] = dl;
+    simt::syncwarp();
+    *hlit_out = hlit;
+    return ST_OK;
 }
 
 // ---- whole stream --------------------------------------------------------------------------
@@ -946,7 +1064,7 @@ FDB_DEVICE int32_t inflate_stream_general(K3Smem& s, const uint8_t* in, uint64_t
     const unsigned lane = simt::lane_id();
     BitReader r;
     br_init(r, in, n);
-    OutCursor o = {out, 0, cap};
+    OutCursor o = {out, 0, cap, 0};
     *out_len = 0;
     *consumed = 0;
 
@@ -1007,93 +1125,14 @@ FDB_DEVICE int32_t inflate_stream_general(K3Smem& s, const uint8_t* in, uint64_t
             }
             if (st == ST_OK) st = decode_block(s, r, o, fixed_eof_code, fixed_eof_bits, &too_large);
         } else if (btype == 2) {  // dynamic (:415-434, :440-555)
-            if (br_avail(r) < 17) {
-                *out_len = o.pos;
-                return ST_INSUFFICIENT_INPUT;
-            }
-            uint32_t hlit = (br_peek(r, 8) >> 3) + 257;
-            uint32_t hdist = (br_peek(r, 13) >> 8) + 1;
-            uint32_t hclen = (br_peek(r, 17) >> 13) + 4;
-            if (hlit > 286) return ST_INVALID_HLIT;
-            if (hdist > 30) return ST_INVALID_HDIST;
-            br_consume(r, 17);
+            uint32_t hlit = 0;
+            st = read_dynamic_header(s, r, &hlit);
             fixed_ready = false;
-            if (br_avail(r) < 3ull * hclen) {
+            if (st == ST_INSUFFICIENT_INPUT) {
                 *out_len = o.pos;
-                return ST_INSUFFICIENT_INPUT;
+                return st;
             }
-            if (lane < 32) s.cl_lens[lane] = 0;
-            simt::syncwarp();
-            for (uint32_t i = 0; i < hclen; i++) {
-                br_refill(r);
-                // reference tables.rs:63-65 CLCL_ORDER, packed 5 bits per entry
-                const uint64_t order_lo = 0x22caa324e804a30ull;  // entries 0..11
-                const uint64_t order_hi = 0x3c2e1346cull;  // entries 12..18
-                uint32_t sym = (i < 12) ? (uint32_t)((order_lo >> (5 * i)) & 31u)
-                                        : (uint32_t)((order_hi >> (5 * (i - 12))) & 31u);
-                if (lane == 0) s.cl_lens[sym] = (uint8_t)br_peek(r, 3);
-                br_consume(r, 3);
-            }
-            simt::syncwarp();
-            canon_setup(s, 2, s.cl_lens, 19, s.sorted_cl, 7);
-            if (!s.info[1]) return ST_BAD_CODE_LENGTH_HUFFMAN_TREE;  // :462-472
-            for (uint32_t idx = lane; idx < 128; idx += 32) {
-                uint32_t v = simt::brev(idx) >> 25;
-                uint32_t e = 0;
-                for (uint32_t L = 1; L <= 7; L++) {
-                    if (v < s.lim[2][L]) {
-                        uint32_t c = v >> (7 - L);
-                        e = ((uint32_t)s.sorted_cl[s.off[2][L] + c - s.first[2][L]] << 3) | L;
-                        break;
-                    }
-                }
-                s.cl_table[idx] = (uint8_t)e;
-            }
-            simt::syncwarp();
-            // code lengths (:479-539)
-            uint32_t total = hlit + hdist, nread = 0;
-            while (nread < total) {
-                br_refill(r);
-                uint64_t avail = br_avail(r);
-                if (avail < 7) {
-                    *out_len = o.pos;
-                    return ST_INSUFFICIENT_INPUT;
-                }
-                uint32_t ce = s.cl_table[br_peek(r, 7)];
-                uint32_t clen = ce & 7u, sym = ce >> 3;
-                if (sym <= 15) {
-                    if (lane == 0) s.lens[nread] = (uint8_t)sym;
-                    nread += 1;
-                    br_consume(r, clen);
-                } else {
-                    uint32_t base_repeat = sym == 18 ? 11u : 3u;
-                    uint32_t extra = sym == 16 ? 2u : sym == 17 ? 3u : 7u;
-                    if (avail < clen + extra) {
-                        *out_len = o.pos;
-                        return ST_INSUFFICIENT_INPUT;
-                    }
-                    uint32_t value = 0;
-                    if (sym == 16) {
-                        if (nread == 0) return ST_INVALID_CODE_LENGTH_REPEAT;
-                        simt::syncwarp();
-                        value = s.lens[nread - 1];
-                    }
-                    uint32_t repeat = (br_peek(r, clen + extra) >> clen) + base_repeat;
-                    if (nread + repeat > total) return ST_INVALID_CODE_LENGTH_REPEAT;
-                    simt::syncwarp();
-                    if (lane < repeat) s.lens[nread + lane] = (uint8_t)value;
-                    for (uint32_t i = 32 + lane; i < repeat; i += 32) s.lens[nread + i] = (uint8_t)value;
-                    nread += repeat;
-                    br_consume(r, clen + extra);
-                }
-            }
-            simt::syncwarp();
-            // split into litlen[0..288) and dist[288..320) (:541-549); hdist <= 30 so no overlap issues
-            uint8_t dl = (lane < hdist) ? s.lens[hlit + lane] : (uint8_t)0;
-            simt::syncwarp();
-            for (uint32_t i = hlit + lane; i < 288; i += 32) s.lens[i] = 0;
-            s.lens[288 + lane] = dl;
-            simt::syncwarp();
+            if (st != ST_OK) return st;
             uint32_t eof_code = 0, eof_bits = 0;
             st = build_block_tables(s, hlit, &eof_code, &eof_bits);
             if (st == ST_OK) st = decode_block(s, r, o, eof_code, eof_bits, &too_large);
@@ -1157,6 +1196,266 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(32, 1)
             if (b.consumed) b.consumed[i] = consumed;
         }
         simt::syncwarp();
+    }
+}
+
+// ---- streaming decoders: Decompressor::read kept on the device between calls -------------------------------------
+// (reference src/decompress.rs:96-113 struct, :158-219 read contract, :1066-1070 QueuedOutput)
+//
+// One K3StreamState per in-flight decoder lives in device memory owned by the context: where in the stream the decoder
+// stands (zlib header / block header / stored body / Huffman body / checksum), the tables of the block it is inside, a
+// match cut short by a full output, the running adler32.  Next to it a device buffer holds the decoder's recent output
+// (at least the last 32 KiB: the window matches reach into) with the new bytes appended behind it.
+// fdb_stream_read_batch hands every decoder the bytes it has not parsed yet plus the new input; the decoder resumes at
+// its checkpoint -- always a token boundary (or the first bit of a block header, which is parsed again once more of
+// it has arrived) -- decodes until the input ends inside the next item or the caller's room is full, and leaves a new
+// checkpoint.  Work per call is proportional to the bytes of that call (plus one 20 KB table restore), so feeding a
+// stream byte by byte is linear in its length, not quadratic.
+enum : uint32_t { PH_ZLIB = 0, PH_BLOCK = 1, PH_STORED = 2, PH_HUFF = 3, PH_CHECKSUM = 4, PH_DONE = 5, PH_ERROR = 6 };
+static const uint32_t K3_TABLE_WORDS = (uint32_t)(offsetof(K3Smem, pstg) / 4);  // everything decode_block reads
+
+struct K3StreamState {
+    uint32_t phase;
+    uint32_t last;         // the block the decoder is inside is the final one
+    uint32_t stored_left;  // PH_STORED: bytes of the block still to copy
+    uint32_t pend_len, pend_dist;
+    uint32_t eof_code, eof_bits;
+    uint32_t adler_a, adler_b;  // adler32 of everything produced so far
+    int32_t error;              // PH_ERROR: the status every later call reports
+    uint64_t total_out;
+    uint32_t tables[K3_TABLE_WORDS];  // PH_HUFF: the shared-memory tables of the block
+};
+
+// one call of one decoder
+struct K3StreamJob {
+    K3StreamState* state;
+    const uint8_t* in;    // the bytes not parsed yet, then the new ones
+    uint64_t in_len;
+    uint32_t start_bit;   // bits of in[0] already consumed (0..7)
+    uint32_t flags;
+    uint8_t* buf;         // buf[lo .. pos) = the most recent output, new output goes to buf[pos .. pos + room)
+    uint64_t pos, lo, room;
+    // results
+    uint64_t produced, consumed_bits;
+    int32_t status;       // ST_OK = stream complete; ST_STREAM_NEED_INPUT / ST_STREAM_OUTPUT_FULL; or an error
+};
+
+FDB_DEVICE void inflate_stream_resume(K3Smem& s, K3StreamJob& job) {
+    const unsigned lane = simt::lane_id();
+    K3StreamState& ss = *job.state;
+    uint32_t phase = ss.phase, last = ss.last, stored_left = ss.stored_left;
+    uint32_t eof_code = ss.eof_code, eof_bits = ss.eof_bits;
+    K3Resume rs = {ss.pend_len, ss.pend_dist};
+    int32_t st = ST_OK;
+    BitReader r;
+    br_init(r, job.in, job.in_len);
+    if (job.start_bit) br_seek(r, job.start_bit);
+    OutCursor o = {job.buf, job.pos, job.pos + job.room, job.lo};
+    uint32_t stored_sum = 0;
+    bool have_sum = false;
+    simt::syncwarp();
+    if (phase == PH_DONE) {
+        st = ST_OK;
+    } else if (phase == PH_ERROR) {
+        st = ss.error;
+    } else {
+        if (phase == PH_HUFF) {  // back inside a block: its tables
+            uint32_t* dst = reinterpret_cast<uint32_t*>(&s);
+            for (uint32_t i = lane; i < K3_TABLE_WORDS; i += 32) dst[i] = ss.tables[i];
+            simt::syncwarp();
+            if (rs.pend_len) {  // the rest of the match the last call could not finish
+                const uint64_t room = o.cap - o.pos;
+                const uint32_t n = rs.pend_len < room ? rs.pend_len : (uint32_t)room;
+                uint8_t* d = o.out + o.pos;
+                const uint8_t* src = d - rs.pend_dist;
+                if (rs.pend_dist >= n) {
+                    for (uint32_t i = lane; i < n; i += 32) d[i] = src[i];
+                } else {
+                    for (uint32_t i = lane; i < n; i += 32) d[i] = src[i % rs.pend_dist];
+                }
+                simt::syncwarp();
+                o.pos += n;
+                rs.pend_len -= n;
+            }
+        }
+        for (;;) {
+            if (phase == PH_ZLIB) {  // :226-244
+                if (br_avail(r) < 16) {
+                    st = ST_STREAM_NEED_INPUT;
+                    break;
+                }
+                uint32_t cmf = br_peek(r, 8), flg = br_peek(r, 16) >> 8;
+                if ((cmf & 0x0f) != 0x08 || (cmf & 0xf0) > 0x70 || (flg & 0x20) != 0 || ((cmf << 8) | flg) % 31 != 0) {
+                    st = ST_BAD_ZLIB_HEADER;
+                    break;
+                }
+                br_consume(r, 16);
+                phase = PH_BLOCK;
+            } else if (phase == PH_BLOCK) {
+                const uint64_t hdr_pos = r.pos;  // a header the input ends inside is parsed again from here
+                br_refill(r);
+                if (br_avail(r) < 10) {  // :346
+                    st = ST_STREAM_NEED_INPUT;
+                    break;
+                }
+                const uint32_t hdr = br_peek(r, 3);
+                last = hdr & 1u;
+                const uint32_t btype = hdr >> 1;
+                if (btype == 0) {  // stored (:353-370)
+                    const uint32_t align = (8u - (uint32_t)((r.pos + 3) & 7)) & 7u;
+                    if (br_avail(r) < 3 + 32 + align) {
+                        st = ST_STREAM_NEED_INPUT;
+                        break;
+                    }
+                    br_consume(r, 3 + align);
+                    br_refill(r);
+                    const uint32_t v = br_peek(r, 32);
+                    const uint32_t len = v & 0xffffu, nlen = v >> 16;
+                    if (nlen != (len ^ 0xffffu)) {
+                        st = ST_INVALID_UNCOMPRESSED_BLOCK_LENGTH;
+                        break;
+                    }
+                    br_consume(r, 32);
+                    stored_left = len;
+                    phase = PH_STORED;
+                } else if (btype == 1) {  // fixed (:371-414)
+                    br_consume(r, 3);
+                    load_fixed_lengths(s);
+                    st = build_block_tables(s, 288, &eof_code, &eof_bits);
+                    if (st != ST_OK) break;
+                    phase = PH_HUFF;
+                } else if (btype == 2) {  // dynamic (:415-434, :440-555)
+                    uint32_t hlit = 0;
+                    st = read_dynamic_header(s, r, &hlit);
+                    if (st == ST_INSUFFICIENT_INPUT) {
+                        br_seek(r, hdr_pos);
+                        st = ST_STREAM_NEED_INPUT;
+                        break;
+                    }
+                    if (st != ST_OK) break;
+                    st = build_block_tables(s, hlit, &eof_code, &eof_bits);
+                    if (st != ST_OK) break;
+                    phase = PH_HUFF;
+                } else {
+                    st = ST_INVALID_BLOCK_TYPE;  // :435
+                    break;
+                }
+            } else if (phase == PH_STORED) {  // :271-305; the reader stands on a byte boundary
+                const uint64_t src_byte = r.pos >> 3;
+                const uint64_t in_left = job.in_len - src_byte;
+                const uint64_t room = o.cap - o.pos;
+                uint64_t ncopy = stored_left;
+                if (ncopy > in_left) ncopy = in_left;
+                if (ncopy > room) ncopy = room;
+                for (uint64_t i = lane; i < ncopy; i += 32) o.out[o.pos + i] = simt::ldg8(job.in + src_byte + i);
+                o.pos += ncopy;
+                stored_left -= (uint32_t)ncopy;
+                br_seek(r, (src_byte + ncopy) * 8);
+                if (stored_left) {
+                    st = (o.pos == o.cap) ? ST_STREAM_OUTPUT_FULL : ST_STREAM_NEED_INPUT;
+                    break;
+                }
+                phase = last ? PH_CHECKSUM : PH_BLOCK;
+            } else if (phase == PH_HUFF) {
+                if (rs.pend_len) {  // (the room was used up by the pending match)
+                    st = ST_STREAM_OUTPUT_FULL;
+                    break;
+                }
+                bool too_large = false;
+                st = decode_block(s, r, o, eof_code, eof_bits, &too_large, &rs);
+                if (st != ST_OK) break;  // need input / output full (the checkpoint is r.pos), or an error
+                phase = last ? PH_CHECKSUM : PH_BLOCK;
+            } else {  // PH_CHECKSUM (:306-326)
+                const uint32_t align = (8u - (uint32_t)(r.pos & 7)) & 7u;
+                if (br_avail(r) < 32 + align) {
+                    st = ST_STREAM_NEED_INPUT;
+                    break;
+                }
+                br_consume(r, align);
+                br_refill(r);
+                stored_sum = simt::byte_perm(br_peek(r, 32), 0, 0x0123);  // big-endian on the wire
+                br_consume(r, 32);
+                have_sum = true;
+                phase = PH_DONE;
+                st = ST_OK;
+                break;
+            }
+        }
+    }
+    simt::syncwarp();
+    // adler32 of the new bytes, appended to the running value: a' = a + sum d, b' = b + n a + sum (n - i) d_i
+    const uint64_t produced = o.pos - job.pos;
+    uint32_t a = ss.adler_a, b = ss.adler_b;
+    if (produced && !(job.flags & FLAG_IGNORE_ADLER32)) {
+        const uint8_t* d = job.buf + job.pos;
+        for (uint64_t base = 0; base < produced; base += 4096) {  // (4096 * 255 * 4096 < 2^32)
+            const uint32_t n = produced - base < 4096 ? (uint32_t)(produced - base) : 4096u;
+            uint32_t s1 = 0, s2 = 0;
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint32_t v = simt::ldcg8(d + base + i);
+                s1 += v;
+                s2 += (n - i) * v;
+            }
+            s1 = simt::reduce_add(s1);
+            s2 = simt::reduce_add(s2 % ADLER_MOD) % ADLER_MOD;
+            b = (uint32_t)((b + (uint64_t)n * a + s2) % ADLER_MOD);
+            a = (a + s1) % ADLER_MOD;
+        }
+    }
+    if (have_sum && !(job.flags & FLAG_IGNORE_ADLER32) && ((b << 16) | a) != stored_sum) st = ST_WRONG_CHECKSUM;
+    if (st > 0) phase = PH_ERROR;
+    // the checkpoint
+    if (phase == PH_HUFF && ss.phase != PH_ERROR && ss.phase != PH_DONE) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&s);
+        for (uint32_t i = lane; i < K3_TABLE_WORDS; i += 32) ss.tables[i] = src[i];
+    }
+    simt::syncwarp();
+    if (lane == 0 && ss.phase != PH_ERROR && ss.phase != PH_DONE) {
+        ss.phase = phase;
+        ss.last = last;
+        ss.stored_left = stored_left;
+        ss.pend_len = rs.pend_len;
+        ss.pend_dist = rs.pend_dist;
+        ss.eof_code = eof_code;
+        ss.eof_bits = eof_bits;
+        ss.adler_a = a;
+        ss.adler_b = b;
+        ss.total_out += produced;
+        if (st > 0) ss.error = st;
+    }
+    if (lane == 0) {
+        job.produced = produced;
+        job.consumed_bits = r.pos;
+        job.status = st;
+    }
+    simt::syncwarp();
+}
+
+// one warp per decoder
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(32, 1) inflate_stream_kernel(K3StreamJob* jobs, uint32_t n, uint32_t* next) {
+    FDB_DYN_SMEM(smem_raw);
+    K3Smem& s = *reinterpret_cast<K3Smem*>(smem_raw);
+    const unsigned lane = simt::lane_id();
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = simt::atomic_add(next, 1u);
+        idx = simt::shfl(idx, 0);
+        if (idx >= n) break;
+        inflate_stream_resume(s, jobs[idx]);
+    }
+}
+
+// keep the last `keep` bytes of buf[0 .. pos) at the front of the buffer (the window of a decoder whose buffer is full)
+FDB_GLOBAL void stream_compact_kernel(uint8_t* buf, uint64_t pos, uint64_t keep) {
+    const uint64_t shift = pos - keep;  // > 0
+    // dst < src: chunks in ascending order, every chunk read completely before it is written
+    for (uint64_t base = 0; base < keep; base += blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        uint8_t v = 0;
+        if (i < keep) v = buf[shift + i];
+        simt::syncthreads();
+        if (i < keep) buf[i] = v;
+        simt::syncthreads();
     }
 }
 

@@ -230,6 +230,54 @@ int fdb_set_split_threshold(fdb_ctx* ctx, size_t inflate_stream_bytes, size_t de
  * (0 = every stream was decoded by one warp).  Synchronises `cuda_stream`. */
 int64_t fdb_last_split_spans(fdb_ctx* ctx, void* cuda_stream);
 
+/* ---- streaming decoders: Decompressor::read with its state kept on the device (src/decompress.rs:96-113, :158-219) ----
+ * A decoder is opened, fed any number of times with whatever input has arrived and whatever room the caller has, and
+ * closed.  Every call of fdb_stream_read_batch advances all the decoders it names in ONE launch.  For decoder ids[i]
+ * the call TAKES all of in_base[in_off[i] .. + in_len[i]) (what cannot be parsed yet -- the input may end inside a
+ * token or a block header -- is kept by the context), writes at most out_room[i] bytes to out_base + out_off[i] and
+ * reports in produced[i] how many; the bytes come out in stream order, each exactly once, whatever the chunking.
+ * status[i]: FDB_OK = the stream is complete (checksum verified unless FDB_FLAG_IGNORE_ADLER32; later calls produce
+ * nothing, :185-187), FDB_STREAM_NEED_INPUT = everything given so far is decoded, FDB_STREAM_OUTPUT_FULL = the room is
+ * used up and more output is pending (call again, in_len may be 0), or a DecompressionError (1..16), after which the
+ * decoder stays in that state.  The work of a call is proportional to the bytes of that call, not to the length of
+ * the stream so far: the decoder resumes at a token boundary with its tables, its 32 KiB window, a match cut short by
+ * a full output (the reference's QueuedOutput, :1066-1070) and its running adler32 kept in device memory. */
+#define FDB_STREAM_NEED_INPUT (-2)
+#define FDB_STREAM_OUTPUT_FULL (-3)
+int fdb_stream_open_batch(fdb_ctx* ctx, uint32_t* ids, size_t n);
+int fdb_stream_read_batch(fdb_ctx* ctx, const uint32_t* ids, const uint8_t* in_base, const uint64_t* in_off,
+                          const uint64_t* in_len, uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_room,
+                          uint64_t* produced, int32_t* status, size_t n, uint32_t flags);
+int fdb_stream_close_batch(fdb_ctx* ctx, const uint32_t* ids, size_t n);
+
+/* ---- several GPUs of one box behind one handle (SURVEY 8b `device set`, 8e) -----------------------------
+ * A batch shards by stream with no exchange step: fdb_multi_* partitions the streams over the devices of the
+ * set, byte-balanced on in_len + out_cap (resp. in_len) -- contiguous runs of streams when that balances within 3 %
+ * of the longest-processing-time greedy partition (it does with many streams per device, and keeps every device's
+ * slots one range of the caller's buffers), the greedy partition itself otherwise; a stream is never split across
+ * GPUs -- and drives one host thread and one context per device: each runs the ordinary pipelined host-buffer
+ * call on its share, reading and writing the caller's slots in place.  The call returns when every share is done.
+ * With interleaved shares every device copies back exactly its own slots (nothing between them is written).
+ * Arguments and per-stream results are exactly those of the single-device calls; results do not depend on the
+ * device set.  devices[] holds CUDA ordinals (a device may appear more than once: that many contexts on it).
+ * fdb_multi_last_error returns the text of the first device that failed. */
+typedef struct fdb_multi fdb_multi;
+int fdb_multi_create(const int* devices, int n_devices, fdb_multi** out);
+void fdb_multi_destroy(fdb_multi* m);
+int fdb_multi_device_count(const fdb_multi* m);
+const char* fdb_multi_last_error(const fdb_multi* m);
+int fdb_multi_inflate_batch(fdb_multi* m, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                            uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                            uint64_t* consumed, int32_t* status, size_t n, uint32_t flags);
+int fdb_multi_deflate_ultrafast_batch(fdb_multi* m, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                                      uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                                      int32_t* status, size_t n);
+int fdb_multi_deflate_stored_batch(fdb_multi* m, const uint8_t* in_base, const uint64_t* in_off, const uint64_t* in_len,
+                                   uint8_t* out_base, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                                   int32_t* status, size_t n);
+/* which device (index into devices[]) stream i of the most recent fdb_multi_* call ran on; owner[n] */
+int fdb_multi_last_partition(const fdb_multi* m, uint32_t* owner, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,26 @@ private:
     fdb_ctx* h_ = nullptr;
 };
 
+// Several GPUs of one box behind one handle (fdb_multi_*): batches shard by stream, no collective.
+class DeviceSet {
+public:
+    explicit DeviceSet(const std::vector<int>& devices) {
+        int rc = fdb_multi_create(devices.data(), (int)devices.size(), &m_);
+        if (rc != 0 || !m_) throw std::runtime_error("fdb_multi_create failed (code " + std::to_string(rc) + "): no usable CUDA device");
+    }
+    ~DeviceSet() { fdb_multi_destroy(m_); }
+    DeviceSet(const DeviceSet&) = delete;
+    DeviceSet& operator=(const DeviceSet&) = delete;
+    fdb_multi* handle() const { return m_; }
+    int device_count() const { return fdb_multi_device_count(m_); }
+    void check(int rc, const char* what) const {
+        if (rc != 0) throw std::runtime_error(std::string(what) + ": " + fdb_multi_last_error(m_));
+    }
+
+private:
+    fdb_multi* m_ = nullptr;
+};
+
 // ---- batch entry points (new surface) ---------------------------------------------------------
 struct InflateResult {
     std::vector<int32_t> status;
@@ -84,7 +104,8 @@ struct InflateResult {
 
 class Batch {
 public:
-    explicit Batch(Context& ctx) : ctx_(ctx) {}
+    explicit Batch(Context& ctx) : ctx_(&ctx) {}
+    explicit Batch(DeviceSet& set) : set_(&set) {}  // the same calls, sharded over the GPUs of the set
 
     InflateResult inflate(const std::vector<std::vector<uint8_t>>& streams, const std::vector<uint64_t>& out_caps,
                           uint32_t flags = 0) {
@@ -102,9 +123,14 @@ public:
         std::vector<uint8_t> in(ip + 16), out(op + 16);
         for (size_t i = 0; i < n; i++)
             if (in_len[i]) std::memcpy(in.data() + in_off[i], streams[i].data(), in_len[i]);
-        ctx_.check(fdb_inflate_batch(ctx_.handle(), in.data(), in_off.data(), in_len.data(), out.data(), out_off.data(),
-                                     out_caps.data(), out_len.data(), consumed.data(), status.data(), n, flags),
-                   "fdb_inflate_batch");
+        if (set_)
+            set_->check(fdb_multi_inflate_batch(set_->handle(), in.data(), in_off.data(), in_len.data(), out.data(), out_off.data(),
+                                                out_caps.data(), out_len.data(), consumed.data(), status.data(), n, flags),
+                        "fdb_multi_inflate_batch");
+        else
+            ctx_->check(fdb_inflate_batch(ctx_->handle(), in.data(), in_off.data(), in_len.data(), out.data(), out_off.data(),
+                                          out_caps.data(), out_len.data(), consumed.data(), status.data(), n, flags),
+                        "fdb_inflate_batch");
         InflateResult r;
         r.status = status;
         r.consumed = consumed;
@@ -137,11 +163,19 @@ private:
         std::vector<uint8_t> in(ip + 16), out(op + 16);
         for (size_t i = 0; i < n; i++)
             if (in_len[i]) std::memcpy(in.data() + in_off[i], inputs[i].data(), in_len[i]);
-        int rc = stored ? fdb_deflate_stored_batch(ctx_.handle(), in.data(), in_off.data(), in_len.data(), out.data(),
-                                                   out_off.data(), out_cap.data(), out_len.data(), status.data(), n)
-                        : fdb_deflate_ultrafast_batch(ctx_.handle(), in.data(), in_off.data(), in_len.data(), out.data(),
-                                                      out_off.data(), out_cap.data(), out_len.data(), status.data(), n);
-        ctx_.check(rc, "fdb_deflate_*_batch");
+        if (set_) {
+            int rc = stored ? fdb_multi_deflate_stored_batch(set_->handle(), in.data(), in_off.data(), in_len.data(), out.data(),
+                                                             out_off.data(), out_cap.data(), out_len.data(), status.data(), n)
+                            : fdb_multi_deflate_ultrafast_batch(set_->handle(), in.data(), in_off.data(), in_len.data(), out.data(),
+                                                                out_off.data(), out_cap.data(), out_len.data(), status.data(), n);
+            set_->check(rc, "fdb_multi_deflate_*_batch");
+        } else {
+            int rc = stored ? fdb_deflate_stored_batch(ctx_->handle(), in.data(), in_off.data(), in_len.data(), out.data(),
+                                                       out_off.data(), out_cap.data(), out_len.data(), status.data(), n)
+                            : fdb_deflate_ultrafast_batch(ctx_->handle(), in.data(), in_off.data(), in_len.data(), out.data(),
+                                                          out_off.data(), out_cap.data(), out_len.data(), status.data(), n);
+            ctx_->check(rc, "fdb_deflate_*_batch");
+        }
         std::vector<std::vector<uint8_t>> res(n);
         for (size_t i = 0; i < n; i++) {
             if (status[i] != FDB_OK) throw std::runtime_error("deflate status " + std::to_string(status[i]));
@@ -149,7 +183,8 @@ private:
         }
         return res;
     }
-    Context& ctx_;
+    Context* ctx_ = nullptr;
+    DeviceSet* set_ = nullptr;
 };
 
 // ---- single-stream API with the reference's names ------------------------------------------------
@@ -176,6 +211,38 @@ inline std::vector<uint8_t> decompress_to_vec(Context& ctx, const std::vector<ui
         throw;
     }
 }
+
+// src/decompress.rs:96-342: the streaming decoder with the read() contract of :158-184.  Its state machine lives on the
+// device (fdb_stream_*): every call resumes at the token boundary the last one stopped at.  read() takes all of
+// `input` (what cannot be parsed yet is kept by the context) and returns {input.size(), bytes written}; when the output
+// is full, call again with more room and no input.
+class Decompressor {
+public:
+    explicit Decompressor(Context& ctx) : ctx_(ctx) { ctx_.check(fdb_stream_open_batch(ctx_.handle(), &id_, 1), "fdb_stream_open_batch"); }
+    ~Decompressor() { fdb_stream_close_batch(ctx_.handle(), &id_, 1); }
+    Decompressor(const Decompressor&) = delete;
+    Decompressor& operator=(const Decompressor&) = delete;
+    void ignore_adler32() { flags_ |= FDB_FLAG_IGNORE_ADLER32; }
+    bool is_done() const { return done_; }
+    std::pair<size_t, size_t> read(const uint8_t* input, size_t input_len, uint8_t* output, size_t output_len, size_t output_position) {
+        if (done_) return {0, 0};  // :185-187
+        if (output_position > output_len) throw std::out_of_range("output_position out of bounds");  // the reference panics (:189)
+        const uint64_t in_off = 0, in_len = input_len, out_off = output_position, room = output_len - output_position;
+        uint64_t produced = 0;
+        int32_t status = 0;
+        ctx_.check(fdb_stream_read_batch(ctx_.handle(), &id_, input, &in_off, &in_len, output, &out_off, &room, &produced, &status, 1, flags_),
+                   "fdb_stream_read_batch");
+        if (status > 0) throw DecompressionError(status);
+        if (status == FDB_OK) done_ = true;
+        return {input_len, (size_t)produced};
+    }
+
+private:
+    Context& ctx_;
+    uint32_t id_ = 0;
+    uint32_t flags_ = 0;
+    bool done_ = false;
+};
 
 inline std::vector<uint8_t> compress_to_vec_ultra_fast(Context& ctx, const std::vector<uint8_t>& input) {
     return Batch(ctx).deflate_ultra_fast({input})[0];

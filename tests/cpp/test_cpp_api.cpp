@@ -107,6 +107,53 @@ int main() {
     auto r = b.inflate({z, stored, trunc}, {data.size(), data.size(), data.size()});
     CHECK(r.status[0] == FDB_OK && r.status[1] == FDB_OK && r.status[2] == FDB_INSUFFICIENT_INPUT);
     CHECK(r.output[0] == data && r.output[1] == data);
+    // Decompressor::read fed in pieces of every size, small output rooms: same bytes as the whole-buffer call
+    for (size_t step : {size_t(1), size_t(7), size_t(333), z.size()}) {
+        fdeflate::Decompressor d(ctx);
+        std::vector<uint8_t> got, room(257);
+        size_t pos = 0;
+        for (int guard = 0; !d.is_done() && guard < 200000; guard++) {
+            const size_t take = std::min(step, z.size() - pos);
+            auto rr = d.read(z.data() + pos, take, room.data(), room.size(), 0);
+            pos += rr.first;
+            got.insert(got.end(), room.begin(), room.begin() + rr.second);
+        }
+        CHECK(d.is_done() && got == data);
+        CHECK(d.read(z.data(), 4, room.data(), room.size(), 0) == std::make_pair(size_t(0), size_t(0)));
+    }
+    {
+        fdeflate::Decompressor d(ctx);
+        std::vector<uint8_t> room(data.size());
+        try {
+            d.read(bad.data(), bad.size(), room.data(), room.size(), 0);
+            CHECK(false);
+        } catch (const fdeflate::DecompressionError& e) {
+            CHECK(e.kind == fdeflate::DecompressionErrorKind::WrongChecksum);
+        }
+    }
+    // a device set of two contexts (world = 2; on a one-GPU box both sit on device 0): same results as one context
+    {
+        fdeflate::DeviceSet set({0, 0});
+        CHECK(set.device_count() == 2);
+        fdeflate::Batch mb(set);
+        std::vector<std::vector<uint8_t>> inputs;
+        for (size_t k = 0; k < 9; k++) inputs.emplace_back(data.begin() + 100 * k, data.begin() + 100 * k + 1500 * (k + 1));
+        inputs.push_back({});
+        std::vector<std::vector<uint8_t>> zs = mb.deflate_ultra_fast(inputs);
+        std::vector<uint64_t> caps;
+        for (size_t k = 0; k < inputs.size(); k++) {
+            CHECK(zs[k] == oracle_uf(inputs[k]));
+            caps.push_back(inputs[k].size());
+        }
+        zs.push_back(trunc);
+        caps.push_back(data.size());
+        auto mr = mb.inflate(zs, caps);
+        for (size_t k = 0; k < inputs.size(); k++) CHECK(mr.status[k] == FDB_OK && mr.output[k] == inputs[k]);
+        CHECK(mr.status[inputs.size()] == FDB_INSUFFICIENT_INPUT);
+        std::vector<uint32_t> owner(zs.size());
+        CHECK(fdb_multi_last_partition(set.handle(), owner.data(), owner.size()) == 0);
+        CHECK(*std::max_element(owner.begin(), owner.end()) == 1);
+    }
     std::puts("cpp api ok");
     return 0;
 }
