@@ -68,10 +68,11 @@ def measured_peak():
 class ClockSampler(threading.Thread):
     """samples SM clock and throttle reasons of one GPU while the timed region runs"""
 
-    def __init__(self, index: int, period_s: float = 0.01):
+    def __init__(self, index: int, period_s: float = 0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.window = [0.0, float("inf")]  # only samples taken inside [t0, t1] (perf_counter) are reported
         self._stop_evt = threading.Event()
         self.ok = False
         try:
@@ -97,23 +98,27 @@ class ClockSampler(threading.Thread):
         }
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
+                self.samples.append((time.perf_counter(), mhz, r))
             except Exception:
                 pass
             time.sleep(self.period)
+        self._names = names
 
     def stop(self) -> dict:
         self._stop_evt.set()
         if self.is_alive():
             self.join(timeout=2)
-        s = sorted(self.samples)
+        inside = [x for x in self.samples if self.window[0] <= x[0] <= self.window[1]]
+        for _, _, r in inside:
+            for k, bit in getattr(self, "_names", {}).items():
+                if r & bit:
+                    self.reasons.add(k)
+        s = sorted(x[1] for x in inside)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
@@ -459,16 +464,18 @@ def ours(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)  # runs from before the warm-up; only its samples inside the timed region count
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
     launches0 = ctx.launch_count
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.window[0] = time.perf_counter()
     for k in range(args.steps):
         step_device(evs[k])
     barrier()
+    sampler.window[1] = time.perf_counter()
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
     ms_inf = sum(e[0].elapsed_time(e[1]) for e in evs)
