@@ -154,7 +154,8 @@ def test_config2_config3_full_size_properties(gpu_ctx, oracle):
     host_tiles = tiles.view(n, 262400)
     lens = c_len.cpu().numpy()
     offs = c_off.cpu().numpy()
-    for i in (0, 1, 17, 1000, 2047, 4095):
+    sample = [0, 4095] + [int(i) for i in np.random.default_rng().choice(n, size=6, replace=False)]  # a fresh sample every run
+    for i in sample:
         t = host_tiles[i].cpu().numpy().tobytes()
         ref = oracle.compress_ultra_fast(t)
         got = comp[int(offs[i]): int(offs[i]) + int(lens[i])].cpu().numpy().tobytes()
@@ -293,6 +294,65 @@ def test_config5_ragged_large_streams_roundtrip(gpu_ctx, oracle):
         assert o == d and k == len(s)
     for d, s in zip(datas, comp):
         assert zlib.adler32(d) == int.from_bytes(s[-4:], "big")
+
+
+def test_config5_sweep_shape_device_resident(gpu_ctx, oracle):
+    """BASELINE configs[4] at a quarter of one GPU's share: 2048 streams of 64 KiB .. 16 MiB (log-uniform, ~6 GB),
+    device-resident, ultra-fast deflate (segments) then inflate (spans) the way bench.py's sweep runs them.  Size-
+    independent properties on everything (statuses, lengths, round trip, every stream on the fast path) and byte parity
+    with the oracle in both directions on a random sample."""
+    import torch
+
+    import fdeflate_b200 as F
+
+    n, W = 2048, 1024
+    row = 1 + 4 * W
+    rng = np.random.default_rng(5)
+    sizes = np.exp(rng.uniform(np.log(64 << 10), np.log(16 << 20), n))
+    heights = np.maximum(1, (sizes / row).astype(np.int64))
+    lens = heights * row
+    offs = np.zeros(n, dtype=np.int64)
+    offs[1:] = np.cumsum((lens[:-1] + 15) & ~15)
+    total = int(offs[-1] + lens[-1])
+    dev = torch.device("cuda:0")
+    s = torch.cuda.current_stream().cuda_stream
+    raw = torch.empty(total + 16, dtype=torch.uint8, device=dev)
+    for i in range(n):
+        gpu_ctx.synth_tiles_device(raw.data_ptr() + int(offs[i]), 1000 + i, 1, W, int(heights[i]), 5, s)
+    bounds = np.array([gpu_ctx.ultrafast_bound(int(l)) for l in lens], dtype=np.int64)
+    coffs = np.zeros(n, dtype=np.int64)
+    coffs[1:] = np.cumsum(bounds[:-1])
+    comp = torch.empty(int(coffs[-1] + bounds[-1]), dtype=torch.uint8, device=dev)
+    out = torch.zeros(total + 16, dtype=torch.uint8, device=dev)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_off, d_len, d_coff, d_ccap = T(offs), T(lens), T(coffs), T(bounds)
+    c_len = torch.zeros(n, dtype=torch.int64, device=dev)
+    c_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    o_len = torch.zeros(n, dtype=torch.int64, device=dev)
+    o_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    try:
+        gpu_ctx.set_split_large(True)
+        gpu_ctx.deflate_ultrafast_device(raw.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), comp.data_ptr(), d_coff.data_ptr(),
+                                         d_ccap.data_ptr(), c_len.data_ptr(), c_st.data_ptr(), n, s)
+        gpu_ctx.inflate_device(comp.data_ptr(), d_coff.data_ptr(), c_len.data_ptr(), out.data_ptr(), d_off.data_ptr(), d_len.data_ptr(),
+                               o_len.data_ptr(), 0, o_st.data_ptr(), n, F.FLAG_SPLIT_LARGE, s)
+        torch.cuda.synchronize()
+    finally:
+        gpu_ctx.set_split_large(False)
+    assert int(c_st.abs().sum()) == 0 and int(o_st.abs().sum()) == 0
+    assert gpu_ctx.last_general_count(s) == 0 and gpu_ctx.last_split_spans(s) > n
+    assert torch.equal(o_len, d_len)
+    for i in range(n):  # encode -> decode round trip over all 6 GB (slot by slot: the padding between slots is not output)
+        a = int(offs[i])
+        assert torch.equal(out[a:a + int(lens[i])], raw[a:a + int(lens[i])]), i
+    h_clen = c_len.cpu().numpy()
+    order = np.argsort(lens)
+    sample = list(order[:2]) + [int(order[-1])] + [int(i) for i in np.random.default_rng().choice(n, size=5, replace=False)]
+    for i in sample:
+        src = raw[int(offs[i]):int(offs[i]) + int(lens[i])].cpu().numpy().tobytes()
+        z = comp[int(coffs[i]):int(coffs[i]) + int(h_clen[i])].cpu().numpy().tobytes()
+        assert z == oracle.compress_ultra_fast(src), f"stream {i} ({len(src)} bytes): deflate bytes differ from the oracle"
+        assert oracle.inflate_into(z, len(src))[:2] == (0, src)
 
 
 def test_deflate_long_inputs_segment_by_segment(gpu_ctx, oracle):
