@@ -46,7 +46,8 @@ def _suite(multi, oracle, world):
     skew.insert(6, (zlib.compress(bytes(9), 6), 9))
     parity.check_inflate(multi, skew, 0)
     owner = multi.last_partition(len(skew))
-    assert not all(owner[i] <= owner[i + 1] for i in range(len(skew) - 1))
+    if world == 2:  # (with many devices the long stream gets a device of its own either way)
+        assert not all(owner[i] <= owner[i + 1] for i in range(len(skew) - 1))
     # fewer streams than devices, and none at all
     parity.check_deflate_ultrafast(multi, inputs[:1])
     assert multi.inflate_batch([], [])[1] == []
