@@ -301,6 +301,8 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
         return bail(e);
     if ((e = cudaFuncSetAttribute(inflate_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem))) != cudaSuccess)
         return bail(e);
+    if ((e = cudaFuncSetAttribute(deflate_stored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StoredSmem))) != cudaSuccess)
+        return bail(e);
     *out = ctx;
     return 0;
 }
@@ -526,7 +528,7 @@ static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_
                    counter, split_item0);
     } else {
         uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * 8);
-        FDB_LAUNCH(deflate_stored_kernel, dim3(grid), dim3(STORED_THREADS), 0, st, b, counter);
+        FDB_LAUNCH(deflate_stored_kernel, dim3(grid), dim3(STORED_THREADS), sizeof(StoredSmem), st, b, counter);
     }
     ctx->launches++;
     FDB_TRY(cudaGetLastError());

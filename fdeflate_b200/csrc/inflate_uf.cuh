@@ -99,12 +99,24 @@ FDB_DEVICE void lb_start(LaneBits& b, simt::saddr row, uint32_t rp) {
 FDB_DEVICE uint32_t lb_peek(const LaneBits& b) { return simt::funnel_r(b.w0, b.w1, b.rp); }  // shift is mod 32
 FDB_DEVICE void lb_advance(LaneBits& b, uint32_t n) {  // n < 32
     const uint32_t nrp = b.rp + n;
+#if defined(K4_ADV_PTX) && !defined(FDB_EMUL)
+    // the same four predicated instructions, spelled out (the compiler's version shuffles the three words through
+    // temporaries: ten instructions per advance in the round-1 SASS)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 x;\n\t"
+        "xor.b32 x, %4, %5;\n\tand.b32 x, x, 32;\n\tsetp.ne.u32 p, x, 0;\n\t"
+        "@p mov.u32 %0, %1;\n\t@p mov.u32 %1, %2;\n\t@p ld.shared.u32 %2, [%3];\n\t@p add.u32 %3, %3, 128;\n\t}"
+        : "+r"(b.w0), "+r"(b.w1), "+r"(b.w2), "+r"(b.nx)
+        : "r"(nrp), "r"(b.rp)
+        : "memory");
+#else
     if ((nrp ^ b.rp) & 32u) {
         b.w0 = b.w1;
         b.w1 = b.w2;
         b.w2 = simt::lds32(b.nx);
         b.nx += 128u;
     }
+#endif
     b.rp = nrp;
 }
 
@@ -177,6 +189,35 @@ FDB_DEVICE LaneCount count_tokens(const UfTabs& t, simt::saddr row, uint32_t sta
         }
         lb_advance(b, n);
     }
+#ifdef K4_PRETAIL
+    // one table entry at a time while a whole entry (<= 12 bits) still ends at or before LIM_HI: most of what the pair
+    // loop leaves goes in one or two such steps instead of a token at a time
+    while (!stop && b.rp <= K4_LIM_HI - 12u) {
+        const uint32_t bits = lb_peek(b);
+        const uint32_t c1 = ct_at(t, bits);
+        uint32_t n;
+        if (c1 == 0) {
+            const uint32_t w = wt_at(t, bits);
+            if (w & UW_EOB) {
+                flags |= CF_EOB;
+                stop = 1;
+                n = 0;
+            } else {
+                uint32_t len, bd;
+                uf_long_run(w, bits, n, len, bd);
+                cnt += len;
+                bad |= (bd << 4) | prev;
+                prev = 0;
+            }
+        } else {
+            n = c1 & 15u;
+            cnt += c1 >> 12;
+            bad |= prev & c1;
+            prev = c1 >> 1;
+        }
+        lb_advance(b, n);
+    }
+#endif
     // tail: single tokens up to the first token boundary >= LIM_HI
     while (!stop && b.rp < K4_LIM_HI) {
         const uint32_t bits = lb_peek(b);
@@ -238,6 +279,23 @@ FDB_DEVICE uint32_t warm_up(const UfTabs& t, simt::saddr row, uint32_t active) {
         }
         lb_advance(b, n);
     }
+#ifdef K4_PRETAIL
+    while (!stop && b.rp <= K4_LIM_LO - 12u) {
+        const uint32_t bits = lb_peek(b);
+        const uint32_t c1 = ct_at(t, bits);
+        uint32_t n = c1 & 15u;
+        if (c1 == 0) {
+            const uint32_t w = wt_at(t, bits);
+            n = (w & 15u) + ((w >> 4) & 7u) + 1u;
+            if (w & UW_EOB) {
+                dead = 1;
+                stop = 1;
+                n = 0;
+            }
+        }
+        lb_advance(b, n);
+    }
+#endif
     while (!stop && b.rp < K4_LIM_LO) {
         const uint32_t bits = lb_peek(b);
         const uint32_t c1 = ct_at(t, bits);
@@ -605,6 +663,31 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                     }
                     lb_advance(b, n);
                 }
+#ifdef K4_PRETAIL
+                while (!fin && b.rp <= K4_LIM_HI - 12u) {  // whole entries that still end at or before LIM_HI
+                    const uint32_t bits = lb_peek(b);
+                    const uint32_t e1 = wt_at(t, bits);
+                    const uint32_t k1 = e1 >> 28;
+                    uint32_t n;
+                    if (k1 == 0) {
+                        if (e1 & UW_EOB) {
+                            fin = 1;
+                            n = 0;
+                        } else {
+                            uint32_t len, bd;
+                            uf_long_run(e1, bits, n, len, bd);
+                            wptr += len;
+                        }
+                    } else {
+                        simt::sts8(wptr, e1);
+                        simt::sts8_if(wptr + 1, e1 >> 8, k1 >= 2);
+                        simt::sts8_if(wptr + 2, e1 >> 16, k1 >= 3);
+                        wptr += k1;
+                        n = (e1 >> 24) & 15u;
+                    }
+                    lb_advance(b, n);
+                }
+#endif
                 while (!fin && b.rp < K4_LIM_HI) {  // single tokens up to the first boundary >= LIM_HI
                     const uint32_t bits = lb_peek(b);
                     const uint32_t e = wt_at(t, bits);

@@ -121,6 +121,34 @@ FDB_DEVICE void sts8_if(saddr a, uint32_t v, bool p) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u8 [%0], %1;\n\t}" ::"r"(a), "r"(v), "r"((uint32_t)p) : "memory");
 }
 FDB_DEVICE void sts32(saddr a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+FDB_DEVICE uint4 lds128(saddr a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
+// ---- bulk asynchronous copy global -> shared, completion on an mbarrier (sm_90+; SASS: UBLKCP / SYNCS) ----------
+// One thread arms the barrier with the byte count and issues the copy; the copy engine moves the bytes without any
+// register or load/store-unit traffic; every consumer waits on the barrier's phase parity.  src, dst: 16-byte aligned,
+// bytes: a multiple of 16.
+FDB_DEVICE void mbar_init(saddr bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(arrivals) : "memory");
+}
+FDB_DEVICE void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+FDB_DEVICE void mbar_expect_tx(saddr bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+FDB_DEVICE void bulk_g2s(saddr dst, const void* src, uint32_t bytes, saddr bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+FDB_DEVICE void mbar_wait(saddr bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
 }  // namespace simt
 #endif
 

@@ -234,6 +234,22 @@ static inline uint32_t lds32(saddr a) { return *(const uint32_t*)a; }
 static inline void sts8(saddr a, uint32_t v) { *(uint8_t*)a = (uint8_t)v; }
 static inline void sts8_if(saddr a, uint32_t v, bool p) { if (p) sts8(a, v); }
 static inline void sts32(saddr a, uint32_t v) { *(uint32_t*)a = v; }
+static inline uint4 lds128(saddr a) { return *(const uint4*)a; }
+// bulk asynchronous copy + mbarrier: the emulator copies when the copy is issued and counts completed phases in the
+// barrier word (one copy per phase); a wait yields until the phase of the given parity has completed
+static inline void mbar_init(saddr bar, uint32_t) { *(uint64_t*)bar = 0; }
+static inline void mbar_fence_init() {}
+static inline void mbar_expect_tx(saddr, uint32_t) {}
+static inline void bulk_g2s(saddr dst, const void* src, uint32_t bytes, saddr bar) {
+    memcpy((void*)dst, src, bytes);
+    (*(uint64_t*)bar)++;
+}
+static inline void mbar_wait(saddr bar, uint32_t parity) {
+    while (((*(volatile uint64_t*)bar) & 1u) == (parity & 1u)) {
+        fdb_emul::stuck_check();
+        fdb_emul::yield();
+    }
+}
 }  // namespace simt
 
 // ---- CUDA runtime stubs used by capi.cu --------------------------------------------------------
