@@ -432,13 +432,13 @@ static int launch_inflate(fdb_ctx* ctx, const InflateBatch& b, uint32_t* counter
                    *worklist, counters + 1, split_item0);
         ctx->launches++;
         FDB_TRY(cudaGetLastError());
-        uint32_t grid3 = (uint32_t)std::min<size_t>(n, (size_t)sms * 10);
+        uint32_t grid3 = (uint32_t)std::min<size_t>(n, (size_t)sms * 16);
         FDB_LAUNCH(inflate_general_kernel, dim3(grid3), dim3(32), sizeof(K3Smem), st, b, (const uint32_t*)*worklist,
                    (const uint32_t*)(counters + 1), counters + 2);
         ctx->launches++;
         FDB_TRY(cudaGetLastError());
     } else {
-        uint32_t grid3 = (uint32_t)std::min<size_t>(n, (size_t)sms * 10);
+        uint32_t grid3 = (uint32_t)std::min<size_t>(n, (size_t)sms * 16);
         FDB_LAUNCH(inflate_general_kernel, dim3(grid3), dim3(32), sizeof(K3Smem), st, b, (const uint32_t*)nullptr,
                    (const uint32_t*)nullptr, counters + 2);
         ctx->launches++;

@@ -29,8 +29,24 @@
 
 namespace fdb {
 
+// Primary litlen table: 2^K3_TB entries indexed by the next K3_TB stream bits (the reference's has 4096, tables of
+// 12 bits; a smaller one keeps more warps on an SM: the table is most of a warp's shared memory).  Codes longer than
+// K3_TB bits are decoded canonically.  Which literals share a table entry only shows at a truncated end of input
+// (the reference wants the bits of both literals of a pair, decompress.rs:852); the careful loop restates that rule
+// for the reference's 12-bit pairing whatever K3_TB is.
+#ifndef K3_TABLE_BITS
+#define K3_TABLE_BITS 12
+#endif
+static const uint32_t K3_TB = K3_TABLE_BITS;
+static const uint32_t K3_TMASK = (1u << K3_TB) - 1u;
+static_assert(K3_TB >= 9 && K3_TB <= 12, "fixed-code literals need 9 bits; the entry format has 4 bits for a length");
+
+#ifndef K3_PARKED_MATCHES
+#define K3_PARKED_MATCHES 640  // matches one segment of the parallel block decode may park (more: the sequential reader takes over)
+#endif
+
 struct K3Smem {
-    uint32_t litlen[4096];
+    uint32_t litlen[1u << K3_TB];
     uint32_t dist[512];
     uint32_t first[3][16];  // canonical first code per length  [0]=litlen [1]=dist [2]=code-length code
     uint32_t lim[3][16];    // (first+cnt) left-aligned to the table width
@@ -47,7 +63,7 @@ struct K3Smem {
     // parallel block decode (decode_block_parallel): transposed per-lane staging rows and the
     // parked matches of one segment in stream order
     uint32_t pstg[17 * 32];
-    uint2 pmatch[640];      // {x = destination relative to the segment's first byte, y = len | dist << 16}
+    uint2 pmatch[K3_PARKED_MATCHES];      // {x = destination relative to the segment's first byte, y = len | dist << 16}
 };
 
 // ---- bit reader: warp-shuffle reservoir over coalesced chunk loads ---------------------------
@@ -188,12 +204,12 @@ FDB_DEVICE bool canon_long_decode(const K3Smem& s, int which, const uint16_t* so
 // second pass upgrades single literals to two-literal entries (replaces huffman.rs:92-136).
 FDB_DEVICE void build_litlen_table(K3Smem& s) {
     const unsigned lane = simt::lane_id();
-    for (uint32_t idx = lane; idx < 4096; idx += 32) {
-        uint32_t v = simt::brev(idx) >> 20;
+    for (uint32_t idx = lane; idx < (1u << K3_TB); idx += 32) {
+        uint32_t v = simt::brev(idx) >> (32 - K3_TB);
         uint32_t e = 0;  // none of LIT/LEN/EOB => long code
-        for (uint32_t L = 1; L <= 12; L++) {
+        for (uint32_t L = 1; L <= K3_TB; L++) {
             if (v < s.lim[0][L]) {
-                uint32_t c = v >> (12 - L);
+                uint32_t c = v >> (K3_TB - L);
                 e = make_litlen_entry(s.sorted_lit[s.off[0][L] + c - s.first[0][L]], L);
                 break;
             }
@@ -205,7 +221,7 @@ FDB_DEVICE void build_litlen_table(K3Smem& s) {
     // from), barrier, write -- so no lane reads an entry another lane is upgrading at that moment.
     // An entry read here may already be a pair from an earlier round: its first literal and that
     // literal's bit count are the same in both forms.
-    for (uint32_t base = 0; base < 4096; base += 128) {
+    for (uint32_t base = 0; base < (1u << K3_TB); base += 128) {
         uint32_t ne[4];
 #pragma unroll
         for (uint32_t k = 0; k < 4; k++) {
@@ -214,11 +230,11 @@ FDB_DEVICE void build_litlen_table(K3Smem& s) {
             ne[k] = e;
             if (!(e & LL_LIT) || (e & LL_LIT2)) continue;
             const uint32_t l1 = e & 15u;
-            if (l1 >= 12) continue;
+            if (l1 >= K3_TB) continue;
             const uint32_t e2 = s.litlen[idx >> l1];
             if (!(e2 & LL_LIT)) continue;
             const uint32_t l2 = (e2 >> 24) & 15u;
-            if (l1 + l2 > 12) continue;
+            if (l1 + l2 > K3_TB) continue;
             ne[k] = make_litlen_pair(e, (e2 >> 8) & 0xffu, l1, l2);
         }
         simt::syncwarp();
@@ -249,7 +265,7 @@ FDB_DEVICE void build_dist_table(K3Smem& s) {
 FDB_DEVICE int32_t build_block_tables(K3Smem& s, uint32_t hlit, uint32_t* eof_code, uint32_t* eof_bits) {
     const unsigned lane = simt::lane_id();
     if (s.lens[256] == 0) return ST_BAD_LITERAL_LENGTH_HUFFMAN_TREE;  // :563-566
-    canon_setup(s, 0, s.lens, hlit, s.sorted_lit, 12);
+    canon_setup(s, 0, s.lens, hlit, s.sorted_lit, K3_TB);
     if (!s.info[1]) return ST_BAD_CODE_LENGTH_HUFFMAN_TREE;  // :570-580 (sic: the reference's variant)
     build_litlen_table(s);
     {  // eof code = bit-reversed canonical code of symbol 256 (:582-584)
@@ -383,7 +399,7 @@ static const uint32_t P_SUBW = 8, P_WARM = 4, P_TAILW = 4;
 static const uint32_t P_ROWW = P_WARM + P_SUBW + P_TAILW;        // 16 words seen by one lane (+1 look-ahead)
 static const uint32_t P_SEG_WORDS = P_WARM + 32 * P_SUBW + 4;    // staged per segment (vectors of 4)
 static const uint32_t P_LIM_LO = 32u * P_WARM, P_LIM_HI = 32u * (P_WARM + P_SUBW);
-static const uint32_t P_MAXM = 640;
+static const uint32_t P_MAXM = K3_PARKED_MATCHES;
 static const uint32_t P_INVALID = 0xffffffffu;
 
 struct GLane {  // lane-private LSB-first reader over a transposed staging row (cf. LaneBits in inflate_uf.cuh)
@@ -437,7 +453,7 @@ struct GTok {
 // decompress.rs:852, so status and output there depend on the pairing.)
 FDB_DEVICE void g_token(const K3Smem& s, const GTabs& tb, const GLane& b, GTok& t) {
     const uint32_t bits = simt::funnel_r(b.w0, b.w1, b.rp);
-    const uint32_t e = simt::lds32_ro(tb.litlen + ((bits & 0xfffu) << 2));
+    const uint32_t e = simt::lds32_ro(tb.litlen + ((bits & K3_TMASK) << 2));
     uint32_t nbits = e & 15u;
     t.dist = 0;
     if (e & LL_LIT) {
@@ -459,7 +475,7 @@ FDB_DEVICE void g_token(const K3Smem& s, const GTabs& tb, const GLane& b, GTok& 
         len_extra = (e >> 8) & 7u;
     } else {  // code longer than the table
         uint32_t sym = 0;
-        if (!canon_long_decode(s, 0, s.sorted_lit, bits & 0x7fffu, 13, &sym, &nbits)) {
+        if (!canon_long_decode(s, 0, s.sorted_lit, bits & 0x7fffu, K3_TB + 1, &sym, &nbits)) {
             t.kind = GT_BAD;
             t.nbits = 0;
             t.bytes = 0;
@@ -794,7 +810,7 @@ FDB_DEVICE void decode_block_fast(K3Smem& s, BitReader& r, OutCursor& o, MatchQu
     uint64_t pos = o.pos;
     while (used <= max_used && pos <= out_limit) {
         const uint32_t bits = simt::funnel_r(w0, w1, rp);
-        const uint32_t e = s.litlen[bits & 0xfffu];
+        const uint32_t e = s.litlen[bits & K3_TMASK];
         const uint32_t n = e & 15u;
         if (e & LL_LIT) {
             const uint32_t k = e >> 28;  // 1 or 2 literals
@@ -877,11 +893,26 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
             *too_large = true;
             K3_RETURN(ST_OK);
         }
-        uint32_t e = s.litlen[br_peek(r, 12)];
+        uint32_t e = s.litlen[br_peek(r, K3_TB)];
         uint32_t nbits = e & 15u;
         if (e & LL_LIT) {  // :846-877
             if (avail < nbits) K3_STARVED();
             bool two = (e & LL_LIT2) != 0;
+            if (K3_TB < 12 && !two && avail < 12) {
+                // The last bits of the input.  The reference's 4096-entry table pairs this literal with the next one
+                // when both codes fit in 12 bits together, and then wants the bits of BOTH before it emits either
+                // (:852) -- looked up, as there, in the zero-padded bit window.  With avail >= 12 the rule cannot bind.
+                const uint32_t rest = br_peek(r, 12) >> nbits;
+                const uint32_t e2 = s.litlen[rest & K3_TMASK];
+                uint32_t l2 = 16;
+                if (e2 & LL_LIT) {
+                    l2 = (e2 >> 24) & 15u;
+                } else if (!(e2 & (LL_LEN | LL_EOB)) && nbits + K3_TB + 1 <= 12) {
+                    uint32_t sym2 = 0, n2 = 0;
+                    if (canon_long_decode(s, 0, s.sorted_lit, rest, K3_TB + 1, &sym2, &n2) && sym2 < 256) l2 = n2;
+                }
+                if (nbits + l2 <= 12 && avail < nbits + l2) K3_STARVED();
+            }
             if (lane == 0) o.out[o.pos] = (uint8_t)(e >> 8);
             if (two && o.pos + 1 == o.cap) {  // second literal does not fit (queued in the reference)
                 o.pos += 1;
@@ -908,7 +939,7 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
             len_extra = (e >> 8) & 7u;
         } else {  // code longer than 12 bits (:886-909)
             uint32_t sym = 0;
-            if (!canon_long_decode(s, 0, s.sorted_lit, br_peek(r, 15), 13, &sym, &nbits))
+            if (!canon_long_decode(s, 0, s.sorted_lit, br_peek(r, 15), K3_TB + 1, &sym, &nbits))
                 K3_RETURN(ST_INVALID_LITERAL_LENGTH_CODE);
             if (avail < nbits) K3_STARVED();
             if (sym < 256) {
@@ -1170,7 +1201,10 @@ FDB_DEVICE int32_t inflate_stream_general(K3Smem& s, const uint8_t* in, uint64_t
 
 // Persistent kernel: one warp per CTA, warps pull stream indices from a device counter.
 // worklist == nullptr: all streams 0..n-1; else the first *work_count entries of worklist.
-FDB_GLOBAL void FDB_LAUNCH_BOUNDS(32, 1)
+#ifndef K3_MIN_CTAS
+#define K3_MIN_CTAS 1
+#endif
+FDB_GLOBAL void FDB_LAUNCH_BOUNDS(32, K3_MIN_CTAS)
     inflate_general_kernel(InflateBatch b, const uint32_t* worklist, const uint32_t* work_count, uint32_t* next) {
     FDB_DYN_SMEM(smem_raw);
     K3Smem& s = *reinterpret_cast<K3Smem*>(smem_raw);

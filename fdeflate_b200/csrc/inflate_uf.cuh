@@ -99,7 +99,7 @@ FDB_DEVICE void lb_start(LaneBits& b, simt::saddr row, uint32_t rp) {
 FDB_DEVICE uint32_t lb_peek(const LaneBits& b) { return simt::funnel_r(b.w0, b.w1, b.rp); }  // shift is mod 32
 FDB_DEVICE void lb_advance(LaneBits& b, uint32_t n) {  // n < 32
     const uint32_t nrp = b.rp + n;
-#if defined(K4_ADV_PTX) && !defined(FDB_EMUL)
+#if !defined(FDB_EMUL)
     // the same four predicated instructions, spelled out (the compiler's version shuffles the three words through
     // temporaries: ten instructions per advance in the round-1 SASS)
     asm volatile(
@@ -189,7 +189,7 @@ FDB_DEVICE LaneCount count_tokens(const UfTabs& t, simt::saddr row, uint32_t sta
         }
         lb_advance(b, n);
     }
-#ifdef K4_PRETAIL
+#if 1  // (measured -3.5 % on the bench tiles: profiles/r02_k4_variants.txt)
     // one table entry at a time while a whole entry (<= 12 bits) still ends at or before LIM_HI: most of what the pair
     // loop leaves goes in one or two such steps instead of a token at a time
     while (!stop && b.rp <= K4_LIM_HI - 12u) {
@@ -279,7 +279,7 @@ FDB_DEVICE uint32_t warm_up(const UfTabs& t, simt::saddr row, uint32_t active) {
         }
         lb_advance(b, n);
     }
-#ifdef K4_PRETAIL
+#if 1  // (measured -3.5 % on the bench tiles: profiles/r02_k4_variants.txt)
     while (!stop && b.rp <= K4_LIM_LO - 12u) {
         const uint32_t bits = lb_peek(b);
         const uint32_t c1 = ct_at(t, bits);
@@ -663,7 +663,7 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                     }
                     lb_advance(b, n);
                 }
-#ifdef K4_PRETAIL
+#if 1  // (measured -3.5 % on the bench tiles: profiles/r02_k4_variants.txt)
                 while (!fin && b.rp <= K4_LIM_HI - 12u) {  // whole entries that still end at or before LIM_HI
                     const uint32_t bits = lb_peek(b);
                     const uint32_t e1 = wt_at(t, bits);

@@ -6,8 +6,9 @@ import numpy as np, torch
 import fdeflate_b200 as F
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-ctx = F.Context(0)
-tiles = F.synth_tiles_host(0, n, 256, 256, 1)
+lib = F.NativeLib(sys.argv[2]) if len(sys.argv) > 2 else None   # a variant build (A/B runs)
+ctx = F.Context(0, lib)
+tiles = F.synth_tiles_host(0, n, 256, 256, 1, lib)
 raw = [t.tobytes() for t in tiles]
 for level, name in ((6, "zlib-6"), (1, "zlib-1"), (0, "stored")):
     with ThreadPoolExecutor(16) as ex:
@@ -35,4 +36,4 @@ for level, name in ((6, "zlib-6"), (1, "zlib-1"), (0, "stored")):
     e0.record(); run(); run(); run(); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     assert int(d_st.abs().sum()) == 0
-    print(f"{name}: ratio {sum(map(len, comp)) / (n * len(raw[0])):.3f}  {n * len(raw[0]) / ms / 1e6:.1f} GB/s uncompressed ({ms:.2f} ms, {n} streams)")
+    print(f"{sys.argv[2] if len(sys.argv) > 2 else 'default'} {name}: ratio {sum(map(len, comp)) / (n * len(raw[0])):.3f}  {n * len(raw[0]) / ms / 1e6:.1f} GB/s uncompressed ({ms:.2f} ms, {n} streams)")
