@@ -35,7 +35,7 @@ namespace fdb {
 // (the reference wants the bits of both literals of a pair, decompress.rs:852); the careful loop restates that rule
 // for the reference's 12-bit pairing whatever K3_TB is.
 #ifndef K3_TABLE_BITS
-#define K3_TABLE_BITS 12
+#define K3_TABLE_BITS 10  // measured on zlib-6 tiles: 12 bits (8 warps / SM) 55 GB/s, 10 bits (14 warps / SM) 90 GB/s
 #endif
 static const uint32_t K3_TB = K3_TABLE_BITS;
 static const uint32_t K3_TMASK = (1u << K3_TB) - 1u;
@@ -311,6 +311,61 @@ FDB_DEVICE void load_fixed_lengths(K3Smem& s) {  // RFC 1951 3.2.6 (reference ta
         uint8_t L = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
         s.lens[i] = L;
     }
+    simt::syncwarp();
+}
+
+// Warp-wide copy of n bytes between two byte addresses of any alignment (the payload of a stored block): head bytes up
+// to the first 16-byte boundary of the destination, then 16-byte vectors -- two aligned source vectors funnel-shifted
+// into one aligned store, four vectors per lane in flight --, then the tail bytes.  src must be readable up to the next
+// 16-byte boundary past src + n (the contract of every input buffer, include/fdeflate_b200.h).
+FDB_DEVICE void warp_copy_bytes(uint8_t* dst, const uint8_t* src, uint64_t n) {
+    const unsigned lane = simt::lane_id();
+    uint64_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+    if (head > n) head = n;
+    if (lane < head) dst[lane] = simt::ldg8(src + lane);
+    const uint64_t nvec = (n - head) >> 4;
+    const uint8_t* s0 = src + head;
+    const uint32_t sh = (uint32_t)((uintptr_t)s0 & 15u);
+    const uint4* a0 = (const uint4*)(s0 - sh);
+    uint4* d0 = (uint4*)(dst + head);
+    const uint32_t s4 = sh >> 2, sb = 8u * (sh & 3u);
+    auto shifted = [&](const uint4& lo, const uint4& hi) -> uint4 {
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        uint4 r;
+        r.x = simt::funnel_r(w[s4], w[s4 + 1], sb);
+        r.y = simt::funnel_r(w[s4 + 1], w[s4 + 2], sb);
+        r.z = simt::funnel_r(w[s4 + 2], w[s4 + 3], sb);
+        r.w = simt::funnel_r(w[s4 + 3], w[s4 + 4], sb);
+        return r;
+    };
+    uint64_t v = lane;
+    if (sh == 0) {
+        for (; v + 96 < nvec; v += 128) {
+            const uint4 q0 = simt::ldg128(a0 + v), q1 = simt::ldg128(a0 + v + 32), q2 = simt::ldg128(a0 + v + 64), q3 = simt::ldg128(a0 + v + 96);
+            d0[v] = q0;
+            d0[v + 32] = q1;
+            d0[v + 64] = q2;
+            d0[v + 96] = q3;
+        }
+        for (; v < nvec; v += 32) d0[v] = simt::ldg128(a0 + v);
+    } else {
+        for (; v + 96 < nvec; v += 128) {
+            const uint4 l0 = simt::ldg128(a0 + v), h0 = simt::ldg128(a0 + v + 1);
+            const uint4 l1 = simt::ldg128(a0 + v + 32), h1 = simt::ldg128(a0 + v + 33);
+            const uint4 l2 = simt::ldg128(a0 + v + 64), h2 = simt::ldg128(a0 + v + 65);
+            const uint4 l3 = simt::ldg128(a0 + v + 96), h3 = simt::ldg128(a0 + v + 97);
+            d0[v] = shifted(l0, h0);
+            d0[v + 32] = shifted(l1, h1);
+            d0[v + 64] = shifted(l2, h2);
+            d0[v + 96] = shifted(l3, h3);
+        }
+        for (; v < nvec; v += 32) {
+            const uint4 l0 = simt::ldg128(a0 + v), h0 = simt::ldg128(a0 + v + 1);
+            d0[v] = shifted(l0, h0);
+        }
+    }
+    const uint64_t tail0 = head + (nvec << 4);
+    if (tail0 + lane < n) dst[tail0 + lane] = simt::ldg8(src + tail0 + lane);
     simt::syncwarp();
 }
 
@@ -852,11 +907,33 @@ FDB_DEVICE void decode_block_fast(K3Smem& s, BitReader& r, OutCursor& o, MatchQu
 // whole-buffer call would report InsufficientInput or OutputTooLarge, the reader goes back to the start of the token it
 // could not finish and returns ST_STREAM_NEED_INPUT / ST_STREAM_OUTPUT_FULL; the next call carries on from there with
 // more input / more room (what the reference's read() does with its bit reservoir and its QueuedOutput, :194-219).
+// exact: the reference's table entries, one at a time (no fast or parallel path).  With a primary table smaller than
+// the reference's 4096 entries (K3_TB < 12) different literals share an entry than there, and the reference wants the
+// bits of BOTH literals of an entry before it emits either (:852): at a truncated end of input, status and output
+// depend on where its entries begin, which follows from the greedy pairing since the last non-literal token.  The
+// kernel therefore decodes a stream that did NOT end with Ok near the end of its input a second time in this mode,
+// which restates the 12-bit pairing token by token -- error streams only; valid streams never get here.
 FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t eof_code, uint32_t eof_bits,
-                                bool* too_large, K3Resume* rs = nullptr) {
+                                bool* too_large, K3Resume* rs = nullptr, bool exact = false) {
     const unsigned lane = simt::lane_id();
     const uint32_t eof_mask = (1u << eof_bits) - 1u;
     MatchQueue mq = {0, 0, 0, 0};
+    // is the token at bit offset `off` of the (zero-padded) window a literal?  (codes up to 15 bits)
+    auto lit_at = [&](uint32_t off, uint32_t* sym, uint32_t* len) -> bool {
+        const uint32_t v = br_peek(r, 32) >> off;
+        const uint32_t e = s.litlen[v & K3_TMASK];
+        if (e & LL_LIT) {
+            *sym = (e >> 8) & 0xffu;
+            *len = (e >> 24) & 15u;
+            return true;
+        }
+        if (e & (LL_LEN | LL_EOB)) return false;
+        uint32_t sy = 0, nb = 0;
+        if (!canon_long_decode(s, 0, s.sorted_lit, v & 0x7fffu, K3_TB + 1, &sy, &nb) || sy >= 256) return false;
+        *sym = sy;
+        *len = nb;
+        return true;
+    };
 // every way out of the block first completes the parked matches
 #define K3_RETURN(x)          \
     do {                      \
@@ -864,12 +941,12 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
         return (x);           \
     } while (0)
 #ifndef K3_NO_PARALLEL
-    if (decode_block_parallel(s, r, o)) return ST_OK;
+    if (!exact && decode_block_parallel(s, r, o)) return ST_OK;
 #endif
     for (;;) {
         // as far as the fast path gets, then ONE token (or the end of the block) the careful way
 #ifndef K3_NO_FAST
-        decode_block_fast(s, r, o, mq);
+        if (!exact) decode_block_fast(s, r, o, mq);
 #endif
         br_refill(r);
         uint64_t avail = br_avail(r);
@@ -893,26 +970,37 @@ FDB_DEVICE int32_t decode_block(K3Smem& s, BitReader& r, OutCursor& o, uint32_t 
             *too_large = true;
             K3_RETURN(ST_OK);
         }
+        if (exact) {
+            // one entry of the reference's 12-bit table: a literal of <= 12 bits, paired with the literal behind it
+            // when both codes fit in 12 bits together (huffman.rs:110-130)
+            uint32_t a = 0, l1 = 0;
+            if (lit_at(0, &a, &l1) && l1 <= 12) {
+                uint32_t b2 = 0, l2 = 0;
+                const bool pair = l1 < 12 && lit_at(l1, &b2, &l2) && l1 + l2 <= 12;
+                const uint32_t nb = pair ? l1 + l2 : l1;
+                if (avail < nb) K3_STARVED();
+                if (lane == 0) o.out[o.pos] = (uint8_t)a;
+                if (pair && o.pos + 1 == o.cap) {  // the second literal is queued in the reference (:866-876)
+                    o.pos += 1;
+                    if (rs) {
+                        br_consume(r, l1);
+                        K3_RETURN(ST_STREAM_OUTPUT_FULL);
+                    }
+                    br_consume(r, nb);
+                    *too_large = true;
+                    K3_RETURN(ST_OK);
+                }
+                if (pair && lane == 1) o.out[o.pos + 1] = (uint8_t)b2;
+                o.pos += pair ? 2 : 1;
+                br_consume(r, nb);
+                continue;
+            }
+        }
         uint32_t e = s.litlen[br_peek(r, K3_TB)];
         uint32_t nbits = e & 15u;
         if (e & LL_LIT) {  // :846-877
             if (avail < nbits) K3_STARVED();
             bool two = (e & LL_LIT2) != 0;
-            if (K3_TB < 12 && !two && avail < 12) {
-                // The last bits of the input.  The reference's 4096-entry table pairs this literal with the next one
-                // when both codes fit in 12 bits together, and then wants the bits of BOTH before it emits either
-                // (:852) -- looked up, as there, in the zero-padded bit window.  With avail >= 12 the rule cannot bind.
-                const uint32_t rest = br_peek(r, 12) >> nbits;
-                const uint32_t e2 = s.litlen[rest & K3_TMASK];
-                uint32_t l2 = 16;
-                if (e2 & LL_LIT) {
-                    l2 = (e2 >> 24) & 15u;
-                } else if (!(e2 & (LL_LEN | LL_EOB)) && nbits + K3_TB + 1 <= 12) {
-                    uint32_t sym2 = 0, n2 = 0;
-                    if (canon_long_decode(s, 0, s.sorted_lit, rest, K3_TB + 1, &sym2, &n2) && sym2 < 256) l2 = n2;
-                }
-                if (nbits + l2 <= 12 && avail < nbits + l2) K3_STARVED();
-            }
             if (lane == 0) o.out[o.pos] = (uint8_t)(e >> 8);
             if (two && o.pos + 1 == o.cap) {  // second literal does not fit (queued in the reference)
                 o.pos += 1;
@@ -1090,10 +1178,8 @@ FDB_DEVICE int32_t read_dynamic_header(K3Smem& s, BitReader& r, uint32_t* hlit_o
 }
 
 // ---- whole stream --------------------------------------------------------------------------
-FDB_DEVICE int32_t inflate_stream_general(K3Smem& s, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap,
-                                          uint32_t flags, uint64_t* out_len, uint64_t* consumed) {
-    const unsigned lane = simt::lane_id();
-    BitReader r;
+FDB_DEVICE int32_t inflate_stream_general_impl(K3Smem& s, BitReader& r, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap,
+                                               uint32_t flags, uint64_t* out_len, uint64_t* consumed, bool exact) {
     br_init(r, in, n);
     OutCursor o = {out, 0, cap, 0};
     *out_len = 0;
@@ -1139,7 +1225,7 @@ FDB_DEVICE int32_t inflate_stream_general(K3Smem& s, const uint8_t* in, uint64_t
             uint64_t ncopy = len;
             if (ncopy > in_left) ncopy = in_left;
             if (ncopy > room) ncopy = room;
-            for (uint64_t i = lane; i < ncopy; i += 32) o.out[o.pos + i] = simt::ldg8(in + src_byte + i);
+            warp_copy_bytes(o.out + o.pos, in + src_byte, ncopy);
             o.pos += ncopy;
             if (ncopy < len) {
                 *out_len = o.pos;
@@ -1154,7 +1240,7 @@ FDB_DEVICE int32_t inflate_stream_general(K3Smem& s, const uint8_t* in, uint64_t
                 st = build_block_tables(s, 288, &fixed_eof_code, &fixed_eof_bits);
                 fixed_ready = true;
             }
-            if (st == ST_OK) st = decode_block(s, r, o, fixed_eof_code, fixed_eof_bits, &too_large);
+            if (st == ST_OK) st = decode_block(s, r, o, fixed_eof_code, fixed_eof_bits, &too_large, nullptr, exact);
         } else if (btype == 2) {  // dynamic (:415-434, :440-555)
             uint32_t hlit = 0;
             st = read_dynamic_header(s, r, &hlit);
@@ -1166,7 +1252,7 @@ FDB_DEVICE int32_t inflate_stream_general(K3Smem& s, const uint8_t* in, uint64_t
             if (st != ST_OK) return st;
             uint32_t eof_code = 0, eof_bits = 0;
             st = build_block_tables(s, hlit, &eof_code, &eof_bits);
-            if (st == ST_OK) st = decode_block(s, r, o, eof_code, eof_bits, &too_large);
+            if (st == ST_OK) st = decode_block(s, r, o, eof_code, eof_bits, &too_large, nullptr, exact);
         } else {
             return ST_INVALID_BLOCK_TYPE;  // :435
         }
@@ -1199,10 +1285,22 @@ FDB_DEVICE int32_t inflate_stream_general(K3Smem& s, const uint8_t* in, uint64_t
     return ST_OK;
 }
 
+FDB_DEVICE int32_t inflate_stream_general(K3Smem& s, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap,
+                                          uint32_t flags, uint64_t* out_len, uint64_t* consumed) {
+    BitReader r;
+    int32_t st = inflate_stream_general_impl(s, r, in, n, out, cap, flags, out_len, consumed, false);
+    // (see decode_block: a stream that failed within 64 bits of the end of its input is decoded again entry by entry)
+    if (K3_TB < 12 && st != ST_OK && br_avail(r) < 64) {
+        simt::syncwarp();
+        st = inflate_stream_general_impl(s, r, in, n, out, cap, flags, out_len, consumed, true);
+    }
+    return st;
+}
+
 // Persistent kernel: one warp per CTA, warps pull stream indices from a device counter.
 // worklist == nullptr: all streams 0..n-1; else the first *work_count entries of worklist.
 #ifndef K3_MIN_CTAS
-#define K3_MIN_CTAS 1
+#define K3_MIN_CTAS 14  // one warp per CTA: what 15.5 KB of shared memory per warp allow (128 registers, no spills)
 #endif
 FDB_GLOBAL void FDB_LAUNCH_BOUNDS(32, K3_MIN_CTAS)
     inflate_general_kernel(InflateBatch b, const uint32_t* worklist, const uint32_t* work_count, uint32_t* next) {
@@ -1381,7 +1479,7 @@ FDB_DEVICE void inflate_stream_resume(K3Smem& s, K3StreamJob& job) {
                 uint64_t ncopy = stored_left;
                 if (ncopy > in_left) ncopy = in_left;
                 if (ncopy > room) ncopy = room;
-                for (uint64_t i = lane; i < ncopy; i += 32) o.out[o.pos + i] = simt::ldg8(job.in + src_byte + i);
+                warp_copy_bytes(o.out + o.pos, job.in + src_byte, ncopy);
                 o.pos += ncopy;
                 stored_left -= (uint32_t)ncopy;
                 br_seek(r, (src_byte + ncopy) * 8);

@@ -272,3 +272,34 @@ def _check_deflate_slot_sizes(ctx, oracle, data):
         assert st[0] == want and ln[0] == (len(ref) if want == 0 else 0)
         if want == 0:
             assert out[:len(ref)].tobytes() == ref
+
+
+def _truncation_sweep_cases(oracle, lib, small=False):
+    """valid streams cut at every byte of their last tokens, with slots around the exact size: the corner where the
+    reference's status depends on which literals share one of ITS table entries (decompress.rs:852) -- the general
+    kernel's table is smaller than the reference's and restates that pairing when a stream fails near its end"""
+    from fdeflate_b200 import synth_tiles_host
+
+    rng = random.Random(31)
+    k = 5 if small else 1
+    tile = synth_tiles_host(9, 1, 256, 256, 5, lib)[0].tobytes()[:30000 // k]
+    text = bytes(rng.choice(b"abcdefghij klmnop\n") for _ in range(20000 // k))
+    short = bytes(rng.choice(b"ab") for _ in range(6000 // k))      # 1..2-bit literal codes: long runs of paired literals
+    skew = bytes(min(255, int(rng.expovariate(0.08))) for _ in range(20000 // k))
+    out = []
+    for data in (tile, text, short, skew):
+        streams = [zlib.compress(data, 6), zlib.compress(data, 1)]
+        for strat in (zlib.Z_HUFFMAN_ONLY, zlib.Z_FIXED):
+            co = zlib.compressobj(6, zlib.DEFLATED, 15, 8, strat)
+            streams.append(co.compress(data) + co.flush())
+        for z in streams:
+            n = len(data)
+            for cut in range(1, 9 if small else 14):
+                for cap in ((n, n - 1) if small else (n, n - 1, n + 1, n - 2)):
+                    out.append((z[:len(z) - cut], cap))
+    return out
+
+
+def test_inflate_truncated_ends_match_the_reference_pairing(emul_ctx, oracle):
+    c = _truncation_sweep_cases(oracle, emul_ctx.lib, small=True)
+    parity.check_inflate(emul_ctx, c, FLAG_GENERAL_ONLY)

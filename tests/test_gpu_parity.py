@@ -375,3 +375,12 @@ def test_deflate_long_inputs_segment_by_segment(gpu_ctx, oracle):
         _check_deflate_slot_sizes(gpu_ctx, oracle, inputs[4])
     finally:
         gpu_ctx.set_split_threshold(0, 0)
+
+
+def test_inflate_truncated_ends_match_the_reference_pairing(gpu_ctx, oracle):
+    """GPU twin of the emulator test: streams cut inside their last tokens, slots around the exact size"""
+    from test_emul_kernels import _truncation_sweep_cases
+
+    c = _truncation_sweep_cases(oracle, gpu_ctx.lib)
+    parity.check_inflate(gpu_ctx, c, FLAG_GENERAL_ONLY)
+    parity.check_inflate(gpu_ctx, c, 0, align=1)
