@@ -470,6 +470,22 @@ FDB_DEVICE void gl_start(GLane& b, simt::saddr row, uint32_t rp) {
     b.nx = p + 384u;
 }
 FDB_DEVICE void gl_advance(GLane& b, uint32_t n) {  // n <= 48
+#if !defined(FDB_EMUL)
+    // the two conditional word shifts as predicated instructions (cf. lb_advance in inflate_uf.cuh: the compiler's
+    // version moves the three words through temporaries)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 x, y;\n\t"
+        "setp.ge.u32 p, %5, 32;\n\t"
+        "@p mov.u32 %0, %1;\n\t@p mov.u32 %1, %2;\n\t@p ld.shared.u32 %2, [%3];\n\t@p add.u32 %3, %3, 128;\n\t"
+        "@p add.u32 %4, %4, 32;\n\t@p sub.u32 %5, %5, 32;\n\t"
+        "add.u32 y, %4, %5;\n\txor.b32 x, y, %4;\n\tand.b32 x, x, 32;\n\tsetp.ne.u32 p, x, 0;\n\t"
+        "@p mov.u32 %0, %1;\n\t@p mov.u32 %1, %2;\n\t@p ld.shared.u32 %2, [%3];\n\t@p add.u32 %3, %3, 128;\n\t"
+        "mov.u32 %4, y;\n\t}"
+        : "+r"(b.w0), "+r"(b.w1), "+r"(b.w2), "+r"(b.nx), "+r"(b.rp), "+r"(n)
+        :
+        : "memory");
+    return;
+#endif
     if (n >= 32) {
         b.w0 = b.w1;
         b.w1 = b.w2;
