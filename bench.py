@@ -306,6 +306,9 @@ def sweep(ctx, args, rank: int, world: int, dev, dist, stream, peak: float) -> d
 
     launches0 = ctx.launch_count
     ms_def = timed(deflate, args.sweep_steps)
+    # a device-pointer call does not see the stream sizes: the caller sizes the pool of lane records the span-by-span
+    # inflate keeps between its two passes (1/8 of the compressed bytes + one partial span per stream)
+    ctx.set_split_scratch(int(c_len.sum()) // 8 + n * 8192 + (1 << 20))
     ms_inf = timed(inflate, args.sweep_steps)
     launches = ctx.launch_count - launches0
     spans = ctx.last_split_spans(stream)
@@ -332,6 +335,7 @@ def sweep(ctx, args, rank: int, world: int, dev, dist, stream, peak: float) -> d
     except ImportError:
         pass
     ctx.set_split_large(False)
+    ctx.set_split_scratch(256 << 20)
     unc = int(lens.sum())
     cbytes = int(c_len.sum())
     t = torch.tensor([ms_inf, ms_def], dtype=torch.float64, device=dev)

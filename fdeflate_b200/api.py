@@ -116,9 +116,13 @@ class Context:
         self._check(self.lib.L.fdb_set_split_large(self._h, 1 if on else 0), "fdb_set_split_large")
 
     def set_split_threshold(self, inflate_stream_bytes: int = 0, deflate_input_bytes: int = 0):
-        """sizes from which a stream is decoded / encoded by many warps (0 = default: 256 KiB / 1 MiB)"""
+        """sizes from which a stream is decoded / encoded by many warps (0 = default: 128 KiB / 256 KiB, host-buffer deflate calls 1 MiB)"""
         self._check(self.lib.L.fdb_set_split_threshold(self._h, inflate_stream_bytes, deflate_input_bytes),
                     "fdb_set_split_threshold")
+
+    def set_split_scratch(self, nbytes: int):
+        """size of the lane-record pool of span-by-span device-pointer inflate calls (fdb_set_split_scratch)"""
+        self._check(self.lib.L.fdb_set_split_scratch(self._h, nbytes), "fdb_set_split_scratch")
 
     def last_split_spans(self, stream: int = 0) -> int:
         """spans the long streams of the most recent inflate batch were cut into (0 = one warp per stream)"""

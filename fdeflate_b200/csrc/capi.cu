@@ -38,13 +38,15 @@ struct fdb_split_scratch {
     size_t items_bytes = 0;
     uint32_t* per_stream = nullptr;  // item0 | nspans | need | done | failed, n words each
     size_t per_stream_bytes = 0;
+    uint32_t* rec = nullptr;         // lane records the count pass leaves for the write pass (inflate_uf.cuh), 8 KiB per span
+    size_t rec_bytes = 0;
 };
 static const uint32_t FDB_SPLIT_ITEMS = 1u << 20;  // spans per batch (64 GiB of compressed input); scratch is allocated on first use
 // ... and of the segment-by-segment deflate path
 struct fdb_dsplit_scratch {
     DfItem* items = nullptr;
     size_t items_bytes = 0;
-    uint32_t* per_stream = nullptr;  // item0 | nseg | adler, n words each
+    uint32_t* per_stream = nullptr;  // item0 | nseg | adler | work order, n words each, then 2 x DF_ORDER_CLASSES counters
     size_t per_stream_bytes = 0;
 };
 
@@ -83,6 +85,7 @@ struct fdb_ctx {
     fdb_dsplit_scratch dsplit;
     int split_large = 0;            // device-pointer calls: long streams by many warps (fdb_set_split_large)
     uint64_t inflate_split_min = K4_SPLIT_MIN_BYTES;  // fdb_set_split_threshold
+    uint64_t split_scratch = 256ull << 20;            // fdb_set_split_scratch: lane-record pool of a device-pointer inflate call
     uint64_t deflate_split_min = DF_SPLIT_MIN_BYTES;
     uint64_t deflate_auto_min = DF_AUTO_SPLIT_BYTES;  // host-buffer deflate: a chunk with an input this long takes the segment path
     UfEncTables* d_enc = nullptr;
@@ -217,6 +220,12 @@ extern "C" int fdb_set_split_threshold(fdb_ctx* ctx, size_t inflate_bytes, size_
     return 0;
 }
 
+extern "C" int fdb_set_split_scratch(fdb_ctx* ctx, size_t bytes) {
+    if (!ctx) return -1;
+    ctx->split_scratch = bytes;
+    return 0;
+}
+
 extern "C" int64_t fdb_last_split_spans(fdb_ctx* ctx, void* cuda_stream) {
     if (!ctx) return -1;
     if (ctx->last_split_host >= 0) return ctx->last_split_host;
@@ -319,6 +328,7 @@ extern "C" void fdb_destroy(fdb_ctx* ctx) {
         cudaFree(ctx->lanes[l].d_worklist);
         cudaFree(ctx->lanes[l].split.items);
         cudaFree(ctx->lanes[l].split.per_stream);
+        cudaFree(ctx->lanes[l].split.rec);
         cudaFree(ctx->lanes[l].dsplit.items);
         cudaFree(ctx->lanes[l].dsplit.per_stream);
     }
@@ -333,6 +343,7 @@ extern "C" void fdb_destroy(fdb_ctx* ctx) {
     cudaFree(ctx->d_worklist);
     cudaFree(ctx->split.items);
     cudaFree(ctx->split.per_stream);
+    cudaFree(ctx->split.rec);
     cudaFree(ctx->dsplit.items);
     cudaFree(ctx->dsplit.per_stream);
     cudaFree(ctx->d_enc);
@@ -374,12 +385,31 @@ static int grow(fdb_ctx* ctx, void** p, size_t* cap, size_t need) {
 // kernels of the chunks in flight (and of other contexts) run side by side instead of each one holding
 // every SM with a warp or two.
 static int launch_inflate(fdb_ctx* ctx, const InflateBatch& b, uint32_t* counters, uint32_t** worklist,
-                          size_t* worklist_cap, cudaStream_t st, bool dense = false, fdb_split_scratch* ss = nullptr) {
+                          size_t* worklist_cap, cudaStream_t st, bool dense = false, fdb_split_scratch* ss = nullptr,
+                          uint64_t in_total = 0 /* bytes of input in the batch if the host knows them */) {
     const size_t n = b.n;
     const bool split = ss && (b.flags & FDB_FLAG_SPLIT_LARGE) && !(b.flags & FDB_FLAG_GENERAL_ONLY);
+    uint32_t rec_items = 0;
     if (split) {
         int r;
-        void* p = ss->items;
+        // lane records: one span per 64 KiB of compressed data plus a partial one per split stream when the sizes are
+        // known, the context's pool size otherwise; spans beyond the pool are counted again by the write pass
+        uint64_t want_items = ctx->split_scratch / (K4_REC_WORDS * sizeof(uint32_t));
+        if (in_total) {
+            const uint64_t streams = std::min<uint64_t>(n, in_total / ctx->inflate_split_min + 1);
+            want_items = in_total / (K4_SPAN_WORDS * 4) + streams;
+        }
+        want_items = std::min<uint64_t>(want_items, FDB_SPLIT_ITEMS);
+        void* p = ss->rec;
+        if (want_items && grow(ctx, &p, &ss->rec_bytes, (size_t)want_items * K4_REC_WORDS * sizeof(uint32_t)) == 0) {
+            ss->rec = (uint32_t*)p;
+            rec_items = (uint32_t)std::min<uint64_t>(ss->rec_bytes / (K4_REC_WORDS * sizeof(uint32_t)), FDB_SPLIT_ITEMS);
+        } else {
+            ss->rec = nullptr;  // (no memory for the pool: the write pass counts for itself)
+            ss->rec_bytes = 0;
+            cudaGetLastError();
+        }
+        p = ss->items;
         if ((r = grow(ctx, &p, &ss->items_bytes, (size_t)FDB_SPLIT_ITEMS * sizeof(K4Item)))) return r;
         ss->items = (K4Item*)p;
         p = ss->per_stream;
@@ -413,6 +443,8 @@ static int launch_inflate(fdb_ctx* ctx, const InflateBatch& b, uint32_t* counter
         sp.next_scan = counters + 6;
         sp.next_write = counters + 7;
         sp.min_bytes = ctx->inflate_split_min;
+        sp.rec = rec_items ? ss->rec : nullptr;
+        sp.rec_items = rec_items;
         split_item0 = sp.item0;
         FDB_LAUNCH(inflate_uf_plan_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0, st, b, (const UfDecTables*)ctx->d_dec, sp);
         FDB_LAUNCH(inflate_uf_split_count_kernel, dim3(sms), dim3(K4_WARPS * 32), sizeof(K4Smem), st, b,
@@ -482,6 +514,7 @@ static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_
     FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
     const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
     const uint32_t* split_item0 = nullptr;
+    uint32_t* order = nullptr;
     if (kind == 0 && ss) {
         // long inputs, segment by segment: plan, count, scan, write (deflate_uf.cuh)
         int r;
@@ -489,7 +522,7 @@ static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_
         if ((r = grow(ctx, &p, &ss->items_bytes, (size_t)FDB_SPLIT_ITEMS * sizeof(DfItem)))) return r;
         ss->items = (DfItem*)p;
         p = ss->per_stream;
-        r = grow(ctx, &p, &ss->per_stream_bytes, 3 * n * sizeof(uint32_t));
+        r = grow(ctx, &p, &ss->per_stream_bytes, (4 * n + 2 * DF_ORDER_CLASSES) * sizeof(uint32_t));
         ss->per_stream = (uint32_t*)p;
         if (r) return r;
         uint32_t* c8 = counter + 5;
@@ -516,7 +549,14 @@ static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_
         FDB_LAUNCH(deflate_uf_split_count_kernel, dim3(pgrid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc, sp);
         FDB_LAUNCH(deflate_uf_split_scan_kernel, dim3((uint32_t)std::min<size_t>((n + 7) / 8, (size_t)sms * 4)), dim3(256), 0, st, b, sp);
         FDB_LAUNCH(deflate_uf_split_write_kernel, dim3(pgrid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc, sp);
-        ctx->launches += 5;
+        // the inputs that stay with one warp each are handed out longest first
+        order = ss->per_stream + 3 * n;
+        uint32_t* hist = ss->per_stream + 4 * n;
+        FDB_TRY(cudaMemsetAsync(hist, 0, 2 * DF_ORDER_CLASSES * sizeof(uint32_t), st));
+        const uint32_t ogrid = (uint32_t)std::min<size_t>((n + 255) / 256, 256);
+        FDB_LAUNCH(order_hist_kernel, dim3(ogrid), dim3(256), 0, st, b.in_len, b.n, hist);
+        FDB_LAUNCH(order_scatter_kernel, dim3(ogrid), dim3(256), 0, st, b.in_len, b.n, (const uint32_t*)hist, hist + DF_ORDER_CLASSES, order);
+        ctx->launches += 7;
         FDB_TRY(cudaGetLastError());
     }
     if (kind == 0) {
@@ -525,7 +565,7 @@ static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_
         uint32_t grid = (uint32_t)std::min<size_t>(dense ? (n + DEFLATE_WARPS - 1) / DEFLATE_WARPS : n,
                                                    (size_t)sms * DEFLATE_MIN_CTAS);
         FDB_LAUNCH(deflate_uf_kernel, dim3(grid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc,
-                   counter, split_item0);
+                   counter, split_item0, (const uint32_t*)order);
     } else {
         uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * 8);
         FDB_LAUNCH(deflate_stored_kernel, dim3(grid), dim3(STORED_THREADS), sizeof(StoredSmem), st, b, counter);
@@ -815,8 +855,11 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     auto issue = [&](size_t k) -> int {  // input, kernels and results of chunk k
         const size_t a = k * per, b = std::min(n, a + per);
         fdb_lane& ln = ctx->lanes[k % L];
-        uint64_t max_in = 0;
-        for (size_t i = a; i < b; i++) max_in = std::max(max_in, in_len[i]);
+        uint64_t max_in = 0, sum_in = 0;
+        for (size_t i = a; i < b; i++) {
+            max_in = std::max(max_in, in_len[i]);
+            sum_in += in_len[i];
+        }
         mark(k, 0, hs);
         int rr = copy_rows(ctx, ctx->d_in, in_base, in_off, in_len, nullptr, a, b, in_uniform, in_stride, cudaMemcpyHostToDevice, hs);
         if (rr) return rr;
@@ -839,7 +882,7 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             if (max_in >= ctx->inflate_split_min) ib.flags |= FDB_FLAG_SPLIT_LARGE;  // long streams: many warps each
             ib.general_out = h_general + k;
             ib.split_out = h_split + k;
-            if ((rr = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, dense, &ln.split)))
+            if ((rr = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, dense, &ln.split, kind == 0 ? sum_in : 0)))
                 return rr;
         } else {
             DeflateBatch db;
@@ -1121,8 +1164,11 @@ extern "C" int fdb_png_decode_batch(fdb_ctx* ctx, const uint8_t* idat_base, cons
     for (size_t k = 0; k < nchunk; k++) {
         const size_t a = k * per, b = std::min(n, a + per);
         fdb_lane& ln = ctx->lanes[k % L];
-        uint64_t max_in = 0;
-        for (size_t i = a; i < b; i++) max_in = std::max(max_in, idat_len[i]);
+        uint64_t max_in = 0, sum_in = 0;
+        for (size_t i = a; i < b; i++) {
+            max_in = std::max(max_in, idat_len[i]);
+            sum_in += idat_len[i];
+        }
         const uint64_t in_lo = nchunk == 1 ? 0 : idat_off[a], in_hi = nchunk == 1 ? in_span : idat_off[b - 1] + idat_len[b - 1];
         if (in_hi > in_lo) FDB_TRY(cudaMemcpyAsync(ctx->d_in + in_lo, idat_base + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, hs));
         FDB_TRY(cudaEventRecord(ctx->ev_in[k], hs));
@@ -1139,7 +1185,7 @@ extern "C" int fdb_png_decode_batch(fdb_ctx* ctx, const uint8_t* idat_base, cons
         ib.status = h_st1 + a;
         ib.n = (uint32_t)(b - a);
         ib.flags = max_in >= ctx->inflate_split_min ? FDB_FLAG_SPLIT_LARGE : 0u;
-        if ((r = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, nchunk > 1, &ln.split))) return r;
+        if ((r = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, nchunk > 1, &ln.split, sum_in))) return r;
         if ((r = png_launch(ctx, true, ctx->d_mid, d_filt_off + a, ctx->d_out, d_raw_off + a, d_h + a, d_s + a, d_b + a, 0,
                             h_st2 + a, b - a, ln.st, ln.d_counters + 12)))
             return r;
@@ -1577,10 +1623,13 @@ extern "C" int fdb_png_decode_files_batch(fdb_ctx* ctx, const uint8_t* file_base
         ib.consumed = d_consumed + a;
         ib.status = d_st1 + a;
         ib.n = (uint32_t)(b - a);
-        uint64_t max_in = 0;
-        for (size_t i = a; i < b; i++) max_in = std::max(max_in, m[n + i]);
+        uint64_t max_in = 0, sum_in = 0;
+        for (size_t i = a; i < b; i++) {
+            max_in = std::max(max_in, m[n + i]);
+            sum_in += m[n + i];
+        }
         ib.flags = max_in >= ctx->inflate_split_min ? FDB_FLAG_SPLIT_LARGE : 0u;
-        if ((r = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, nchunk > 1, &ln.split))) return r;
+        if ((r = launch_inflate(ctx, ib, ln.d_counters, &ln.d_worklist, &ln.worklist_cap, ln.st, nchunk > 1, &ln.split, sum_in))) return r;
         if ((r = png_launch(ctx, true, ctx->d_mid, d_filt_off + a, ctx->d_out, d_raw_off + a, d_geo + a, d_geo + n + a,
                             d_geo + 2 * n + a, 0, d_st2 + a, b - a, ln.st, ln.d_counters + 12)))
             return r;

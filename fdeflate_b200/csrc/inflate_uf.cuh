@@ -336,7 +336,16 @@ static const uint32_t K4_SPAN_SEGS = 64;                            // segments 
 static const uint64_t K4_SPAN_WORDS = (uint64_t)K4_SPAN_SEGS * 32 * K4_SUBW;
 enum : uint32_t { SP_EOB = 1, SP_FIRSTRUN = 2, SP_LASTNZ = 4, SP_DEAD = 8, SP_SKIP = 16, SP_SYNCFAIL = 32 };
 static const uint32_t K4_NO_ITEM = 0xffffffffu;
-static const uint64_t K4_SPLIT_MIN_BYTES = 4ull * K4_SPAN_WORDS * 4;  // default: streams of >= 4 spans (256 KiB) are split
+static const uint64_t K4_SPLIT_MIN_BYTES = 2ull * K4_SPAN_WORDS * 4;  // default: streams of >= 2 spans (128 KiB) are split (with lane records a cut costs one extra segment per span)
+
+// LANE RECORDS.  The count pass knows, for every lane of every segment of its span, where the lane's sub-sequence
+// starts and how many bytes it holds -- exactly what the write pass would otherwise find again with a warm-up and a
+// count of its own (1.5 of its 2.5 walks over the bits).  So the count pass leaves one word per lane and segment in
+// device scratch (128 B per KiB of compressed data) and the write pass of a span that has records goes straight from
+// staging to the prefix sum.  Word = start bit in the lane's row (9 bits) | REC_INVALID | REC_EOB | bytes << 16
+// (a lane holds at most 27 run tokens of 258 bytes).  Spans beyond the pool (fdb_set_split_scratch) count again.
+enum : uint32_t { REC_INVALID = 0x4000u, REC_EOB = 0x8000u };
+static const uint32_t K4_REC_WORDS = K4_SPAN_SEGS * 32;
 
 // One span of one split stream (device scratch, filled by the three passes in turn).
 struct K4Item {
@@ -361,6 +370,8 @@ struct K4Split {
     uint32_t* next_scan;
     uint32_t* next_write;
     uint64_t min_bytes;    // streams at least this long are split
+    uint32_t* rec;         // lane records (K4_REC_WORDS per item) of the first rec_items items, or null
+    uint32_t rec_items;
 };
 
 struct K4Span {
@@ -384,7 +395,8 @@ struct K4SpanOut {
 // K4_COUNT / K4_WRITE: ST_OK with *so filled, or ST_PENDING_GENERAL.
 template <int MODE>
 FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& ws, const K4Stream& s, uint32_t flags,
-                                  uint64_t* out_len, uint64_t* consumed, const K4Span* sp, K4SpanOut* so) {
+                                  uint64_t* out_len, uint64_t* consumed, const K4Span* sp, K4SpanOut* so,
+                                  uint32_t* rec = nullptr) {
     const unsigned lane = simt::lane_id();
     uint32_t* stg = ws.stg;
     const simt::saddr row = simt::smem_addr(ws.stg + lane);
@@ -548,50 +560,64 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
         }
         simt::syncwarp();
 
-        // ---- 2. count ----
-        uint32_t start = warm_up(t, row, lane != 0);
-        if (lane == 0) start = (uint32_t)(p0 - (s0 << 5));
-        LaneCount c = count_tokens(t, row, start, start != K4_INVALID);
-
-        // ---- 3. verify the chain: my start must be my predecessor's end (rows are 32*SUBW bits apart) ----
+        // ---- 2. count ----  (or, for a span whose count pass left lane records, just read them)
+        const bool replay = MODE == K4_WRITE && rec != nullptr;
+        const uint32_t rec_seg = MODE == K4_WHOLE ? 0u : (uint32_t)((seg_word - (sp->stop_word - K4_SPAN_WORDS)) / (32 * K4_SUBW));
+        uint32_t start;
+        LaneCount c;
         uint32_t eob_lane = 32;
-        for (;;) {
-            uint32_t prev_end = simt::shfl_up(c.end, 1);
-            uint32_t prev_flags = simt::shfl_up(c.flags, 1);
-            uint32_t want = prev_end - 32u * K4_SUBW;
-            bool mismatch = (lane > 0) && (prev_end == K4_INVALID || start != want || (prev_flags & CF_EOB));
-            uint32_t mm = simt::ballot(mismatch);
-            uint32_t em = simt::ballot((c.flags & CF_EOB) != 0 && start != K4_INVALID);
-            uint32_t first_mis = mm ? simt::ffs(mm) - 1 : 32;
-            uint32_t first_eob = em ? simt::ffs(em) - 1 : 32;
-            if (first_eob < first_mis) {  // the stream ends inside a verified lane
-                eob_lane = first_eob;
-                break;
-            }
-            if (first_mis == 32) break;  // every lane verified, no EOB in this segment
-            // re-run the lanes whose start disagrees with their predecessor's end
-            bool redo = mismatch && !(prev_flags & CF_EOB) && prev_end != K4_INVALID;
-            if (mismatch) start = redo ? want : K4_INVALID;
-            LaneCount c2 = count_tokens(t, row, start, redo);
-            if (mismatch) c = c2;  // (unresolved lanes get end = INVALID, cnt = 0, flags = 0)
-        }
-        if (lane > eob_lane) {
-            c.cnt = 0;
+        if (replay) {
+            const uint32_t r = rec[rec_seg * 32 + lane];
+            start = (r & REC_INVALID) ? K4_INVALID : (r & 0x1ffu);
+            c.end = K4_INVALID;  // (known after the write loop: where the lane's reader stops)
+            c.cnt = r >> 16;
             c.flags = 0;
-        }
-        if (MODE == K4_COUNT && sync_seg) {
-            // only where this segment ends matters; a walk that began on a guess may have read anything
-            if (eob_lane < 32) {  // the guessed walk read an end-of-block code before it synchronised: guess again
-                so->flags |= SP_SYNCFAIL;
-                return ST_PENDING_GENERAL;
+            const uint32_t em = simt::ballot((r & REC_EOB) != 0);
+            if (em) eob_lane = simt::ffs(em) - 1;
+        } else {
+            start = warm_up(t, row, lane != 0);
+            if (lane == 0) start = (uint32_t)(p0 - (s0 << 5));
+            c = count_tokens(t, row, start, start != K4_INVALID);
+
+            // ---- 3. verify the chain: my start must be my predecessor's end (rows are 32*SUBW bits apart) ----
+            for (;;) {
+                uint32_t prev_end = simt::shfl_up(c.end, 1);
+                uint32_t prev_flags = simt::shfl_up(c.flags, 1);
+                uint32_t want = prev_end - 32u * K4_SUBW;
+                bool mismatch = (lane > 0) && (prev_end == K4_INVALID || start != want || (prev_flags & CF_EOB));
+                uint32_t mm = simt::ballot(mismatch);
+                uint32_t em = simt::ballot((c.flags & CF_EOB) != 0 && start != K4_INVALID);
+                uint32_t first_mis = mm ? simt::ffs(mm) - 1 : 32;
+                uint32_t first_eob = em ? simt::ffs(em) - 1 : 32;
+                if (first_eob < first_mis) {  // the stream ends inside a verified lane
+                    eob_lane = first_eob;
+                    break;
+                }
+                if (first_mis == 32) break;  // every lane verified, no EOB in this segment
+                // re-run the lanes whose start disagrees with their predecessor's end
+                bool redo = mismatch && !(prev_flags & CF_EOB) && prev_end != K4_INVALID;
+                if (mismatch) start = redo ? want : K4_INVALID;
+                LaneCount c2 = count_tokens(t, row, start, redo);
+                if (mismatch) c = c2;  // (unresolved lanes get end = INVALID, cnt = 0, flags = 0)
             }
-            sync_seg = 0;
-            p0 = ((s0 + (uint64_t)K4_SUBW * 31) << 5) + simt::shfl(c.end, 31);
-            so->p_start = p0;
-            seg_word += 32 * K4_SUBW;
-            continue;
+            if (lane > eob_lane) {
+                c.cnt = 0;
+                c.flags = 0;
+            }
+            if (MODE == K4_COUNT && sync_seg) {
+                // only where this segment ends matters; a walk that began on a guess may have read anything
+                if (eob_lane < 32) {  // the guessed walk read an end-of-block code before it synchronised: guess again
+                    so->flags |= SP_SYNCFAIL;
+                    return ST_PENDING_GENERAL;
+                }
+                sync_seg = 0;
+                p0 = ((s0 + (uint64_t)K4_SUBW * 31) << 5) + simt::shfl(c.end, 31);
+                so->p_start = p0;
+                seg_word += 32 * K4_SUBW;
+                continue;
+            }
+            if (simt::any((c.flags & CF_BAD) != 0)) return ST_PENDING_GENERAL;
         }
-        if (simt::any((c.flags & CF_BAD) != 0)) return ST_PENDING_GENERAL;
 
         // ---- 4. scan ----
         const uint32_t incl = simt::scan_incl_add(c.cnt);
@@ -599,7 +625,7 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
         if (o0 + seg_bytes > s.cap) return ST_PENDING_GENERAL;  // K3 reports OutputTooLarge
         uint64_t op = oalign + o0 + (incl - c.cnt);             // my virtual output position
         const uint64_t my_end_vo = op + c.cnt;
-        {
+        if (!replay) {  // (the count pass of a span with records has checked all of this)
             // a lane that opens with a run needs a zero byte before it: the last byte of the nearest
             // lane below that produced anything, else the last byte of the previous segment
             const uint32_t has_mask = simt::ballot(c.cnt != 0);
@@ -615,6 +641,10 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                 if ((fr_mask >> (simt::ffs(has_mask) - 1u)) & 1u) so->flags |= SP_FIRSTRUN;
             }
             if (has_mask) prev_nz = (nz_mask >> (31u - simt::clz(has_mask))) & 1u;
+        }
+        if (MODE == K4_COUNT && rec) {  // what the write pass needs of this segment
+            const bool valid = start != K4_INVALID && lane <= eob_lane;
+            rec[rec_seg * 32 + lane] = valid ? (start | (lane == eob_lane ? REC_EOB : 0u) | (c.cnt << 16)) : REC_INVALID;
         }
 
         // ---- 5. write ----
@@ -759,6 +789,7 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
         }
 
         // ---- next segment or finish ----
+        if (replay) c.end = b.rp;  // first token boundary at or after the lane's sub-sequence, or the end-of-block code
         adler_fold(ad);
         o0 += seg_bytes;
         if (eob_lane < 32) {
@@ -951,12 +982,13 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
             span.discard = 1;
         }
         K4SpanOut so;
-        int32_t st = inflate_uf_run<K4_COUNT>(kt.t, nullptr, *kt.ws, s, b.flags, nullptr, nullptr, &span, &so);
+        uint32_t* const rec = (sp.rec && idx < sp.rec_items) ? sp.rec + (size_t)idx * K4_REC_WORDS : nullptr;
+        int32_t st = inflate_uf_run<K4_COUNT>(kt.t, nullptr, *kt.ws, s, b.flags, nullptr, nullptr, &span, &so, rec);
         // A walk that starts on a guessed bit can run into an end-of-block pattern before it reaches a true
         // token boundary (likely only on data made of 12-bit codes); another starting bit reads other tokens.
         for (uint32_t retry = 1; retry < 10 && st != ST_OK && (so.flags & SP_SYNCFAIL); retry++) {
             span.p0 = (span.seg_word << 5) + 3u * retry;
-            st = inflate_uf_run<K4_COUNT>(kt.t, nullptr, *kt.ws, s, b.flags, nullptr, nullptr, &span, &so);
+            st = inflate_uf_run<K4_COUNT>(kt.t, nullptr, *kt.ws, s, b.flags, nullptr, nullptr, &span, &so, rec);
         }
         if (lane == 0) {
             it.p_start = so.p_start;
@@ -1066,7 +1098,8 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
         span.prev_nz = it.prev_nz;
         span.discard = 0;
         K4SpanOut so;
-        const int32_t st = inflate_uf_run<K4_WRITE>(kt.t, nullptr, *kt.ws, s, b.flags, nullptr, nullptr, &span, &so);
+        uint32_t* const rec = (sp.rec && idx < sp.rec_items) ? sp.rec + (size_t)idx * K4_REC_WORDS : nullptr;
+        const int32_t st = inflate_uf_run<K4_WRITE>(kt.t, nullptr, *kt.ws, s, b.flags, nullptr, nullptr, &span, &so, rec);
         uint64_t s1 = 0, s2 = 0;
         if (st == ST_OK) {
             s1 = simt::reduce_add(so.ad.s1);

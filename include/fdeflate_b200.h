@@ -69,7 +69,7 @@ enum fdb_status {
 /* flags for the inflate entry points */
 #define FDB_FLAG_IGNORE_ADLER32 1u /* Decompressor::ignore_adler32, src/decompress.rs:154-156 */
 #define FDB_FLAG_GENERAL_ONLY 2u   /* skip the ultra-fast-format fast path (testing / profiling) */
-#define FDB_FLAG_SPLIT_LARGE 4u    /* device-pointer calls: decode ultra-fast-format streams of >= 256 KiB with many
+#define FDB_FLAG_SPLIT_LARGE 4u    /* device-pointer calls: decode ultra-fast-format streams of >= 128 KiB with many
                                       warps each (three extra small launches per batch).  The host-buffer calls
                                       turn it on by themselves when a batch holds such a stream. */
 
@@ -216,16 +216,22 @@ uint64_t fdb_launch_count(const fdb_ctx* ctx);
 /* how many streams of the most recent inflate batch on this context were declined by the
  * ultra-fast-format fast path and decoded by the general kernel.  Synchronises `cuda_stream`. */
 int64_t fdb_last_general_count(fdb_ctx* ctx, void* cuda_stream);
-/* Long streams, many warps each.  An ultra-fast-format stream of >= 256 KiB is inflated span by span and an
+/* Long streams, many warps each.  An ultra-fast-format stream of >= 128 KiB is inflated span by span and an
  * input of >= 256 KiB is ultra-fast-deflated segment by segment (64 KiB units, three passes),
  * so that a batch of few or very uneven streams still fills the GPU.  A deflate batch with more inputs than the device
  * runs warps only cuts an input that holds an eighth of the batch's bytes (the work counter balances the rest).
  * Results are identical either way.  The host-buffer calls turn this on by themselves for a batch
- * (chunk) that holds a stream of >= 256 KiB (inflate) or an input of >= 1 MiB (deflate); for the device-pointer
+ * (chunk) that holds a stream of >= 128 KiB (inflate) or an input of >= 1 MiB (deflate); for the device-pointer
  * calls, which do not see the sizes, it is off unless fdb_set_split_large(ctx, 1) (costs a few extra small
  * launches per batch).  fdb_set_split_threshold changes the two sizes (0 = default). */
 int fdb_set_split_large(fdb_ctx* ctx, int on);
 int fdb_set_split_threshold(fdb_ctx* ctx, size_t inflate_stream_bytes, size_t deflate_input_bytes);
+/* Span-by-span inflate keeps what its first pass learns about every span (one word per lane and segment: 1/8 of the
+ * compressed bytes) so that the pass that writes does not count again.  The host-buffer calls size that scratch from
+ * the batch; a device-pointer call, which does not see the sizes, uses a pool of `bytes` (default 256 MiB = 2 GiB of
+ * compressed input per call; spans beyond the pool are simply counted twice; 0 = no pool).  Device memory, allocated
+ * on the first span-by-span call. */
+int fdb_set_split_scratch(fdb_ctx* ctx, size_t bytes);
 /* how many spans the long streams of the most recent inflate batch on this context were cut into
  * (0 = every stream was decoded by one warp).  Synchronises `cuda_stream`. */
 int64_t fdb_last_split_spans(fdb_ctx* ctx, void* cuda_stream);

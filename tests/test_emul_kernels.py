@@ -254,7 +254,7 @@ def test_deflate_long_inputs_segment_by_segment(emul_ctx, emul_lib, oracle):
         small = cases.compress_inputs(3, 6, [10, 3000])
         l0 = emul_ctx.launch_count
         parity.check_deflate_ultrafast(emul_ctx, small[:5] + inputs[2:5] + small[5:10], align=16)
-        assert emul_ctx.launch_count - l0 == 6  # total, plan, count, scan, write + the one-warp-per-stream kernel
+        assert emul_ctx.launch_count - l0 == 8  # total, plan, count, scan, write, the two work-order kernels + the one-warp-per-stream kernel
         _check_deflate_slot_sizes(emul_ctx, oracle, inputs[2])
     finally:
         emul_ctx.set_split_threshold(0, 0)

@@ -1,0 +1,54 @@
+"""configs[4] shape, device-resident: span-by-span inflate with and without the lane records the count pass leaves for the
+write pass, as a function of the size above which a stream is cut.   python tools/gpu_sweep_records.py [n_streams]"""
+import sys
+sys.path.insert(0, ".")
+import numpy as np, torch
+import fdeflate_b200 as F
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+W = 1024; ROW = 1 + 4 * W
+rng = np.random.default_rng(5)
+sizes = np.exp(rng.uniform(np.log(64 << 10), np.log(16 << 20), n))
+heights = np.maximum(1, (sizes / ROW).astype(np.int64))
+lens = heights * ROW
+ctx = F.Context(0); dev = torch.device("cuda:0"); i64 = torch.int64
+s = torch.cuda.current_stream().cuda_stream
+offs = np.zeros(n, dtype=np.int64); offs[1:] = np.cumsum((lens[:-1] + 15) & ~15)
+total = int(offs[-1] + lens[-1])
+raw = torch.empty(total + 16, dtype=torch.uint8, device=dev)
+for i in range(n):
+    ctx.synth_tiles_device(raw.data_ptr() + int(offs[i]), 1000 + i, 1, W, int(heights[i]), 5, s)
+bounds = np.array([ctx.ultrafast_bound(int(l)) for l in lens], dtype=np.int64)
+coffs = np.zeros(n, dtype=np.int64); coffs[1:] = np.cumsum(bounds[:-1])
+comp = torch.empty(int(coffs[-1] + bounds[-1]), dtype=torch.uint8, device=dev)
+out = torch.empty(total + 16, dtype=torch.uint8, device=dev)
+T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+d_off, d_len, d_coff, d_ccap = T(offs), T(lens), T(coffs), T(bounds)
+c_len = torch.zeros(n, dtype=i64, device=dev); c_st = torch.zeros(n, dtype=torch.int32, device=dev)
+o_len = torch.zeros(n, dtype=i64, device=dev); o_st = torch.zeros(n, dtype=torch.int32, device=dev)
+ctx.set_split_large(True)
+ctx.deflate_ultrafast_device(raw.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), comp.data_ptr(), d_coff.data_ptr(),
+                             d_ccap.data_ptr(), c_len.data_ptr(), c_st.data_ptr(), n, s)
+torch.cuda.synchronize()
+def inflate():
+    ctx.inflate_device(comp.data_ptr(), d_coff.data_ptr(), c_len.data_ptr(), out.data_ptr(), d_off.data_ptr(), d_len.data_ptr(),
+                       o_len.data_ptr(), 0, o_st.data_ptr(), n, F.FLAG_SPLIT_LARGE, s)
+def timed(f, reps=2):
+    f(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): f()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+unc = int(lens.sum()); cmp_total = int(c_len.sum())
+print(f"{n} streams, {unc/1e9:.2f} GB, ratio {cmp_total/unc:.3f}")
+for pool in (0, cmp_total // 8 + (n << 13) + (1 << 20)):
+    ctx.set_split_scratch(pool)
+    for thr in (64 << 10, 128 << 10, 256 << 10, 1 << 20, 4 << 20):
+        ctx.set_split_threshold(thr, 0)
+        out.zero_()
+        ms = timed(inflate)
+        assert int(o_st.abs().sum()) == 0 and torch.equal(o_len, d_len) and ctx.last_general_count(s) == 0
+        for i in range(0, n, max(1, n // 32)):
+            a = int(offs[i]); assert torch.equal(out[a:a + int(lens[i])], raw[a:a + int(lens[i])])
+        print(f"records pool {pool/2**20:8.0f} MiB, cut streams >= {thr/2**10:6.0f} KiB: {ms:8.2f} ms = {unc/ms/1e6:7.1f} GB/s  ({ctx.last_split_spans(s)} spans)")
