@@ -135,24 +135,28 @@ FDB_HD uint32_t make_dist_entry(uint32_t sym, uint32_t nbits) {
 }
 
 // ---- constant decode tables of the ultra-fast format (K4 only; index = the next 12 stream bits) ----
+// The layouts put every field where the decode loops can use the entry AS IT IS: the bit count sits in the low five bits
+// (a funnel shift takes its amount mod 32, so `bits >> n` needs no mask), and a count entry can be ADDED to the lane's
+// position / byte accumulator in one instruction.
 // UW "write table", u32:
-//   regular  [23:0]  up to three literal bytes in stream order (unused bytes are 0)
-//            [27:24] bits consumed (1..12)      [31:28] bytes produced (1..12)
-//            - literal entry: the 1..3 leading literals whose codes fit in the 12 bits together
-//            - short-run entry: ONE length token whose code + extra bits + distance bit ("0") fit in
-//              the 12 bits; bytes = 0, produced = the match length (3..12)
-//   special  [31:24] == 0:  [3:0] code bits  [6:4] extra-bit count  [7] end of block  [16:8] base length
-//            - end of block, a length token longer than 12 bits, or a length token with distance bit 1
-// UC "count table", u16 (0 = special, see the write table):
-//   [3:0] bits consumed by the 1..6 leading literals / the one short run     [15:12] bytes they produce
-//   [4] RUN: the entry is a short-run token   [5] ENDNZ: its last byte is non-zero
-//   [6] FIRSTNZ: its first token is a non-zero literal   [10:7] bits of the first token alone
+//   literal  [4:0] bits consumed (1..12)   [12:5] [20:13] [28:21] up to three literal bytes in stream order (unused = 0)
+//            [31:30] bytes produced (1..3): the leading literals whose codes fit in the 12 bits together
+//   special  [31:30] == 0 and [4:0] == 0 (a special entry read as a second entry consumes and produces nothing):
+//            [8:5] code bits  [11:9] extra-bit count  [12] end of block  [21:13] base length
+//            - end of block, or a length token (every run: the write loop checks the byte before it there)
+// UC "count table", u32 (0 = special: end of block, a length token longer than 12 bits or with distance bit 1):
+//   [4:0] bits consumed by the 1..6 leading literals / the one short run    [13:10] bytes they produce
+//   [27:24] bits of the first token alone   [28] RUN: the entry is a short-run token
+//   [29] ENDNZ: its last byte is non-zero   [30] FIRSTNZ: its first token is a non-zero literal
+//   A lane keeps  acc = position in its row + K4_BIAS | bytes << 10  and adds whole entries to it; what the flag bits
+//   add up to above bit 24 is never read.
 // Both tables are stored BIT-REVERSED: the entry for index x lives at slot uf_slot(x) = the 12 index
 // bits in reverse order.  The low index bits are the first code of the window and are far from uniform
 // (39 % of the bench bytes are the 2-bit code 00), so a table in natural order sends most lanes to a
 // few banks (measured 4.1-4.9 wavefronts per lookup); reversed, the bank is chosen by index bits 7..11.
 // On the device this is BREV + one shift, cheaper than masking the index.
-enum : uint32_t { UC_RUN = 1u << 4, UC_ENDNZ = 1u << 5, UC_FIRSTNZ = 1u << 6, UW_EOB = 1u << 7 };
+enum : uint32_t { UC_CNT_SHIFT = 10, UC_FIRST_SHIFT = 24, UC_RUN = 1u << 28, UC_ENDNZ = 1u << 29, UC_FIRSTNZ = 1u << 30 };
+enum : uint32_t { UW_SPECIAL_SHIFT = 5, UW_EOB = 1u << 7 /* of the special fields, i.e. entry >> UW_SPECIAL_SHIFT */, UW_LITERAL_MIN = 1u << 30 };
 FDB_HD uint32_t uf_slot(uint32_t bits) {
     uint32_t r = 0;
     for (uint32_t i = 0; i < 12; i++) r |= ((bits >> i) & 1u) << (11u - i);

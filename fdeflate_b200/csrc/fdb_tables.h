@@ -30,7 +30,7 @@ struct UfHostTables {
     uint32_t tail_tok[258];
     uint32_t header[14];
     uint32_t wt[4096];  // UW write table (fdb_common.h)
-    uint16_t ct[4096];  // UC count table
+    uint32_t ct[4096];  // UC count table
 };
 
 static inline uint32_t rev_bits(uint32_t v, uint32_t n) {
@@ -126,21 +126,21 @@ static inline bool build_uf_host_tables(UfHostTables& t) {
                 k++;
                 last = (uint32_t)s2;
             }
-            t.wt[uf_slot(idx)] = bytes | (wbits << 24) | (wk << 28);
-            t.ct[uf_slot(idx)] = (uint16_t)(pos | (last ? UC_ENDNZ : 0u) | (s ? UC_FIRSTNZ : 0u) | (L << 7) | (k << 12));
+            t.wt[uf_slot(idx)] = wbits | (bytes << 5) | (wk << 30);
+            t.ct[uf_slot(idx)] = pos | (k << UC_CNT_SHIFT) | (L << UC_FIRST_SHIFT) | (last ? UC_ENDNZ : 0u) | (s ? UC_FIRSTNZ : 0u);
         } else if (s == 256) {
-            t.wt[uf_slot(idx)] = L | UW_EOB;
+            t.wt[uf_slot(idx)] = (L | UW_EOB) << UW_SPECIAL_SHIFT;
             t.ct[uf_slot(idx)] = 0;
         } else {
             const uint32_t xb = len_sym_extra((uint32_t)s), base = len_sym_base((uint32_t)s), tot = L + xb + 1u;
             const uint32_t len = base + ((idx >> L) & ((1u << xb) - 1u));  // (only meaningful when tot <= 12)
-            if (tot <= 12 && len <= 12 && ((idx >> (L + xb)) & 1u) == 0) {  // (symbol 285 = 258 bytes stays special)
-                t.wt[uf_slot(idx)] = (tot << 24) | (len << 28);
-                t.ct[uf_slot(idx)] = (uint16_t)(tot | UC_RUN | (tot << 7) | (len << 12));
-            } else {
-                t.wt[uf_slot(idx)] = L | (xb << 4) | (base << 8);
+            // the write loop takes every run through its special path (where it looks at the byte before the run);
+            // the count loop steps over a run that fits in the 12 bits like over literals
+            t.wt[uf_slot(idx)] = (L | (xb << 4) | (base << 8)) << UW_SPECIAL_SHIFT;
+            if (tot <= 12 && len <= 12 && ((idx >> (L + xb)) & 1u) == 0)  // (symbol 285 = 258 bytes stays special)
+                t.ct[uf_slot(idx)] = tot | (len << UC_CNT_SHIFT) | (tot << UC_FIRST_SHIFT) | UC_RUN;
+            else
                 t.ct[uf_slot(idx)] = 0;
-            }
         }
     }
     return true;

@@ -63,13 +63,13 @@ struct K4Warp {
 
 struct K4Smem {
     uint32_t wt[4096];
-    uint16_t ct[4096];
+    uint32_t ct[4096];
     K4Warp warp[K4_WARPS];
 };
 
 struct UfDecTables {
     uint32_t wt[4096];     // UW write table (fdb_common.h) for HUFFMAN_LENGTHS
-    uint16_t ct[4096];     // UC count table
+    uint32_t ct[4096];     // UC count table
     uint32_t header[14];   // the constant 54 header bytes
 };
 
@@ -78,7 +78,7 @@ struct UfTabs {
     simt::saddr wt, ct;
 };
 FDB_DEVICE uint32_t wt_at(const UfTabs& t, uint32_t bits) { return simt::lds32_ro(t.wt + ((simt::brev(bits) >> 18) & 0x3ffcu)); }  // 4 * uf_slot(bits)
-FDB_DEVICE uint32_t ct_at(const UfTabs& t, uint32_t bits) { return simt::lds16_ro(t.ct + ((simt::brev(bits) >> 19) & 0x1ffeu)); }  // 2 * uf_slot(bits)
+FDB_DEVICE uint32_t ct_at(const UfTabs& t, uint32_t bits) { return simt::lds32_ro(t.ct + ((simt::brev(bits) >> 18) & 0x3ffcu)); }
 
 // lane-private LSB-first bit reader over the lane's staging row: a 32-bit window is one funnel
 // shift of (w0, w1); w2 is fetched one word ahead so the shared-memory latency stays off the
@@ -97,8 +97,9 @@ FDB_DEVICE void lb_start(LaneBits& b, simt::saddr row, uint32_t rp) {
     b.nx = p + 384u;
 }
 FDB_DEVICE uint32_t lb_peek(const LaneBits& b) { return simt::funnel_r(b.w0, b.w1, b.rp); }  // shift is mod 32
-FDB_DEVICE void lb_advance(LaneBits& b, uint32_t n) {  // n < 32
-    const uint32_t nrp = b.rp + n;
+// move to position nrp (b.rp <= nrp < b.rp + 32; only bit 5 of the two is compared, so callers may keep other fields
+// above bit 9 of the position word: count_tokens does)
+FDB_DEVICE void lb_advance_to(LaneBits& b, uint32_t nrp) {
 #if !defined(FDB_EMUL)
     // the same four predicated instructions, spelled out (the compiler's version shuffles the three words through
     // temporaries: ten instructions per advance in the round-1 SASS)
@@ -119,10 +120,12 @@ FDB_DEVICE void lb_advance(LaneBits& b, uint32_t n) {  // n < 32
 #endif
     b.rp = nrp;
 }
+FDB_DEVICE void lb_advance(LaneBits& b, uint32_t n) { lb_advance_to(b, b.rp + n); }  // n < 32
 
 // A special write-table entry that is not the end of block: a length token read from the 32-bit
-// window `bits`.  Sets the bits it occupies (code + extra + distance bit), its length, and whether
-// its distance bit is 1 (a distance the ultra-fast code does not have).
+// window `bits`.  w = the entry's special fields (entry >> UW_SPECIAL_SHIFT).  Sets the bits the token occupies
+// (code + extra + distance bit), its length, and whether its distance bit is 1 (a distance the ultra-fast code does
+// not have).
 FDB_DEVICE void uf_long_run(uint32_t w, uint32_t bits, uint32_t& n, uint32_t& len, uint32_t& bad_dist) {
     const uint32_t nc = w & 15u, xb = (w >> 4) & 7u, v = bits >> nc;
     len = ((w >> 8) & 0x1ffu) + (v & ((1u << xb) - 1u));
@@ -135,123 +138,125 @@ struct LaneCount {
     uint32_t cnt;    // bytes produced in [start, end)
     uint32_t flags;  // CF_*
 };
-// CF_BAD: a token the fast path does not decode (distance bit 1, or a run that follows a non-zero
-// byte inside this lane).  CF_FIRSTRUN / CF_LASTNZ let the warp check the same across lanes.
+// CF_BAD: a token the fast path does not decode (distance bit 1).  CF_FIRSTRUN / CF_LASTNZ let the warp check that no
+// lane opens with a run behind a non-zero byte; a run behind a non-zero byte INSIDE a lane is found by the write loop.
 enum : uint32_t { CF_EOB = 1, CF_BAD = 2, CF_FIRSTRUN = 4, CF_LASTNZ = 8 };
+
+// The count and warm-up loops keep ONE word per lane:  acc = position in the row + K4_BIAS | bytes << 10 | (junk above
+// bit 24), and add whole count-table entries to it (fdb_common.h).  The bias is a multiple of 32 (funnel shifts and the
+// word-crossing test see the position mod 32 / its bit 5) chosen so that the bound of each pair loop is one bit test.
+static const uint32_t K4_BIAS = 160;
+static const uint32_t K4_POS_MASK = 0x3ffu;
+static_assert(K4_LIM_HI + 40 + K4_BIAS < 1024 && K4_BIAS % 32 == 0, "position field of acc");
+static_assert(512 - K4_BIAS <= K4_LIM_HI - K4_PAIR + 1 && 256 - K4_BIAS <= K4_LIM_LO - K4_PAIR + 1, "pair-loop bounds as bit tests");
+FDB_DEVICE uint32_t acc_pos(uint32_t acc) { return (acc & K4_POS_MASK) - K4_BIAS; }
 
 // Count the bytes of the tokens in [start, LIM_HI); stop at the first token boundary >= LIM_HI or at
 // EOB (then end = position of the EOB code).  No early exits inside the loops, so lanes that still
-// iterate stay converged and the others wait at the loop exit.
+// iterate stay converged and the others wait at the loop exit.  A lane that is done (end of block, or not taking
+// part) has all position bits of acc set, which ends every loop without a separate flag.
 FDB_DEVICE LaneCount count_tokens(const UfTabs& t, simt::saddr row, uint32_t start, uint32_t active) {
     LaneCount c = {K4_INVALID, 0, 0};
     LaneBits b;
     lb_start(b, row, active ? start : 0u);
-    uint32_t cnt = 0, flags = 0;
-    uint32_t prev = 0;  // bit 4 = the previous byte is non-zero (UC_ENDNZ of the last entry, moved onto UC_RUN)
-    uint32_t bad = 0;   // bit 4 = some run followed a non-zero byte, or had distance bit 1
-    uint32_t stop = active ? 0u : 1u;
+    b.rp += K4_BIAS;  // b.rp is `acc` from here on
+    uint32_t flags = 0;
+    uint32_t bad = 0;      // some run had distance bit 1
+    uint32_t eob_acc = 0;  // acc when the end-of-block code was read
     {  // does the lane open with a run token?
         const uint32_t bits = lb_peek(b);
         const uint32_t c1 = ct_at(t, bits);
         uint32_t fr = c1 & UC_RUN;
-        if (c1 == 0) fr = (wt_at(t, bits) & UW_EOB) ? 0u : 1u;
+        if (c1 == 0) fr = ((wt_at(t, bits) >> UW_SPECIAL_SHIFT) & UW_EOB) ? 0u : 1u;
         if (fr) flags |= CF_FIRSTRUN;
     }
+    if (!active) b.rp |= K4_POS_MASK;
     // main loop: two entries per 32-bit window; together they consume <= 24 bits, so neither can
-    // cross LIM_HI.  A special second entry reads as "0 bits, 0 bytes" and comes back as a first entry.
-    while (!stop && b.rp <= K4_LIM_HI - K4_PAIR) {
+    // cross LIM_HI.  A special second entry is 0 ("0 bits, 0 bytes") and comes back as a first entry.
+    uint32_t l1 = 0, l2 = 0;  // the entries of the last trip (what the lane's last byte is)
+    while (!(b.rp & 0x200u)) {  // position < 512 - K4_BIAS
         const uint32_t bits = lb_peek(b);
         const uint32_t c1 = ct_at(t, bits);
-        uint32_t n;
+        uint32_t nacc;
         if (c1 == 0) {
-            const uint32_t w = wt_at(t, bits);
+            const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
             if (w & UW_EOB) {
                 flags |= CF_EOB;
-                stop = 1;
-                n = 0;
+                eob_acc = b.rp;
+                nacc = b.rp | K4_POS_MASK;
             } else {
-                uint32_t len, bd;
+                uint32_t n, len, bd;
                 uf_long_run(w, bits, n, len, bd);
-                cnt += len;
-                bad |= (bd << 4) | prev;
-                prev = 0;
+                nacc = b.rp + n + (len << UC_CNT_SHIFT);
+                bad |= bd;
+                l1 = 0;
+                l2 = 0;
             }
         } else {
-            n = c1 & 15u;
-            cnt += c1 >> 12;
-            bad |= prev & c1;
-            prev = c1 >> 1;
-            const uint32_t c2 = ct_at(t, bits >> n);
-            n += c2 & 15u;
-            cnt += c2 >> 12;
-            bad |= prev & c2;
-            prev = c2 ? (c2 >> 1) : prev;
+            const uint32_t c2 = ct_at(t, simt::funnel_r(bits, 0u, c1));  // bits >> n1: the shift is taken mod 32
+            nacc = b.rp + c1 + c2;
+            l1 = c1;
+            l2 = c2;
         }
-        lb_advance(b, n);
+        lb_advance_to(b, nacc);
     }
-#if 1  // (measured -3.5 % on the bench tiles: profiles/r02_k4_variants.txt)
+    uint32_t lastc = l2 ? l2 : l1;
     // one table entry at a time while a whole entry (<= 12 bits) still ends at or before LIM_HI: most of what the pair
     // loop leaves goes in one or two such steps instead of a token at a time
-    while (!stop && b.rp <= K4_LIM_HI - 12u) {
+    while ((b.rp & K4_POS_MASK) <= K4_LIM_HI - 12u + K4_BIAS) {
         const uint32_t bits = lb_peek(b);
         const uint32_t c1 = ct_at(t, bits);
-        uint32_t n;
+        uint32_t nacc = b.rp + c1;
         if (c1 == 0) {
-            const uint32_t w = wt_at(t, bits);
+            const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
             if (w & UW_EOB) {
                 flags |= CF_EOB;
-                stop = 1;
-                n = 0;
+                eob_acc = b.rp;
+                nacc = b.rp | K4_POS_MASK;
             } else {
-                uint32_t len, bd;
+                uint32_t n, len, bd;
                 uf_long_run(w, bits, n, len, bd);
-                cnt += len;
-                bad |= (bd << 4) | prev;
-                prev = 0;
+                nacc += n + (len << UC_CNT_SHIFT);
+                bad |= bd;
+                lastc = 0;
             }
         } else {
-            n = c1 & 15u;
-            cnt += c1 >> 12;
-            bad |= prev & c1;
-            prev = c1 >> 1;
+            lastc = c1;
         }
-        lb_advance(b, n);
+        lb_advance_to(b, nacc);
     }
-#endif
     // tail: single tokens up to the first token boundary >= LIM_HI
-    while (!stop && b.rp < K4_LIM_HI) {
+    while ((b.rp & K4_POS_MASK) < K4_LIM_HI + K4_BIAS) {
         const uint32_t bits = lb_peek(b);
         const uint32_t c1 = ct_at(t, bits);
-        uint32_t n;
+        uint32_t nacc = b.rp;
         if (c1 == 0) {
-            const uint32_t w = wt_at(t, bits);
+            const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
             if (w & UW_EOB) {
                 flags |= CF_EOB;
-                stop = 1;
-                n = 0;
+                eob_acc = b.rp;
+                nacc = b.rp | K4_POS_MASK;
             } else {
-                uint32_t len, bd;
+                uint32_t n, len, bd;
                 uf_long_run(w, bits, n, len, bd);
-                cnt += len;
-                bad |= (bd << 4) | prev;
-                prev = 0;
+                nacc += n + (len << UC_CNT_SHIFT);
+                bad |= bd;
+                lastc = 0;
             }
         } else if (c1 & UC_RUN) {
-            n = c1 & 15u;
-            cnt += c1 >> 12;
-            bad |= prev & c1;
-            prev = 0;
+            nacc += c1;
+            lastc = 0;
         } else {
-            n = (c1 >> 7) & 15u;
-            cnt += 1u;
-            prev = (c1 & UC_FIRSTNZ) >> 2;
+            nacc += ((c1 >> UC_FIRST_SHIFT) & 15u) + (1u << UC_CNT_SHIFT);
+            lastc = (c1 & UC_FIRSTNZ) ? UC_ENDNZ : 0u;
         }
-        lb_advance(b, n);
+        lb_advance_to(b, nacc);
     }
     if (active) {
-        c.end = b.rp;
-        c.cnt = cnt;
-        c.flags = flags | ((bad & UC_RUN) ? CF_BAD : 0u) | ((prev & UC_RUN) ? CF_LASTNZ : 0u);
+        const uint32_t acc = (flags & CF_EOB) ? eob_acc : b.rp;
+        c.end = acc_pos(acc);
+        c.cnt = (acc >> UC_CNT_SHIFT) & 0x3fffu;
+        c.flags = flags | (bad ? CF_BAD : 0u) | ((lastc & UC_ENDNZ) ? CF_LASTNZ : 0u);
     }
     return c;
 }
@@ -260,58 +265,53 @@ FDB_DEVICE LaneCount count_tokens(const UfTabs& t, simt::saddr row, uint32_t sta
 FDB_DEVICE uint32_t warm_up(const UfTabs& t, simt::saddr row, uint32_t active) {
     LaneBits b;
     lb_start(b, row, 0u);
-    uint32_t stop = active ? 0u : 1u, dead = 0;
-    while (!stop && b.rp <= K4_LIM_LO - K4_PAIR) {
+    b.rp = active ? K4_BIAS : K4_POS_MASK;  // `acc` as in count_tokens (the byte field is never read here)
+    uint32_t dead = 0;
+    while (!(b.rp & 0x300u)) {  // position < 256 - K4_BIAS
         const uint32_t bits = lb_peek(b);
         const uint32_t c1 = ct_at(t, bits);
-        uint32_t n;
+        uint32_t nacc;
         if (c1 == 0) {
-            const uint32_t w = wt_at(t, bits);
-            n = (w & 15u) + ((w >> 4) & 7u) + 1u;
+            const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
+            nacc = b.rp + (w & 15u) + ((w >> 4) & 7u) + 1u;
             if (w & UW_EOB) {  // speculative EOB: this lane has no valid guess
                 dead = 1;
-                stop = 1;
-                n = 0;
+                nacc = b.rp | K4_POS_MASK;
             }
         } else {
-            n = c1 & 15u;
-            n += ct_at(t, bits >> n) & 15u;
+            nacc = b.rp + c1 + ct_at(t, simt::funnel_r(bits, 0u, c1));
         }
-        lb_advance(b, n);
+        lb_advance_to(b, nacc);
     }
-#if 1  // (measured -3.5 % on the bench tiles: profiles/r02_k4_variants.txt)
-    while (!stop && b.rp <= K4_LIM_LO - 12u) {
+    while ((b.rp & K4_POS_MASK) <= K4_LIM_LO - 12u + K4_BIAS) {
         const uint32_t bits = lb_peek(b);
         const uint32_t c1 = ct_at(t, bits);
-        uint32_t n = c1 & 15u;
+        uint32_t nacc = b.rp + c1;
         if (c1 == 0) {
-            const uint32_t w = wt_at(t, bits);
-            n = (w & 15u) + ((w >> 4) & 7u) + 1u;
+            const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
+            nacc += (w & 15u) + ((w >> 4) & 7u) + 1u;
             if (w & UW_EOB) {
                 dead = 1;
-                stop = 1;
-                n = 0;
+                nacc = b.rp | K4_POS_MASK;
             }
         }
-        lb_advance(b, n);
+        lb_advance_to(b, nacc);
     }
-#endif
-    while (!stop && b.rp < K4_LIM_LO) {
+    while ((b.rp & K4_POS_MASK) < K4_LIM_LO + K4_BIAS) {
         const uint32_t bits = lb_peek(b);
         const uint32_t c1 = ct_at(t, bits);
-        uint32_t n = (c1 >> 7) & 15u;  // the first token alone
+        uint32_t nacc = b.rp + ((c1 >> UC_FIRST_SHIFT) & 15u);  // the first token alone
         if (c1 == 0) {
-            const uint32_t w = wt_at(t, bits);
-            n = (w & 15u) + ((w >> 4) & 7u) + 1u;
+            const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
+            nacc += (w & 15u) + ((w >> 4) & 7u) + 1u;
             if (w & UW_EOB) {
                 dead = 1;
-                stop = 1;
-                n = 0;
+                nacc = b.rp | K4_POS_MASK;
             }
         }
-        lb_advance(b, n);
+        lb_advance_to(b, nacc);
     }
-    return (active && !dead) ? b.rp : K4_INVALID;
+    return (active && !dead) ? acc_pos(b.rp) : K4_INVALID;
 }
 
 struct K4Stream {
@@ -655,6 +655,12 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
         LaneBits b;
         lb_start(b, row, start != K4_INVALID ? start : 0u);
         uint32_t fin = (start == K4_INVALID || lane > eob_lane) ? 1u : 0u;  // no more tokens to decode
+        // A run replicates the byte before it, and this decoder only knows runs of zeros: a run behind a non-zero byte
+        // sends the stream to K3.  Across lanes that is settled before anything is written (CF_FIRSTRUN / CF_LASTNZ);
+        // inside a lane the write loop looks at the byte it stored last, which is still in the window -- or, where the
+        // window has moved on in between, at what the careful path remembers of it.
+        uint32_t run_bad = 0;   // some run of this lane follows a non-zero byte
+        uint32_t gone_nz = 0;   // my last byte has left the window and was non-zero
         for (; MODE != K4_COUNT;) {
             const uint64_t wend = win_vo + K4_WIN;
             const bool mine = !fin && op < wend;
@@ -662,86 +668,82 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
             if (mine && my_end_vo <= wend) {
                 // fast path: everything this lane still has to write fits in the window
                 simt::saddr wptr = win_s + wp;
+                const simt::saddr wfirst = wptr;
+                // (a run: the byte before it is mine and in the window unless nothing of mine is there yet)
+                auto run_check = [&]() { run_bad |= wptr != wfirst ? simt::lds8(wptr - 1u) : gone_nz; };
                 while (!fin && b.rp <= K4_LIM_HI - K4_PAIR) {
                     const uint32_t bits = lb_peek(b);
                     const uint32_t e1 = wt_at(t, bits);
-                    const uint32_t k1 = e1 >> 28;
                     uint32_t n;
-                    if (k1 == 0) {
-                        if (e1 & UW_EOB) {
+                    if (e1 < UW_LITERAL_MIN) {
+                        const uint32_t w = e1 >> UW_SPECIAL_SHIFT;
+                        if (w & UW_EOB) {
                             fin = 1;
                             n = 0;
                         } else {
                             uint32_t len, bd;
-                            uf_long_run(e1, bits, n, len, bd);
+                            uf_long_run(w, bits, n, len, bd);
+                            run_check();
                             wptr += len;
                         }
                     } else {
                         // exact stores: the byte after this lane's last one belongs to the next lane
-                        simt::sts8(wptr, e1);
-                        simt::sts8_if(wptr + 1, e1 >> 8, k1 >= 2);
-                        simt::sts8_if(wptr + 2, e1 >> 16, k1 >= 3);
-                        wptr += k1;
-                        n = (e1 >> 24) & 15u;
-                        const uint32_t e2 = wt_at(t, bits >> n);  // special: 0 bytes, 0 bits -> next trip
-                        const uint32_t k2 = e2 >> 28;
-                        simt::sts8_if(wptr, e2, k2 >= 1);
-                        simt::sts8_if(wptr + 1, e2 >> 8, k2 >= 2);
-                        simt::sts8_if(wptr + 2, e2 >> 16, k2 >= 3);
-                        wptr += k2;
-                        n += (e2 >> 24) & 15u;
+                        simt::sts8(wptr, e1 >> 5);
+                        simt::sts8_if(wptr + 1, e1 >> 13, (int32_t)e1 < 0);
+                        simt::sts8_if(wptr + 2, e1 >> 21, e1 >= (3u << 30));
+                        wptr += e1 >> 30;
+                        const uint32_t e2 = wt_at(t, simt::funnel_r(bits, 0u, e1));  // bits >> n1; special: 0 bytes, 0 bits -> next trip
+                        simt::sts8_if(wptr, e2 >> 5, e2 >= (1u << 30));
+                        simt::sts8_if(wptr + 1, e2 >> 13, (int32_t)e2 < 0);
+                        simt::sts8_if(wptr + 2, e2 >> 21, e2 >= (3u << 30));
+                        wptr += e2 >> 30;
+                        n = (e1 & 31u) + (e2 & 31u);
                     }
                     lb_advance(b, n);
                 }
-#if 1  // (measured -3.5 % on the bench tiles: profiles/r02_k4_variants.txt)
                 while (!fin && b.rp <= K4_LIM_HI - 12u) {  // whole entries that still end at or before LIM_HI
                     const uint32_t bits = lb_peek(b);
                     const uint32_t e1 = wt_at(t, bits);
-                    const uint32_t k1 = e1 >> 28;
                     uint32_t n;
-                    if (k1 == 0) {
-                        if (e1 & UW_EOB) {
+                    if (e1 < UW_LITERAL_MIN) {
+                        const uint32_t w = e1 >> UW_SPECIAL_SHIFT;
+                        if (w & UW_EOB) {
                             fin = 1;
                             n = 0;
                         } else {
                             uint32_t len, bd;
-                            uf_long_run(e1, bits, n, len, bd);
+                            uf_long_run(w, bits, n, len, bd);
+                            run_check();
                             wptr += len;
                         }
                     } else {
-                        simt::sts8(wptr, e1);
-                        simt::sts8_if(wptr + 1, e1 >> 8, k1 >= 2);
-                        simt::sts8_if(wptr + 2, e1 >> 16, k1 >= 3);
-                        wptr += k1;
-                        n = (e1 >> 24) & 15u;
+                        simt::sts8(wptr, e1 >> 5);
+                        simt::sts8_if(wptr + 1, e1 >> 13, (int32_t)e1 < 0);
+                        simt::sts8_if(wptr + 2, e1 >> 21, e1 >= (3u << 30));
+                        wptr += e1 >> 30;
+                        n = e1 & 31u;
                     }
                     lb_advance(b, n);
                 }
-#endif
                 while (!fin && b.rp < K4_LIM_HI) {  // single tokens up to the first boundary >= LIM_HI
                     const uint32_t bits = lb_peek(b);
                     const uint32_t e = wt_at(t, bits);
-                    const uint32_t k = e >> 28;
                     uint32_t n;
-                    if (k == 0) {
-                        if (e & UW_EOB) {
+                    if (e < UW_LITERAL_MIN) {
+                        const uint32_t w = e >> UW_SPECIAL_SHIFT;
+                        if (w & UW_EOB) {
                             fin = 1;
                             n = 0;
                         } else {
                             uint32_t len, bd;
-                            uf_long_run(e, bits, n, len, bd);
+                            uf_long_run(w, bits, n, len, bd);
+                            run_check();
                             wptr += len;
                         }
                     } else {
-                        const uint32_t c1 = ct_at(t, bits);
-                        if (c1 & UC_RUN) {
-                            wptr += k;
-                            n = (e >> 24) & 15u;
-                        } else {
-                            simt::sts8(wptr, e);
-                            wptr += 1u;
-                            n = (c1 >> 7) & 15u;
-                        }
+                        simt::sts8(wptr, e >> 5);
+                        wptr += 1u;
+                        n = (ct_at(t, bits) >> UC_FIRST_SHIFT) & 15u;
                     }
                     lb_advance(b, n);
                 }
@@ -753,27 +755,25 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                 while (wp < K4_WIN && !fin) {
                     const uint32_t bits = lb_peek(b);
                     const uint32_t e = wt_at(t, bits);
-                    const uint32_t k = e >> 28;
                     uint32_t n;
-                    if (k == 0) {
-                        if (e & UW_EOB) {
+                    if (e < UW_LITERAL_MIN) {
+                        const uint32_t w = e >> UW_SPECIAL_SHIFT;
+                        if (w & UW_EOB) {
                             fin = 1;
                             n = 0;
                         } else {
                             uint32_t len, bd;
-                            uf_long_run(e, bits, n, len, bd);
+                            uf_long_run(w, bits, n, len, bd);
+                            run_bad |= gone_nz;
+                            gone_nz = 0;
                             wp += len;
                         }
                     } else {
-                        const uint32_t c1 = ct_at(t, bits);
-                        if (c1 & UC_RUN) {
-                            wp += k;
-                            n = (e >> 24) & 15u;
-                        } else {
-                            simt::sts8(win_s + wp, e);
-                            wp += 1u;
-                            n = (c1 >> 7) & 15u;
-                        }
+                        const uint32_t byte = (e >> 5) & 0xffu;
+                        simt::sts8(win_s + wp, byte);
+                        gone_nz = byte;
+                        wp += 1u;
+                        n = (ct_at(t, bits) >> UC_FIRST_SHIFT) & 15u;
                     }
                     lb_advance(b, n);
                     if (b.rp >= K4_LIM_HI) fin = 1;
@@ -787,6 +787,7 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
             simt::syncwarp();
             win_vo = wend;
         }
+        if (MODE != K4_COUNT && simt::any(run_bad != 0)) return ST_PENDING_GENERAL;  // K3 replicates the byte
 
         // ---- next segment or finish ----
         if (replay) c.end = b.rp;  // first token boundary at or after the lane's sub-sequence, or the end-of-block code
@@ -857,9 +858,10 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
     FDB_DYN_SMEM(smem_raw);
     K4Smem& sm = *reinterpret_cast<K4Smem*>(smem_raw);
     FDB_SHARED uint32_t hdr[14];
-    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) sm.wt[i] = tables->wt[i];
-    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x)
-        ((uint32_t*)sm.ct)[i] = ((const uint32_t*)tables->ct)[i];
+    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) {
+        sm.wt[i] = tables->wt[i];
+        sm.ct[i] = tables->ct[i];
+    }
     if (threadIdx.x < 14) hdr[threadIdx.x] = tables->header[threadIdx.x];
     simt::syncthreads();
     const unsigned lane = simt::lane_id();
@@ -940,9 +942,10 @@ struct K4Tables {
 };
 FDB_DEVICE K4Tables k4_load_tables(unsigned char* smem_raw, const UfDecTables* tables) {
     K4Smem& sm = *reinterpret_cast<K4Smem*>(smem_raw);
-    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) sm.wt[i] = tables->wt[i];
-    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x)
-        ((uint32_t*)sm.ct)[i] = ((const uint32_t*)tables->ct)[i];
+    for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) {
+        sm.wt[i] = tables->wt[i];
+        sm.ct[i] = tables->ct[i];
+    }
     simt::syncthreads();
     K4Tables r = {{simt::smem_addr(sm.wt), simt::smem_addr(sm.ct)}, &sm.warp[simt::warp_in_block()]};
     return r;

@@ -114,6 +114,11 @@ FDB_DEVICE uint32_t lds32(saddr a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
+FDB_DEVICE uint32_t lds8(saddr a) {
+    uint32_t v;
+    asm volatile("{\n\t.reg .u16 t;\n\tld.shared.u8 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 FDB_DEVICE void sts8(saddr a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 // predicated byte store: never a branch (the compiler turns `if (p) sts8(..)` into a divergent region with its
 // BSSY / BSYNC pair when several of them nest)

@@ -231,6 +231,7 @@ static inline uint32_t lds32_ro(saddr a) { return *(const uint32_t*)a; }
 static inline uint32_t lds16_ro(saddr a) { return *(const uint16_t*)a; }
 static inline uint2 lds64_ro(saddr a) { return *(const uint2*)a; }
 static inline uint32_t lds32(saddr a) { return *(const uint32_t*)a; }
+static inline uint32_t lds8(saddr a) { return *(const uint8_t*)a; }
 static inline void sts8(saddr a, uint32_t v) { *(uint8_t*)a = (uint8_t)v; }
 static inline void sts8_if(saddr a, uint32_t v, bool p) { if (p) sts8(a, v); }
 static inline void sts32(saddr a, uint32_t v) { *(uint32_t*)a = v; }
