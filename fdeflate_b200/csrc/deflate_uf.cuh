@@ -505,10 +505,17 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(DEFLATE_WARPS * 32, DEFLATE_MIN_CTAS)
     simt::syncthreads();
     const unsigned lane = simt::lane_id();
     uint32_t* stg = s.stg[simt::warp_in_block()];
+    // every warp's first input is fixed (input c + grid * w for warp w of CTA c): a batch of about one input per
+    // resident warp then loads every SM alike (see inflate_uf_kernel); further inputs come from the counter
+    const uint32_t slots = gridDim.x * DEFLATE_WARPS;
+    bool first = true;
     for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = simt::atomic_add(next, 1u);
-        i = simt::shfl(i, 0);
+        uint32_t i = blockIdx.x + gridDim.x * simt::warp_in_block();
+        if (!first) {
+            if (lane == 0) i = slots + simt::atomic_add(next, 1u);
+            i = simt::shfl(i, 0);
+        }
+        first = false;
         if (i >= b.n) break;
         if (order) i = order[i];
         if (split_item0 && split_item0[i] != DF_NO_ITEM) continue;  // encoded segment by segment (below)

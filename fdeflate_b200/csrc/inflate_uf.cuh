@@ -867,10 +867,19 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
     const unsigned lane = simt::lane_id();
     K4Warp& ws = sm.warp[simt::warp_in_block()];
     const UfTabs t = {simt::smem_addr(sm.wt), simt::smem_addr(sm.ct)};
+    // The first stream of every warp is fixed: stream c + grid * w for warp w of CTA c, so that a batch of about one
+    // stream per resident warp (the bench: 4096 streams on 4736 warps) gives every SM the same number of streams.
+    // Handed out through the counter, the streams go to whichever warps ask first, an SM ends up with anything from
+    // ~22 to 32 of them, and the kernel lasts as long as the fullest SM.  Further streams come from the counter.
+    const uint32_t slots = gridDim.x * K4_WARPS;
+    bool first = true;
     for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = simt::atomic_add(next, 1u);
-        i = simt::shfl(i, 0);
+        uint32_t i = blockIdx.x + gridDim.x * simt::warp_in_block();
+        if (!first) {
+            if (lane == 0) i = slots + simt::atomic_add(next, 1u);
+            i = simt::shfl(i, 0);
+        }
+        first = false;
         if (i >= b.n) break;
         if (split_item0 && split_item0[i] != K4_NO_ITEM) continue;  // decoded span by span (below)
         K4Stream s = {b.in_base + b.in_off[i], b.in_len[i], b.out_base + b.out_off[i], b.out_cap[i]};
