@@ -23,6 +23,7 @@
 #include "inflate_general.cuh"
 #include "inflate_uf.cuh"
 #include "deflate_uf.cuh"
+#include "deflate_ufb.cuh"
 #include "deflate_stored.cuh"
 #include "synth.cuh"
 #include "png_filter.cuh"
@@ -312,6 +313,8 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
         return bail(e);
     if ((e = cudaFuncSetAttribute(deflate_stored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StoredSmem))) != cudaSuccess)
         return bail(e);
+    if ((e = cudaFuncSetAttribute(deflate_ufb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UbSmem))) != cudaSuccess)
+        return bail(e);
     *out = ctx;
     return 0;
 }
@@ -562,10 +565,18 @@ static int launch_deflate(fdb_ctx* ctx, int kind, const DeflateBatch& b, uint32_
     if (kind == 0) {
         // persistent: every resident warp pulls streams from one counter, so SMs stay evenly loaded
         // even when the batch is not a multiple of the chip's warp slots
-        uint32_t grid = (uint32_t)std::min<size_t>(dense ? (n + DEFLATE_WARPS - 1) / DEFLATE_WARPS : n,
-                                                   (size_t)sms * DEFLATE_MIN_CTAS);
-        FDB_LAUNCH(deflate_uf_kernel, dim3(grid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc,
-                   counter, split_item0, (const uint32_t*)order);
+        // (FDB_DEFLATE_LANE16=1: the first-generation kernel, a lane per 16 bytes, which still encodes the segments)
+        static const bool lane16 = [] { const char* e = getenv("FDB_DEFLATE_LANE16"); return e && atoi(e) != 0; }();
+        if (lane16) {
+            uint32_t grid = (uint32_t)std::min<size_t>(dense ? (n + DEFLATE_WARPS - 1) / DEFLATE_WARPS : n,
+                                                       (size_t)sms * DEFLATE_MIN_CTAS);
+            FDB_LAUNCH(deflate_uf_kernel, dim3(grid), dim3(DEFLATE_WARPS * 32), 0, st, b, (const UfEncTables*)ctx->d_enc,
+                       counter, split_item0, (const uint32_t*)order);
+        } else {
+            uint32_t grid = (uint32_t)std::min<size_t>(dense ? (n + UB_WARPS - 1) / UB_WARPS : n, (size_t)sms * UB_MIN_CTAS);
+            FDB_LAUNCH(deflate_ufb_kernel, dim3(grid), dim3(UB_WARPS * 32), sizeof(UbSmem), st, b, (const UfEncTables*)ctx->d_enc,
+                       counter, split_item0, (const uint32_t*)order);
+        }
     } else {
         uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * 8);
         FDB_LAUNCH(deflate_stored_kernel, dim3(grid), dim3(STORED_THREADS), sizeof(StoredSmem), st, b, counter);

@@ -56,6 +56,8 @@ FDB_DEVICE uint32_t clz(uint32_t v) { return (uint32_t)__clz((int)v); }
 FDB_DEVICE uint32_t ffs(uint32_t v) { return (uint32_t)__ffs((int)v); }  // 1-based, 0 if none
 FDB_DEVICE uint32_t brev(uint32_t v) { return __brev(v); }
 FDB_DEVICE uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+// ((hi:lo) << (s mod 32)) >> 32
+FDB_DEVICE uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 // clamped variant: a shift of 32 or more returns hi (funnel_r takes the shift mod 32)
 FDB_DEVICE uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }
 FDB_DEVICE uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }

@@ -180,6 +180,10 @@ static inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return (uint32_t)(v >> (s & 31u));
 }
+static inline uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (uint32_t)((v << (s & 31u)) >> 32);
+}
 static inline uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t s) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return (uint32_t)(v >> (s > 32u ? 32u : s));
