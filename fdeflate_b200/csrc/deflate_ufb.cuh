@@ -34,6 +34,10 @@ static const uint32_t UB_ROW_WORDS = 33;               // private bit string: 8 
 static const uint32_t UB_WIN_WORDS = 32 * UB_IN_STRIDE;  // the warp's output window = the staging rows (544 words: a step of
                                                          // up to 8.5 bits per input byte leaves in one round, else in several)
 static const int UB_WARPS = 8;
+#ifndef UB_UNROLL
+#define UB_UNROLL 2
+#endif
+static const int UB_UNROLL_N = UB_UNROLL;  // chunks of the encode loop unrolled together
 #ifndef UB_MIN_CTAS
 #define UB_MIN_CTAS 4
 #endif
@@ -103,6 +107,8 @@ FDB_DEVICE uint64_t deflate_ufb_stream(const uint2* lit, const uint32_t* tail_to
         const uint32_t nfb = nfb_next;
         if (it + 2 < iters) nfb_next = simt::ldg8(in + base + 2 * UB_STEP);
 
+        // the next step's 16 lines are needed in a few thousand cycles: start them towards L2 now
+        if (lane < 16 && base + UB_STEP + 128ull * lane < n) simt::prefetch_l2(in + base + UB_STEP + 128ull * lane);
         // 1. stage: vector v = lane + 32 k holds bytes [16 v, 16 v + 16) of the step = words 4 (v & 3) .. of row v >> 2
         simt::syncwarp();
 #pragma unroll
@@ -179,7 +185,7 @@ FDB_DEVICE uint64_t deflate_ufb_stream(const uint2* lit, const uint32_t* tail_to
         uint32_t rr = x0 % 258u, pend = x0 > 0 ? 1u : 0u;
         uint32_t hold_v = 0, hold_n = 0;  // the tail tokens of the chunk before, emitted together with the next head
         uint32_t lo = first_word, hi = simt::lds32(my_in + 4u);
-#pragma unroll 2
+#pragma unroll UB_UNROLL_N
         for (uint32_t c = 0; c < 8; c++) {
             // (the row has 17 words: the loads for c == 7 read the pad word and the next row's first word, unused)
             const uint32_t nlo = simt::lds32(my_in + 8u * c + 8u), nhi = simt::lds32(my_in + 8u * c + 12u);
