@@ -593,7 +593,7 @@ def ours(args, rank: int, local_rank: int, world: int):
     if rank == 0:
         alg_bytes = unc + comp_bytes  # per launch, both kernels: read once + written once
         inf_ms, def_ms = ms_inf / args.steps, ms_def / args.steps
-        dominant = "inflate_uf_kernel" if inf_ms >= def_ms else "deflate_uf_kernel"
+        dominant = "inflate_uf_kernel" if inf_ms >= def_ms else "deflate_ufb_kernel"
         dom_ms = max(inf_ms, def_ms)
         traffic = None
         tp = ROOT / "profiles" / "traffic.json"
@@ -617,7 +617,7 @@ def ours(args, rank: int, local_rank: int, world: int):
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "per_kernel": {
                     "inflate_uf_kernel": {"ms": round(inf_ms, 4), "frac": round(alg_bytes / (inf_ms / 1e3) / 1e9 / peak, 4)},
-                    "deflate_uf_kernel": {"ms": round(def_ms, 4), "frac": round(alg_bytes / (def_ms / 1e3) / 1e9 / peak, 4)},
+                    "deflate_ufb_kernel": {"ms": round(def_ms, 4), "frac": round(alg_bytes / (def_ms / 1e3) / 1e9 / peak, 4)},
                 },
             },
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
