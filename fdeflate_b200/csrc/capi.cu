@@ -22,6 +22,7 @@
 #include "adler.cuh"
 #include "inflate_general.cuh"
 #include "inflate_uf.cuh"
+#include "inflate_uf2.cuh"
 #include "deflate_uf.cuh"
 #include "deflate_ufb.cuh"
 #include "deflate_stored.cuh"

@@ -36,8 +36,14 @@
 
 namespace fdb {
 
+// K4_PAIR_UNITS: whole streams are decoded two segments at a time, every lane counting two units behind one warm-up
+// (inflate_uf2.cuh).  Staging for two segments costs 2 KB more per warp: 28 warps per SM and a 3 KB window instead of
+// 32 warps and 4 KB.
+#ifndef K4_PAIR_UNITS
+#define K4_PAIR_UNITS 0
+#endif
 #ifndef K4_WARPS_PER_CTA
-#define K4_WARPS_PER_CTA 32
+#define K4_WARPS_PER_CTA (K4_PAIR_UNITS ? 28 : 32)
 #endif
 static const int K4_WARPS = K4_WARPS_PER_CTA;  // warps per CTA (one CTA per SM; they share the 24 KiB of tables)
 static const uint32_t K4_SUBW = 8;     // 32-bit words of compressed data per lane per segment
@@ -49,7 +55,7 @@ static const uint32_t K4_SEG_WORDS = K4_WARM + 32 * K4_SUBW + 4;  // words stage
 static const uint32_t K4_LIM_LO = 32u * K4_WARM;               // a lane's sub-sequence, in bits of its row
 static const uint32_t K4_LIM_HI = 32u * (K4_WARM + K4_SUBW);
 static const uint32_t K4_PAIR = 24;    // two table entries consume at most 2 x 12 bits
-static const uint32_t K4_WIN = 4096;   // output window bytes (a segment normally expands to ~2.5 KiB)
+static const uint32_t K4_WIN = K4_PAIR_UNITS ? 3008 : 4096;  // output window bytes (a segment normally expands to ~2.3 KiB)
 static const uint32_t K4_INVALID = 0xffffffffu;
 
 // Staging is TRANSPOSED and PRIVATE per lane: row i holds the words lane i can ever touch
@@ -57,7 +63,7 @@ static const uint32_t K4_INVALID = 0xffffffffu;
 // stg[c * 32 + i].  Every lane therefore reads bank == lane (never a conflict) and walks its row
 // with a constant +128-byte pointer step.  Overlapping words are simply stored twice.
 struct K4Warp {
-    uint32_t stg[K4_ROWS_ALLOC * 32];
+    uint32_t stg[(K4_PAIR_UNITS ? 2 : 1) * K4_ROWS_ALLOC * 32];
     uint8_t win[K4_WIN + 16];
 };
 
@@ -77,12 +83,32 @@ struct UfDecTables {
 struct UfTabs {
     simt::saddr wt, ct;
 };
-FDB_DEVICE uint32_t wt_at(const UfTabs& t, uint32_t bits) { return simt::lds32_ro(t.wt + ((simt::brev(bits) >> 18) & 0x3ffcu)); }  // 4 * uf_slot(bits)
-FDB_DEVICE uint32_t ct_at(const UfTabs& t, uint32_t bits) { return simt::lds32_ro(t.ct + ((simt::brev(bits) >> 18) & 0x3ffcu)); }
+// `bits` is an MSB-FIRST window (lb_peek): its top twelve bits are the next twelve stream bits, first bit on top --
+// which is the bit-reversed slot the tables are stored at, so a lookup is mask, shift-and-add, load.
+#ifndef K4_MADHI
+#define K4_MADHI 1
+#endif
+// base + 4 * uf_slot(bits).  K4_MADHI: the shift and the add are one multiply-add on the FMA pipe (hi32(x * 2^14) + base);
+// the integer ALU pipe is the kernel's binding pipe, the compiler's own version is shift, mask, add.
+FDB_DEVICE simt::saddr uf_entry_addr(simt::saddr base, uint32_t bits) {
+#if K4_MADHI && !defined(FDB_EMUL)
+    uint32_t a;
+    asm("mad.hi.u32 %0, %1, 16384, %2;" : "=r"(a) : "r"(bits & 0xfff00000u), "r"(base));
+    return a;
+#else
+    return base + ((bits & 0xfff00000u) >> 18);
+#endif
+}
+FDB_DEVICE uint32_t wt_at(const UfTabs& t, uint32_t bits) { return simt::lds32_ro(uf_entry_addr(t.wt, bits)); }
+FDB_DEVICE uint32_t ct_at(const UfTabs& t, uint32_t bits) { return simt::lds32_ro(uf_entry_addr(t.ct, bits)); }
+// the window behind the first n bits of `bits` (n = the low five bits of a table entry: the shift is taken mod 32)
+FDB_DEVICE uint32_t lb_skip(uint32_t bits, uint32_t n) { return simt::funnel_l(0u, bits, n); }
 
-// lane-private LSB-first bit reader over the lane's staging row: a 32-bit window is one funnel
-// shift of (w0, w1); w2 is fetched one word ahead so the shared-memory latency stays off the
-// decode dependency chain.
+// lane-private bit reader over the lane's staging row.  The staged words are BIT-REVERSED once, when they are staged
+// (stream bit k of a word sits at bit 31 - k), so the reader is MSB-first: a 32-bit window is one funnel shift of
+// (w0, w1) with the next stream bit on top, and its top twelve bits index the tables directly -- no BREV per lookup
+// (it was 7 % of the kernel's instructions, on the slow XU pipe, in the middle of the decode dependency chain).
+// w2 is fetched one word ahead so the shared-memory latency stays off that chain.
 struct LaneBits {
     uint32_t w0, w1, w2;
     uint32_t rp;      // bit position relative to the start of the row
@@ -96,7 +122,7 @@ FDB_DEVICE void lb_start(LaneBits& b, simt::saddr row, uint32_t rp) {
     b.w2 = simt::lds32(p + 256u);
     b.nx = p + 384u;
 }
-FDB_DEVICE uint32_t lb_peek(const LaneBits& b) { return simt::funnel_r(b.w0, b.w1, b.rp); }  // shift is mod 32
+FDB_DEVICE uint32_t lb_peek(const LaneBits& b) { return simt::funnel_l(b.w1, b.w0, b.rp); }  // ((w0:w1) << rp mod 32) >> 32
 // move to position nrp (b.rp <= nrp < b.rp + 32; only bit 5 of the two is compared, so callers may keep other fields
 // above bit 9 of the position word: count_tokens does)
 FDB_DEVICE void lb_advance_to(LaneBits& b, uint32_t nrp) {
@@ -127,10 +153,47 @@ FDB_DEVICE void lb_advance(LaneBits& b, uint32_t n) { lb_advance_to(b, b.rp + n)
 // (code + extra + distance bit), its length, and whether its distance bit is 1 (a distance the ultra-fast code does
 // not have).
 FDB_DEVICE void uf_long_run(uint32_t w, uint32_t bits, uint32_t& n, uint32_t& len, uint32_t& bad_dist) {
-    const uint32_t nc = w & 15u, xb = (w >> 4) & 7u, v = bits >> nc;
+    const uint32_t nc = w & 15u, xb = (w >> 4) & 7u, v = simt::brev(bits) >> nc;  // (extra bits are LSB-first values)
     len = ((w >> 8) & 0x1ffu) + (v & ((1u << xb) - 1u));
     bad_dist = (v >> xb) & 1u;
     n = nc + xb + 1u;
+}
+
+// K4_WORD_STORES: the write loop gathers a lane's literals in a register and stores whole 32-bit words.
+// A lane's bytes are consecutive, so it keeps the word under construction in `acc` (its low wptr & 3 bytes are filled) and
+// stores it when an entry crosses into the next word: one store per four bytes instead of one per byte (the byte stores
+// were a third of the kernel's shared-memory wavefronts, conflicting 2.5-3.2 ways each).  Words two lanes share: the lane
+// that fills the word's LAST byte stores it in the loop, seeded with what the window already held below its first byte
+// (bytes of earlier segments and rounds); every lane's unfinished last word is OR-ed in behind a warp barrier, after all
+// the plain stores (the window is zero wherever nothing has been written).
+#ifndef K4_WORD_STORES
+#define K4_WORD_STORES 1
+#endif
+struct WinWriter {
+    simt::saddr wptr;  // shared-window address of the next byte
+    uint32_t acc;      // the bytes of the word at wptr & ~3 below wptr
+};
+FDB_DEVICE void ww_start(WinWriter& w, simt::saddr at) {
+    w.wptr = at;
+    const uint32_t s = ((uint32_t)at & 3u) * 8u;
+    w.acc = simt::lds32(at & ~(simt::saddr)3) & ~(0xffffffffu << s);
+}
+// the 0..3 literals of write-table entry e (0: none)
+FDB_DEVICE void ww_put(WinWriter& w, uint32_t e) {
+    const uint32_t lits = (e >> 5) & 0xffffffu;
+    const uint32_t s = (uint32_t)w.wptr << 3;  // funnel shifts take it mod 32: 8 * (wptr & 3)
+    const uint32_t lo = w.acc | simt::funnel_l(0u, lits, s);
+    const uint32_t hi = simt::funnel_l(lits, 0u, s);  // what does not fit in this word (0 when s == 0)
+    const simt::saddr nw = w.wptr + (e >> 30);
+    const bool cross = ((nw ^ w.wptr) & 4u) != 0;
+    simt::sts32_if(w.wptr & ~(simt::saddr)3, lo, cross);
+    w.acc = cross ? hi : lo;
+    w.wptr = nw;
+}
+// before a run: the unfinished word goes out as it is (the run's zeros complete it: a run is at least 3 bytes long)
+FDB_DEVICE void ww_run(WinWriter& w) {
+    if ((uint32_t)w.wptr & 3u) simt::sts32(w.wptr & ~(simt::saddr)3, w.acc);
+    w.acc = 0;
 }
 
 struct LaneCount {
@@ -193,7 +256,7 @@ FDB_DEVICE LaneCount count_tokens(const UfTabs& t, simt::saddr row, uint32_t sta
                 l2 = 0;
             }
         } else {
-            const uint32_t c2 = ct_at(t, simt::funnel_r(bits, 0u, c1));  // bits >> n1: the shift is taken mod 32
+            const uint32_t c2 = ct_at(t, lb_skip(bits, c1));  // bits >> n1: the shift is taken mod 32
             nacc = b.rp + c1 + c2;
             l1 = c1;
             l2 = c2;
@@ -279,7 +342,7 @@ FDB_DEVICE uint32_t warm_up(const UfTabs& t, simt::saddr row, uint32_t active) {
                 nacc = b.rp | K4_POS_MASK;
             }
         } else {
-            nacc = b.rp + c1 + ct_at(t, simt::funnel_r(bits, 0u, c1));
+            nacc = b.rp + c1 + ct_at(t, lb_skip(bits, c1));
         }
         lb_advance_to(b, nacc);
     }
@@ -554,8 +617,9 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
             const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (uint32_t j = 0; j < 4; j++) {
-                if (r1 < 32) stg[(c1 + j) * 32 + r1] = w4[j];
-                if (r1 >= 1 && c1 + j + 8 < K4_ROWW) stg[(c1 + j + 8) * 32 + (r1 - 1)] = w4[j];
+                const uint32_t wr = simt::brev(w4[j]);  // MSB-first from here on (LaneBits)
+                if (r1 < 32) stg[(c1 + j) * 32 + r1] = wr;
+                if (r1 >= 1 && c1 + j + 8 < K4_ROWW) stg[(c1 + j + 8) * 32 + (r1 - 1)] = wr;
             }
         }
         simt::syncwarp();
@@ -665,8 +729,91 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
             const uint64_t wend = win_vo + K4_WIN;
             const bool mine = !fin && op < wend;
             uint32_t wp = mine ? (uint32_t)(op - win_vo) : 0u;
+#if K4_WORD_STORES
+            simt::saddr tail_at = 0;
+            uint32_t tail_word = 0;
+#endif
             if (mine && my_end_vo <= wend) {
                 // fast path: everything this lane still has to write fits in the window
+#if K4_WORD_STORES
+                WinWriter ww;
+                ww_start(ww, win_s + wp);
+                const simt::saddr wfirst = ww.wptr;
+                // (a run: the byte before it is mine and in the window unless nothing of mine is there yet)
+                auto run_token = [&](uint32_t len) {
+                    ww_run(ww);
+                    run_bad |= ww.wptr != wfirst ? simt::lds8(ww.wptr - 1u) : gone_nz;
+                    ww.wptr += len;
+                };
+                while (!fin && b.rp <= K4_LIM_HI - K4_PAIR) {
+                    const uint32_t bits = lb_peek(b);
+                    const uint32_t e1 = wt_at(t, bits);
+                    uint32_t n;
+                    if (e1 < UW_LITERAL_MIN) {
+                        const uint32_t w = e1 >> UW_SPECIAL_SHIFT;
+                        if (w & UW_EOB) {
+                            fin = 1;
+                            n = 0;
+                        } else {
+                            uint32_t len, bd;
+                            uf_long_run(w, bits, n, len, bd);
+                            run_token(len);
+                        }
+                    } else {
+                        ww_put(ww, e1);
+                        const uint32_t e2 = wt_at(t, lb_skip(bits, e1));  // special: 0 bytes, 0 bits -> next trip
+                        ww_put(ww, e2 >= UW_LITERAL_MIN ? e2 : 0u);
+                        n = (e1 & 31u) + (e2 & 31u);
+                    }
+                    lb_advance(b, n);
+                }
+                while (!fin && b.rp <= K4_LIM_HI - 12u) {  // whole entries that still end at or before LIM_HI
+                    const uint32_t bits = lb_peek(b);
+                    const uint32_t e1 = wt_at(t, bits);
+                    uint32_t n;
+                    if (e1 < UW_LITERAL_MIN) {
+                        const uint32_t w = e1 >> UW_SPECIAL_SHIFT;
+                        if (w & UW_EOB) {
+                            fin = 1;
+                            n = 0;
+                        } else {
+                            uint32_t len, bd;
+                            uf_long_run(w, bits, n, len, bd);
+                            run_token(len);
+                        }
+                    } else {
+                        ww_put(ww, e1);
+                        n = e1 & 31u;
+                    }
+                    lb_advance(b, n);
+                }
+                while (!fin && b.rp < K4_LIM_HI) {  // single tokens up to the first boundary >= LIM_HI
+                    const uint32_t bits = lb_peek(b);
+                    const uint32_t e = wt_at(t, bits);
+                    uint32_t n;
+                    if (e < UW_LITERAL_MIN) {
+                        const uint32_t w = e >> UW_SPECIAL_SHIFT;
+                        if (w & UW_EOB) {
+                            fin = 1;
+                            n = 0;
+                        } else {
+                            uint32_t len, bd;
+                            uf_long_run(w, bits, n, len, bd);
+                            run_token(len);
+                        }
+                    } else {
+                        ww_put(ww, (e & 0x1fe0u) | (1u << 30));  // its first literal alone
+                        n = (ct_at(t, bits) >> UC_FIRST_SHIFT) & 15u;
+                    }
+                    lb_advance(b, n);
+                }
+                fin = 1;
+                wp = (uint32_t)(ww.wptr - win_s);
+                if (wp & 3u) {  // my unfinished last word, OR-ed in below
+                    tail_at = ww.wptr & ~(simt::saddr)3;
+                    tail_word = ww.acc;
+                }
+#else
                 simt::saddr wptr = win_s + wp;
                 const simt::saddr wfirst = wptr;
                 // (a run: the byte before it is mine and in the window unless nothing of mine is there yet)
@@ -692,7 +839,7 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                         simt::sts8_if(wptr + 1, e1 >> 13, (int32_t)e1 < 0);
                         simt::sts8_if(wptr + 2, e1 >> 21, e1 >= (3u << 30));
                         wptr += e1 >> 30;
-                        const uint32_t e2 = wt_at(t, simt::funnel_r(bits, 0u, e1));  // bits >> n1; special: 0 bytes, 0 bits -> next trip
+                        const uint32_t e2 = wt_at(t, lb_skip(bits, e1));  // bits >> n1; special: 0 bytes, 0 bits -> next trip
                         simt::sts8_if(wptr, e2 >> 5, e2 >= (1u << 30));
                         simt::sts8_if(wptr + 1, e2 >> 13, (int32_t)e2 < 0);
                         simt::sts8_if(wptr + 2, e2 >> 21, e2 >= (3u << 30));
@@ -749,6 +896,7 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                 }
                 fin = 1;
                 wp = (uint32_t)(wptr - win_s);
+#endif
             } else if (mine) {
                 // careful path: this lane's output crosses the window end (long runs); single tokens,
                 // stop at the window end and resume after the flush
@@ -781,6 +929,10 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
             }
             if (mine) op = win_vo + wp;
             simt::syncwarp();
+#if K4_WORD_STORES
+            if (tail_word) simt::atoms_or(tail_at, tail_word);
+            simt::syncwarp();
+#endif
             if (seg_end_vo < wend) break;  // the rest of this segment fits: leave it in the window
             // the window is complete: flush all of it and slide by K4_WIN
             flush_vectors(K4_WIN / 16, ~0ull);
@@ -844,9 +996,17 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
     }
 }
 
+#if K4_PAIR_UNITS
+FDB_DEVICE int32_t inflate_uf_whole2(const UfTabs& t, const uint32_t* hdr, K4Warp& ws, const K4Stream& s, uint32_t flags,
+                                     uint64_t* out_len, uint64_t* consumed);  // inflate_uf2.cuh
+#endif
 FDB_DEVICE int32_t inflate_uf_stream(const UfTabs& t, const uint32_t* hdr, K4Warp& ws, const K4Stream& s,
                                      uint32_t flags, uint64_t* out_len, uint64_t* consumed) {
+#if K4_PAIR_UNITS
+    return inflate_uf_whole2(t, hdr, ws, s, flags, out_len, consumed);
+#else
     return inflate_uf_run<K4_WHOLE>(t, hdr, ws, s, flags, out_len, consumed, nullptr, nullptr);
+#endif
 }
 
 // Persistent kernel, one CTA per SM.  Streams the fast path declines are appended to worklist[]

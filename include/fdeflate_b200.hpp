@@ -67,6 +67,7 @@ public:
     }
     // long streams by many warps each, for device-pointer calls (host-buffer calls decide by themselves)
     void set_split_large(bool on) { check(fdb_set_split_large(h_, on ? 1 : 0), "fdb_set_split_large"); }
+    void set_split_scratch(size_t bytes) { check(fdb_set_split_scratch(h_, bytes), "fdb_set_split_scratch"); }
     void set_split_threshold(size_t inflate_stream_bytes, size_t deflate_input_bytes) {
         check(fdb_set_split_threshold(h_, inflate_stream_bytes, deflate_input_bytes), "fdb_set_split_threshold");
     }

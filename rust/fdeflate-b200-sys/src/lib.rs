@@ -105,6 +105,7 @@ extern "C" {
     pub fn fdb_last_general_count(ctx: *mut fdb_ctx, cuda_stream: *mut c_void) -> i64;
     pub fn fdb_set_split_large(ctx: *mut fdb_ctx, on: c_int) -> c_int;
     pub fn fdb_set_split_threshold(ctx: *mut fdb_ctx, inflate_stream_bytes: usize, deflate_input_bytes: usize) -> c_int;
+    pub fn fdb_set_split_scratch(ctx: *mut fdb_ctx, bytes: usize) -> c_int;
     pub fn fdb_last_split_spans(ctx: *mut fdb_ctx, cuda_stream: *mut c_void) -> i64;
 
     // ---- streaming decoders: Decompressor::read with its state on the device (src/decompress.rs:158-219) ----

@@ -239,6 +239,8 @@ static inline uint32_t lds8(saddr a) { return *(const uint8_t*)a; }
 static inline void sts8(saddr a, uint32_t v) { *(uint8_t*)a = (uint8_t)v; }
 static inline void sts8_if(saddr a, uint32_t v, bool p) { if (p) sts8(a, v); }
 static inline void sts32(saddr a, uint32_t v) { *(uint32_t*)a = v; }
+static inline void sts32_if(saddr a, uint32_t v, bool p) { if (p) sts32(a, v); }
+static inline void atoms_or(saddr a, uint32_t v) { *(uint32_t*)a |= v; }
 static inline uint4 lds128(saddr a) { return *(const uint4*)a; }
 // bulk asynchronous copy + mbarrier: the emulator copies when the copy is issued and counts completed phases in the
 // barrier word (one copy per phase); a wait yields until the phase of the given parity has completed
