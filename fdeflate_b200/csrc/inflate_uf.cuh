@@ -185,9 +185,20 @@ FDB_DEVICE void ww_put(WinWriter& w, uint32_t e) {
     const uint32_t lo = w.acc | simt::funnel_l(0u, lits, s);
     const uint32_t hi = simt::funnel_l(lits, 0u, s);  // what does not fit in this word (0 when s == 0)
     const simt::saddr nw = w.wptr + (e >> 30);
+#if !defined(FDB_EMUL)
+    // one predicate for the store and the select (the compiler's version turns the bool into a register and back)
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b32 x;\n\t"
+        "xor.b32 x, %1, %2;\n\tand.b32 x, x, 4;\n\tsetp.ne.u32 q, x, 0;\n\t"
+        "and.b32 x, %2, 0xfffffffc;\n\t@q st.shared.u32 [x], %3;\n\tselp.b32 %0, %4, %3, q;\n\t}"
+        : "=r"(w.acc)
+        : "r"(nw), "r"(w.wptr), "r"(lo), "r"(hi)
+        : "memory");
+#else
     const bool cross = ((nw ^ w.wptr) & 4u) != 0;
     simt::sts32_if(w.wptr & ~(simt::saddr)3, lo, cross);
     w.acc = cross ? hi : lo;
+#endif
     w.wptr = nw;
 }
 // before a run: the unfinished word goes out as it is (the run's zeros complete it: a run is at least 3 bytes long)
