@@ -263,6 +263,7 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
     memcpy(enc.header, ht->header, sizeof enc.header);
     memcpy(dec.wt, ht->wt, sizeof dec.wt);
     memcpy(dec.ct, ht->ct, sizeof dec.ct);
+    memcpy(dec.bt, ht->bt, sizeof dec.bt);
     memcpy(dec.header, ht->header, sizeof dec.header);
     delete ht;
     auto bail = [&](cudaError_t err) {

@@ -150,7 +150,11 @@ FDB_HD uint32_t make_dist_entry(uint32_t sym, uint32_t nbits) {
 //   [29] ENDNZ: its last byte is non-zero   [30] FIRSTNZ: its first token is a non-zero literal
 //   A lane keeps  acc = position in its row + K4_BIAS | bytes << 10  and adds whole entries to it; what the flag bits
 //   add up to above bit 24 is never read.
-// Both tables are stored BIT-REVERSED: the entry for index x lives at slot uf_slot(x) = the 12 index
+// UB "boundary table", u16: for a window whose count entry is a group of literals, bit k-1 is set when one of those
+//   literals ends k bits into the window (the top set bit is the entry's bit count); 0 for every other window.  With it
+//   the first token boundary at or after a given bit of an entry is two shifts and a find-first-set, and the bytes up to
+//   there a population count: the count and warm-up walks cross their limit with whole entries and step back.
+// All tables are stored BIT-REVERSED: the entry for index x lives at slot uf_slot(x) = the 12 index
 // bits in reverse order.  The low index bits are the first code of the window and are far from uniform
 // (39 % of the bench bytes are the 2-bit code 00), so a table in natural order sends most lanes to a
 // few banks (measured 4.1-4.9 wavefronts per lookup); reversed, the bank is chosen by index bits 7..11.

@@ -31,6 +31,7 @@ struct UfHostTables {
     uint32_t header[14];
     uint32_t wt[4096];  // UW write table (fdb_common.h)
     uint32_t ct[4096];  // UC count table
+    uint16_t bt[4096];  // UB boundary table
 };
 
 static inline uint32_t rev_bits(uint32_t v, uint32_t n) {
@@ -112,7 +113,7 @@ static inline bool build_uf_host_tables(UfHostTables& t) {
         const int s = first_sym(idx, 12, &L);
         if (s < 0) return false;  // every code is <= 12 bits
         if (s < 256) {
-            uint32_t pos = 0, k = 0, bytes = 0, wbits = 0, wk = 0, last = 0;
+            uint32_t pos = 0, k = 0, bytes = 0, wbits = 0, wk = 0, last = 0, ends = 0;
             for (;;) {
                 uint32_t l2 = 0;
                 const int s2 = first_sym(idx >> pos, 12 - pos, &l2);
@@ -123,11 +124,13 @@ static inline bool build_uf_host_tables(UfHostTables& t) {
                     wk = k + 1;
                 }
                 pos += l2;
+                ends |= 1u << (pos - 1u);
                 k++;
                 last = (uint32_t)s2;
             }
             t.wt[uf_slot(idx)] = wbits | (bytes << 5) | (wk << 30);
             t.ct[uf_slot(idx)] = pos | (k << UC_CNT_SHIFT) | (L << UC_FIRST_SHIFT) | (last ? UC_ENDNZ : 0u) | (s ? UC_FIRSTNZ : 0u);
+            t.bt[uf_slot(idx)] = (uint16_t)ends;
         } else if (s == 256) {
             t.wt[uf_slot(idx)] = (L | UW_EOB) << UW_SPECIAL_SHIFT;
             t.ct[uf_slot(idx)] = 0;

@@ -55,7 +55,7 @@ static const uint32_t K4_SEG_WORDS = K4_WARM + 32 * K4_SUBW + 4;  // words stage
 static const uint32_t K4_LIM_LO = 32u * K4_WARM;               // a lane's sub-sequence, in bits of its row
 static const uint32_t K4_LIM_HI = 32u * (K4_WARM + K4_SUBW);
 static const uint32_t K4_PAIR = 24;    // two table entries consume at most 2 x 12 bits
-static const uint32_t K4_WIN = K4_PAIR_UNITS ? 3008 : 4096;  // output window bytes (a segment normally expands to ~2.3 KiB)
+static const uint32_t K4_WIN = K4_PAIR_UNITS ? 3008 : 3904;  // output window bytes (a segment normally expands to ~2.3 KiB)
 static const uint32_t K4_INVALID = 0xffffffffu;
 
 // Staging is TRANSPOSED and PRIVATE per lane: row i holds the words lane i can ever touch
@@ -70,28 +70,50 @@ struct K4Warp {
 struct K4Smem {
     uint32_t wt[4096];
     uint32_t ct[4096];
+    uint16_t bt[4096];
     K4Warp warp[K4_WARPS];
 };
 
 struct UfDecTables {
     uint32_t wt[4096];     // UW write table (fdb_common.h) for HUFFMAN_LENGTHS
     uint32_t ct[4096];     // UC count table
+    uint16_t bt[4096];     // UB boundary table
     uint32_t header[14];   // the constant 54 header bytes
 };
 
 // shared-window addresses of the two tables
 struct UfTabs {
-    simt::saddr wt, ct;
+    simt::saddr wt, ct, bt;
 };
 // `bits` is an MSB-FIRST window (lb_peek): its top twelve bits are the next twelve stream bits, first bit on top --
 // which is the bit-reversed slot the tables are stored at, so a lookup is mask, shift-and-add, load.
-#ifndef K4_MADHI
-#define K4_MADHI 1
+// K4_FMA_PIPE: field extraction on the FMA pipe.  The integer ALU pipe (shifts, logic, selects, compares: one warp
+// instruction per two cycles) is the kernel's binding unit (75 % busy, the FMA pipe 15 %), and a shift by a constant is a
+// multiply: x >> k = hi32(x * 2^(32-k)), x << k = x * 2^k.  The factors are read from constant memory so that the
+// compiler cannot turn the multiplies back into shifts; IMAD / IMAD.HI take a constant-bank operand directly.
+// Measured (profiles/r03_k4_variants.txt): with the table lookups done this way the kernel is 8.5 % SLOWER (IMAD.HI sits
+// in the decode dependency chain and is slower than the two ALU instructions it replaces); K4_FMA_PIPE == 2 moves only
+// the literal extraction of the write loop, which is off that chain.
+#ifndef K4_FMA_PIPE
+#define K4_FMA_PIPE 0
 #endif
-// base + 4 * uf_slot(bits).  K4_MADHI: the shift and the add are one multiply-add on the FMA pipe (hi32(x * 2^14) + base);
-// the integer ALU pipe is the kernel's binding pipe, the compiler's own version is shift, mask, add.
+#if K4_FMA_PIPE && !defined(FDB_EMUL)
+__constant__ uint32_t k4_mul[4] = {4u, 4096u, 1u << 25, 0u};
+#define K4_M4 k4_mul[0]
+#define K4_M4096 k4_mul[1]
+#define K4_M2P25 k4_mul[2]
+FDB_DEVICE uint32_t k4_mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+// base + 4 * uf_slot(bits): two multiply-adds, no ALU instruction
+#endif
+#if K4_FMA_PIPE == 1 && !defined(FDB_EMUL)
+FDB_DEVICE simt::saddr uf_entry_addr(simt::saddr base, uint32_t bits) { return base + k4_mulhi(bits, K4_M4096) * K4_M4; }
+#elif K4_FMA_PIPE == 3 && !defined(FDB_EMUL)
+// shift on the ALU pipe, scale-and-add on the FMA pipe
+FDB_DEVICE simt::saddr uf_entry_addr(simt::saddr base, uint32_t bits) { return base + (bits >> 20) * K4_M4; }
+#else
+// mask, then shift-and-add in one LEA.HI
 FDB_DEVICE simt::saddr uf_entry_addr(simt::saddr base, uint32_t bits) {
-#if K4_MADHI && !defined(FDB_EMUL)
+#if !defined(FDB_EMUL)
     uint32_t a;
     asm("mad.hi.u32 %0, %1, 16384, %2;" : "=r"(a) : "r"(bits & 0xfff00000u), "r"(base));
     return a;
@@ -99,8 +121,10 @@ FDB_DEVICE simt::saddr uf_entry_addr(simt::saddr base, uint32_t bits) {
     return base + ((bits & 0xfff00000u) >> 18);
 #endif
 }
+#endif
 FDB_DEVICE uint32_t wt_at(const UfTabs& t, uint32_t bits) { return simt::lds32_ro(uf_entry_addr(t.wt, bits)); }
 FDB_DEVICE uint32_t ct_at(const UfTabs& t, uint32_t bits) { return simt::lds32_ro(uf_entry_addr(t.ct, bits)); }
+FDB_DEVICE uint32_t bt_at(const UfTabs& t, uint32_t bits) { return simt::lds16_ro(t.bt + ((bits >> 20) << 1)); }
 // the window behind the first n bits of `bits` (n = the low five bits of a table entry: the shift is taken mod 32)
 FDB_DEVICE uint32_t lb_skip(uint32_t bits, uint32_t n) { return simt::funnel_l(0u, bits, n); }
 
@@ -180,11 +204,16 @@ FDB_DEVICE void ww_start(WinWriter& w, simt::saddr at) {
 }
 // the 0..3 literals of write-table entry e (0: none)
 FDB_DEVICE void ww_put(WinWriter& w, uint32_t e) {
+#if (K4_FMA_PIPE == 1 || K4_FMA_PIPE == 2) && !defined(FDB_EMUL)
+    const uint32_t lits = k4_mulhi(e * K4_M4, K4_M2P25);  // (e << 2) >> 7: bits 28..5, nothing else
+    const simt::saddr nw = w.wptr + k4_mulhi(e, K4_M4);   // e >> 30
+#else
     const uint32_t lits = (e >> 5) & 0xffffffu;
+    const simt::saddr nw = w.wptr + (e >> 30);
+#endif
     const uint32_t s = (uint32_t)w.wptr << 3;  // funnel shifts take it mod 32: 8 * (wptr & 3)
     const uint32_t lo = w.acc | simt::funnel_l(0u, lits, s);
     const uint32_t hi = simt::funnel_l(lits, 0u, s);  // what does not fit in this word (0 when s == 0)
-    const simt::saddr nw = w.wptr + (e >> 30);
 #if !defined(FDB_EMUL)
     // one predicate for the store and the select (the compiler's version turns the bool into a register and back)
     asm volatile(
@@ -218,17 +247,41 @@ enum : uint32_t { CF_EOB = 1, CF_BAD = 2, CF_FIRSTRUN = 4, CF_LASTNZ = 8 };
 
 // The count and warm-up loops keep ONE word per lane:  acc = position in the row + K4_BIAS | bytes << 10 | (junk above
 // bit 24), and add whole count-table entries to it (fdb_common.h).  The bias is a multiple of 32 (funnel shifts and the
-// word-crossing test see the position mod 32 / its bit 5) chosen so that the bound of each pair loop is one bit test.
-static const uint32_t K4_BIAS = 160;
+// word-crossing test see the position mod 32 / its bit 5) chosen so that "position >= limit" is one bit test.
+static const uint32_t K4_BIAS = 128;
 static const uint32_t K4_POS_MASK = 0x3ffu;
-static_assert(K4_LIM_HI + 40 + K4_BIAS < 1024 && K4_BIAS % 32 == 0, "position field of acc");
-static_assert(512 - K4_BIAS <= K4_LIM_HI - K4_PAIR + 1 && 256 - K4_BIAS <= K4_LIM_LO - K4_PAIR + 1, "pair-loop bounds as bit tests");
+static_assert(K4_LIM_HI + K4_PAIR + 20 + K4_BIAS < 1024 && K4_BIAS % 32 == 0, "position field of acc");
+static_assert(K4_LIM_HI + K4_BIAS == 512 && K4_LIM_LO + K4_BIAS == 256, "loop bounds as bit tests");
+static_assert(K4_LIM_HI + K4_PAIR + 32 <= 32 * K4_ROWW, "the walk may cross its limit by a pair of entries");
 FDB_DEVICE uint32_t acc_pos(uint32_t acc) { return (acc & K4_POS_MASK) - K4_BIAS; }
 
+// Where a walk that crossed `lim` (position + K4_BIAS) with its last pair of entries (e1, e2: literal groups or one short
+// run each; e2 may be 0) should have stopped: at the first TOKEN boundary at or after the limit.  prev = acc before that
+// trip (position < lim), bits = its window.  Returns acc at that boundary (bytes counted up to it) and whether the byte
+// before it is non-zero.  The boundary table gives the answer without walking the tokens (fdb_common.h): this replaces
+// the token-at-a-time tails, which ran at half the lanes and were a fifth of the kernel's instructions.
+FDB_DEVICE uint32_t uf_land(const UfTabs& t, uint32_t prev, uint32_t bits, uint32_t e1, uint32_t e2, uint32_t lim, uint32_t& last_nz) {
+    const uint32_t d = lim - (prev & K4_POS_MASK);          // 1 .. 24: bits from prev to the limit
+    const uint32_t n1 = e1 & 31u;
+    const bool in1 = d <= n1;                               // the limit falls into the first entry
+    const uint32_t e = in1 ? e1 : e2;
+    const uint32_t base = in1 ? prev : prev + e1;
+    const uint32_t dd = in1 ? d : d - n1;                   // 1 .. 12: bits from the entry's start to the limit
+    if (e & UC_RUN) {                                       // one token: it ends at or after the limit
+        last_nz = 0;
+        return base + e;
+    }
+    const uint32_t m = bt_at(t, in1 ? bits : lb_skip(bits, e1));
+    const uint32_t off = dd - 1u + simt::ffs(m >> (dd - 1u));            // first boundary >= dd (the entry's end is one)
+    const uint32_t k = simt::popc(m & ~(0xffffffffu << off));          // literals up to it
+    last_nz = ((((m << 1) | 1u) >> (off - 2u)) & 1u) ^ 1u;             // a literal of two bits is the byte 0, no other is
+    return base + off + (k << UC_CNT_SHIFT);
+}
+
 // Count the bytes of the tokens in [start, LIM_HI); stop at the first token boundary >= LIM_HI or at
-// EOB (then end = position of the EOB code).  No early exits inside the loops, so lanes that still
+// EOB (then end = position of the EOB code).  No early exits inside the loop, so lanes that still
 // iterate stay converged and the others wait at the loop exit.  A lane that is done (end of block, or not taking
-// part) has all position bits of acc set, which ends every loop without a separate flag.
+// part) has all position bits of acc set, which ends the loop without a separate flag.
 FDB_DEVICE LaneCount count_tokens(const UfTabs& t, simt::saddr row, uint32_t start, uint32_t active) {
     LaneCount c = {K4_INVALID, 0, 0};
     LaneBits b;
@@ -245,16 +298,20 @@ FDB_DEVICE LaneCount count_tokens(const UfTabs& t, simt::saddr row, uint32_t sta
         if (fr) flags |= CF_FIRSTRUN;
     }
     if (!active) b.rp |= K4_POS_MASK;
-    // main loop: two entries per 32-bit window; together they consume <= 24 bits, so neither can
-    // cross LIM_HI.  A special second entry is 0 ("0 bits, 0 bytes") and comes back as a first entry.
-    uint32_t l1 = 0, l2 = 0;  // the entries of the last trip (what the lane's last byte is)
-    while (!(b.rp & 0x200u)) {  // position < 512 - K4_BIAS
+    // two entries per 32-bit window (together <= 24 bits) until the position is at or behind LIM_HI; the last trip is
+    // then taken back to the first token boundary (uf_land).  A special second entry is 0 ("0 bits, 0 bytes") and comes
+    // back as a first entry; a special first entry is one token, which may cross the limit as it is.
+    uint32_t l1 = 0, l2 = 0;       // the entries of the last trip (0, 0: a special token, or no trip)
+    uint32_t pacc = b.rp, pbits = 0;  // acc and window before the last trip
+    while (!(b.rp & 0x200u)) {  // position < LIM_HI
         const uint32_t bits = lb_peek(b);
         const uint32_t c1 = ct_at(t, bits);
         uint32_t nacc;
+        pacc = b.rp;
+        pbits = bits;
         if (c1 == 0) {
             const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
-            if (w & UW_EOB) {
+            if (w & UW_EOB) {  // (l1, l2 stay: what the byte before the end of block is)
                 flags |= CF_EOB;
                 eob_acc = b.rp;
                 nacc = b.rp | K4_POS_MASK;
@@ -267,70 +324,24 @@ FDB_DEVICE LaneCount count_tokens(const UfTabs& t, simt::saddr row, uint32_t sta
                 l2 = 0;
             }
         } else {
-            const uint32_t c2 = ct_at(t, lb_skip(bits, c1));  // bits >> n1: the shift is taken mod 32
+            const uint32_t c2 = ct_at(t, lb_skip(bits, c1));  // the shift is taken mod 32
             nacc = b.rp + c1 + c2;
             l1 = c1;
             l2 = c2;
         }
         lb_advance_to(b, nacc);
     }
-    uint32_t lastc = l2 ? l2 : l1;
-    // one table entry at a time while a whole entry (<= 12 bits) still ends at or before LIM_HI: most of what the pair
-    // loop leaves goes in one or two such steps instead of a token at a time
-    while ((b.rp & K4_POS_MASK) <= K4_LIM_HI - 12u + K4_BIAS) {
-        const uint32_t bits = lb_peek(b);
-        const uint32_t c1 = ct_at(t, bits);
-        uint32_t nacc = b.rp + c1;
-        if (c1 == 0) {
-            const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
-            if (w & UW_EOB) {
-                flags |= CF_EOB;
-                eob_acc = b.rp;
-                nacc = b.rp | K4_POS_MASK;
-            } else {
-                uint32_t n, len, bd;
-                uf_long_run(w, bits, n, len, bd);
-                nacc += n + (len << UC_CNT_SHIFT);
-                bad |= bd;
-                lastc = 0;
-            }
-        } else {
-            lastc = c1;
-        }
-        lb_advance_to(b, nacc);
-    }
-    // tail: single tokens up to the first token boundary >= LIM_HI
-    while ((b.rp & K4_POS_MASK) < K4_LIM_HI + K4_BIAS) {
-        const uint32_t bits = lb_peek(b);
-        const uint32_t c1 = ct_at(t, bits);
-        uint32_t nacc = b.rp;
-        if (c1 == 0) {
-            const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
-            if (w & UW_EOB) {
-                flags |= CF_EOB;
-                eob_acc = b.rp;
-                nacc = b.rp | K4_POS_MASK;
-            } else {
-                uint32_t n, len, bd;
-                uf_long_run(w, bits, n, len, bd);
-                nacc += n + (len << UC_CNT_SHIFT);
-                bad |= bd;
-                lastc = 0;
-            }
-        } else if (c1 & UC_RUN) {
-            nacc += c1;
-            lastc = 0;
-        } else {
-            nacc += ((c1 >> UC_FIRST_SHIFT) & 15u) + (1u << UC_CNT_SHIFT);
-            lastc = (c1 & UC_FIRSTNZ) ? UC_ENDNZ : 0u;
-        }
-        lb_advance_to(b, nacc);
-    }
     if (active) {
-        const uint32_t acc = (flags & CF_EOB) ? eob_acc : b.rp;
+        uint32_t acc = b.rp, last_nz = 0;
+        if (flags & CF_EOB) {
+            acc = eob_acc;
+            last_nz = ((l2 ? l2 : l1) & UC_ENDNZ) ? 1u : 0u;
+        } else if (l1) {
+            acc = uf_land(t, pacc, pbits, l1, l2, K4_LIM_HI + K4_BIAS, last_nz);
+        }
         c.end = acc_pos(acc);
         c.cnt = (acc >> UC_CNT_SHIFT) & 0x3fffu;
-        c.flags = flags | (bad ? CF_BAD : 0u) | ((lastc & UC_ENDNZ) ? CF_LASTNZ : 0u);
+        c.flags = flags | (bad ? CF_BAD : 0u) | (last_nz ? CF_LASTNZ : 0u);
     }
     return c;
 }
@@ -341,51 +352,34 @@ FDB_DEVICE uint32_t warm_up(const UfTabs& t, simt::saddr row, uint32_t active) {
     lb_start(b, row, 0u);
     b.rp = active ? K4_BIAS : K4_POS_MASK;  // `acc` as in count_tokens (the byte field is never read here)
     uint32_t dead = 0;
-    while (!(b.rp & 0x300u)) {  // position < 256 - K4_BIAS
+    uint32_t l1 = 0, l2 = 0, pacc = b.rp, pbits = 0;
+    while (!(b.rp & 0x300u)) {  // position < LIM_LO
         const uint32_t bits = lb_peek(b);
         const uint32_t c1 = ct_at(t, bits);
         uint32_t nacc;
+        pacc = b.rp;
+        pbits = bits;
         if (c1 == 0) {
             const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
+            l1 = 0;
+            l2 = 0;
             nacc = b.rp + (w & 15u) + ((w >> 4) & 7u) + 1u;
             if (w & UW_EOB) {  // speculative EOB: this lane has no valid guess
                 dead = 1;
                 nacc = b.rp | K4_POS_MASK;
             }
         } else {
-            nacc = b.rp + c1 + ct_at(t, lb_skip(bits, c1));
+            const uint32_t c2 = ct_at(t, lb_skip(bits, c1));
+            nacc = b.rp + c1 + c2;
+            l1 = c1;
+            l2 = c2;
         }
         lb_advance_to(b, nacc);
     }
-    while ((b.rp & K4_POS_MASK) <= K4_LIM_LO - 12u + K4_BIAS) {
-        const uint32_t bits = lb_peek(b);
-        const uint32_t c1 = ct_at(t, bits);
-        uint32_t nacc = b.rp + c1;
-        if (c1 == 0) {
-            const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
-            nacc += (w & 15u) + ((w >> 4) & 7u) + 1u;
-            if (w & UW_EOB) {
-                dead = 1;
-                nacc = b.rp | K4_POS_MASK;
-            }
-        }
-        lb_advance_to(b, nacc);
-    }
-    while ((b.rp & K4_POS_MASK) < K4_LIM_LO + K4_BIAS) {
-        const uint32_t bits = lb_peek(b);
-        const uint32_t c1 = ct_at(t, bits);
-        uint32_t nacc = b.rp + ((c1 >> UC_FIRST_SHIFT) & 15u);  // the first token alone
-        if (c1 == 0) {
-            const uint32_t w = wt_at(t, bits) >> UW_SPECIAL_SHIFT;
-            nacc += (w & 15u) + ((w >> 4) & 7u) + 1u;
-            if (w & UW_EOB) {
-                dead = 1;
-                nacc = b.rp | K4_POS_MASK;
-            }
-        }
-        lb_advance_to(b, nacc);
-    }
-    return (active && !dead) ? acc_pos(b.rp) : K4_INVALID;
+    if (!active || dead) return K4_INVALID;
+    uint32_t last_nz;
+    const uint32_t acc = l1 ? uf_land(t, pacc, pbits, l1, l2, K4_LIM_LO + K4_BIAS, last_nz) : b.rp;
+    return acc_pos(acc);
 }
 
 struct K4Stream {
@@ -1032,12 +1026,13 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
     for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) {
         sm.wt[i] = tables->wt[i];
         sm.ct[i] = tables->ct[i];
+        sm.bt[i] = tables->bt[i];
     }
     if (threadIdx.x < 14) hdr[threadIdx.x] = tables->header[threadIdx.x];
     simt::syncthreads();
     const unsigned lane = simt::lane_id();
     K4Warp& ws = sm.warp[simt::warp_in_block()];
-    const UfTabs t = {simt::smem_addr(sm.wt), simt::smem_addr(sm.ct)};
+    const UfTabs t = {simt::smem_addr(sm.wt), simt::smem_addr(sm.ct), simt::smem_addr(sm.bt)};
     // The first stream of every warp is fixed: stream c + grid * w for warp w of CTA c, so that a batch of about one
     // stream per resident warp (the bench: 4096 streams on 4736 warps) gives every SM the same number of streams.
     // Handed out through the counter, the streams go to whichever warps ask first, an SM ends up with anything from
@@ -1125,9 +1120,10 @@ FDB_DEVICE K4Tables k4_load_tables(unsigned char* smem_raw, const UfDecTables* t
     for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) {
         sm.wt[i] = tables->wt[i];
         sm.ct[i] = tables->ct[i];
+        sm.bt[i] = tables->bt[i];
     }
     simt::syncthreads();
-    K4Tables r = {{simt::smem_addr(sm.wt), simt::smem_addr(sm.ct)}, &sm.warp[simt::warp_in_block()]};
+    K4Tables r = {{simt::smem_addr(sm.wt), simt::smem_addr(sm.ct), simt::smem_addr(sm.bt)}, &sm.warp[simt::warp_in_block()]};
     return r;
 }
 
