@@ -202,18 +202,12 @@ FDB_DEVICE void ww_start(WinWriter& w, simt::saddr at) {
     const uint32_t s = ((uint32_t)at & 3u) * 8u;
     w.acc = simt::lds32(at & ~(simt::saddr)3) & ~(0xffffffffu << s);
 }
-// the 0..3 literals of write-table entry e (0: none)
-FDB_DEVICE void ww_put(WinWriter& w, uint32_t e) {
-#if (K4_FMA_PIPE == 1 || K4_FMA_PIPE == 2) && !defined(FDB_EMUL)
-    const uint32_t lits = k4_mulhi(e * K4_M4, K4_M2P25);  // (e << 2) >> 7: bits 28..5, nothing else
-    const simt::saddr nw = w.wptr + k4_mulhi(e, K4_M4);   // e >> 30
-#else
-    const uint32_t lits = (e >> 5) & 0xffffffu;
-    const simt::saddr nw = w.wptr + (e >> 30);
-#endif
+// `take` literals (0..3), in the low bytes of `lits` with zeros above them
+FDB_DEVICE void ww_put_lits(WinWriter& w, uint32_t lits, uint32_t take) {
     const uint32_t s = (uint32_t)w.wptr << 3;  // funnel shifts take it mod 32: 8 * (wptr & 3)
     const uint32_t lo = w.acc | simt::funnel_l(0u, lits, s);
     const uint32_t hi = simt::funnel_l(lits, 0u, s);  // what does not fit in this word (0 when s == 0)
+    const simt::saddr nw = w.wptr + take;
 #if !defined(FDB_EMUL)
     // one predicate for the store and the select (the compiler's version turns the bool into a register and back)
     asm volatile(
@@ -229,6 +223,28 @@ FDB_DEVICE void ww_put(WinWriter& w, uint32_t e) {
     w.acc = cross ? hi : lo;
 #endif
     w.wptr = nw;
+}
+// the 0..3 literals of write-table entry e (0: none)
+FDB_DEVICE void ww_put(WinWriter& w, uint32_t e) {
+#if (K4_FMA_PIPE == 1 || K4_FMA_PIPE == 2) && !defined(FDB_EMUL)
+    ww_put_lits(w, k4_mulhi(e * K4_M4, K4_M2P25), k4_mulhi(e, K4_M4));  // (e << 2) >> 7: bits 28..5; e >> 30
+#else
+    ww_put_lits(w, (e >> 5) & 0xffffffu, e >> 30);
+#endif
+}
+// the leading literals of literal entry e (window `bits`), at most rem >= 1 of them; returns the bits they occupy when
+// that matters to the caller (EXACT), else the bits of the whole entry
+template <bool EXACT>
+FDB_DEVICE uint32_t ww_put_upto(WinWriter& w, const UfTabs& t, uint32_t e, uint32_t bits, uint32_t rem) {
+    const uint32_t cnt = e >> 30;
+    if (rem >= cnt) {
+        ww_put_lits(w, (e >> 5) & 0xffffffu, cnt);
+        return e & 31u;
+    }
+    ww_put_lits(w, (e >> 5) & ~(0xffffffffu << (8u * rem)), rem);  // rem is 1 or 2
+    if (!EXACT) return e & 31u;
+    const uint32_t m = bt_at(t, bits);  // the same leading literals (fdb_common.h)
+    return simt::ffs(rem == 1u ? m : (m & (m - 1u)));
 }
 // before a run: the unfinished word goes out as it is (the run's zeros complete it: a run is at least 3 bytes long)
 FDB_DEVICE void ww_run(WinWriter& w) {
@@ -750,7 +766,11 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                     run_bad |= ww.wptr != wfirst ? simt::lds8(ww.wptr - 1u) : gone_nz;
                     ww.wptr += len;
                 };
-                while (!fin && b.rp <= K4_LIM_HI - K4_PAIR) {
+                // The lane knows how many bytes it has to produce, so the walk is bounded by bytes, not by bits: blind
+                // pairs of entries while six more bytes are mine, then entries cut to what is left -- no token-at-a-time
+                // tail (it ran at half the lanes).  Where the walk ends in bits only matters to a span's write pass.
+                const simt::saddr wlast = win_s + (uint32_t)(my_end_vo - win_vo);
+                while (!fin && ww.wptr + 6u <= wlast) {
                     const uint32_t bits = lb_peek(b);
                     const uint32_t e1 = wt_at(t, bits);
                     uint32_t n;
@@ -772,13 +792,13 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                     }
                     lb_advance(b, n);
                 }
-                while (!fin && b.rp <= K4_LIM_HI - 12u) {  // whole entries that still end at or before LIM_HI
+                while (!fin && ww.wptr < wlast) {
                     const uint32_t bits = lb_peek(b);
                     const uint32_t e1 = wt_at(t, bits);
                     uint32_t n;
                     if (e1 < UW_LITERAL_MIN) {
                         const uint32_t w = e1 >> UW_SPECIAL_SHIFT;
-                        if (w & UW_EOB) {
+                        if (w & UW_EOB) {  // (the count pass saw more bytes before it: cannot happen)
                             fin = 1;
                             n = 0;
                         } else {
@@ -787,28 +807,11 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
                             run_token(len);
                         }
                     } else {
-                        ww_put(ww, e1);
-                        n = e1 & 31u;
-                    }
-                    lb_advance(b, n);
-                }
-                while (!fin && b.rp < K4_LIM_HI) {  // single tokens up to the first boundary >= LIM_HI
-                    const uint32_t bits = lb_peek(b);
-                    const uint32_t e = wt_at(t, bits);
-                    uint32_t n;
-                    if (e < UW_LITERAL_MIN) {
-                        const uint32_t w = e >> UW_SPECIAL_SHIFT;
-                        if (w & UW_EOB) {
-                            fin = 1;
-                            n = 0;
-                        } else {
-                            uint32_t len, bd;
-                            uf_long_run(w, bits, n, len, bd);
-                            run_token(len);
-                        }
-                    } else {
-                        ww_put(ww, (e & 0x1fe0u) | (1u << 30));  // its first literal alone
-                        n = (ct_at(t, bits) >> UC_FIRST_SHIFT) & 15u;
+                        n = ww_put_upto<MODE == K4_WRITE>(ww, t, e1, bits, (uint32_t)(wlast - ww.wptr));
+                        const uint32_t bits2 = lb_skip(bits, e1);
+                        const uint32_t e2 = wt_at(t, bits2);
+                        const uint32_t rem = (uint32_t)(wlast - ww.wptr);
+                        if (rem != 0 && e2 >= UW_LITERAL_MIN) n += ww_put_upto<MODE == K4_WRITE>(ww, t, e2, bits2, rem);
                     }
                     lb_advance(b, n);
                 }
