@@ -68,12 +68,23 @@ FDB_DEVICE uint32_t clz64(uint64_t v) {  // v != 0
 // Packs (value, nbits <= 32) groups LSB-first into the warp's staging window.  Every word a lane
 // completes is stored by that lane; the first one may lack the bits earlier lanes put below this
 // lane's start, which the caller ORs in afterwards (patch_first).
+#ifndef DF_WIDE_MUL
+#define DF_WIDE_MUL 0
+#endif
 struct BitPacker {
     uint32_t lo, hi;     // accumulator: bits [accn) of lo|hi<<32 are valid
     uint32_t accn;       // < 32 between emits
     simt::saddr wa;      // staging address of the word `lo` maps to
     FDB_MEMBER void emit(uint32_t v, uint32_t n) {  // v < 2^n, n <= 32
+#if DF_WIDE_MUL && !defined(FDB_EMUL)
+        // the 64-bit shift as one wide multiply on the FMA pipe (the ALU pipe is the binding one); the factor is made
+        // opaque so that the compiler does not turn the multiply back into two funnel shifts
+        uint32_t m = 1u << accn;
+        asm volatile("" : "+r"(m));
+        const uint64_t sh = (uint64_t)v * m;
+#else
         const uint64_t sh = (uint64_t)v << accn;
+#endif
         lo |= (uint32_t)sh;
         hi = (uint32_t)(sh >> 32);  // (hi carries nothing between emits: accn < 32)
         accn += n;
