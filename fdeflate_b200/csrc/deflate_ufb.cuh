@@ -42,6 +42,40 @@ static const int UB_UNROLL_N = UB_UNROLL;  // chunks of the encode loop unrolled
 #define UB_MIN_CTAS 4
 #endif
 
+// Bit packer of a lane's private row.  `pos` is the bit position in the row and never wraps: the funnel shifts take it
+// mod 32, a completed word shows as a flip of bit 5, and the row's length is pos itself -- one instruction less per emit
+// than an accumulator count that is reduced by 32 after every store (deflate_uf.cuh's BitPacker), five emits per chunk.
+#ifndef UB_POS_PACKER
+#define UB_POS_PACKER 1
+#endif
+struct RowPacker {
+    uint32_t lo;       // the word under construction: its bits below pos
+    uint32_t pos;      // bits emitted so far
+    simt::saddr wa;    // row address of that word
+    FDB_MEMBER void emit(uint32_t v, uint32_t n) {  // v < 2^n, n <= 32
+        const uint32_t nlo = lo | simt::funnel_l(0u, v, pos);  // v << (pos mod 32)
+        const uint32_t nhi = simt::funnel_l(v, 0u, pos);       // what does not fit (0 when pos mod 32 == 0)
+        const uint32_t npos = pos + n;
+#if !defined(FDB_EMUL)
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t.reg .b32 x;\n\t"
+            "xor.b32 x, %2, %3;\n\tand.b32 x, x, 32;\n\tsetp.ne.u32 q, x, 0;\n\t"
+            "@q st.shared.u32 [%1], %4;\n\t@q add.u32 %1, %1, 4;\n\tselp.b32 %0, %5, %4, q;\n\t}"
+            : "=r"(lo), "+r"(wa)
+            : "r"(npos), "r"(pos), "r"(nlo), "r"(nhi)
+            : "memory");
+#else
+        const bool full = ((npos ^ pos) & 32u) != 0;
+        if (full) {
+            simt::sts32(wa, nlo);
+            wa += 4;
+        }
+        lo = full ? nhi : nlo;
+#endif
+        pos = npos;
+    }
+};
+
 struct UbWarp {
     uint32_t win[UB_WIN_WORDS + 1];  // input staging rows, then the output window (+1: chunk 7 of lane 31 looks one word ahead)
     uint32_t rows[32 * UB_ROW_WORDS];
@@ -178,10 +212,17 @@ FDB_DEVICE uint64_t deflate_ufb_stream(const uint2* lit, const uint32_t* tail_to
         if (lane == 31) next_first_zero = (it + 1 < iters && base + UB_STEP + 8 <= n8 && nfb == 0) ? 1u : 0u;
 
         // 3. encode my eight chunks into my row
+#if UB_POS_PACKER
+        RowPacker bp;
+        bp.lo = 0;
+        bp.pos = 0;
+        bp.wa = my_row;
+#else
         BitPacker bp;
         bp.lo = bp.hi = 0;
         bp.accn = 0;
         bp.wa = my_row;
+#endif
         uint32_t rr = x0 % 258u, pend = x0 > 0 ? 1u : 0u;
         uint32_t hold_v = 0, hold_n = 0;  // the tail tokens of the chunk before, emitted together with the next head
         uint32_t lo = first_word, hi = simt::lds32(my_in + 4u);
@@ -209,7 +250,11 @@ FDB_DEVICE uint64_t deflate_ufb_stream(const uint2* lit, const uint32_t* tail_to
         bp.emit(hold_v, hold_n);
         simt::sts32(bp.wa, bp.lo);   // the incomplete last word (zeros above the last bit)
         simt::sts32(bp.wa + 4u, 0u);  // ... and a zero word behind it (the move reads one word past the end)
+#if UB_POS_PACKER
+        const uint32_t my_bits = bp.pos;
+#else
         const uint32_t my_bits = 8u * (uint32_t)(bp.wa - my_row) + bp.accn;
+#endif
 
         // 4. bit offsets
         const uint32_t incl_bits = simt::scan_incl_add(my_bits);

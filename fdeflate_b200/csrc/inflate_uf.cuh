@@ -197,10 +197,14 @@ struct WinWriter {
     simt::saddr wptr;  // shared-window address of the next byte
     uint32_t acc;      // the bytes of the word at wptr & ~3 below wptr
 };
-FDB_DEVICE void ww_start(WinWriter& w, simt::saddr at) {
-    w.wptr = at;
+// what the window holds below byte `at` in at's word (bytes of earlier segments and rounds): the seed of a lane's first word
+FDB_DEVICE uint32_t ww_seed(simt::saddr at) {
     const uint32_t s = ((uint32_t)at & 3u) * 8u;
-    w.acc = simt::lds32(at & ~(simt::saddr)3) & ~(0xffffffffu << s);
+    return simt::lds32(at & ~(simt::saddr)3) & ~(0xffffffffu << s);
+}
+FDB_DEVICE void ww_start(WinWriter& w, simt::saddr at, uint32_t seed) {
+    w.wptr = at;
+    w.acc = seed;
 }
 // `take` literals (0..3), in the low bytes of `lits` with zeros above them
 FDB_DEVICE void ww_put_lits(WinWriter& w, uint32_t lits, uint32_t take) {
@@ -753,12 +757,16 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
 #if K4_WORD_STORES
             simt::saddr tail_at = 0;
             uint32_t tail_word = 0;
+            // (read before any lane stores into the window in this round: a lane on the careful path may store bytes
+            // into the same word, above the ones kept here)
+            const uint32_t seed = mine ? ww_seed(win_s + wp) : 0u;
+            simt::syncwarp();
 #endif
             if (mine && my_end_vo <= wend) {
                 // fast path: everything this lane still has to write fits in the window
 #if K4_WORD_STORES
                 WinWriter ww;
-                ww_start(ww, win_s + wp);
+                ww_start(ww, win_s + wp, seed);
                 const simt::saddr wfirst = ww.wptr;
                 // (a run: the byte before it is mine and in the window unless nothing of mine is there yet)
                 auto run_token = [&](uint32_t len) {
