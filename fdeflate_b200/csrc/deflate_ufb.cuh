@@ -46,7 +46,7 @@ static const int UB_UNROLL_N = UB_UNROLL;  // chunks of the encode loop unrolled
 // mod 32, a completed word shows as a flip of bit 5, and the row's length is pos itself -- one instruction less per emit
 // than an accumulator count that is reduced by 32 after every store (deflate_uf.cuh's BitPacker), five emits per chunk.
 #ifndef UB_POS_PACKER
-#define UB_POS_PACKER 1
+#define UB_POS_PACKER 0
 #endif
 struct RowPacker {
     uint32_t lo;       // the word under construction: its bits below pos
@@ -56,7 +56,7 @@ struct RowPacker {
         const uint32_t nlo = lo | simt::funnel_l(0u, v, pos);  // v << (pos mod 32)
         const uint32_t nhi = simt::funnel_l(v, 0u, pos);       // what does not fit (0 when pos mod 32 == 0)
         const uint32_t npos = pos + n;
-#if !defined(FDB_EMUL)
+#if !defined(FDB_EMUL) && UB_POS_PACKER == 2
         asm volatile(
             "{\n\t.reg .pred q;\n\t.reg .b32 x;\n\t"
             "xor.b32 x, %2, %3;\n\tand.b32 x, x, 32;\n\tsetp.ne.u32 q, x, 0;\n\t"
