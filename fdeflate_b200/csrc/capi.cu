@@ -70,6 +70,8 @@ struct fdb_ctx {
     fdb_lane lanes[FDB_LANES];
     int n_lanes = 4;                // lanes in use (FDB_PIPELINE_LANES overrides; a tuning knob)
     int depth = 4;                  // chunks in flight ahead of the payload copies (FDB_PIPELINE_DEPTH)
+    int direct_out = 0;             // ultra-fast deflate writes into pinned host output buffers itself (FDB_DIRECT_OUT=1;
+                                    // measured slower than the payload copies on the bench step, so it is opt-in)
     cudaStream_t h2d_st = nullptr;  // every chunk's input travels on this stream, in order   (shared per device,
     cudaStream_t d2h_st = nullptr;  // every chunk's payload travels back on this one          see fdb_xfer)
     cudaEvent_t ev_in[FDB_MAX_CHUNKS] = {nullptr};   // chunk k's input is on the device
@@ -284,6 +286,7 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
         int v = atoi(nl);
         if (v >= 1 && v <= FDB_LANES) ctx->n_lanes = v;
     }
+    if (const char* dq = getenv("FDB_DIRECT_OUT")) ctx->direct_out = atoi(dq) != 0;
     if (const char* nd = getenv("FDB_PIPELINE_DEPTH")) {
         int v = atoi(nd);
         if (v >= 1 && v <= FDB_MAX_CHUNKS) ctx->depth = v;
@@ -865,6 +868,25 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     }
     const bool dense = nchunk > 1;
 
+    // Ultra-fast deflate into a PINNED host buffer: the kernel stores its output words straight into the caller's
+    // slots (mapped host memory, coalesced 128-byte stores over PCIe) -- exactly the bytes each stream produced, where
+    // the 2-D payload copy moves the longest stream's width for every row (a quarter more on the bench tiles), and no
+    // payload stage behind the kernels at all.  The kernel never reads its output back.  Chunks that take the segment
+    // path (long inputs) and everything else use the device buffer and the copy.  OPT-IN (FDB_DIRECT_OUT=1): on the bench
+    // step the stores of a chunk's few SMs over PCIe are slower than the copy engine, over-fetch included (e2e 51-55
+    // against 57.5 GB/s, profiles/r03_e2e_direct_out.txt).
+    uint8_t* direct_base = nullptr;
+    if (kind == 1 && !png && ctx->direct_out && sp.out_span) {
+        cudaPointerAttributes at0, at1;
+        if (cudaPointerGetAttributes(&at0, out_base) == cudaSuccess && at0.type == cudaMemoryTypeHost && at0.devicePointer &&
+            cudaPointerGetAttributes(&at1, out_base + sp.out_span - 1) == cudaSuccess && at1.type == cudaMemoryTypeHost &&
+            (uint8_t*)at1.devicePointer == (uint8_t*)at0.devicePointer + (sp.out_span - 1))
+            direct_base = (uint8_t*)at0.devicePointer;
+        else
+            cudaGetLastError();  // (older runtimes report unregistered memory as an error)
+    }
+    std::vector<uint8_t> direct_chunk(nchunk, 0);
+
     auto issue = [&](size_t k) -> int {  // input, kernels and results of chunk k
         const size_t a = k * per, b = std::min(n, a + per);
         fdb_lane& ln = ctx->lanes[k % L];
@@ -919,6 +941,10 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             db.n = (uint32_t)(b - a);
             uint64_t max_len = png ? max_filtered : 0;
             for (size_t i = a; i < b; i++) max_len = std::max(max_len, in_len[i]);
+            if (direct_base && max_len < ctx->deflate_auto_min) {
+                db.out_base = direct_base;
+                direct_chunk[k] = 1;
+            }
             if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st, dense,
                                      max_len >= ctx->deflate_auto_min ? &ln.dsplit : nullptr)))
                 return rr;
@@ -936,6 +962,10 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     auto finish = [&](size_t k) -> int {  // the results (already on the host) decide how much payload comes back
         const size_t a = k * per, b = std::min(n, a + per);
         mark(k, 3, ds);
+        if (direct_chunk[k]) {  // the kernel has written the caller's slots itself
+            mark(k, 4, ds);
+            return 0;
+        }
         int rr = copy_rows(ctx, out_base, ctx->d_out, out_off, h_out_len, out_cap, a, b, out_uniform, out_stride,
                            cudaMemcpyDeviceToHost, ds, exact);
         mark(k, 4, ds);

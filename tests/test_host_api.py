@@ -143,3 +143,47 @@ def test_host_api_on_emulator(emul_ctx, oracle):
 @pytest.mark.gpu
 def test_host_api_on_gpu(gpu_ctx, oracle):
     _suite(gpu_ctx, oracle)
+
+
+@pytest.mark.gpu
+def test_ultrafast_deflate_writes_pinned_host_slots_itself(monkeypatch, oracle):
+    """fdb_deflate_ultrafast_batch with a PINNED output buffer and FDB_DIRECT_OUT=1: the kernel stores into the caller's
+    slots directly (mapped host memory), so every stream is byte-identical to the oracle and nothing outside
+    [off, off + out_len) is touched -- not even the rest of the slot, which the copy path would overwrite up to the
+    widest row's width."""
+    import torch
+
+    monkeypatch.setenv("FDB_DIRECT_OUT", "1")  # read when the context is created
+    gpu_ctx = F.Context(0)
+
+    rng = random.Random(7)
+    sizes = [0, 1, 7, 8, 9, 63, 64, 65, 1000, 2047, 2048, 2049, 70000, 262400, 5, 300000]
+    raw = [cases.sparse_bytes(rng, n) for n in sizes] + [bytes(40000), bytes([3]) * 5000]
+    n = len(raw)
+    in_base, in_off, in_len = F.Context._pack(raw, 16)
+    stride = (max(gpu_ctx.ultrafast_bound(len(r)) for r in raw) + 64 + 15) // 16 * 16
+    # evenly spaced slots (the layout the 2-D payload copy handles), every other one starting at an odd address
+    out_off = np.array([64 + i * stride + (3 if i % 2 else 0) for i in range(n)], dtype=np.uint64)
+    out_cap = np.array([gpu_ctx.ultrafast_bound(len(r)) for r in raw], dtype=np.uint64)
+    h_out = torch.full((64 + n * stride + 64,), 0xAB, dtype=torch.uint8, pin_memory=True)
+    out_len, st = gpu_ctx.deflate_ultrafast_packed(in_base, in_off, in_len, h_out.numpy(), out_off, out_cap)
+    assert (st == 0).all()
+    got = h_out.numpy()
+    mask = np.ones(got.shape[0], dtype=bool)
+    for i in range(n):
+        a, l = int(out_off[i]), int(out_len[i])
+        assert got[a:a + l].tobytes() == oracle.compress_ultra_fast(raw[i]), "stream %d" % i
+        mask[a:a + l] = False
+    assert (got[mask] == 0xAB).all(), "bytes outside the streams were written"
+    # a slot that is too small reports it and leaves the other streams alone
+    h_out.fill_(0xAB)
+    small = out_cap.copy()
+    small[13] = 100
+    out_len2, st2 = gpu_ctx.deflate_ultrafast_packed(in_base, in_off, in_len, h_out.numpy(), out_off, small)
+    assert st2[13] == 18 and (np.delete(st2, 13) == 0).all() and (np.delete(out_len2, 13) == np.delete(out_len, 13)).all()
+    got = h_out.numpy()
+    a = int(out_off[13])
+    assert (got[a + 100:a + stride - 3] == 0xAB).all()
+    for i in (0, 9, 12, 14, 17):
+        a, l = int(out_off[i]), int(out_len[i])
+        assert got[a:a + l].tobytes() == oracle.compress_ultra_fast(raw[i])
