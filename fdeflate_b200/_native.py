@@ -20,7 +20,7 @@ EXPORTS = [
     "fdb_deflate_ultrafast_bound", "fdb_deflate_ultrafast_batch_device", "fdb_deflate_ultrafast_batch",
     "fdb_deflate_stored_bound", "fdb_deflate_stored_batch_device", "fdb_deflate_stored_batch",
     "fdb_synth_tile_bytes", "fdb_synth_tiles_host", "fdb_synth_tiles_device", "fdb_launch_count", "fdb_last_general_count",
-    "fdb_set_pipeline_chunk", "fdb_last_split_spans", "fdb_set_split_large", "fdb_set_split_threshold", "fdb_set_split_scratch", "fdb_png_unfilter_batch_device", "fdb_png_filter_batch_device", "fdb_png_unfilter_batch", "fdb_png_filter_batch", "fdb_png_decode_batch", "fdb_png_encode_batch", "fdb_crc32_batch_device", "fdb_crc32_batch", "fdb_png_probe_batch", "fdb_png_decode_files_batch", "fdb_png_file_bound", "fdb_png_encode_files_batch",
+    "fdb_set_pipeline_chunk", "fdb_last_split_spans", "fdb_set_split_large", "fdb_set_split_threshold", "fdb_set_split_scratch", "fdb_png_unfilter_batch_device", "fdb_png_filter_batch_device", "fdb_png_encode_batch_device", "fdb_png_unfilter_batch", "fdb_png_filter_batch", "fdb_png_decode_batch", "fdb_png_encode_batch", "fdb_crc32_batch_device", "fdb_crc32_batch", "fdb_png_probe_batch", "fdb_png_decode_files_batch", "fdb_png_file_bound", "fdb_png_encode_files_batch",
     "fdb_stream_open_batch", "fdb_stream_read_batch", "fdb_stream_close_batch",
     "fdb_multi_create", "fdb_multi_destroy", "fdb_multi_device_count", "fdb_multi_last_error", "fdb_multi_inflate_batch",
     "fdb_multi_deflate_ultrafast_batch", "fdb_multi_deflate_stored_batch", "fdb_multi_last_partition",
@@ -87,6 +87,8 @@ class NativeLib:
         L.fdb_png_unfilter_batch_device.argtypes = [vp] * 9 + [sz, vp]
         L.fdb_png_filter_batch_device.restype = C.c_int
         L.fdb_png_filter_batch_device.argtypes = [vp] * 8 + [C.c_uint32, vp, sz, vp]
+        L.fdb_png_encode_batch_device.restype = C.c_int
+        L.fdb_png_encode_batch_device.argtypes = [vp] * 6 + [C.c_uint32] + [vp] * 6 + [sz, vp]
         L.fdb_png_unfilter_batch.restype = C.c_int
         L.fdb_png_unfilter_batch.argtypes = [vp] * 9 + [sz]
         L.fdb_png_filter_batch.restype = C.c_int

@@ -283,6 +283,13 @@ class Context:
                                                     d_stride, d_bpp, mode, d_status, n, stream)
         self._check(rc, "fdb_png_filter_batch_device")
 
+    def png_encode_device(self, d_raw, d_raw_off, d_height, d_stride, d_bpp, mode: int, d_out, d_out_off, d_out_cap, d_out_len,
+                          d_filter_status, d_status, n: int, stream: int = 0):
+        """filter (mode 0..4) + ultra-fast deflate of raw images in one kernel, device pointers (fdb_png_encode_batch_device)"""
+        rc = self.lib.L.fdb_png_encode_batch_device(self._h, d_raw, d_raw_off, d_height, d_stride, d_bpp, mode, d_out, d_out_off,
+                                                    d_out_cap, d_out_len, d_filter_status, d_status, n, stream)
+        self._check(rc, "fdb_png_encode_batch_device")
+
     def _png_batch(self, unfilter: bool, images: Sequence[bytes], geometry: Sequence[tuple], mode: int = 0):
         """images[i] with geometry[i] = (height, stride, bpp) -> (status[n], list of bytes)"""
         n = len(images)

@@ -28,6 +28,7 @@
 #include "deflate_stored.cuh"
 #include "synth.cuh"
 #include "png_filter.cuh"
+#include "deflate_png.cuh"
 #include "crc32.cuh"
 
 using namespace fdb;
@@ -70,6 +71,9 @@ struct fdb_ctx {
     fdb_lane lanes[FDB_LANES];
     int n_lanes = 4;                // lanes in use (FDB_PIPELINE_LANES overrides; a tuning knob)
     int depth = 4;                  // chunks in flight ahead of the payload copies (FDB_PIPELINE_DEPTH)
+    int png_fused = 0;              // PNG encode, filter modes 0..4: the filter runs inside the encoder (FDB_PNG_FUSED=1).  Opt-in:
+                                    // it saves the filtered image's trip through device memory but measures 1.6-2.7x slower
+                                    // than filter kernel + encoder (profiles/r03_png_fused_speed.txt)
     int direct_out = 0;             // ultra-fast deflate writes into pinned host output buffers itself (FDB_DIRECT_OUT=1;
                                     // measured slower than the payload copies on the bench step, so it is opt-in)
     cudaStream_t h2d_st = nullptr;  // every chunk's input travels on this stream, in order   (shared per device,
@@ -287,6 +291,7 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
         if (v >= 1 && v <= FDB_LANES) ctx->n_lanes = v;
     }
     if (const char* dq = getenv("FDB_DIRECT_OUT")) ctx->direct_out = atoi(dq) != 0;
+    if (const char* pf = getenv("FDB_PNG_FUSED")) ctx->png_fused = atoi(pf) != 0;
     if (const char* nd = getenv("FDB_PIPELINE_DEPTH")) {
         int v = atoi(nd);
         if (v >= 1 && v <= FDB_MAX_CHUNKS) ctx->depth = v;
@@ -317,6 +322,8 @@ extern "C" int fdb_create(int device, fdb_ctx** out) {
     if ((e = cudaFuncSetAttribute(inflate_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem))) != cudaSuccess)
         return bail(e);
     if ((e = cudaFuncSetAttribute(deflate_stored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StoredSmem))) != cudaSuccess)
+        return bail(e);
+    if ((e = cudaFuncSetAttribute(deflate_ufb_png_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UbSmem))) != cudaSuccess)
         return bail(e);
     if ((e = cudaFuncSetAttribute(deflate_ufb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UbSmem))) != cudaSuccess)
         return bail(e);
@@ -759,6 +766,9 @@ static int png_launch(fdb_ctx* ctx, bool unfilter, const void* d_in_base, const 
 
 static int crc_launch(fdb_ctx* ctx, const void* d_base, const uint64_t* d_off, const uint64_t* d_len, uint32_t seed,
                       uint32_t* d_crc, size_t n, void* cuda_stream, uint32_t* counter);
+static int launch_deflate_png(fdb_ctx* ctx, const DeflateBatch& b, const uint32_t* d_height, const uint32_t* d_stride,
+                              const uint32_t* d_bpp, uint32_t mode, int32_t* d_fstatus, uint32_t* counter, cudaStream_t st,
+                              bool dense);
 
 // PNG encode rides the same pipeline: the inputs are raw images, and between "input landed" and the deflate
 // kernels a filter kernel writes the filtered images into a second device buffer, which is what gets compressed.
@@ -792,6 +802,7 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
     int32_t* d_fst = (int32_t*)(d_geo + 3 * n);
     std::vector<uint64_t> filt;
     uint64_t max_filtered = 0;
+    bool png_fused = false;
     if (png) {
         filt.resize(2 * n);
         uint64_t span = 0;
@@ -802,7 +813,9 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             max_filtered = std::max(max_filtered, f);
             span += (f + 15) & ~15ull;
         }
-        if ((r = grow(ctx, (void**)&ctx->d_mid, &ctx->d_mid_cap, span + 64))) return r;
+        // (nothing is staged when the encoder computes the filtered bytes itself, see `fused` below)
+        png_fused = ctx->png_fused && kind == 1 && png->mode <= 4 && max_filtered <= 0xffffffffull && max_filtered < ctx->deflate_auto_min;
+        if (!png_fused && (r = grow(ctx, (void**)&ctx->d_mid, &ctx->d_mid_cap, span + 64))) return r;
     }
 
     // chunking needs slots laid out in ascending order (what every packer produces); anything else is one chunk
@@ -924,7 +937,11 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
             db.in_base = ctx->d_in;
             db.in_off = d_in_off + a;
             db.in_len = d_in_len + a;
-            if (png) {
+            // PNG encode with one filter type for all rows: the encoder computes the filtered bytes itself from the raw
+            // image (deflate_png.cuh) -- no filtered image in device memory.  The adaptive filter (mode 5), images whose
+            // filtered size does not fit 32 bits and chunks that take the segment path keep the filter kernel.
+            const bool fused = png_fused;
+            if (png && !fused) {
                 if ((rr = png_launch(ctx, false, ctx->d_in, d_in_off + a, ctx->d_mid, d_filt_off + a, d_geo + a, d_geo + n + a,
                                      d_geo + 2 * n + a, png->mode, d_fst + a, b - a, ln.st, ln.d_counters + 12)))
                     return rr;
@@ -945,8 +962,13 @@ static int host_batch(fdb_ctx* ctx, int kind, const uint8_t* in_base, const uint
                 db.out_base = direct_base;
                 direct_chunk[k] = 1;
             }
-            if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st, dense,
-                                     max_len >= ctx->deflate_auto_min ? &ln.dsplit : nullptr)))
+            if (fused) {
+                if ((rr = launch_deflate_png(ctx, db, d_geo + a, d_geo + n + a, d_geo + 2 * n + a, png->mode, d_fst + a,
+                                             ln.d_counters + 3, ln.st, dense)))
+                    return rr;
+                FDB_TRY(cudaMemcpyAsync(png->filter_status + a, d_fst + a, (b - a) * 4, cudaMemcpyDeviceToHost, ln.st));
+            } else if ((rr = launch_deflate(ctx, kind - 1, db, ln.d_counters + 3, ln.st, dense,
+                                            max_len >= ctx->deflate_auto_min ? &ln.dsplit : nullptr)))
                 return rr;
             // the CRC of each IDAT chunk ("IDAT" + stream): the stream lengths are read where the deflate kernel
             // wrote them (mapped host memory)
@@ -1084,6 +1106,45 @@ extern "C" int fdb_png_filter_batch_device(fdb_ctx* ctx, const void* d_in_base, 
                                            void* cuda_stream) {
     return png_launch(ctx, false, d_in_base, d_in_off, d_out_base, d_out_off, d_height, d_stride, d_bpp, mode, d_status, n,
                       cuda_stream);
+}
+
+// filter fused into the encoder (deflate_png.cuh)
+static int launch_deflate_png(fdb_ctx* ctx, const DeflateBatch& b, const uint32_t* d_height, const uint32_t* d_stride,
+                              const uint32_t* d_bpp, uint32_t mode, int32_t* d_fstatus, uint32_t* counter, cudaStream_t st,
+                              bool dense) {
+    const uint32_t sms = (uint32_t)std::max(ctx->sm_count, 1);
+    const size_t n = b.n;
+    const uint32_t grid = (uint32_t)std::min<size_t>(dense ? (n + UB_WARPS - 1) / UB_WARPS : n, (size_t)sms * UB_MIN_CTAS);
+    FDB_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+    FDB_LAUNCH(deflate_ufb_png_kernel, dim3(grid), dim3(UB_WARPS * 32), sizeof(UbSmem), st, b, d_height, d_stride, d_bpp, mode,
+               d_fstatus, (const UfEncTables*)ctx->d_enc, counter);
+    ctx->launches++;
+    FDB_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int fdb_png_encode_batch_device(fdb_ctx* ctx, const void* d_raw_base, const uint64_t* d_raw_off,
+                                           const uint32_t* d_height, const uint32_t* d_stride, const uint32_t* d_bpp,
+                                           uint32_t mode, void* d_out_base, const uint64_t* d_out_off,
+                                           const uint64_t* d_out_cap, uint64_t* d_out_len, int32_t* d_filter_status,
+                                           int32_t* d_status, size_t n, void* cuda_stream) {
+    if (!ctx) return -1;
+    if (n == 0) return 0;
+    if (n > 0xffffffffull || !d_raw_off || !d_height || !d_stride || !d_bpp || !d_out_off || !d_out_cap || !d_out_len ||
+        !d_filter_status || !d_status)
+        return fail(ctx, "fdb_png_encode_batch_device", cudaSuccess);
+    FDB_TRY(cudaSetDevice(ctx->device));
+    DeflateBatch b;
+    b.in_base = (const uint8_t*)d_raw_base;
+    b.in_off = d_raw_off;
+    b.in_len = nullptr;  // (the kernel derives the lengths from the geometry)
+    b.out_base = (uint8_t*)d_out_base;
+    b.out_off = d_out_off;
+    b.out_cap = d_out_cap;
+    b.out_len = d_out_len;
+    b.status = d_status;
+    b.n = (uint32_t)n;
+    return launch_deflate_png(ctx, b, d_height, d_stride, d_bpp, mode, d_filter_status, ctx->d_counters + 3,
+                              (cudaStream_t)cuda_stream, false);
 }
 
 // host-buffer variants: stage through the context's device buffers on its first lane (one copy up, the kernel,

@@ -88,16 +88,28 @@ struct UbSmem {
     UbWarp warp[UB_WARPS];
 };
 
+// Where the bytes to encode come from.  UbPlainSrc: n bytes in device memory.  deflate_png.cuh adds a source that
+// computes the bytes of a PNG-filtered image from the raw pixels on the fly (the filter fused into this prologue).
+//   load16(g): bytes [g, g + 16) of the stream (g a multiple of 16; zeros past the end)   byte(g): one byte, g < n
+struct UbPlainSrc {
+    const uint8_t* in;
+    uint64_t n;
+    bool aligned;
+    FDB_MEMBER uint4 load16(uint64_t g) const { return load16_guarded(in, g, n, aligned); }
+    FDB_MEMBER uint32_t byte(uint64_t g) const { return simt::ldg8(in + g); }
+    FDB_MEMBER void prefetch(uint64_t g) const { simt::prefetch_l2(in + g); }
+};
+
 // One stream, one warp; returns the encoded length, or 0 with *status != ST_OK.
+template <class SRC>
 FDB_DEVICE uint64_t deflate_ufb_stream(const uint2* lit, const uint32_t* tail_tok, const uint32_t* header, UbWarp& ws,
-                                       const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, int32_t* status) {
+                                       const SRC& src, uint64_t n, uint8_t* out, uint64_t cap, int32_t* status) {
     const unsigned lane = simt::lane_id();
     const simt::saddr win_s = simt::smem_addr(ws.win);
     const simt::saddr my_in = win_s + 4u * UB_IN_STRIDE * lane;                     // my staging row
     const simt::saddr my_row = simt::smem_addr(ws.rows) + 4u * UB_ROW_WORDS * lane;  // my bit string
     const uint32_t oab = (uint32_t)((uintptr_t)out & 3u);  // out's offset inside its aligned word
     uint32_t* const obase = (uint32_t*)(out - oab);
-    const bool in_aligned = ((uintptr_t)in & 15u) == 0;
     const uint64_t n8 = n & ~(uint64_t)7;
     const uint32_t rem = (uint32_t)(n - n8);
     bool overflow = false;
@@ -133,16 +145,16 @@ FDB_DEVICE uint64_t deflate_ufb_stream(const uint2* lit, const uint32_t* tail_to
     uint32_t run_carry = 0;
     const uint64_t iters = (n + UB_STEP - 1) / UB_STEP;
     // "is the first byte of the next step zero" (lane 31's last chunk needs it)
-    uint32_t nfb_next = iters > 1 ? simt::ldg8(in + UB_STEP) : 1u;
+    uint32_t nfb_next = iters > 1 ? src.byte(UB_STEP) : 1u;
 
     auto step = [&](uint64_t it, auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
         const uint64_t base = it * UB_STEP;
         const uint32_t nfb = nfb_next;
-        if (it + 2 < iters) nfb_next = simt::ldg8(in + base + 2 * UB_STEP);
+        if (it + 2 < iters) nfb_next = src.byte(base + 2 * UB_STEP);
 
         // the next step's 16 lines are needed in a few thousand cycles: start them towards L2 now
-        if (lane < 16 && base + UB_STEP + 128ull * lane < n) simt::prefetch_l2(in + base + UB_STEP + 128ull * lane);
+        if (lane < 16 && base + UB_STEP + 128ull * lane < n) src.prefetch(base + UB_STEP + 128ull * lane);
         // 1. stage: vector v = lane + 32 k holds bytes [16 v, 16 v + 16) of the step = words 4 (v & 3) .. of row v >> 2
         simt::syncwarp();
 #pragma unroll
@@ -150,7 +162,7 @@ FDB_DEVICE uint64_t deflate_ufb_stream(const uint2* lit, const uint32_t* tail_to
             const uint32_t v = lane + 32u * k;
             const uint64_t g = base + 16ull * v;
             uint4 q = make_uint4(0, 0, 0, 0);
-            if (FULL || g < n) q = load16_guarded(in, g, n, in_aligned);
+            if (FULL || g < n) q = src.load16(g);
             if (FULL || g + 16 <= n) {
                 adler_add16(ad, q, g);
             } else if (g < n) {
@@ -386,8 +398,8 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(UB_WARPS * 32, UB_MIN_CTAS)
         if (order) i = order[i];
         if (split_item0 && split_item0[i] != DF_NO_ITEM) continue;  // encoded segment by segment (deflate_uf.cuh)
         int32_t st = ST_OK;
-        uint64_t len = deflate_ufb_stream(s.lit, s.tail_tok, s.header, ws, b.in_base + b.in_off[i], b.in_len[i],
-                                          b.out_base + b.out_off[i], b.out_cap[i], &st);
+        const UbPlainSrc src = {b.in_base + b.in_off[i], b.in_len[i], ((uintptr_t)(b.in_base + b.in_off[i]) & 15u) == 0};
+        uint64_t len = deflate_ufb_stream(s.lit, s.tail_tok, s.header, ws, src, src.n, b.out_base + b.out_off[i], b.out_cap[i], &st);
         if (lane == 0) {
             b.out_len[i] = len;
             b.status[i] = st;

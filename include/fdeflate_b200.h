@@ -140,6 +140,20 @@ int fdb_png_filter_batch_device(fdb_ctx* ctx, const void* d_raw_base, const uint
                                 const uint64_t* d_filtered_off, const uint32_t* d_height, const uint32_t* d_stride,
                                 const uint32_t* d_bpp, uint32_t mode, int32_t* d_status, size_t n, void* cuda_stream);
 
+/* filter + ultra-fast deflate of raw images in ONE kernel, device pointers: the encoder computes the filtered bytes of
+ * image i (mode 0..4, one type on every row) from the raw rows while it stages them, so the filtered image is never
+ * stored.  Output as fdb_deflate_ultrafast_batch_device (slot i >= fdb_deflate_ultrafast_bound(height * (1 + stride)));
+ * d_filter_status[i] = 0, or 20 for bpp outside 1..8, mode > 4 (the adaptive mode 5 takes the two calls
+ * fdb_png_filter_batch_device + fdb_deflate_ultrafast_batch_device) or an image of 4 GiB and more -- such an image
+ * produces no stream (d_out_len[i] = 0).  The raw buffer must be readable up to the end of the 32-bit word that holds
+ * its last byte.  Measured 1.6-2.7x SLOWER than the two calls on 4096 RGBA tiles (the raw bytes are fetched word by word
+ * through L1 instead of in coalesced 16-byte vectors): use it when the filtered copy's device memory is what matters.
+ * fdb_png_encode_batch / fdb_png_encode_files_batch take this path when the context was created with FDB_PNG_FUSED=1. */
+int fdb_png_encode_batch_device(fdb_ctx* ctx, const void* d_raw_base, const uint64_t* d_raw_off, const uint32_t* d_height,
+                                const uint32_t* d_stride, const uint32_t* d_bpp, uint32_t mode, void* d_out_base,
+                                const uint64_t* d_out_off, const uint64_t* d_out_cap, uint64_t* d_out_len,
+                                int32_t* d_filter_status, int32_t* d_status, size_t n, void* cuda_stream);
+
 /* the same with host buffers (staged through the context; every array is a host array) */
 int fdb_png_unfilter_batch(fdb_ctx* ctx, const uint8_t* filtered_base, const uint64_t* filtered_off, uint8_t* raw_base,
                            const uint64_t* raw_off, const uint32_t* height, const uint32_t* stride, const uint32_t* bpp,

@@ -81,6 +81,12 @@ extern "C" {
         ctx: *mut fdb_ctx, raw_base: *const u8, raw_off: *const u64, height: *const u32, stride: *const u32, bpp: *const u32,
         mode: u32, out_base: *mut u8, out_off: *const u64, out_cap: *const u64, out_len: *mut u64, status: *mut i32, n: usize,
     ) -> c_int;
+    // filter (mode 0..4) + ultra-fast deflate in one kernel, device pointers: the filtered image is never stored
+    pub fn fdb_png_encode_batch_device(
+        ctx: *mut fdb_ctx, d_raw_base: *const c_void, d_raw_off: *const u64, d_height: *const u32, d_stride: *const u32,
+        d_bpp: *const u32, mode: u32, d_out_base: *mut c_void, d_out_off: *const u64, d_out_cap: *const u64, d_out_len: *mut u64,
+        d_filter_status: *mut i32, d_status: *mut i32, n: usize, cuda_stream: *mut c_void,
+    ) -> c_int;
     pub fn fdb_png_probe_batch(
         file_base: *const u8, file_off: *const u64, file_len: *const u64, width: *mut u32, height: *mut u32, bit_depth: *mut u32,
         color_type: *mut u32, stride: *mut u32, status: *mut i32, n: usize,

@@ -14,6 +14,8 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+import cases
+
 GOLD = Path(__file__).resolve().parent / "golden" / "png"
 MANIFEST = json.loads((GOLD / "manifest.json").read_text())
 
@@ -337,3 +339,71 @@ def test_png_encode_roundtrip_on_gpu(gpu_ctx):
     for f, a in zip(files, arrays):
         if a.dtype == np.uint8:  # an independent decoder reads what we wrote
             assert np.array_equal(np.asarray(Image.open(io.BytesIO(f))), a)
+
+
+def _encode_streams(ctx, raws, geometry, mode):
+    """fdb_png_encode_batch -> the zlib stream of every image (statuses must be Ok)."""
+    from fdeflate_b200.api import _ptr
+
+    n = len(raws)
+    raw_base, raw_off, _ = ctx._pack(raws)
+    h = np.array([g[0] for g in geometry], dtype=np.uint32)
+    s = np.array([g[1] for g in geometry], dtype=np.uint32)
+    b = np.array([g[2] for g in geometry], dtype=np.uint32)
+    caps = np.array([ctx.ultrafast_bound(int(hh) * (1 + int(ss))) for hh, ss in zip(h, s)], dtype=np.uint64)
+    out_off = np.zeros(n, dtype=np.uint64)
+    out_off[1:] = np.cumsum(caps[:-1])
+    out = np.zeros(int(out_off[-1] + caps[-1]), dtype=np.uint8)
+    out_len = np.zeros(n, dtype=np.uint64)
+    status = np.zeros(n, dtype=np.int32)
+    rc = ctx.lib.L.fdb_png_encode_batch(ctx._h, _ptr(raw_base), _ptr(raw_off), _ptr(h), _ptr(s), _ptr(b), mode, _ptr(out),
+                                        _ptr(out_off), _ptr(caps), _ptr(out_len), _ptr(status), n)
+    assert rc == 0 and (status == 0).all(), (rc, list(status))
+    return [out[int(out_off[i]): int(out_off[i]) + int(out_len[i])].tobytes() for i in range(n)]
+
+
+def _check_fused_filter_deflate(ctx, oracle, big: bool):
+    """PNG encode with one filter type per image (modes 0..4) computes the filtered bytes inside the encoder
+    (deflate_png.cuh): the stream must be the oracle's ultra-fast deflate of the oracle's filtered image, byte for byte,
+    for row lengths that put the type bytes and row wraps at every position of the encoder's 16-byte loads."""
+    rng = random.Random(11)
+    geometry = [(1, 1, 1), (3, 2, 1), (5, 3, 3), (7, 14, 2), (4, 15, 3), (6, 16, 4), (9, 17, 1), (3, 63, 3), (5, 64, 4), (4, 65, 8),
+                (2, 100, 6), (33, 31, 4), (1, 5000, 4), (17, 256, 8)]
+    if big:
+        geometry += [(256, 1024, 4), (100, 3001, 3), (64, 2048, 8), (300, 700, 2), (1024, 1, 1)]
+    raws = []
+    for k, (h, s, bpp) in enumerate(geometry):
+        if k % 3 == 0:
+            raws.append(cases.sparse_bytes(rng, h * s))  # zero runs across rows
+        elif k % 3 == 1:
+            raws.append(bytes(rng.getrandbits(8) for _ in range(h * s)))
+        else:  # smooth: small residuals after filtering
+            raws.append(bytes((3 * (i % s) + 7 * (i // s) + rng.randrange(3)) & 0xFF for i in range(h * s)))
+    for mode in range(5):
+        got = _encode_streams(ctx, raws, geometry, mode)
+        for i, (h, s, bpp) in enumerate(geometry):
+            want = oracle.compress_ultra_fast(oracle.png_filter(raws[i], h, s, bpp, mode))
+            assert got[i] == want, "mode %d image %d (%d rows of %d, bpp %d)" % (mode, i, h, s, bpp)
+
+
+@pytest.mark.emul
+def test_png_encode_fused_filter_on_emulator(emul_lib, oracle, monkeypatch):
+    import fdeflate_b200 as F
+
+    monkeypatch.setenv("FDB_PNG_FUSED", "1")  # read when a context is created (the default is the two-kernel path)
+    _check_fused_filter_deflate(F.Context(0, emul_lib), oracle, big=False)
+
+
+@pytest.mark.gpu
+def test_png_encode_fused_filter_on_gpu(gpu_ctx, oracle, monkeypatch):
+    import fdeflate_b200 as F
+
+    monkeypatch.setenv("FDB_PNG_FUSED", "1")
+    fused = F.Context(0)
+    _check_fused_filter_deflate(fused, oracle, big=True)
+    # and the two-kernel path (filter kernel, then the encoder: the default) gives the same streams
+    rng = random.Random(12)
+    geometry = [(64, 1024, 4), (37, 333, 3), (5, 16, 4)]
+    raws = [cases.sparse_bytes(rng, h * s) for h, s, _ in geometry]
+    for mode in range(5):
+        assert _encode_streams(fused, raws, geometry, mode) == _encode_streams(gpu_ctx, raws, geometry, mode)
