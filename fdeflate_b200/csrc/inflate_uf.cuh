@@ -9,19 +9,21 @@
 // counts.  That is what makes intra-stream parallelism possible:
 //
 //   per segment of 32 x SUBW words of compressed bits
-//   1. stage   : coalesced 16-byte loads -> padded shared memory (conflict-free per-lane reads)
-//   2. count   : lane i starts WARM words BEFORE its sub-sequence at a guessed bit position, decodes
-//                single tokens until it crosses its boundary (Huffman codes self-synchronise within
-//                a few tokens), then counts the bytes of its own sub-sequence.  Lane 0 starts at the
-//                known true position.
+//   1. stage   : coalesced 16-byte loads -> transposed per-lane rows in shared memory (conflict-free reads), every word
+//                bit-reversed once so that the lane readers are MSB-first and a window's top 12 bits index the tables
+//   2. count   : lane i starts WARM words BEFORE its sub-sequence at a guessed bit position and walks table entries
+//                (up to six literals or one short run each, two entries per 32-bit window) until it has crossed its
+//                boundary -- Huffman codes self-synchronise within a few tokens -- and is taken back to the first TOKEN
+//                boundary behind it by the boundary table (uf_land); then it counts the bytes of its own sub-sequence
+//                the same way.  Lane 0 starts at the known true position.
 //   3. verify  : lane i's start must equal lane i-1's end; since lane 0 is exact this proves every
 //                lane.  A lane that had not synchronised is re-run from its predecessor's end
 //                (loop until consistent; normally zero rounds).
-//   4. scan    : exclusive prefix sum of byte counts -> output offsets; last-literal propagation
-//                gives every lane the byte its leading match replicates.
-//   5. write   : lanes decode again (two-literal table entries) and drop literals into a
-//                zero-initialised shared-memory window; zero runs are skipped, not written.  Full
-//                windows leave with 16-byte coalesced stores and feed adler32 on the way out.
+//   4. scan    : exclusive prefix sum of byte counts -> output offsets; ballots check that no lane opens with a run
+//                behind a non-zero byte (the decoder only knows runs of zeros).
+//   5. write   : lanes decode again (entries of up to three literals), bounded by their byte counts, gather the literals
+//                in a register and store 32-bit words into a zero-initialised shared-memory window; zero runs are
+//                skipped, not written.  Finished 16-byte vectors leave with coalesced stores and feed adler32 on the way.
 //
 // Anything irregular (foreign header, distance bit 1, truncation, output larger than the slot,
 // match at position 0) is not diagnosed here: the stream is appended to a work list and the general
@@ -45,7 +47,7 @@ namespace fdb {
 #ifndef K4_WARPS_PER_CTA
 #define K4_WARPS_PER_CTA (K4_PAIR_UNITS ? 28 : 32)
 #endif
-static const int K4_WARPS = K4_WARPS_PER_CTA;  // warps per CTA (one CTA per SM; they share the 24 KiB of tables)
+static const int K4_WARPS = K4_WARPS_PER_CTA;  // warps per CTA (one CTA per SM; they share the 40 KiB of tables)
 static const uint32_t K4_SUBW = 8;     // 32-bit words of compressed data per lane per segment
 static const uint32_t K4_WARM = 4;     // warm-up words before a lane's sub-sequence
 static const uint32_t K4_TAILW = 3;    // words after it (token overrun + two-word look-ahead)
