@@ -157,12 +157,20 @@ FDB_DEVICE uint64_t deflate_ufb_stream(const uint2* lit, const uint32_t* tail_to
         if (lane < 16 && base + UB_STEP + 128ull * lane < n) src.prefetch(base + UB_STEP + 128ull * lane);
         // 1. stage: vector v = lane + 32 k holds bytes [16 v, 16 v + 16) of the step = words 4 (v & 3) .. of row v >> 2
         simt::syncwarp();
+        // (all four loads first: the stores below are ordered asm statements, and a load issued behind the store of
+        // the vector before it waits out its own trip to L2 -- four latencies per step instead of one)
+        uint4 q4[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint64_t g = base + 16ull * (lane + 32u * k);
+            q4[k] = make_uint4(0, 0, 0, 0);
+            if (FULL || g < n) q4[k] = src.load16(g);
+        }
 #pragma unroll
         for (uint32_t k = 0; k < 4; k++) {
             const uint32_t v = lane + 32u * k;
             const uint64_t g = base + 16ull * v;
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if (FULL || g < n) q = src.load16(g);
+            const uint4 q = q4[k];
             if (FULL || g + 16 <= n) {
                 adler_add16(ad, q, g);
             } else if (g < n) {
