@@ -113,7 +113,8 @@ FDB_DEVICE uint64_t deflate_ufb_stream(const uint2* lit, const uint32_t* tail_to
     const uint64_t n8 = n & ~(uint64_t)7;
     const uint32_t rem = (uint32_t)(n - n8);
     bool overflow = false;
-    const uint64_t cap_words = (cap + oab) >> 2;  // virtual words that end inside the caller's slot
+    // (cap_words = (cap + oab) >> 2, the virtual words that end inside the caller's slot, is recomputed where it is used:
+    // one value less to keep across the encode loop, which runs at the register limit)
 
     // ---- header (ultrafast.rs:81-91): 53 bytes + the low 5 bits of byte 53 ----
     uint64_t vbit = 8ull * oab + UF_HEADER_BITS;  // virtual bit cursor (bit 0 = bit 0 of obase[0])
@@ -317,6 +318,7 @@ FDB_DEVICE uint64_t deflate_ufb_stream(const uint2* lit, const uint32_t* tail_to
         vbit += total_bits;
         const uint32_t nwords = (uint32_t)((vbit >> 5) - wbase);
         // (the header is 53 bytes, so these are never the stream's first, possibly partial, word)
+        const uint64_t cap_words = (cap + oab) >> 2;
         const uint32_t fit = cap_words > wbase ? (uint32_t)(cap_words - wbase < nwords ? cap_words - wbase : nwords) : 0u;
         uint32_t* const dst = obase + wbase;
         if (fit < nwords) overflow = true;
