@@ -71,6 +71,25 @@ FDB_DEVICE uint32_t clz64(uint64_t v) {  // v != 0
 #ifndef DF_WIDE_MUL
 #define DF_WIDE_MUL 0
 #endif
+// DF_FMA_ADD: the packer's three additions (bit count, the word-full step back, the staging address) as multiply-adds
+// x * 1 + y, the 1 read from constant memory so that the compiler keeps the multiply.  IMAD runs on the FMA pipe, which
+// idles at 19 % while the integer ALU pipe is the encoder's binding unit (74 %): 1.266 -> 1.245 ms.  What did NOT help
+// (profiles/r04_variants.txt): the same for the pair widths of word_pairs, for the constant additions of chunk_plan, for
+// the head's bit count, for only the predicated two or only the sum, and for the row pointer step of K4's lane reader.
+#ifndef DF_FMA_ADD
+#define DF_FMA_ADD 1
+#endif
+#if DF_FMA_ADD && !defined(FDB_EMUL)
+__constant__ uint32_t df_one = 1u;
+FDB_DEVICE uint32_t df_add(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(df_one), "r"(b));
+    return r;
+}
+#else
+template <class T>
+FDB_DEVICE T df_add(T a, uint32_t b) { return a + b; }  // (a shared-window address is wider than 32 bits in the emulator)
+#endif
 struct BitPacker {
     uint32_t lo, hi;     // accumulator: bits [accn) of lo|hi<<32 are valid
     uint32_t accn;       // < 32 between emits
@@ -87,12 +106,12 @@ struct BitPacker {
 #endif
         lo |= (uint32_t)sh;
         hi = (uint32_t)(sh >> 32);  // (hi carries nothing between emits: accn < 32)
-        accn += n;
+        accn = df_add(accn, n);
         if (accn >= 32) {
             simt::sts32(wa, lo);
-            wa += 4;
+            wa = df_add(wa, 4u);
             lo = hi;
-            accn -= 32;
+            accn = df_add(accn, 0xffffffe0u);  // - 32 (mod 2^32)
         }
     }
 };
