@@ -33,7 +33,10 @@ static const uint32_t UB_IN_STRIDE = 17;               // words per staging row
 static const uint32_t UB_ROW_WORDS = 33;               // private bit string: 8 chunks x <= 124 bits = 31 words, + the zero word behind it
 static const uint32_t UB_WIN_WORDS = 32 * UB_IN_STRIDE;  // the warp's output window = the staging rows (544 words: a step of
                                                          // up to 8.5 bits per input byte leaves in one round, else in several)
-static const int UB_WARPS = 8;
+#ifndef UB_WARPS_PER_CTA
+#define UB_WARPS_PER_CTA 8
+#endif
+static const int UB_WARPS = UB_WARPS_PER_CTA;
 #ifndef UB_UNROLL
 #define UB_UNROLL 2
 #endif

@@ -44,8 +44,11 @@ namespace fdb {
 #ifndef K4_PAIR_UNITS
 #define K4_PAIR_UNITS 0
 #endif
+// 28 warps, not 32: 72 registers per thread instead of 64 (room for the hoisted staging loads, K4_STAGE_HOIST), and
+// 148 x 28 = 4144 warps still take the bench's 4096 streams in one round.  Measured (profiles/r04_variants.txt): 32 warps
+// 1.272 ms, 32 + hoist 1.248, 30 + hoist 1.248, 28 1.268, 28 + hoist 1.232 ms.
 #ifndef K4_WARPS_PER_CTA
-#define K4_WARPS_PER_CTA (K4_PAIR_UNITS ? 28 : 32)
+#define K4_WARPS_PER_CTA 28
 #endif
 static const int K4_WARPS = K4_WARPS_PER_CTA;  // warps per CTA (one CTA per SM; they share the 40 KiB of tables)
 static const uint32_t K4_SUBW = 8;     // 32-bit words of compressed data per lane per segment
@@ -96,6 +99,11 @@ struct UfTabs {
 // Measured (profiles/r03_k4_variants.txt): with the table lookups done this way the kernel is 8.5 % SLOWER (IMAD.HI sits
 // in the decode dependency chain and is slower than the two ALU instructions it replaces); K4_FMA_PIPE == 2 moves only
 // the literal extraction of the write loop, which is off that chain.
+// K4_STAGE_HOIST: the three staging loads of a segment are issued together, ahead of the stores of the first (one trip
+// to L2 per segment instead of three; profiles/r04_variants.txt)
+#ifndef K4_STAGE_HOIST
+#define K4_STAGE_HOIST 1
+#endif
 #ifndef K4_FMA_PIPE
 #define K4_FMA_PIPE 0
 #endif
@@ -621,13 +629,29 @@ FDB_DEVICE int32_t inflate_uf_run(const UfTabs& t, const uint32_t* hdr, K4Warp& 
             const uint64_t pf = (s0 << 2) + 4u * 32u * K4_SUBW + 128u * lane;
             if (lane < 9 && pf < end_byte) simt::prefetch_l2(abase + pf);  // (only lines that hold stream bytes)
         }
+#if K4_STAGE_HOIST
+        // all loads of the segment first (a load issued behind the stores of the vector before it waits out its own trip
+        // to L2); needs the registers of a 28-warp CTA
+        uint4 q3[3];
+#pragma unroll
+        for (uint32_t it = 0; it < 3; it++) {
+            const uint32_t v = it < 2 ? 2u * lane + it : 64u + lane;
+            q3[it] = make_uint4(0, 0, 0, 0);
+            if (seg_inside && v < K4_SEG_WORDS / 4) q3[it] = simt::ldg128((const uint4*)(abase + (s0 << 2) + 16ull * v));
+        }
+#pragma unroll
+#endif
         for (uint32_t it = 0; it < 3; it++) {
             const uint32_t v = it < 2 ? 2u * lane + it : 64u + lane;
             if (v >= K4_SEG_WORDS / 4) continue;
             uint64_t byte0 = (s0 << 2) + 16ull * v;  // relative to abase
             uint4 q = make_uint4(0, 0, 0, 0);
             if (seg_inside) {
+#if K4_STAGE_HOIST
+                q = q3[it];
+#else
                 q = simt::ldg128((const uint4*)(abase + byte0));
+#endif
             } else if (byte0 + 16 > first_byte && byte0 < end_byte) {
                 q = simt::ldg128((const uint4*)(abase + byte0));
                 if (byte0 < first_byte || byte0 + 16 > end_byte) {
