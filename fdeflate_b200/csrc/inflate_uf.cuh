@@ -60,7 +60,10 @@ static const uint32_t K4_SEG_WORDS = K4_WARM + 32 * K4_SUBW + 4;  // words stage
 static const uint32_t K4_LIM_LO = 32u * K4_WARM;               // a lane's sub-sequence, in bits of its row
 static const uint32_t K4_LIM_HI = 32u * (K4_WARM + K4_SUBW);
 static const uint32_t K4_PAIR = 24;    // two table entries consume at most 2 x 12 bits
-static const uint32_t K4_WIN = K4_PAIR_UNITS ? 3008 : 3904;  // output window bytes (a segment normally expands to ~2.3 KiB)
+#ifndef K4_WIN_BYTES
+#define K4_WIN_BYTES (K4_PAIR_UNITS ? 3008 : 3904)
+#endif
+static const uint32_t K4_WIN = K4_WIN_BYTES;  // output window bytes (a segment normally expands to ~2.3 KiB)
 static const uint32_t K4_INVALID = 0xffffffffu;
 
 // Staging is TRANSPOSED and PRIVATE per lane: row i holds the words lane i can ever touch
@@ -1071,7 +1074,7 @@ FDB_GLOBAL void FDB_LAUNCH_BOUNDS(K4_WARPS * 32, 1)
     K4Warp& ws = sm.warp[simt::warp_in_block()];
     const UfTabs t = {simt::smem_addr(sm.wt), simt::smem_addr(sm.ct), simt::smem_addr(sm.bt)};
     // The first stream of every warp is fixed: stream c + grid * w for warp w of CTA c, so that a batch of about one
-    // stream per resident warp (the bench: 4096 streams on 4736 warps) gives every SM the same number of streams.
+    // stream per resident warp (the bench: 4096 streams on 4144 warps) gives every SM the same number of streams.
     // Handed out through the counter, the streams go to whichever warps ask first, an SM ends up with anything from
     // ~22 to 32 of them, and the kernel lasts as long as the fullest SM.  Further streams come from the counter.
     const uint32_t slots = gridDim.x * K4_WARPS;
